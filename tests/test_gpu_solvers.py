@@ -1,0 +1,220 @@
+"""GPU solver passes and whole steps vs the oracle, through the C ABI.
+
+The CUDA translation unit is compiled without FMA contraction and with IEEE division / square root and keeps the
+reference's evaluation and summation order, so the comparison is BIT-EXACT; the north-star tolerance (1e-4 relative)
+is asserted as well so that a future relaxed-arithmetic mode has its bar written down.
+"""
+import numpy as np
+import pytest
+
+import yasph2d_b200 as y
+from oracle import pyoracle as po
+from util import REL_TOL, assert_close, assert_lists_equal
+
+pytestmark = pytest.mark.gpu
+capi = y.capi
+
+
+def make_worlds(scene="dam"):
+    w = y.FluidParticleWorld(2.0, 10000.0, 100.0)
+    ow = po.World()
+    if scene == "dam":
+        y.dam_break_scene(w)
+        po.dam_break_scene(ow)
+    else:  # bench scene of benches/benchmarks/update_densities.rs:71-79: fluid rect jitter 0.5 + 20-thick boundary line
+        w.add_fluid_rect(y.Rect(0.0, 0.0, 1.0, 1.0), 0.5)
+        w.add_boundary_thick_line((-0.5, 0.5), (1.5, 0.5), 20)
+        ow.add_fluid_rect(0.0, 0.0, 1.0, 1.0, 0.5)
+        ow.add_boundary_thick_line((-0.5, 0.5), (1.5, 0.5), 20)
+    assert np.array_equal(w.particles.positions, ow.positions()) and np.array_equal(w.particles.boundary_particles, ow.boundary())
+    return w, ow
+
+
+def gpu_ctx(w, solver=capi.SOLVER_DFSPH, **kw):
+    cfg = capi.default_config(2.0, 10000.0, 100.0, solver)
+    cfg.max_particles = len(w.particles.positions)
+    cfg.max_boundary = len(w.particles.boundary_particles)
+    for k, v in kw.items():
+        setattr(cfg, k, v)
+    ctx = y.GpuContext(cfg)
+    ctx.set_boundary(w.particles.boundary_particles)
+    ctx.upload_particles(w.particles.positions, w.particles.velocities)
+    return ctx
+
+
+@pytest.mark.parametrize("scene", ["dam", "bench"])
+@pytest.mark.parametrize("kernel", [po.K_WENDLAND, po.K_POLY6, po.K_SPIKY, po.K_CUBIC])
+def test_update_densities(scene, kernel):
+    """FluidParticleWorld::update_densities (fluidparticleworld.rs:197-231) with each kernel of the reference's bench."""
+    w, ow = make_worlds(scene)
+    ctx = gpu_ctx(w)
+    ctx.neighborhood_update()
+    ow.update_neighborhood()
+    assert_lists_equal(ctx.neighbors(), ow.neighbors())
+    ctx.update_densities(kernel)
+    ow.update_densities(kernel)
+    got, ref = ctx.field(capi.FIELD_DENSITY), ow.densities()
+    assert_close(got, ref, "density")
+    assert np.array_equal(got, ref), "density not bit-exact: %d differ" % (got != ref).sum()
+    assert ref.max() > 100.0  # not all clamped
+
+
+@pytest.mark.parametrize("scene", ["dam", "bench"])
+def test_alpha_factors(scene):
+    """DFSPHSolver::compute_alpha_factors (dfsph.rs:68-97)."""
+    w, ow = make_worlds(scene)
+    ctx = gpu_ctx(w)
+    ctx.neighborhood_update()
+    ow.update_neighborhood()
+    ctx.compute_alpha()
+    ref = po.DFSPHSolver(ow).alpha_factors(ow)
+    got = ctx.field(capi.FIELD_ALPHA)
+    assert_close(got, ref, "alpha")
+    assert np.array_equal(got, ref)
+
+
+def compare_state(ctx, ow, step, exact=True):
+    pos, vel, dens = ctx.download_particles()
+    for name, got, ref in (("position", pos, ow.positions()), ("velocity", vel, ow.velocities()), ("density", dens, ow.densities())):
+        assert_close(got, ref, "%s after step %d" % (name, step))
+        if exact:
+            assert np.array_equal(got, ref), "%s after step %d not bit-exact (%d of %d differ)" % (name, step, (got != ref).sum(), got.size)
+
+
+def test_dfsph_first_step_fields():
+    """One DFSPH step of the dam-break scene: lists, rho, alpha, non-pressure accel, v*, x (BASELINE.json config 2)."""
+    w, ow = make_worlds()
+    ctx = gpu_ctx(w)
+    otm, osolver = po.TimeManager(cfl_factor=1.5), po.DFSPHSolver(ow)
+    rep, orep = ctx.step(), osolver.simulation_step(ow, otm)
+    assert (rep.dt_prev_ns, rep.dt_ns) == (41667, orep.dt_ns)
+    assert rep.dt == orep.dt and rep.max_velocity == orep.max_velocity
+    assert (rep.iters_density, rep.iters_divergence, rep.warm_density, rep.warm_divergence) == (
+        orep.iters_density, orep.iters_divergence, orep.warm_density, orep.warm_divergence)
+    assert_lists_equal(ctx.neighbors(), ow.neighbors())
+    compare_state(ctx, ow, 0)
+    oa, ok, os_ = osolver.state(ow.n)
+    for f, ref in ((capi.FIELD_ALPHA, oa), (capi.FIELD_KAPPA, ok), (capi.FIELD_STIFFNESS, os_)):
+        got = ctx.field(f)
+        assert_close(got, ref, "field %d" % f)
+        assert np.array_equal(got, ref)
+
+
+def run_dfsph(steps, check_every, scene="dam", **kw):
+    w, ow = make_worlds(scene)
+    ctx = gpu_ctx(w, **kw)
+    otm, osolver = po.TimeManager(cfl_factor=1.5), po.DFSPHSolver(ow)
+    it_max = [0, 0]
+    warm = [0, 0]
+    for s in range(steps):
+        rep, orep = ctx.step(), osolver.simulation_step(ow, otm)
+        assert rep.dt_ns == orep.dt_ns, (s, rep.dt_ns, orep.dt_ns)
+        assert (rep.iters_density, rep.iters_divergence) == (orep.iters_density, orep.iters_divergence), s
+        assert (rep.warm_density, rep.warm_divergence) == (orep.warm_density, orep.warm_divergence), s
+        assert rep.avg_density_error == orep.avg_density_error and rep.avg_divergence == orep.avg_divergence, s
+        it_max = [max(it_max[0], rep.iters_density), max(it_max[1], rep.iters_divergence)]
+        warm = [warm[0] + rep.warm_density, warm[1] + rep.warm_divergence]
+        if s % check_every == 0 or s == steps - 1:
+            compare_state(ctx, ow, s)
+    return it_max, warm, ctx, ow
+
+
+def test_dfsph_trajectory_dam_break():
+    """400 DFSPH steps of the dam break: dt, iteration counts, residuals and the full state stay identical to the oracle;
+    the run covers the impact on the slope, where the divergence solver iterates and warm-starts."""
+    it_max, warm, ctx, ow = run_dfsph(400, 25)
+    assert it_max[1] >= 2 and warm[1] > 0, (it_max, warm)
+    # global invariants at the end of the run
+    pos, vel, dens = ctx.download_particles()
+    assert np.isfinite(pos).all() and np.isfinite(vel).all()
+    ekin = 0.5 * 0.01 * float((vel.astype(np.float64) ** 2).sum())
+    oekin = 0.5 * 0.01 * float((ow.velocities().astype(np.float64) ** 2).sum())
+    assert abs(ekin - oekin) <= 1e-9 * max(oekin, 1.0)
+
+
+def test_dfsph_tight_tolerance_iterates():
+    """With tolerances 100x tighter than the reference's defaults both Jacobi loops run many iterations (and the density
+    warm start triggers): exercises the device-side loop control across several speculative chunks."""
+    w, ow = make_worlds()
+    ctx = gpu_ctx(w, dfsph_max_avg_density_error=1e-6, dfsph_max_divergence_error=1e-5)
+    # the oracle has the same knobs as public fields only through its constructor defaults; emulate by stepping with the
+    # defaults first is not possible, so compare GPU against itself with a different chunking instead
+    ctx2 = gpu_ctx(w, dfsph_max_avg_density_error=1e-6, dfsph_max_divergence_error=1e-5, speculative_iterations=5)
+    big = 0
+    for s in range(120):
+        r1, r2 = ctx.step(), ctx2.step()
+        assert (r1.iters_density, r1.iters_divergence, r1.dt_ns) == (r2.iters_density, r2.iters_divergence, r2.dt_ns), s
+        big = max(big, r1.iters_density, r1.iters_divergence)
+    p1, v1, d1 = ctx.download_particles()
+    p2, v2, d2 = ctx2.download_particles()
+    assert np.array_equal(p1, p2) and np.array_equal(v1, v2) and np.array_equal(d1, d2)
+    assert big >= 4, big
+
+
+def test_dfsph_step_host_equals_resident():
+    """yasph_step_host (host arrays in/out every step, the drop-in call) == device-resident stepping."""
+    w, ow = make_worlds()
+    ctx = gpu_ctx(w)
+    w2, _ = make_worlds()
+    tm = y.TimeManager(y.SimulationStepConfig.AdaptiveTimeStep(cfl_factor=1.5))
+    solver = y.DFSPHSolver(y.XSPHViscosityModel(w2.properties.smoothing_length()), w2.properties.smoothing_length())
+    for s in range(30):
+        rep = ctx.step()
+        rep2 = solver.simulation_step(w2, tm)
+        assert rep.dt_ns == rep2.dt_ns == tm.simulation_step()
+    pos, vel, dens = ctx.download_particles()
+    assert np.array_equal(pos, w2.particles.positions) and np.array_equal(vel, w2.particles.velocities)
+    assert np.array_equal(dens, w2.particles.densities)
+
+
+def test_wcsph_trajectory_dam_break():
+    """WCSPH (wscsph.rs:126-179), cfl 0.2 (main.rs:116): 300 steps identical to the oracle incl. accelerations."""
+    w, ow = make_worlds()
+    cfg_kw = dict(cfl_factor=0.2)
+    ctx = gpu_ctx(w, solver=capi.SOLVER_WCSPH, **cfg_kw)
+    otm, osolver = po.TimeManager(cfl_factor=0.2), po.WCSPHSolver(ow)
+    assert np.float32(ctx.cfg.wcsph_stiffness) == np.float32(osolver.stiffness())
+    for s in range(300):
+        rep, orep = ctx.step(), osolver.simulation_step(ow, otm)
+        assert rep.dt_ns == orep.dt_ns, (s, rep.dt_ns, orep.dt_ns)
+        assert rep.max_velocity == orep.max_velocity, s
+        if s % 30 == 0 or s == 299:
+            compare_state(ctx, ow, s)
+            acc = ctx.field(capi.FIELD_ACCELERATION)
+            assert_close(acc, osolver.accelerations(ow.n), "acceleration after step %d" % s)
+            assert np.array_equal(acc, osolver.accelerations(ow.n))
+
+
+def test_physical_viscosity_model():
+    """PhysicalViscosityModel (physical.rs:19-24) with mu = 0.01 (main.rs:96)."""
+    w, ow = make_worlds()
+    ctx = gpu_ctx(w, viscosity=capi.VISCOSITY_PHYSICAL, viscosity_param=0.01)
+    otm, osolver = po.TimeManager(cfl_factor=1.5), po.DFSPHSolver(ow, po.VISC_PHYSICAL, 0.01)
+    for s in range(80):
+        rep, orep = ctx.step(), osolver.simulation_step(ow, otm)
+        assert rep.dt_ns == orep.dt_ns
+    compare_state(ctx, ow, 79)
+
+
+def test_clear_cached_and_reset():
+    """reset_simulation (main.rs:292-298): clear_cached_data + TimeManager::restart + scene rebuild reproduces the run."""
+    w, ow = make_worlds()
+    ctx = gpu_ctx(w)
+    first = [ctx.step().dt_ns for _ in range(20)]
+    p_first = ctx.download_particles()
+    ctx.clear_cached()
+    capi.check(capi.lib().yasph_time_restart(ctx.h), ctx.h)
+    ctx.upload_particles(w.particles.positions, w.particles.velocities)
+    second = [ctx.step().dt_ns for _ in range(20)]
+    p_second = ctx.download_particles()
+    assert first == second
+    for a, b in zip(p_first, p_second):
+        assert np.array_equal(a, b)
+
+
+def test_step_without_particles_fails():
+    cfg = capi.default_config()
+    ctx = y.GpuContext(cfg)
+    with pytest.raises(capi.YasphError) as e:
+        ctx.step()
+    assert e.value.status == 4  # YASPH_ERR_STATE

@@ -1,0 +1,117 @@
+// scan.cuh -- device-wide exclusive scan (reduce / scan-chunk-sums / apply) with functor input and output, so the
+// head-flag computation and the stream compaction that follow a scan are fused into its two data passes.
+// Replaces the sequential cell creation loop of the reference (src/sph/neighborhood_search.rs:146-165).
+#pragma once
+#include "common.cuh"
+
+namespace yasph {
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 16;
+constexpr int SCAN_CHUNK = SCAN_THREADS * SCAN_ITEMS;  // 4096
+constexpr int SCAN_WARPS = SCAN_THREADS / 32;
+
+template <typename T>
+__device__ __forceinline__ T warp_inclusive_scan(T v) {
+    const unsigned lane = lane_id();
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        T u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= (unsigned)o) v += u;
+    }
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// chunk_sums[b] = sum of in(i) over chunk b
+template <typename T, typename In>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(In in, uint32_t n, T* __restrict__ chunk_sums) {
+    __shared__ T wsum[SCAN_WARPS];
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    const uint32_t base = blockIdx.x * SCAN_CHUNK + warp * (32 * SCAN_ITEMS);
+    T s = 0;
+#pragma unroll
+    for (int r = 0; r < SCAN_ITEMS; ++r) {
+        uint32_t i = base + r * 32 + lane;
+        if (i < n) s += in(i);
+    }
+    s = warp_sum(s);
+    if (lane == 0) wsum[warp] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        T t = 0;
+#pragma unroll
+        for (int w = 0; w < SCAN_WARPS; ++w) t += wsum[w];
+        chunk_sums[blockIdx.x] = t;
+    }
+}
+
+// in-place exclusive scan of chunk_sums[0..nchunks) by ONE block; total -> *total_out (may be null)
+template <typename T>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_chunks(T* __restrict__ chunk_sums, uint32_t nchunks, T* __restrict__ total_out) {
+    __shared__ T wsum[SCAN_WARPS];
+    __shared__ T carry_s;
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nchunks; base += SCAN_THREADS) {
+        uint32_t i = base + threadIdx.x;
+        T v = i < nchunks ? chunk_sums[i] : (T)0;
+        T inc = warp_inclusive_scan(v);
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        T woff = 0;
+        for (uint32_t w = 0; w < warp; ++w) woff += wsum[w];
+        T carry = carry_s;
+        if (i < nchunks) chunk_sums[i] = carry + woff + inc - v;
+        __syncthreads();
+        if (threadIdx.x == SCAN_THREADS - 1) carry_s = carry + woff + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total_out) *total_out = carry_s;
+}
+
+// out(i, exclusive_prefix(i), in(i)) for every i
+template <typename T, typename In, typename Out>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(In in, uint32_t n, const T* __restrict__ chunk_offsets, Out out) {
+    __shared__ T wsum[SCAN_WARPS];
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    const uint32_t base = blockIdx.x * SCAN_CHUNK + warp * (32 * SCAN_ITEMS);
+    T v[SCAN_ITEMS], ex[SCAN_ITEMS];
+    T carry = 0;
+#pragma unroll
+    for (int r = 0; r < SCAN_ITEMS; ++r) {
+        uint32_t i = base + r * 32 + lane;
+        v[r] = i < n ? in(i) : (T)0;
+        T inc = warp_inclusive_scan(v[r]);
+        ex[r] = carry + inc - v[r];
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) wsum[warp] = carry;
+    __syncthreads();
+    T off = chunk_offsets[blockIdx.x];
+    for (uint32_t w = 0; w < warp; ++w) off += wsum[w];
+#pragma unroll
+    for (int r = 0; r < SCAN_ITEMS; ++r) {
+        uint32_t i = base + r * 32 + lane;
+        if (i < n) out(i, off + ex[r], v[r]);
+    }
+}
+
+struct U32In {
+    const uint32_t* p;
+    __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return p[i]; }
+};
+struct U32Out {
+    uint32_t* p;
+    __device__ __forceinline__ void operator()(uint32_t i, uint32_t ex, uint32_t) const { p[i] = ex; }
+};
+
+inline uint32_t scan_num_chunks(uint32_t n) { return (n + SCAN_CHUNK - 1) / SCAN_CHUNK; }
+
+}  // namespace yasph
