@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py -- particle-steps/sec of the DFSPH hot path on B200 (BASELINE.json metric), one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload tank|dam_break]
+
+A "step" is one Solver::simulation_step (dfsph.rs:414-525) over the whole particle set.  Default workload: the DFSPH
+dam-break tank of BASELINE.json configs[3] at its per-GPU size (2 000 x 1 000 = 2 M fluid particles per GPU; 8 GPUs =
+the 16 M-particle tank), advanced `--presteps` steps before anything is timed so the column is collapsing.
+`value` is timed with the state resident in HBM; `e2e` goes through yasph_step_host with pinned HOST buffers
+(upload pos+vel, step, download pos+vel+densities every step) -- what the reference's `simulation_step(&mut world, ..)`
+does to the Vecs the Rust host owns.  `--impl reference` times the CPU restatement of the reference (oracle/, C++/OpenMP,
+all host cores) on a bounded sample of the same workload; the Rust binary itself cannot be built in this image.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle-steps/sec (DFSPH, 2D dam-break)"
+UNIT = "particle-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="tank", choices=["tank", "dam_break"])
+    ap.add_argument("--columns-per-gpu", type=int, default=2000)
+    ap.add_argument("--rows", type=int, default=1000)
+    ap.add_argument("--presteps", type=int, default=200)
+    ap.add_argument("--cpu-columns", type=int, default=250, help="fluid columns of the bounded CPU sample (rows as the workload)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# algorithmic bytes per particle and pass; K = mean total neighbours, L = 8 + 4K
+# ----------------------------------------------------------------------------------------------------------------------
+def pass_bytes(K):
+    L = 8.0 + 4.0 * K
+    return {
+        "viscosity": 28 + L,
+        "predict": 24,
+        "density_warm": 36 + L,
+        "density_iter": 64 + 2 * L,   # A (24+L) + B (40+L)
+        "advect_keygen": 24,
+        "neighborhood": 140 + 4 * K,  # key-gen, 4-pass radix sort, gathers, cells, list build
+        "lists": 16 + 4 * K,
+        "density_alpha": 40 + 8 * K,
+        "divergence_warm": 36 + L,
+        "divergence_iter": 60 + 2 * L,
+    }
+
+
+def clocks_sampler(stop, out, device_index):
+    """nvidia-smi clocks line of /opt/skills/guides/B200_PROFILING.md, sampled during the timed region."""
+    q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    while not stop.is_set():
+        try:
+            r = subprocess.run(["nvidia-smi", "-i", str(device_index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                               capture_output=True, text=True, timeout=5)
+            f = [x.strip() for x in r.stdout.strip().split(",")]
+            if len(f) >= 7:
+                out.append(f)
+        except Exception:
+            pass
+        stop.wait(0.2)
+
+
+def summarize_clocks(samples):
+    if not samples:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+    sm = sorted(float(s[0]) for s in samples)
+    reasons = []
+    for idx, name in ((3, "hw_slowdown"), (4, "hw_thermal_slowdown"), (5, "sw_thermal_slowdown"), (6, "sw_power_cap")):
+        if any(s[idx].lower().startswith("active") for s in samples):
+            reasons.append(name)
+    return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(samples[0][1]), "power_w_max": max(float(s[2]) for s in samples),
+            "samples": len(samples), "reasons": reasons}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (C++/OpenMP restatement of the reference) on a bounded sample of the workload
+# ----------------------------------------------------------------------------------------------------------------------
+def build_oracle_tank(po, columns, rows):
+    import yasph2d_b200 as y
+
+    hw = y.tank_scene(y.FluidParticleWorld(2.0, 10000.0, 100.0), columns, rows)
+    w = po.World()
+    w.set_particles(hw.particles.positions)
+    w.set_boundary(hw.particles.boundary_particles)
+    return w
+
+
+def run_cpu(args, columns, steps, warmup):
+    from oracle import pyoracle as po
+
+    cores = po.num_threads(os.cpu_count() or 1)
+    if args.workload == "tank":
+        w = build_oracle_tank(po, columns, args.rows)
+        sample = "tank %d x %d = %d fluid particles (+%d boundary), %d presteps, %d timed steps" % (columns, args.rows, w.n, w.m, args.presteps, steps)
+        presteps = args.presteps
+    else:
+        w = po.dam_break_scene(po.World())
+        sample = "application dam-break scene, %d fluid + %d boundary particles, %d presteps, %d timed steps" % (w.n, w.m, args.presteps, steps)
+        presteps = args.presteps
+    tm = po.TimeManager(cfl_factor=1.5)
+    s = po.DFSPHSolver(w)
+    for _ in range(presteps + warmup):
+        s.simulation_step(w, tm)
+    its = [0, 0]
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        r = s.simulation_step(w, tm)
+        its[0] += r.iters_density
+        its[1] += r.iters_divergence
+    dt = time.perf_counter() - t0
+    return {"value": w.n * steps / dt, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+            "ms_per_step": 1e3 * dt / steps, "n": w.n, "iters_density_mean": its[0] / steps, "iters_divergence_mean": its[1] / steps}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        cb = run_cpu(args, args.cpu_columns * 2, args.steps, args.warmup)
+        line = {
+            "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "DFSPH dam-break tank, CPU restatement of the reference (C++/OpenMP) -- not the Rust binary", "sample": cb["sample"]},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import yasph2d_b200 as y
+
+    capi = y.capi
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    # ---- scene (host) ----
+    hw = y.FluidParticleWorld(2.0, 10000.0, 100.0)
+    if args.workload == "tank":
+        y.tank_scene(hw, args.columns_per_gpu, args.rows)
+        workload = "DFSPH dam-break tank (BASELINE configs[3] per-GPU share): %d x %d fluid particles per GPU" % (args.columns_per_gpu, args.rows)
+    else:
+        y.dam_break_scene(hw)
+        workload = "DFSPH application dam-break scene (BASELINE configs[1], main.rs:177-196)"
+    n, m = hw.particles.num_dynamic_particles(), hw.particles.num_boundary_particles()
+
+    cfg = capi.default_config(2.0, 10000.0, 100.0, capi.SOLVER_DFSPH)
+    cfg.device = local_rank
+    cfg.max_particles, cfg.max_boundary = n, m
+    ctx = y.GpuContext(cfg)
+    ctx.set_boundary(hw.particles.boundary_particles)
+    ctx.upload_particles(hw.particles.positions, hw.particles.velocities)
+    stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=torch.device("cuda", local_rank))
+
+    for _ in range(args.presteps):
+        ctx.step()
+
+    def timed(step_fn, steps, warmup):
+        for _ in range(warmup):
+            step_fn()
+        torch.cuda.synchronize()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = []
+        l0 = ctx.launch_count()
+        e0.record(stream)
+        for _ in range(steps):
+            reps.append(step_fn())
+        e1.record(stream)
+        torch.cuda.synchronize()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = ctx.launch_count() - l0
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, reps, launches
+
+    # ---- device-resident throughput (`value`) with clocks sampled during the timed region ----
+    stop, samples = threading.Event(), []
+    th = threading.Thread(target=clocks_sampler, args=(stop, samples, local_rank), daemon=True)
+    th.start()
+    ms, reps, launches = timed(ctx.step, args.steps, args.warmup)
+    stop.set()
+    th.join(timeout=3)
+    value = n * world * args.steps / (ms * 1e-3)
+    it_rho = float(np.mean([r.iters_density for r in reps]))
+    it_div = float(np.mean([r.iters_divergence for r in reps]))
+    w_rho = float(np.mean([r.warm_density for r in reps]))
+    w_div = float(np.mean([r.warm_divergence for r in reps]))
+    K = float(np.mean([r.total_neighbors for r in reps])) / n
+
+    # ---- per-pass device times (CUDA event pairs around every pass, on the launching stream) -> roofline ----
+    ctx.set_flags(capi.FLAG_PROFILE_PASSES)
+    acc = {}
+    psteps = max(3, min(args.steps, 10))
+    piters = [0.0, 0.0]
+    for _ in range(psteps):
+        r = ctx.step()
+        piters[0] += r.iters_density
+        piters[1] += r.iters_divergence
+        for k, v in ctx.pass_times_us().items():
+            acc[k] = acc.get(k, 0.0) + v
+    ctx.set_flags(0)
+    pt = {k: v / psteps for k, v in acc.items()}  # us per step
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    B = pass_bytes(K)
+    # bytes per step for each timed pass group
+    groups = {
+        "viscosity": (pt["viscosity"], B["viscosity"]),
+        "density_solve": (pt["density_solve"], B["density_iter"] * piters[0] / psteps),
+        "divergence_solve": (pt["divergence_solve"], B["divergence_iter"] * piters[1] / psteps),
+        "density_alpha": (pt["density_alpha"], B["density_alpha"]),
+        "lists": (pt["lists"], B["lists"]),
+        "neighborhood(sort+gather+cells+lists)": (pt["sort"] + pt["gather"] + pt["cells_tiles"] + pt["lists"], B["neighborhood"]),
+    }
+    passes = {}
+    for k, (us, bpp) in groups.items():
+        gbs = (bpp * n) / (us * 1e-6) / 1e9 if us > 0 else 0.0
+        passes[k] = {"us_per_step": round(us, 2), "alg_bytes_per_particle": round(bpp, 1), "GBps": round(gbs, 1), "frac": round(gbs / peak, 4)}
+    dominant = max(("viscosity", "density_solve", "divergence_solve", "density_alpha", "lists"), key=lambda k: groups[k][0])
+    d_us, d_bpp = groups[dominant]
+    achieved = (d_bpp * n) / (d_us * 1e-6) / 1e9
+    step_bytes = (B["viscosity"] + B["predict"] + it_rho * B["density_iter"] + w_rho * B["density_warm"] + 4 + B["advect_keygen"] + B["neighborhood"]
+                  + B["density_alpha"] + it_div * B["divergence_iter"] + w_div * B["divergence_warm"] + 4)
+    roofline = {
+        "bound": "hbm", "kernel": dominant + " (k_sweep)", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+        "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_kind,
+        "whole_step": {"alg_bytes_per_particle_step": round(step_bytes, 1), "GBps": round(step_bytes * n * world * args.steps / (ms * 1e-3) / 1e9, 1),
+                       "frac": round(step_bytes * n * args.steps / (ms * 1e-3) / 1e9 / peak, 4)},
+        "passes": passes, "pass_us_per_step": {k: round(v, 2) for k, v in pt.items()},
+    }
+
+    # ---- end to end through the reference-facing call with pinned HOST buffers ----
+    e2e = None
+    if not args.no_e2e:
+        pos_t = torch.empty((n, 2), dtype=torch.float32, pin_memory=True)
+        vel_t = torch.empty((n, 2), dtype=torch.float32, pin_memory=True)
+        den_t = torch.empty((n,), dtype=torch.float32, pin_memory=True)
+        pos, vel, den = pos_t.numpy(), vel_t.numpy(), den_t.numpy()
+        p0, v0, _ = ctx.download_particles()
+        pos[:], vel[:] = p0, v0
+        ems, ereps, _ = timed(lambda: ctx.step_host(pos, vel, den), args.steps, args.warmup)
+        e2e = {"value": n * world * args.steps / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(n * 16), "d2h_bytes_per_step": int(n * 20),
+               "ms_per_step": ems / args.steps, "api": "yasph_step_host (upload pos+vel, simulation_step, download pos+vel+densities)"}
+
+    # ---- CPU baseline (rank 0, single-GPU run only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = run_cpu(args, args.cpu_columns, max(3, min(args.steps, 10)), 1)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "ms_per_step", "iters_density_mean", "iters_divergence_mean")}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": workload, "particles_per_gpu": n, "boundary_particles": m, "presteps": args.presteps,
+                "parallelism": "1 GPU" if world == 1 else "%d independent per-GPU tanks (slab halo exchange not built yet)" % world,
+                "l2": "working set %.0f MB per GPU > 126 MB L2 (no explicit flush)" % (n * 240 / 1e6) if n * 240 > 126e6 else "working set fits L2 (small scene)",
+                "mean_neighbors": round(K, 2), "iters_density": it_rho, "iters_divergence": it_div, "warm_density": w_rho, "warm_divergence": w_div,
+                "arithmetic": "strict f32, no FMA contraction, IEEE div/sqrt (bit-exact vs oracle)",
+            },
+            "gpu_launches": int(launches), "clocks": summarize_clocks(samples), "roofline": roofline,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

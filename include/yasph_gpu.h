@@ -96,7 +96,7 @@ typedef struct yasph_config {
     uint64_t timestep_max_ns;            /* from_secs_f32(1/120/3)  = 2777778 */
     float cfl_factor;                    /* 1.5 (DFSPH) / 0.2 (WCSPH), main.rs:115-118 */
     /* implementation knobs (0 = default) */
-    uint32_t max_tiles;                  /* capacity for 8x8-cell tiles; default max_particles/8 + 4096 */
+    uint32_t max_tiles;                  /* capacity for 8x8-cell tiles; default max_particles/32 + 4096 */
     uint32_t tile_dynamic_capacity;      /* staged dynamic candidates per tile (default 2048) */
     uint32_t tile_static_capacity;       /* staged boundary candidates per tile (default 1024) */
     uint32_t speculative_iterations;     /* Jacobi iterations launched between two convergence read-backs (default 2) */
@@ -135,6 +135,8 @@ int32_t yasph_create(const yasph_config* cfg, yasph_ctx** out);
 int32_t yasph_destroy(yasph_ctx* ctx);
 const char* yasph_last_error(const yasph_ctx* ctx); /* ctx may be NULL: error of the last failed yasph_create */
 int32_t yasph_get_config(const yasph_ctx* ctx, yasph_config* out);
+/* replaces cfg.flags (YASPH_FLAG_*) at run time */
+int32_t yasph_set_flags(yasph_ctx* ctx, uint32_t flags);
 /* derived ConstantFluidProperties: out[0]=particle_mass, out[1]=particle_radius (fluidparticleworld.rs:74-89) */
 int32_t yasph_get_properties(const yasph_ctx* ctx, float* out2);
 

@@ -24,7 +24,7 @@ STATUS_NAMES = {0: "OK", 1: "INVALID_ARGUMENT", 2: "CUDA", 3: "CAPACITY", 4: "ST
 
 # every symbol include/yasph_gpu.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
-    "yasph_config_default", "yasph_create", "yasph_destroy", "yasph_last_error", "yasph_get_config", "yasph_get_properties",
+    "yasph_config_default", "yasph_create", "yasph_destroy", "yasph_last_error", "yasph_get_config", "yasph_set_flags", "yasph_get_properties",
     "yasph_set_boundary", "yasph_upload_particles", "yasph_download_particles", "yasph_download_field", "yasph_num_particles",
     "yasph_clear_cached", "yasph_step", "yasph_step_host", "yasph_time_get_step_ns", "yasph_time_set_step_ns", "yasph_time_restart",
     "yasph_neighborhood_update", "yasph_neighbors_download", "yasph_update_densities", "yasph_compute_alpha", "yasph_pass_times",
@@ -94,6 +94,7 @@ def lib():
     sig("yasph_destroy", C.c_int32, vp)
     sig("yasph_last_error", C.c_char_p, vp)
     sig("yasph_get_config", C.c_int32, vp, C.POINTER(Config))
+    sig("yasph_set_flags", C.c_int32, vp, C.c_uint32)
     sig("yasph_get_properties", C.c_int32, vp, f32p)
     sig("yasph_set_boundary", C.c_int32, vp, f32p, C.c_uint32)
     sig("yasph_upload_particles", C.c_int32, vp, f32p, f32p, C.c_uint32)

@@ -262,6 +262,9 @@ extern "C" int32_t yasph_create(const yasph_config* cfg, yasph_ctx** out) {
     c->cap_dyn = (c->cap_dyn + 15u) & ~15u;
     c->cap_stat = (c->cap_stat + 15u) & ~15u;
     if (c->cap_dyn > 16384 || c->cap_stat > 16384) CREATE_FAIL(YASPH_ERR_INVALID_ARGUMENT, "tile capacities must be <= 16384 slots");
+    if (sweep_smem_bytes(c, sizeof(float4)) > (size_t)prop.sharedMemPerBlockOptin)
+        CREATE_FAIL(YASPH_ERR_CAPACITY, "tile capacities %u/%u need %zu bytes of shared memory per CTA, the device allows %zu", c->cap_dyn, c->cap_stat,
+                    sweep_smem_bytes(c, sizeof(float4)), (size_t)prop.sharedMemPerBlockOptin);
     if (c->cfg.speculative_iterations == 0) c->cfg.speculative_iterations = 2;
     c->cfg.max_tiles = c->max_tiles;
     c->cfg.tile_dynamic_capacity = c->cap_dyn;
@@ -376,6 +379,11 @@ extern "C" const char* yasph_last_error(const yasph_ctx* c) { return c ? c->err.
 extern "C" int32_t yasph_get_config(const yasph_ctx* c, yasph_config* out) {
     if (!c || !out) return YASPH_ERR_INVALID_ARGUMENT;
     *out = c->cfg;
+    return YASPH_OK;
+}
+extern "C" int32_t yasph_set_flags(yasph_ctx* c, uint32_t flags) {
+    if (!c) return YASPH_ERR_INVALID_ARGUMENT;
+    c->cfg.flags = flags;
     return YASPH_OK;
 }
 extern "C" int32_t yasph_get_properties(const yasph_ctx* c, float* out2) {

@@ -123,6 +123,9 @@ class GpuContext:
     def clear_cached(self):
         self._ck(capi.lib().yasph_clear_cached(self.h))
 
+    def set_flags(self, flags):
+        self._ck(capi.lib().yasph_set_flags(self.h, flags))
+
     def step(self):
         rep = capi.StepReport()
         self._ck(capi.lib().yasph_step(self.h, C.byref(rep)))
