@@ -8,10 +8,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#define YASPH_CELLS_PER_TILE_AXIS 8          // a tile is an aligned 8x8 block of cells == 64 consecutive Morton codes
-#define YASPH_TILE_SHIFT 6                   // key >> 6 == tile key
-#define YASPH_REGION_AXIS 10                 // tile + 1-cell apron
-#define YASPH_REGION_CELLS 100
+#ifndef YASPH_TILE_LOG2
+#define YASPH_TILE_LOG2 3                    // a tile is an aligned 8x8 block of cells == 64 consecutive Morton codes
+#endif
 #define YASPH_MAXN 64                        // neighborhood_search.rs:322
 #define YASPH_MIN_DISTANCE 1.0e-10f          // neighborhood_search.rs:323
 #define YASPH_NUM_SMS_B200 148
@@ -193,7 +192,9 @@ struct Control {
     float max_velocity;
     // counts produced by the neighbourhood update
     unsigned int num_cells, num_tiles;
-    unsigned int num_cells_static, pad_counts;
+    unsigned int num_cells_static, num_tiles_static;
+    // per-tile maxima of the last tile-table build: they size the shared memory of every tile kernel
+    unsigned int max_dyn_total, max_stat_total, max_pcount, pad_max;
     // list-build statistics: 16 contiguous bytes, zeroed together before every list build
     unsigned long long total_neighbors;
     unsigned int capped, dropped;
@@ -205,7 +206,7 @@ struct Control {
     unsigned int not_converged;
     unsigned int nonfinite;
     // error flags
-    unsigned int err_tile_capacity;   // a tile's staged candidates exceed the configured smem capacity
+    unsigned int err_tile_capacity;   // a tile stages more than 65535 candidates (slots are 16 bit) or a cell holds more than 65535 particles
     unsigned int err_tile_count;      // more tiles than max_tiles
     // last-block tickets
     unsigned int ticket[4];

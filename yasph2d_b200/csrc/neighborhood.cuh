@@ -1,24 +1,40 @@
-// neighborhood.cuh -- Morton-sorted compact cell grid, 8x8-cell tiles and compact per-particle neighbour lists.
+// neighborhood.cuh -- Morton-sorted compact cell grid, cell tiles, per-tile staging tables and the neighbour-list build.
 //
-// Replaces CompactMortonCellGrid::update (src/sph/neighborhood_search.rs:90-166) and NeighborLists::try_update
-// (:312-397).  Semantics kept from the reference: candidates of a particle are all particles in the 3x3 cell box
-// of its cell, visited in ascending sorted index (== ascending Morton code of the cell, neighborhood_search.rs:191-259
-// produces exactly that order as <=5 index runs); a candidate is a neighbour iff d2 <= r2 && d2 > 1e-10 with
-// d2 = fl(fl(dx*dx) + fl(dy*dy)) (:356-357); dynamic neighbours first, then static, at most 64 in total (:322).
+// Replaces CompactMortonCellGrid::update (src/sph/neighborhood_search.rs:90-166), the per-cell run search
+// get_particle_runs_in_neighborbox (:191-259) and NeighborLists::try_update (:312-397).  Semantics kept from the
+// reference: candidates of a particle are all particles in the 3x3 cell box of its cell, visited in ascending sorted
+// index (== ascending Morton code of the cell; :191-259 produces exactly that order as <=5 index runs); a candidate is a
+// neighbour iff d2 <= r2 && d2 > 1e-10 with d2 = fl(fl(dx*dx) + fl(dy*dy)) (:356-357); dynamic neighbours first, then
+// static, at most 64 in total (:322).
 //
-// B200 design: particles are stored Morton-sorted, so an aligned 8x8 block of cells (a "tile") is one contiguous
-// index range.  Every neighbour-dependent pass runs one CTA per tile, stages the tile's particles plus its 1-cell
-// apron (<= 100 cells, looked up once per step into a per-tile table) in shared memory in ascending-key order, and
-// then addresses neighbours by 16-bit shared-memory slot.  Ascending slot == ascending global index, so list order
-// (and with it every floating-point sum order) is the reference's.  Lists are stored as u16 slots, 4 per 8-byte
-// word, interleaved across the tile's particles so a warp reads them coalesced: 2 B per neighbour instead of the
-// reference's 4 B + 8 B range record (neighborhood_search.rs:268-273,299).
+// B200 design: particles are stored Morton-sorted, so an aligned 8x8 block of cells (a "tile") is one contiguous index
+// range.  Every neighbour-dependent pass runs one CTA per tile, copies the tile's particles plus its 1-cell apron into
+// shared memory in ascending-key order and addresses neighbours by 16-bit shared-memory slot.  Ascending slot ==
+// ascending global index, so list order (and with it every floating-point sum order) is the reference's.  Lists are
+// stored as u16 slots, 4 per 8-byte word, interleaved across the tile's particles so a warp reads them coalesced: 2 B per
+// neighbour instead of the reference's 4 B + 8 B range record (neighborhood_search.rs:268-273,299).
+//
+// Per tile k_tile_tables produces
+//   TileRuns   header + the maximal contiguous global index runs ("copy runs") that make up the staged dynamic and
+//              static candidate arrays -- what the staging loops of every tile kernel binary-search (<= 37 entries)
+//   cslot_d/s  per region cell (row-major in the 10x10 region): slot_start << 16 | count -- what the list build uses
+//              to enumerate the 3x3 box of a cell
+// and the maxima over all tiles (Control::max_*), which the host reads back once per neighbourhood update to size the
+// shared memory of the tile kernels exactly (no worst-case capacity, so many CTAs fit on an SM).
 #pragma once
 #include "common.cuh"
 
 namespace yasph {
 
-constexpr int NB_THREADS = 256;
+constexpr int TILE_AXIS = 1 << YASPH_TILE_LOG2;
+constexpr int TILE_CELLS = TILE_AXIS * TILE_AXIS;
+constexpr int TILE_SHIFT = 2 * YASPH_TILE_LOG2;  // key >> TILE_SHIFT == tile key
+constexpr int REGION_AXIS = TILE_AXIS + 2;
+constexpr int REGION_CELLS = REGION_AXIS * REGION_AXIS;
+constexpr int APRON_CELLS = 4 * TILE_AXIS + 4;
+constexpr int MAX_RUNS = (APRON_CELLS + 1 + 3) & ~3;  // every apron cell on its own + the own block, rounded up
+constexpr uint32_t MAX_BLOCK_COORD = 65535u >> YASPH_TILE_LOG2;
+static_assert(REGION_CELLS <= 128, "the tile-table warp handles the region in four rounds of 32 lanes");
 
 struct TileHeader {       // 32 bytes
     uint32_t pstart;      // first particle of the tile (sorted index)
@@ -26,16 +42,21 @@ struct TileHeader {       // 32 bytes
     uint32_t dyn_total;   // staged dynamic candidates (tile + apron)
     uint32_t stat_total;  // staged boundary candidates
     uint32_t own_lo;      // slot of the tile's first own particle in the staged dynamic array
-    uint32_t pad0, pad1, pad2;
+    uint32_t nruns_d, nruns_s;
+    uint32_t pad;
 };
-// Per tile and region cell in RANK order (ascending Morton key): .x = first global index, .y = slot_start | count << 16
-typedef uint2 TileCell;
+// copy run: .x = first global index, .y = first slot; unused entries carry .y = 0xFFFFFFFF
+struct TileRuns {
+    TileHeader hdr;
+    uint2 rd[MAX_RUNS];
+    uint2 rs[MAX_RUNS];
+};
+static_assert(sizeof(TileRuns) % 16 == 0, "TileRuns is copied in 16-byte pieces");
 
 struct TileTables {
-    const TileHeader* hdr;
-    const TileCell* dyn;          // [tile][100]
-    const TileCell* stat;         // [tile][100]
-    const uint8_t* rank_of_cell;  // [tile][128]: region cell (ly*10+lx) -> rank
+    const TileRuns* runs;     // [tile]
+    const uint32_t* cslot_d;  // [tile][REGION_CELLS]
+    const uint32_t* cslot_s;  // [tile][REGION_CELLS]
 };
 
 // ---- keys ---------------------------------------------------------------------------------------------------------
@@ -103,7 +124,7 @@ struct HeadFlagsIn {
         uint32_t k = keys[i];
         uint32_t p = i ? keys[i - 1] : ~k;
         unsigned long long c = (i == 0 || k != p) ? 1ull : 0ull;
-        unsigned long long t = (i == 0 || (k >> YASPH_TILE_SHIFT) != (p >> YASPH_TILE_SHIFT)) ? 1ull : 0ull;
+        unsigned long long t = (i == 0 || (k >> TILE_SHIFT) != (p >> TILE_SHIFT)) ? 1ull : 0ull;
         return c | (t << 32);
     }
 };
@@ -112,51 +133,57 @@ struct HeadCompactOut {
     uint32_t* cell_key;
     uint32_t* cell_start;
     uint32_t* tile_key;
-    uint32_t* tile_pstart;
+    uint32_t* tile_pstart;  // may be null (static grid)
+    uint32_t* tile_cstart;
     uint32_t max_tiles;
     __device__ __forceinline__ void operator()(uint32_t i, unsigned long long ex, unsigned long long v) const {
+        const uint32_t c = (uint32_t)(ex & 0xFFFFFFFFull);
         if (v & 0xFFFFFFFFull) {
-            uint32_t c = (uint32_t)(ex & 0xFFFFFFFFull);
             cell_key[c] = keys[i];
             cell_start[c] = i;
         }
         if (v >> 32) {
             uint32_t t = (uint32_t)(ex >> 32);
             if (t < max_tiles) {
-                tile_key[t] = keys[i] >> YASPH_TILE_SHIFT;
-                tile_pstart[t] = i;
+                tile_key[t] = keys[i] >> TILE_SHIFT;
+                if (tile_pstart) tile_pstart[t] = i;
+                tile_cstart[t] = c;  // a tile head is a cell head: c is the index of the tile's first cell
             }
         }
     }
 };
-// sentinel cell {first_particle = N, cidx = u32::MAX} (neighborhood_search.rs:161-164) and the counts
+// sentinel cell {first_particle = N, cidx = u32::MAX} (neighborhood_search.rs:161-164), tile sentinels and the counts
 __global__ void k_finish_cells(const unsigned long long* __restrict__ total, uint32_t n, uint32_t* cell_key, uint32_t* cell_start,
-                               uint32_t* tile_pstart, uint32_t max_tiles, Control* ctl, int is_static) {
+                               uint32_t* tile_pstart, uint32_t* tile_cstart, uint32_t max_tiles, Control* ctl, int is_static) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         unsigned long long t = n ? *total : 0ull;
         uint32_t c = (uint32_t)(t & 0xFFFFFFFFull), nt = (uint32_t)(t >> 32);
         cell_key[c] = 0xFFFFFFFFu;
         cell_start[c] = n;
+        if (nt > max_tiles) {
+            ctl->err_tile_count = nt;
+            nt = max_tiles;
+        }
+        tile_cstart[nt] = c;
         if (is_static) {
             ctl->num_cells_static = c;
+            ctl->num_tiles_static = nt;
         } else {
             ctl->num_cells = c;
-            if (nt > max_tiles) {
-                ctl->err_tile_count = nt;
-                nt = max_tiles;
-            }
             ctl->num_tiles = nt;
             tile_pstart[nt] = n;
+            ctl->max_dyn_total = 0u;
+            ctl->max_stat_total = 0u;
+            ctl->max_pcount = 0u;
         }
     }
 }
 
-// lower bound over the compact cell list (the role of find_next_cell, neighborhood_search.rs:169-189)
-__device__ __forceinline__ uint32_t cell_lower_bound(const uint32_t* __restrict__ cell_key, uint32_t ncells, uint32_t key) {
-    uint32_t lo = 0, hi = ncells;
+// first index in [lo, hi) whose key is >= `key` (the role of find_next_cell, neighborhood_search.rs:169-189)
+__device__ __forceinline__ uint32_t key_lower_bound(const uint32_t* __restrict__ keys, uint32_t lo, uint32_t hi, uint32_t key) {
     while (lo < hi) {
         uint32_t mid = (lo + hi) >> 1;
-        if (cell_key[mid] < key)
+        if (keys[mid] < key)
             lo = mid + 1;
         else
             hi = mid;
@@ -164,235 +191,388 @@ __device__ __forceinline__ uint32_t cell_lower_bound(const uint32_t* __restrict_
     return lo;
 }
 
-// One CTA (128 threads) per tile, grid-stride: look up the 100 region cells in the dynamic and the static grid, order
-// them by Morton key, assign shared-memory slots.
-__global__ void __launch_bounds__(128)
-    k_tile_tables(const uint32_t* __restrict__ tile_key, const uint32_t* __restrict__ tile_pstart, const uint32_t* __restrict__ cell_key,
-                  const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ scell_key, const uint32_t* __restrict__ scell_start,
-                  Control* ctl, TileHeader* __restrict__ hdr, TileCell* __restrict__ tdyn, TileCell* __restrict__ tstat,
-                  uint8_t* __restrict__ rank_of_cell, uint32_t cap_dyn, uint32_t cap_stat) {
-    __shared__ unsigned long long skey[YASPH_REGION_CELLS];
-    __shared__ uint32_t gs_d[YASPH_REGION_CELLS], cn_d[YASPH_REGION_CELLS], gs_s[YASPH_REGION_CELLS], cn_s[YASPH_REGION_CELLS];
-    __shared__ uint32_t by_d[YASPH_REGION_CELLS], by_s[YASPH_REGION_CELLS];
-    __shared__ uint32_t own_rank;
-    const uint32_t ntiles = ctl->num_tiles, ncells = ctl->num_cells, nscells = ctl->num_cells_static;
-    const uint32_t r = threadIdx.x;
-    for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const uint32_t k0 = tile_key[t] << YASPH_TILE_SHIFT;
-        const int x0 = (int)morton_x(k0), y0 = (int)morton_y(k0);
-        uint32_t myrank = 0;
-        if (r < YASPH_REGION_CELLS) {
-            const int lx = (int)(r % YASPH_REGION_AXIS), ly = (int)(r / YASPH_REGION_AXIS);
-            const int x = x0 + lx - 1, y = y0 + ly - 1;
-            const bool valid = x >= 0 && x <= 65535 && y >= 0 && y <= 65535;
-            uint32_t gd = 0, cd = 0, gs = 0, cs = 0;
-            unsigned long long sk = (1ull << 32) | r;
-            if (valid) {
-                uint32_t key = morton_encode((uint32_t)x, (uint32_t)y);
-                sk = key;
-                uint32_t ci = cell_lower_bound(cell_key, ncells, key);
-                if (ci < ncells && cell_key[ci] == key) {
-                    gd = cell_start[ci];
-                    cd = cell_start[ci + 1] - gd;
-                }
-                ci = cell_lower_bound(scell_key, nscells, key);
-                if (ci < nscells && scell_key[ci] == key) {
-                    gs = scell_start[ci];
-                    cs = scell_start[ci + 1] - gs;
-                }
-            }
-            skey[r] = sk;
-            gs_d[r] = gd;
-            cn_d[r] = cd;
-            gs_s[r] = gs;
-            cn_s[r] = cs;
-        }
-        __syncthreads();
-        if (r < YASPH_REGION_CELLS) {
-            const unsigned long long mine = skey[r];
-            uint32_t rk = 0;
-            for (int q = 0; q < YASPH_REGION_CELLS; ++q) rk += skey[q] < mine ? 1u : 0u;
-            myrank = rk;
-            by_d[rk] = cn_d[r];
-            by_s[rk] = cn_s[r];
-            rank_of_cell[(size_t)t * 128 + r] = (uint8_t)rk;
-            if (r == YASPH_REGION_AXIS + 1) own_rank = rk;  // region cell (1,1) == first own cell
-        }
-        __syncthreads();
-        if (r < YASPH_REGION_CELLS) {
-            uint32_t sd = 0, ss = 0;
-            for (uint32_t q = 0; q < myrank; ++q) {
-                sd += by_d[q];
-                ss += by_s[q];
-            }
-            // slot_start / count are packed in 16 bits each; totals above the capacity are flagged below and the
-            // tile is then never consumed (the step reports YASPH_ERR_CAPACITY)
-            tdyn[(size_t)t * YASPH_REGION_CELLS + myrank] = make_uint2(gs_d[r], (sd & 0xFFFFu) | (cn_d[r] << 16));
-            tstat[(size_t)t * YASPH_REGION_CELLS + myrank] = make_uint2(gs_s[r], (ss & 0xFFFFu) | (cn_s[r] << 16));
-            if (myrank == YASPH_REGION_CELLS - 1) {
-                TileHeader h;
-                h.pstart = tile_pstart[t];
-                h.pcount = tile_pstart[t + 1] - h.pstart;
-                h.dyn_total = sd + cn_d[r];
-                h.stat_total = ss + cn_s[r];
-                uint32_t lo = 0;
-                for (uint32_t q = 0; q < own_rank; ++q) lo += by_d[q];
-                h.own_lo = lo;
-                h.pad0 = h.pad1 = h.pad2 = 0;
-                hdr[t] = h;
-                if (h.dyn_total > cap_dyn || h.stat_total > cap_stat) atomicMax(&ctl->err_tile_capacity, max(h.dyn_total, h.stat_total));
-            }
-        }
-        __syncthreads();
-    }
+// region cell (rx, ry) in [0, REGION_AXIS)^2 -> which of the 3x3 tile-sized blocks it lies in, and its position among
+// the region cells of that block in ascending Morton order
+__device__ __forceinline__ uint32_t region_block(uint32_t rx, uint32_t ry) {
+    const uint32_t bx = rx == 0 ? 0u : (rx == REGION_AXIS - 1 ? 2u : 1u);
+    const uint32_t by = ry == 0 ? 0u : (ry == REGION_AXIS - 1 ? 2u : 1u);
+    return by * 3u + bx;
+}
+__device__ __forceinline__ uint32_t region_order_in_block(uint32_t rx, uint32_t ry, uint32_t b) {
+    const uint32_t bx = b % 3u, by = b / 3u;
+    if (bx == 1u && by == 1u) return morton_encode(rx - 1u, ry - 1u);  // own block: local Morton code
+    if (by == 1u) return ry - 1u;                                      // west / east column: one local x, ascending y
+    if (bx == 1u) return rx - 1u;                                      // south / north row
+    return 0u;                                                         // corner
+}
+__device__ __forceinline__ uint32_t region_cells_in_block(uint32_t b) {
+    const uint32_t bx = b % 3u, by = b / 3u;
+    return (bx == 1u ? (uint32_t)TILE_AXIS : 1u) * (by == 1u ? (uint32_t)TILE_AXIS : 1u);
 }
 
-// ---- staging helpers (shared by the list build and every sweep) ----------------------------------------------------------
-struct TileSmem {
-    TileHeader hdr;
-    TileCell dyn[YASPH_REGION_CELLS];
-    TileCell stat[YASPH_REGION_CELLS];
-    uint8_t rank[128];
+// One warp per tile: look the region cells up in the dynamic and the static grid, order them by Morton key, assign
+// shared-memory slots, merge them into copy runs.
+constexpr int TT_WARPS = 4;
+struct TTScratch {
+    uint32_t cnt[2][REGION_CELLS];   // [dynamic | static][region cell, row-major]
+    uint32_t gs[2][REGION_CELLS];    // first global index
+    uint32_t slot[2][REGION_CELLS];  // first slot
+    uint32_t blk_lo[2][9], blk_hi[2][9];  // the block's range in the cell list
+    uint32_t blk_seq[9];             // position of the block's first region cell in slot order
+    uint8_t seq[128];                // region cells in slot order
 };
-
-__device__ __forceinline__ void load_tile_tables(TileSmem& ts, const TileTables& tt, uint32_t t) {
-    for (uint32_t q = threadIdx.x; q < YASPH_REGION_CELLS; q += blockDim.x) {
-        ts.dyn[q] = tt.dyn[(size_t)t * YASPH_REGION_CELLS + q];
-        ts.stat[q] = tt.stat[(size_t)t * YASPH_REGION_CELLS + q];
+struct TileTableArgs {
+    const uint32_t *tile_key, *tile_pstart, *tile_cstart, *cell_key, *cell_start;  // dynamic grid
+    const uint32_t *stile_key, *stile_cstart, *scell_key, *scell_start;            // static grid
+    TileRuns* truns;
+    uint32_t *cslot_d, *cslot_s;
+};
+__global__ void __launch_bounds__(TT_WARPS * 32) k_tile_tables(TileTableArgs a, Control* ctl) {
+    __shared__ TTScratch scratch[TT_WARPS];
+    TTScratch& S = scratch[threadIdx.x >> 5];
+    const uint32_t lane = lane_id();
+    const unsigned lt = lanemask_lt();
+    const uint32_t ntiles = ctl->num_tiles, nstiles = ctl->num_tiles_static;
+    uint32_t wmax_d = 0, wmax_s = 0, wmax_p = 0;
+    for (uint32_t t = blockIdx.x * TT_WARPS + (threadIdx.x >> 5); t < ntiles; t += gridDim.x * TT_WARPS) {
+        const uint32_t tkey = a.tile_key[t];
+        const uint32_t k0 = tkey << TILE_SHIFT;
+        const int x0 = (int)morton_x(k0), y0 = (int)morton_y(k0);
+        const uint32_t pstart = a.tile_pstart[t], pend = a.tile_pstart[t + 1];
+        for (uint32_t r = lane; r < REGION_CELLS; r += 32) {
+            S.cnt[0][r] = 0;
+            S.cnt[1][r] = 0;
+            S.gs[0][r] = 0;
+            S.gs[1][r] = 0;
+        }
+        // 1. the nine blocks: key, rank, cell ranges in both grids
+        {
+            uint32_t bkey = 0xFFFFFFFFu;
+            if (lane < 9) {
+                const int bx = (x0 >> YASPH_TILE_LOG2) - 1 + (int)(lane % 3u), by = (y0 >> YASPH_TILE_LOG2) - 1 + (int)(lane / 3u);
+                const bool valid = bx >= 0 && bx <= (int)MAX_BLOCK_COORD && by >= 0 && by <= (int)MAX_BLOCK_COORD;
+                if (valid) bkey = morton_encode((uint32_t)bx, (uint32_t)by);
+                uint32_t lo = 0, hi = 0, slo = 0, shi = 0;
+                if (lane == 4) {
+                    lo = a.tile_cstart[t];
+                    hi = a.tile_cstart[t + 1];
+                } else if (valid) {
+                    const uint32_t q = key_lower_bound(a.tile_key, 0, ntiles, bkey);
+                    if (q < ntiles && a.tile_key[q] == bkey) {
+                        lo = a.tile_cstart[q];
+                        hi = a.tile_cstart[q + 1];
+                    }
+                }
+                if (valid && nstiles) {
+                    const uint32_t q = key_lower_bound(a.stile_key, 0, nstiles, bkey);
+                    if (q < nstiles && a.stile_key[q] == bkey) {
+                        slo = a.stile_cstart[q];
+                        shi = a.stile_cstart[q + 1];
+                    }
+                }
+                S.blk_lo[0][lane] = lo;
+                S.blk_hi[0][lane] = hi;
+                S.blk_lo[1][lane] = slo;
+                S.blk_hi[1][lane] = shi;
+            }
+            // position of each block's first region cell in slot order: blocks ascend by key (invalid ones last, ties by lane)
+            uint32_t seq0 = 0;
+#pragma unroll
+            for (uint32_t j = 0; j < 9; ++j) {
+                const uint32_t kj = __shfl_sync(0xffffffffu, bkey, j);
+                if (kj < bkey || (kj == bkey && j < lane)) seq0 += region_cells_in_block(j);
+            }
+            if (lane < 9) S.blk_seq[lane] = seq0;
+        }
+        __syncwarp();
+        // 2. cell lookups.  Own block (both grids): walk the block's cells and scatter them; apron: search the block's range.
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+            const uint32_t* ckey = which ? a.scell_key : a.cell_key;
+            const uint32_t* cstart = which ? a.scell_start : a.cell_start;
+            const uint32_t olo = S.blk_lo[which][4], ohi = S.blk_hi[which][4];
+            for (uint32_t c = olo + lane; c < ohi; c += 32) {
+                const uint32_t key = ckey[c];
+                const uint32_t r = (morton_y(key & (TILE_CELLS - 1)) + 1u) * REGION_AXIS + morton_x(key & (TILE_CELLS - 1)) + 1u;
+                const uint32_t g = cstart[c];
+                S.gs[which][r] = g;
+                S.cnt[which][r] = cstart[c + 1] - g;
+            }
+            for (uint32_t ap = lane; ap < (uint32_t)APRON_CELLS; ap += 32) {
+                uint32_t rx, ry;
+                if (ap < (uint32_t)REGION_AXIS) {
+                    rx = ap;
+                    ry = 0;
+                } else if (ap < 2u * REGION_AXIS) {
+                    rx = ap - REGION_AXIS;
+                    ry = REGION_AXIS - 1;
+                } else if (ap < 2u * REGION_AXIS + TILE_AXIS) {
+                    rx = 0;
+                    ry = ap - 2u * REGION_AXIS + 1u;
+                } else {
+                    rx = REGION_AXIS - 1;
+                    ry = ap - 2u * REGION_AXIS - TILE_AXIS + 1u;
+                }
+                const uint32_t b = region_block(rx, ry);
+                const uint32_t lo = S.blk_lo[which][b], hi = S.blk_hi[which][b];
+                if (lo < hi) {  // the block exists, so the cell coordinates are inside the domain
+                    const uint32_t key = morton_encode((uint32_t)(x0 - 1 + (int)rx), (uint32_t)(y0 - 1 + (int)ry));
+                    const uint32_t c = key_lower_bound(ckey, lo, hi, key);
+                    if (c < hi && ckey[c] == key) {
+                        const uint32_t g = cstart[c];
+                        S.gs[which][ry * REGION_AXIS + rx] = g;
+                        S.cnt[which][ry * REGION_AXIS + rx] = cstart[c + 1] - g;
+                    }
+                }
+            }
+        }
+        // 3. slot order of the region cells
+        for (uint32_t r = lane; r < REGION_CELLS; r += 32) {
+            const uint32_t rx = r % REGION_AXIS, ry = r / REGION_AXIS;
+            const uint32_t b = region_block(rx, ry);
+            S.seq[S.blk_seq[b] + region_order_in_block(rx, ry, b)] = (uint8_t)r;
+        }
+        __syncwarp();
+        // 4. walk the cells in slot order: slot starts (exclusive prefix of the counts) and copy runs
+        uint32_t totals[2], nruns[2];
+        TileRuns* out = a.truns + t;
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+            uint2* runs = which ? out->rs : out->rd;
+            uint32_t carry = 0, carry_runs = 0, carry_end = 0;
+            bool carry_valid = false;
+            for (uint32_t q0 = 0; q0 < REGION_CELLS; q0 += 32) {
+                const uint32_t q = q0 + lane;
+                const bool in = q < REGION_CELLS;
+                const uint32_t r = in ? S.seq[q] : 0u;
+                const uint32_t cn = in ? S.cnt[which][r] : 0u;
+                const uint32_t g = in ? S.gs[which][r] : 0u;
+                uint32_t inc = cn;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= (uint32_t)o) inc += u;
+                }
+                const uint32_t slot = carry + inc - cn;
+                if (in) S.slot[which][r] = slot;
+                const unsigned ne = __ballot_sync(0xffffffffu, cn > 0);
+                const unsigned before = ne & lt;
+                const int pl = before ? 31 - __clz((int)before) : 0;
+                const uint32_t pend_g = __shfl_sync(0xffffffffu, g + cn, pl);
+                const bool has_prev = before ? true : carry_valid;
+                const uint32_t prev_end = before ? pend_g : carry_end;
+                const bool head = cn > 0 && !(has_prev && prev_end == g);
+                const unsigned hm = __ballot_sync(0xffffffffu, head);
+                if (head) {
+                    const uint32_t ri = carry_runs + (uint32_t)__popc(hm & lt);
+                    if (ri < (uint32_t)MAX_RUNS) runs[ri] = make_uint2(g, slot);
+                }
+                carry += __shfl_sync(0xffffffffu, inc, 31);
+                carry_runs += (uint32_t)__popc(hm);
+                if (ne) {
+                    const int ll = 31 - __clz((int)ne);
+                    carry_end = __shfl_sync(0xffffffffu, g + cn, ll);
+                    carry_valid = true;
+                }
+            }
+            totals[which] = carry;
+            nruns[which] = carry_runs < (uint32_t)MAX_RUNS ? carry_runs : (uint32_t)MAX_RUNS;
+            for (uint32_t q = nruns[which] + lane; q < (uint32_t)MAX_RUNS; q += 32) runs[q] = make_uint2(0u, 0xFFFFFFFFu);
+        }
+        __syncwarp();
+        // 5. header, per-cell slot tables, maxima
+        if (lane == 0) {
+            TileHeader h;
+            h.pstart = pstart;
+            h.pcount = pend - pstart;
+            h.dyn_total = totals[0];
+            h.stat_total = totals[1];
+            h.own_lo = S.slot[0][REGION_AXIS + 1];  // region cell (1,1) == the tile's first cell
+            h.nruns_d = nruns[0];
+            h.nruns_s = nruns[1];
+            h.pad = 0;
+            out->hdr = h;
+            if (totals[0] > 0xFFFFu || totals[1] > 0xFFFFu) atomicMax(&ctl->err_tile_capacity, max(totals[0], totals[1]));
+        }
+        for (uint32_t r = lane; r < REGION_CELLS; r += 32) {
+            a.cslot_d[(size_t)t * REGION_CELLS + r] = (S.slot[0][r] << 16) | (S.cnt[0][r] & 0xFFFFu);
+            a.cslot_s[(size_t)t * REGION_CELLS + r] = (S.slot[1][r] << 16) | (S.cnt[1][r] & 0xFFFFu);
+        }
+        wmax_d = max(wmax_d, totals[0]);
+        wmax_s = max(wmax_s, totals[1]);
+        wmax_p = max(wmax_p, pend - pstart);
+        __syncwarp();
     }
-    for (uint32_t q = threadIdx.x; q < 128 / 4; q += blockDim.x)
-        reinterpret_cast<uint32_t*>(ts.rank)[q] = reinterpret_cast<const uint32_t*>(tt.rank_of_cell + (size_t)t * 128)[q];
-    if (threadIdx.x == 0) ts.hdr = tt.hdr[t];
+    if (lane == 0) {  // same-address atomics serialise in L2: only issue the ones that can still raise the maximum
+        if (wmax_d > *(volatile unsigned int*)&ctl->max_dyn_total) atomicMax(&ctl->max_dyn_total, wmax_d);
+        if (wmax_s > *(volatile unsigned int*)&ctl->max_stat_total) atomicMax(&ctl->max_stat_total, wmax_s);
+        if (wmax_p > *(volatile unsigned int*)&ctl->max_pcount) atomicMax(&ctl->max_pcount, wmax_p);
+    }
 }
-// global index of staged slot s: the last table entry (rank order) whose slot_start <= s
-__device__ __forceinline__ uint32_t slot_to_global(const TileCell* tab, uint32_t s) {
-    uint32_t lo = 0, hi = YASPH_REGION_CELLS - 1;
+
+// ---- helpers shared by the tile kernels --------------------------------------------------------------------------------
+__device__ __forceinline__ void load_tile_runs(TileRuns& dst, const TileRuns* __restrict__ src) {
+    const uint4* s = reinterpret_cast<const uint4*>(src);
+    uint4* d = reinterpret_cast<uint4*>(&dst);
+    for (uint32_t q = threadIdx.x; q < sizeof(TileRuns) / 16; q += blockDim.x) d[q] = s[q];
+}
+// global index of staged slot s: the last copy run whose first slot is <= s
+__device__ __forceinline__ uint32_t run_slot_to_global(const uint2* runs, uint32_t s) {
+    uint32_t lo = 0, hi = MAX_RUNS - 1;
     while (lo < hi) {
         uint32_t mid = (lo + hi + 1) >> 1;
-        if ((tab[mid].y & 0xFFFFu) <= s)
+        if (runs[mid].y <= s)
             lo = mid;
         else
             hi = mid - 1;
     }
-    return tab[lo].x + (s - (tab[lo].y & 0xFFFFu));
+    return runs[lo].x + (s - runs[lo].y);
 }
-__device__ __forceinline__ uint32_t dyn_slot_to_global(const TileSmem& ts, uint32_t s) {
-    uint32_t o = s - ts.hdr.own_lo;  // own particles are one contiguous copy
-    if (o < ts.hdr.pcount) return ts.hdr.pstart + o;
-    return slot_to_global(ts.dyn, s);
-}
-// 128-bit mask of the ranks of the 3x3 cells around the particle's cell (key & 63 = cell inside the tile)
-__device__ __forceinline__ void neighbor_cell_mask(const TileSmem& ts, uint32_t key, unsigned long long& m0, unsigned long long& m1) {
-    const uint32_t local = key & 63u;
-    const uint32_t lx = morton_x(local) + 1, ly = morton_y(local) + 1;
-    m0 = 0ull;
-    m1 = 0ull;
-#pragma unroll
-    for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-        for (int dx = -1; dx <= 1; ++dx) {
-            uint32_t rk = ts.rank[(ly + dy) * YASPH_REGION_AXIS + (lx + dx)];
-            if (rk < 64)
-                m0 |= 1ull << rk;
-            else
-                m1 |= 1ull << (rk - 64);
-        }
+__device__ __forceinline__ uint32_t dyn_slot_to_global(const TileRuns& tr, uint32_t s) {
+    uint32_t o = s - tr.hdr.own_lo;  // own particles are one contiguous copy
+    if (o < tr.hdr.pcount) return tr.hdr.pstart + o;
+    return run_slot_to_global(tr.rd, s);
 }
 
-// list storage: per tile, base = pstart * 64 entries; entry (k, tl) lives in 8-byte word (k/4)*pcount + tl, lane k%4
+// list storage: per tile, base = pstart * 16 words; entry (k, tl) lives in 8-byte word (k/4)*pcount + tl, lane k%4
 __device__ __forceinline__ size_t list_word_index(uint32_t pstart, uint32_t pcount, uint32_t kb, uint32_t tl) {
     return (size_t)pstart * (YASPH_MAXN / 4) + (size_t)kb * pcount + tl;
 }
-__device__ __forceinline__ unsigned long long pack_slot(unsigned long long w, uint32_t k, uint32_t slot) {
-    const int sh = (int)(k & 3u) * 16;
-    return (w & ~(0xFFFFull << sh)) | ((unsigned long long)slot << sh);
-}
 __device__ __forceinline__ uint32_t unpack_slot(unsigned long long w, uint32_t k) { return (uint32_t)(w >> ((k & 3u) * 16)) & 0xFFFFu; }
 
-// One CTA per tile (grid-stride): NeighborLists::try_update (neighborhood_search.rs:312-397)
+// compare-exchange for the 9-element sorting network below
+__device__ __forceinline__ void cswap(uint32_t& a, uint32_t& b) {
+    const uint32_t lo = min(a, b), hi = max(a, b);
+    a = lo;
+    b = hi;
+}
+
+// ---- neighbour lists: NeighborLists::try_update (neighborhood_search.rs:312-397) ---------------------------------------
+// One CTA per tile.  Phase 1 stages the candidate positions; meanwhile one thread per own cell turns the 3x3 box of its
+// cell into <= 9 slot runs in ascending slot order (the role of get_particle_runs_in_neighborbox, :191-259).  Phase 2:
+// one thread per particle walks its cell's runs with a branch-free inner loop -- every candidate's slot is stored to the
+// thread's column of a shared-memory list at row min(count, 64) and the count advances by the hit predicate -- so the
+// first 64 hits survive exactly as the reference's early exit leaves them.  Phase 3 packs the column into 8-byte words.
+constexpr int NB_THREADS = 256;
+constexpr int NB_ROWS = YASPH_MAXN + 1;  // row 64 absorbs everything past the cap
+struct ListSmem {
+    TileRuns tr;
+    uint32_t cs[2][REGION_CELLS];
+    uint32_t crun[2][TILE_CELLS][9];  // per own cell: slot_start << 16 | count, ascending, merged
+    uint32_t ncrun[2][TILE_CELLS];
+    unsigned long long total;
+    uint16_t sl[NB_ROWS][NB_THREADS];
+};
+inline size_t list_smem_bytes(uint32_t cap_dyn, uint32_t cap_stat) { return sizeof(ListSmem) + ((size_t)cap_dyn + cap_stat) * sizeof(float2); }
+
 __global__ void __launch_bounds__(NB_THREADS)
     k_build_lists(TileTables tt, const float2* __restrict__ pos, const float2* __restrict__ bpos, const uint32_t* __restrict__ keys,
-                  GridParams g, Control* ctl, unsigned long long* __restrict__ lists, uchar2* __restrict__ counts, uint32_t cap_dyn, uint32_t cap_stat) {
+                  GridParams g, Control* ctl, unsigned long long* __restrict__ lists, uchar2* __restrict__ counts, uint32_t cap_dyn,
+                  uint32_t cap_stat) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    TileSmem& ts = *reinterpret_cast<TileSmem*>(smem_raw);
-    float2* sdyn = reinterpret_cast<float2*>(smem_raw + sizeof(TileSmem));
+    ListSmem& S = *reinterpret_cast<ListSmem*>(smem_raw);
+    float2* sdyn = reinterpret_cast<float2*>(smem_raw + sizeof(ListSmem));
     float2* sstat = sdyn + cap_dyn;
-    __shared__ unsigned long long s_total;
     const uint32_t ntiles = ctl->num_tiles;
+    const uint32_t tid = threadIdx.x;
     unsigned long long my_total = 0;
     uint32_t my_capped = 0, my_dropped = 0;
     for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        load_tile_tables(ts, tt, t);
+        load_tile_runs(S.tr, tt.runs + t);
+        for (uint32_t q = tid; q < 2 * REGION_CELLS; q += NB_THREADS)
+            S.cs[q / REGION_CELLS][q % REGION_CELLS] = (q < REGION_CELLS ? tt.cslot_d : tt.cslot_s)[(size_t)t * REGION_CELLS + q % REGION_CELLS];
         __syncthreads();
-        const TileHeader h = ts.hdr;
+        const TileHeader h = S.tr.hdr;
         if (h.dyn_total <= cap_dyn && h.stat_total <= cap_stat) {
-            for (uint32_t s = threadIdx.x; s < h.dyn_total; s += blockDim.x) sdyn[s] = pos[dyn_slot_to_global(ts, s)];
-            for (uint32_t s = threadIdx.x; s < h.stat_total; s += blockDim.x) sstat[s] = bpos[slot_to_global(ts.stat, s)];
+            for (uint32_t s = tid; s < h.dyn_total; s += NB_THREADS) sdyn[s] = pos[dyn_slot_to_global(S.tr, s)];
+            for (uint32_t s = tid; s < h.stat_total; s += NB_THREADS) sstat[s] = bpos[run_slot_to_global(S.tr.rs, s)];
+            if (tid < 2 * TILE_CELLS) {
+                const uint32_t which = tid / TILE_CELLS, lc = tid % TILE_CELLS;
+                const uint32_t lx = morton_x(lc) + 1u, ly = morton_y(lc) + 1u;
+                uint32_t v[9];
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        const uint32_t e = S.cs[which][(ly + dy - 1) * REGION_AXIS + lx + dx - 1];
+                        v[dy * 3 + dx] = (e & 0xFFFFu) ? e : 0xFFFFFFFFu;  // empty cells sort last
+                    }
+                // 25-exchange sorting network for 9 keys (slot_start in the high half: ascending slot order)
+                cswap(v[0], v[1]); cswap(v[3], v[4]); cswap(v[6], v[7]);
+                cswap(v[1], v[2]); cswap(v[4], v[5]); cswap(v[7], v[8]);
+                cswap(v[0], v[1]); cswap(v[3], v[4]); cswap(v[6], v[7]);
+                cswap(v[0], v[3]); cswap(v[3], v[6]); cswap(v[0], v[3]);
+                cswap(v[1], v[4]); cswap(v[4], v[7]); cswap(v[1], v[4]);
+                cswap(v[2], v[5]); cswap(v[5], v[8]); cswap(v[2], v[5]);
+                cswap(v[1], v[3]); cswap(v[5], v[7]); cswap(v[2], v[6]);
+                cswap(v[4], v[6]); cswap(v[2], v[4]); cswap(v[2], v[3]);
+                cswap(v[5], v[6]);
+                uint32_t nr = 0, cur = 0xFFFFFFFFu;
+#pragma unroll
+                for (int q = 0; q < 9; ++q) {
+                    if (v[q] != 0xFFFFFFFFu) {
+                        if (cur != 0xFFFFFFFFu && (cur >> 16) + (cur & 0xFFFFu) == (v[q] >> 16)) {
+                            cur += v[q] & 0xFFFFu;  // contiguous slots: extend (the sum stays <= 65535, checked by k_tile_tables)
+                        } else {
+                            if (cur != 0xFFFFFFFFu) S.crun[which][lc][nr++] = cur;
+                            cur = v[q];
+                        }
+                    }
+                }
+                if (cur != 0xFFFFFFFFu) S.crun[which][lc][nr++] = cur;
+                S.ncrun[which][lc] = nr;
+            }
             __syncthreads();
-            for (uint32_t tl = threadIdx.x; tl < h.pcount; tl += blockDim.x) {
+            for (uint32_t tl = tid; tl < h.pcount; tl += NB_THREADS) {
                 const uint32_t i = h.pstart + tl;
                 const float2 q = sdyn[h.own_lo + tl];
-                unsigned long long m0, m1;
-                neighbor_cell_mask(ts, keys[i], m0, m1);
-                uint32_t cd = 0;
-                unsigned long long e = 0ull;  // four u16 slots, entry k in bits [16*(k&3), +16)
-                bool full = false;
+                const uint32_t lc = keys[i] & (TILE_CELLS - 1);
+                uint16_t* col = &S.sl[0][tid];
+                uint32_t c = 0;
                 // dynamic candidates, ascending slot == ascending sorted index (neighborhood_search.rs:353-366)
-                for (int half = 0; half < 2 && !full; ++half) {
-                    unsigned long long m = half ? m1 : m0;
-                    while (m && !full) {
-                        const int rk = __ffsll((long long)m) - 1 + half * 64;
-                        m &= m - 1;
-                        const TileCell c = ts.dyn[rk];
-                        const uint32_t s0 = c.y & 0xFFFFu, s1 = s0 + (c.y >> 16);
-                        for (uint32_t s = s0; s < s1; ++s) {
-                            const float2 d = sdyn[s] - q;
-                            const float d2 = d.x * d.x + d.y * d.y;
-                            if (d2 <= g.radius_sq && d2 > YASPH_MIN_DISTANCE) {
-                                e = pack_slot(e, cd, s);
-                                ++cd;
-                                if ((cd & 3) == 0) lists[list_word_index(h.pstart, h.pcount, (cd >> 2) - 1, tl)] = e;
-                                if (cd == YASPH_MAXN) {
-                                    full = true;
-                                    ++my_capped;
-                                    break;
-                                }
-                            }
-                        }
+                const uint32_t nrd = S.ncrun[0][lc];
+                for (uint32_t r = 0; r < nrd; ++r) {
+                    const uint32_t run = S.crun[0][lc][r];
+                    const uint32_t s1 = (run >> 16) + (run & 0xFFFFu);
+                    for (uint32_t s = run >> 16; s < s1; ++s) {
+                        const float2 d = sdyn[s] - q;
+                        const float d2 = d.x * d.x + d.y * d.y;
+                        col[min(c, (uint32_t)YASPH_MAXN) * NB_THREADS] = (uint16_t)s;
+                        c += (d2 <= g.radius_sq && d2 > YASPH_MIN_DISTANCE) ? 1u : 0u;
                     }
                 }
-                uint32_t ct = cd;
-                full = false;
+                const uint32_t hits_d = c;
+                const uint32_t cd = min(c, (uint32_t)YASPH_MAXN);
+                c = cd;
                 // static candidates (neighborhood_search.rs:367-381)
-                for (int half = 0; half < 2 && !full; ++half) {
-                    unsigned long long m = half ? m1 : m0;
-                    while (m && !full) {
-                        const int rk = __ffsll((long long)m) - 1 + half * 64;
-                        m &= m - 1;
-                        const TileCell c = ts.stat[rk];
-                        const uint32_t s0 = c.y & 0xFFFFu, s1 = s0 + (c.y >> 16);
-                        for (uint32_t s = s0; s < s1; ++s) {
-                            const float2 d = sstat[s] - q;
-                            const float d2 = d.x * d.x + d.y * d.y;
-                            if (d2 <= g.radius_sq && d2 > YASPH_MIN_DISTANCE) {
-                                if (ct >= YASPH_MAXN) {  // the reference indexes neighbor_set[64] here and panics (:373)
-                                    ++my_dropped;
-                                    full = true;
-                                    break;
-                                }
-                                e = pack_slot(e, ct, s);
-                                ++ct;
-                                if ((ct & 3) == 0) lists[list_word_index(h.pstart, h.pcount, (ct >> 2) - 1, tl)] = e;
-                                if (ct == YASPH_MAXN) {
-                                    full = true;
-                                    ++my_capped;
-                                    break;
-                                }
-                            }
-                        }
+                const uint32_t nrs = S.ncrun[1][lc];
+                for (uint32_t r = 0; r < nrs; ++r) {
+                    const uint32_t run = S.crun[1][lc][r];
+                    const uint32_t s1 = (run >> 16) + (run & 0xFFFFu);
+                    for (uint32_t s = run >> 16; s < s1; ++s) {
+                        const float2 d = sstat[s] - q;
+                        const float d2 = d.x * d.x + d.y * d.y;
+                        col[min(c, (uint32_t)YASPH_MAXN) * NB_THREADS] = (uint16_t)s;
+                        c += (d2 <= g.radius_sq && d2 > YASPH_MIN_DISTANCE) ? 1u : 0u;
                     }
                 }
-                if (ct & 3) lists[list_word_index(h.pstart, h.pcount, ct >> 2, tl)] = e;
+                const uint32_t ct = min(c, (uint32_t)YASPH_MAXN);
+                // the reference's bookkeeping: "too many neighbors" when the 64th entry is written (:360,375); a static hit
+                // with all 64 slots taken by dynamic neighbours indexes neighbor_set[64] and panics (:373) -- dropped here
+                if (hits_d >= YASPH_MAXN) {
+                    ++my_capped;
+                    if (c > cd) ++my_dropped;
+                } else if (c >= YASPH_MAXN) {
+                    ++my_capped;
+                }
+                const uint32_t nkb = (ct + 3u) >> 2;
+                for (uint32_t kb = 0; kb < nkb; ++kb) {
+                    unsigned long long w = 0ull;
+#pragma unroll
+                    for (uint32_t e = 0; e < 4; ++e)
+                        if (kb * 4 + e < ct) w |= (unsigned long long)col[(kb * 4 + e) * NB_THREADS] << (16 * e);
+                    lists[list_word_index(h.pstart, h.pcount, kb, tl)] = w;
+                }
                 counts[i] = make_uchar2((unsigned char)cd, (unsigned char)ct);
                 my_total += ct;
             }
@@ -400,25 +580,25 @@ __global__ void __launch_bounds__(NB_THREADS)
         __syncthreads();
     }
     // statistics: one atomic per CTA
-    if (threadIdx.x == 0) s_total = 0ull;
+    if (tid == 0) S.total = 0ull;
     __syncthreads();
-    if (my_total) atomicAdd(&s_total, my_total);
+    if (my_total) atomicAdd(&S.total, my_total);
     if (my_capped) atomicAdd(&ctl->capped, my_capped);
     if (my_dropped) atomicAdd(&ctl->dropped, my_dropped);
     __syncthreads();
-    if (threadIdx.x == 0 && s_total) atomicAdd(&ctl->total_neighbors, s_total);
+    if (tid == 0 && S.total) atomicAdd(&ctl->total_neighbors, S.total);
 }
 
 // Export to the reference's layout (neighborhood_search.rs:268-273,433-449): u16 counts + u32 global indices, stride 64.
-__global__ void __launch_bounds__(NB_THREADS)
+__global__ void __launch_bounds__(256)
     k_export_lists(TileTables tt, const Control* __restrict__ ctl, const unsigned long long* __restrict__ lists, const uchar2* __restrict__ counts,
                    uint16_t* __restrict__ out_cd, uint16_t* __restrict__ out_ct, uint32_t* __restrict__ out_lists) {
-    __shared__ TileSmem ts;
+    __shared__ TileRuns tr;
     const uint32_t ntiles = ctl->num_tiles;
     for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        load_tile_tables(ts, tt, t);
+        load_tile_runs(tr, tt.runs + t);
         __syncthreads();
-        const TileHeader h = ts.hdr;
+        const TileHeader h = tr.hdr;
         for (uint32_t tl = threadIdx.x; tl < h.pcount; tl += blockDim.x) {
             const uint32_t i = h.pstart + tl;
             const uchar2 c = counts[i];
@@ -427,7 +607,7 @@ __global__ void __launch_bounds__(NB_THREADS)
             if (out_lists) {
                 for (uint32_t k = 0; k < c.y; ++k) {
                     const uint32_t s = unpack_slot(lists[list_word_index(h.pstart, h.pcount, k >> 2, tl)], k);
-                    out_lists[(size_t)i * YASPH_MAXN + k] = k < c.x ? dyn_slot_to_global(ts, s) : slot_to_global(ts.stat, s);
+                    out_lists[(size_t)i * YASPH_MAXN + k] = k < c.x ? dyn_slot_to_global(tr, s) : run_slot_to_global(tr.rs, s);
                 }
             }
         }

@@ -1,18 +1,20 @@
 // sweeps.cuh -- every neighbour-dependent per-particle pass of the WCSPH / DFSPH solvers as one tile-staged kernel.
 //
-// Skeleton (k_sweep): one CTA per 8x8-cell tile (persistent grid-stride loop).  The tile's own particles plus the
-// 1-cell apron are staged into shared memory once (positions + the per-pass neighbour payload, boundary positions),
-// then one thread per particle walks its compact neighbour list (u16 shared-memory slots, dynamic first, then
-// static) in the reference's order.  Reductions (Jacobi residual sum, CFL max) are fused: per-thread accumulation,
-// block reduce, per-CTA partial, last-arriving CTA combines the partials in fixed order and takes the convergence
-// decision on the device (no host round trip inside a Jacobi iteration).
+// Skeleton (k_sweep): one CTA per 8x8-cell tile.  The tile's own particles plus the 1-cell apron are staged into shared
+// memory once (a record per candidate: position + the per-pass neighbour payload; boundary positions), then one thread
+// per particle walks its compact neighbour list (u16 shared-memory slots, dynamic first, then static) in the reference's
+// order.  Shared memory is sized from the largest tile of the current neighbourhood structure (Control::max_*), a few KB,
+// so 4-8 CTAs are resident per SM and the staging latency of one tile hides behind the arithmetic of the others.
+// Reductions (Jacobi residual sum, CFL max) are fused: per-thread accumulation, block reduce, per-CTA partial, the
+// last-arriving CTA combines the partials in fixed order and takes the convergence decision on the device (no host round
+// trip inside a Jacobi iteration).
 //
 // Pass -> reference:
 //   OpDensityAlpha   FluidParticleWorld::update_densities (fluidparticleworld.rs:197-231) fused with
-//                    DFSPHSolver::compute_alpha_factors (dfsph.rs:68-97)
+//                    DFSPHSolver::compute_alpha_factors (dfsph.rs:68-97); WCSPH: + Tait pressure (wscsph.rs:52-57)
 //   OpViscosity      non-pressure forces (dfsph.rs:436-469) + max |v + a dt|^2 (dfsph.rs:474-477)
 //   OpJacobiA        compute_density_error (dfsph.rs:99-126) / compute_density_change (dfsph.rs:249-280) + residual sum
-//                    and loop decision (dfsph.rs:219-245, 374-400)
+//                    and loop decision (dfsph.rs:219-245, 374-400); writes k_i = err_i * alpha_i (dfsph.rs:141 / 295)
 //   OpJacobiB        correct_velocity_with_density_error (dfsph.rs:128-161), ..._divergence_error (dfsph.rs:282-314) and the
 //                    two warm starts (dfsph.rs:163-193, 316-344) incl. the clamp (dfsph.rs:201-203, 356-358)
 //   OpWcsphAccel     WCSPHSolver::update_accellerations (wscsph.rs:59-118) + CFL max (wscsph.rs:160-163)
@@ -39,69 +41,84 @@ struct SweepCommon {
 
 enum ReduceKind { REDUCE_NONE = 0, REDUCE_SUM = 1, REDUCE_MAX = 2 };
 
-struct NoPayload {};
+struct NoRec {};
+__device__ __forceinline__ float2 rec_pos(float2 r) { return r; }
+__device__ __forceinline__ float2 rec_pos(float4 r) { return f2(r.x, r.y); }
+
+// shared memory of a sweep: TileRuns | RecA[cap_dyn] | RecB[cap_dyn] | float2[cap_stat]  (capacities are multiples of 2)
+template <class Op>
+inline size_t sweep_smem_bytes(uint32_t cap_dyn, uint32_t cap_stat) {
+    return sizeof(TileRuns) + (size_t)cap_dyn * (sizeof(typename Op::RecA) + (Op::HAS_B ? sizeof(typename Op::RecB) : 0)) +
+           (Op::USES_STATIC ? (size_t)cap_stat * sizeof(float2) : 0);
+}
 
 template <class Op>
 __global__ void __launch_bounds__(SW_THREADS) k_sweep(SweepCommon c, Op op) {
-    typedef typename Op::Payload Payload;
+    typedef typename Op::RecA RecA;
+    typedef typename Op::RecB RecB;
     if (op.skip(c.ctl)) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    TileSmem& ts = *reinterpret_cast<TileSmem*>(smem_raw);
-    Payload* spay = reinterpret_cast<Payload*>(smem_raw + sizeof(TileSmem));
-    float2* sdyn = reinterpret_cast<float2*>(smem_raw + sizeof(TileSmem) + (Op::HAS_PAYLOAD ? sizeof(Payload) * (size_t)c.cap_dyn : 0));
-    float2* sstat = sdyn + c.cap_dyn;
+    TileRuns& tr = *reinterpret_cast<TileRuns*>(smem_raw);
+    RecA* sa = reinterpret_cast<RecA*>(smem_raw + sizeof(TileRuns));
+    RecB* sb = reinterpret_cast<RecB*>(smem_raw + sizeof(TileRuns) + sizeof(RecA) * (size_t)c.cap_dyn);
+    float2* sstat = reinterpret_cast<float2*>(smem_raw + sizeof(TileRuns) + (sizeof(RecA) + (Op::HAS_B ? sizeof(RecB) : 0)) * (size_t)c.cap_dyn);
     op.prepare(c);
     const uint32_t ntiles = c.ctl->num_tiles;
     double racc = 0.0;
     for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        load_tile_tables(ts, c.tt, t);
+        load_tile_runs(tr, c.tt.runs + t);
         __syncthreads();
-        const TileHeader h = ts.hdr;
+        const TileHeader h = tr.hdr;
         if (h.dyn_total <= c.cap_dyn && h.stat_total <= c.cap_stat) {
-            for (uint32_t s = threadIdx.x; s < h.dyn_total; s += blockDim.x) {
-                const uint32_t g = dyn_slot_to_global(ts, s);
-                sdyn[s] = c.pos[g];
-                if (Op::HAS_PAYLOAD) spay[s] = op.load(c, g);
+            for (uint32_t s = threadIdx.x; s < h.dyn_total; s += SW_THREADS) {
+                const uint32_t g = dyn_slot_to_global(tr, s);
+                sa[s] = op.load_a(c, g);
+                if (Op::HAS_B) sb[s] = op.load_b(c, g);
             }
             if (Op::USES_STATIC)
-                for (uint32_t s = threadIdx.x; s < h.stat_total; s += blockDim.x) sstat[s] = c.bpos[slot_to_global(ts.stat, s)];
+                for (uint32_t s = threadIdx.x; s < h.stat_total; s += SW_THREADS) sstat[s] = c.bpos[run_slot_to_global(tr.rs, s)];
             __syncthreads();
-            for (uint32_t tl = threadIdx.x; tl < h.pcount; tl += blockDim.x) {
+            for (uint32_t tl = threadIdx.x; tl < h.pcount; tl += SW_THREADS) {
                 const uint32_t i = h.pstart + tl;
                 const uint32_t own = h.own_lo + tl;
-                const float2 pi = sdyn[own];
-                Payload self;
-                if (Op::HAS_PAYLOAD) self = spay[own];
+                const RecA self_a = sa[own];
+                RecB self_b;
+                if (Op::HAS_B) self_b = sb[own];
                 const uchar2 cnt = c.counts[i];
                 const uint32_t cd = cnt.x, ct = Op::USES_STATIC ? cnt.y : cnt.x;
                 typename Op::Acc acc;
-                const bool active = op.init(c, acc, i, pi, self, cnt.y);
+                const bool active = op.init(c, acc, i, self_a, self_b, cnt.y);
                 if (active) {
-                    const uint32_t nkb = (ct + 3u) >> 2;
+                    // dynamic neighbours: entries [0, cd), four per 8-byte word, next word prefetched
+                    const uint32_t nkb = (cd + 3u) >> 2;
                     unsigned long long w = nkb ? c.lists[list_word_index(h.pstart, h.pcount, 0, tl)] : 0ull;
                     for (uint32_t kb = 0; kb < nkb; ++kb) {
                         const unsigned long long wn = (kb + 1 < nkb) ? c.lists[list_word_index(h.pstart, h.pcount, kb + 1, tl)] : 0ull;
 #pragma unroll
                         for (uint32_t q = 0; q < 4; ++q) {
-                            const uint32_t k = kb * 4 + q;
-                            const uint32_t slot = (uint32_t)(w >> (16 * q)) & 0xFFFFu;
-                            if (k < cd) {
-                                Payload pj;
-                                if (Op::HAS_PAYLOAD) pj = spay[slot];
-                                op.dyn(c, acc, pi, self, sdyn[slot], pj);
-                            } else if (k < ct) {
-                                op.stat(c, acc, pi, self, sstat[slot]);
+                            if (kb * 4 + q < cd) {
+                                const uint32_t slot = (uint32_t)(w >> (16 * q)) & 0xFFFFu;
+                                RecB nb_b;
+                                if (Op::HAS_B) nb_b = sb[slot];
+                                op.dyn(c, acc, self_a, self_b, sa[slot], nb_b);
                             }
                         }
                         w = wn;
                     }
+                    // static neighbours: entries [cd, ct) of the same list (only near boundaries)
+                    if (Op::USES_STATIC) {
+                        for (uint32_t k = cd; k < ct; ++k) {
+                            const uint32_t slot = unpack_slot(c.lists[list_word_index(h.pstart, h.pcount, k >> 2, tl)], k);
+                            op.stat(c, acc, self_a, self_b, sstat[slot]);
+                        }
+                    }
                 }
-                const double r = op.finish(c, acc, i, pi, self, active);
+                const double r = op.finish(c, acc, i, self_a, self_b, active);
                 if (Op::REDUCE == REDUCE_SUM) racc += r;
                 if (Op::REDUCE == REDUCE_MAX) racc = fmax(racc, r);
             }
         }
-        __syncthreads();
+        if (t + gridDim.x < ntiles) __syncthreads();
     }
     if (Op::REDUCE != REDUCE_NONE) {
         __shared__ double wred[SW_THREADS / 32];
@@ -148,12 +165,16 @@ __global__ void __launch_bounds__(SW_THREADS) k_sweep(SweepCommon c, Op op) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// density (+ alpha)
+// density (+ alpha, + WCSPH pressure)
 // ---------------------------------------------------------------------------------------------------------------------
-template <int KERNEL, bool WITH_ALPHA>
+__device__ __forceinline__ float tait_pressure(float stiffness, float rho0, float rho) {  // wscsph.rs:52-57
+    return stiffness * (powi_f(fmaxf(rho / rho0, 1.0f), 7) - 1.0f);
+}
+template <int KERNEL, bool WITH_ALPHA, bool WITH_PRESSURE = false>
 struct OpDensityAlpha {
-    typedef NoPayload Payload;
-    static constexpr bool HAS_PAYLOAD = false;
+    typedef float2 RecA;
+    typedef NoRec RecB;
+    static constexpr bool HAS_B = false;
     static constexpr bool USES_STATIC = true;
     static constexpr int REDUCE = REDUCE_NONE;
     static constexpr int TICKET = 0;
@@ -164,16 +185,19 @@ struct OpDensityAlpha {
     };
     float* dens;
     float* alpha;
+    float* pressure;
+    float stiffness;
     __device__ __forceinline__ bool skip(const Control*) const { return false; }
     __device__ __forceinline__ void prepare(const SweepCommon&) {}
-    __device__ __forceinline__ Payload load(const SweepCommon&, uint32_t) const { return Payload(); }
+    __device__ __forceinline__ RecA load_a(const SweepCommon& c, uint32_t g) const { return c.pos[g]; }
+    __device__ __forceinline__ RecB load_b(const SweepCommon&, uint32_t) const { return RecB(); }
     __device__ __forceinline__ float w(const KernelConsts& k, float r_sq, float r) const {
         if (KERNEL == 0) return wendland_w(k, r);
         if (KERNEL == 1) return poly6_w(k, r_sq);
         if (KERNEL == 2) return spiky_w(k, r);
         return cubic_w(k, r);
     }
-    __device__ __forceinline__ bool init(const SweepCommon& c, Acc& a, uint32_t, float2, Payload, uint32_t) const {
+    __device__ __forceinline__ bool init(const SweepCommon& c, Acc& a, uint32_t, RecA, RecB, uint32_t) const {
         a.dens = w(c.kc, 0.0f, 0.0f) * c.mass;  // self contribution, fluidparticleworld.rs:213
         a.gsum = f2(0.0f, 0.0f);
         a.gsq = 0.0f;
@@ -190,11 +214,13 @@ struct OpDensityAlpha {
             a.gsq += mag2(g);
         }
     }
-    __device__ __forceinline__ void dyn(const SweepCommon& c, Acc& a, float2 pi, Payload, float2 pj, Payload) const { pair(c, a, pi, pj); }
-    __device__ __forceinline__ void stat(const SweepCommon& c, Acc& a, float2 pi, Payload, float2 pb) const { pair(c, a, pi, pb); }
-    __device__ __forceinline__ double finish(const SweepCommon& c, Acc& a, uint32_t i, float2, Payload, bool) const {
-        dens[i] = fmaxf(a.dens, c.rho0);  // fluidparticleworld.rs:229
+    __device__ __forceinline__ void dyn(const SweepCommon& c, Acc& a, RecA pi, RecB, RecA pj, RecB) const { pair(c, a, pi, pj); }
+    __device__ __forceinline__ void stat(const SweepCommon& c, Acc& a, RecA pi, RecB, float2 pb) const { pair(c, a, pi, pb); }
+    __device__ __forceinline__ double finish(const SweepCommon& c, Acc& a, uint32_t i, RecA, RecB, bool) const {
+        const float rho = fmaxf(a.dens, c.rho0);  // fluidparticleworld.rs:229
+        dens[i] = rho;
         if (WITH_ALPHA) alpha[i] = 1.0f / fmaxf(mag2(a.gsum) + a.gsq, 1e-6f);  // dfsph.rs:94
+        if (WITH_PRESSURE) pressure[i] = tait_pressure(stiffness, c.rho0, rho);  // wscsph.rs:91-92, once per particle
         return 0.0;
     }
     __device__ __forceinline__ void finalize(const SweepCommon&, double) const {}
@@ -202,7 +228,7 @@ struct OpDensityAlpha {
 
 // alpha only (yasph_compute_alpha: dfsph.rs:68-97 on its own)
 struct OpAlphaOnly : OpDensityAlpha<0, true> {
-    __device__ __forceinline__ double finish(const SweepCommon&, Acc& a, uint32_t i, float2, Payload, bool) const {
+    __device__ __forceinline__ double finish(const SweepCommon&, Acc& a, uint32_t i, RecA, RecB, bool) const {
         alpha[i] = 1.0f / fmaxf(mag2(a.gsum) + a.gsq, 1e-6f);
         return 0.0;
     }
@@ -221,8 +247,9 @@ __device__ __forceinline__ float visc_scalar(const KernelConsts& k, const ViscPa
 }
 
 struct OpViscosity {
-    typedef float4 Payload;  // vx, vy, rho, -
-    static constexpr bool HAS_PAYLOAD = true;
+    typedef float4 RecA;  // px, py, vx, vy
+    typedef float RecB;   // rho
+    static constexpr bool HAS_B = true;
     static constexpr bool USES_STATIC = false;
     static constexpr int REDUCE = REDUCE_MAX;
     static constexpr int TICKET = 1;
@@ -235,25 +262,26 @@ struct OpViscosity {
     float dt;
     __device__ __forceinline__ bool skip(const Control*) const { return false; }
     __device__ __forceinline__ void prepare(const SweepCommon& c) { dt = c.ctl->dt_prev; }
-    __device__ __forceinline__ Payload load(const SweepCommon&, uint32_t g) const {
-        const float2 v = vel[g];
-        return make_float4(v.x, v.y, dens[g], 0.0f);
+    __device__ __forceinline__ RecA load_a(const SweepCommon& c, uint32_t g) const {
+        const float2 p = c.pos[g], v = vel[g];
+        return make_float4(p.x, p.y, v.x, v.y);
     }
-    __device__ __forceinline__ bool init(const SweepCommon&, Acc& a, uint32_t, float2, Payload, uint32_t) const {
+    __device__ __forceinline__ RecB load_b(const SweepCommon&, uint32_t g) const { return dens[g]; }
+    __device__ __forceinline__ bool init(const SweepCommon&, Acc& a, uint32_t, RecA, RecB, uint32_t) const {
         a = base_accel;
         return true;
     }
-    __device__ __forceinline__ void dyn(const SweepCommon& c, Acc& a, float2 pi, Payload self, float2 pj, Payload nb) const {
-        const float2 rij = pj - pi;
+    __device__ __forceinline__ void dyn(const SweepCommon& c, Acc& a, RecA self, RecB, RecA nb, RecB rhoj) const {
+        const float2 rij = f2(nb.x - self.x, nb.y - self.y);
         const float r_sq = mag2(rij);
-        const float r = sqrtf(r_sq);
-        const float s = visc_scalar(c.kc, vp, dt, r_sq, r, nb.z);
-        a = a + s * f2(nb.x - self.x, nb.y - self.y);
+        const float r = vp.kind == 0 ? 0.0f : sqrtf(r_sq);  // XSPH needs r^2 only (xsph.rs:19-24)
+        const float s = visc_scalar(c.kc, vp, dt, r_sq, r, rhoj);
+        a = a + s * f2(nb.z - self.z, nb.w - self.w);
     }
-    __device__ __forceinline__ void stat(const SweepCommon&, Acc&, float2, Payload, float2) const {}
-    __device__ __forceinline__ double finish(const SweepCommon&, Acc& a, uint32_t i, float2, Payload self, bool) const {
+    __device__ __forceinline__ void stat(const SweepCommon&, Acc&, RecA, RecB, float2) const {}
+    __device__ __forceinline__ double finish(const SweepCommon&, Acc& a, uint32_t i, RecA self, RecB, bool) const {
         accel[i] = a;
-        return (double)mag2(f2(self.x, self.y) + a * dt);  // dfsph.rs:476
+        return (double)mag2(f2(self.z, self.w) + a * dt);  // dfsph.rs:476
     }
     __device__ __forceinline__ void finalize(const SweepCommon& c, double mx) const { c.ctl->max_v2_bits = __float_as_uint((float)mx); }
 };
@@ -267,32 +295,38 @@ struct SolverParams {
 };
 template <int SOLVER>
 struct OpJacobiA {
-    typedef float2 Payload;  // predicted velocity
-    static constexpr bool HAS_PAYLOAD = true;
+    typedef float4 RecA;  // px, py, predicted velocity
+    typedef NoRec RecB;
+    static constexpr bool HAS_B = false;
     static constexpr bool USES_STATIC = true;
     static constexpr int REDUCE = REDUCE_SUM;
     static constexpr int TICKET = 2;
     typedef float Acc;
     const float2* vstar;
     const float* dens;
-    float* err;
+    const float* alpha;
+    float* kfac;  // k_i = err_i * alpha_i, the only use of err_i after this pass (dfsph.rs:141,150 / 295,304)
     SolverParams sp;
     uint32_t iter_index;
     float dt;
     __device__ __forceinline__ bool skip(const Control* ctl) const { return iter_index >= ctl->stop_iter[SOLVER]; }
     __device__ __forceinline__ void prepare(const SweepCommon& c) { dt = c.ctl->dt; }
-    __device__ __forceinline__ Payload load(const SweepCommon&, uint32_t g) const { return vstar[g]; }
-    __device__ __forceinline__ bool init(const SweepCommon&, Acc& a, uint32_t, float2, Payload, uint32_t ct) const {
+    __device__ __forceinline__ RecA load_a(const SweepCommon& c, uint32_t g) const {
+        const float2 p = c.pos[g], v = vstar[g];
+        return make_float4(p.x, p.y, v.x, v.y);
+    }
+    __device__ __forceinline__ RecB load_b(const SweepCommon&, uint32_t) const { return RecB(); }
+    __device__ __forceinline__ bool init(const SweepCommon&, Acc& a, uint32_t, RecA, RecB, uint32_t ct) const {
         a = 0.0f;
         return SOLVER == 0 ? true : ct >= 9u;  // particle deficiency, dfsph.rs:261
     }
-    __device__ __forceinline__ void dyn(const SweepCommon& c, Acc& a, float2 pi, Payload vi, float2 pj, Payload vj) const {
-        a += dot2(vi - vj, wendland_grad_from_positions(c.kc, pi, pj));
+    __device__ __forceinline__ void dyn(const SweepCommon& c, Acc& a, RecA self, RecB, RecA nb, RecB) const {
+        a += dot2(f2(self.z - nb.z, self.w - nb.w), wendland_grad_from_positions(c.kc, rec_pos(self), rec_pos(nb)));
     }
-    __device__ __forceinline__ void stat(const SweepCommon& c, Acc& a, float2 pi, Payload vi, float2 pb) const {
-        a += dot2(vi, wendland_grad_from_positions(c.kc, pi, pb));
+    __device__ __forceinline__ void stat(const SweepCommon& c, Acc& a, RecA self, RecB, float2 pb) const {
+        a += dot2(f2(self.z, self.w), wendland_grad_from_positions(c.kc, rec_pos(self), pb));
     }
-    __device__ __forceinline__ double finish(const SweepCommon& c, Acc& a, uint32_t i, float2, Payload, bool active) const {
+    __device__ __forceinline__ double finish(const SweepCommon& c, Acc& a, uint32_t i, RecA, RecB, bool active) const {
         float e;
         if (SOLVER == 0) {
             e = dens[i] + a * c.mass * dt;       // dfsph.rs:121
@@ -300,7 +334,7 @@ struct OpJacobiA {
         } else {
             e = active ? fmaxf(a * c.mass, 0.0f) : 0.0f;  // dfsph.rs:262,277-278
         }
-        err[i] = e;
+        kfac[i] = e * alpha[i];
         return (double)e;
     }
     __device__ __forceinline__ void finalize(const SweepCommon& c, double sum) const {
@@ -337,15 +371,15 @@ struct OpJacobiA {
 // ---------------------------------------------------------------------------------------------------------------------
 template <int SOLVER, bool WARM>
 struct OpJacobiB {
-    typedef float Payload;  // k_j
-    static constexpr bool HAS_PAYLOAD = true;
+    typedef float2 RecA;  // position
+    typedef float RecB;   // k_j
+    static constexpr bool HAS_B = true;
     static constexpr bool USES_STATIC = true;
     static constexpr int REDUCE = REDUCE_NONE;
     static constexpr int TICKET = 0;
     typedef float2 Acc;
     float2* vstar;
-    const float* err;
-    const float* alpha;
+    const float* kfac;
     float* warm;  // warmstart_kappa (SOLVER 0) / warmstart_stiffness (SOLVER 1)
     float clamp_min;  // -0.5 * rho0 * rho0
     uint32_t iter_index;
@@ -357,21 +391,22 @@ struct OpJacobiB {
         dt = c.ctl->dt;
         inv_dt = 1.0f / dt;  // dfsph.rs:132,167
     }
-    __device__ __forceinline__ Payload load(const SweepCommon&, uint32_t g) const {
+    __device__ __forceinline__ RecA load_a(const SweepCommon& c, uint32_t g) const { return c.pos[g]; }
+    __device__ __forceinline__ RecB load_b(const SweepCommon&, uint32_t g) const {
         if (WARM) return 0.5f * fmaxf(warm[g], clamp_min);  // dfsph.rs:201-203 / 356-358
-        return err[g] * alpha[g];                           // dfsph.rs:141,150 / 295,304
+        return kfac[g];
     }
-    __device__ __forceinline__ bool init(const SweepCommon&, Acc& a, uint32_t, float2, Payload, uint32_t) const {
+    __device__ __forceinline__ bool init(const SweepCommon&, Acc& a, uint32_t, RecA, RecB, uint32_t) const {
         a = f2(0.0f, 0.0f);
         return true;
     }
-    __device__ __forceinline__ void dyn(const SweepCommon& c, Acc& a, float2 pi, Payload ki, float2 pj, Payload kj) const {
+    __device__ __forceinline__ void dyn(const SweepCommon& c, Acc& a, RecA pi, RecB ki, RecA pj, RecB kj) const {
         a = a + (ki + kj) * wendland_grad_from_positions(c.kc, pi, pj);
     }
-    __device__ __forceinline__ void stat(const SweepCommon& c, Acc& a, float2 pi, Payload ki, float2 pb) const {
+    __device__ __forceinline__ void stat(const SweepCommon& c, Acc& a, RecA pi, RecB ki, float2 pb) const {
         a = a + ki * wendland_grad_from_positions(c.kc, pi, pb);
     }
-    __device__ __forceinline__ double finish(const SweepCommon& c, Acc& a, uint32_t i, float2, Payload ki, bool) const {
+    __device__ __forceinline__ double finish(const SweepCommon& c, Acc& a, uint32_t i, RecA, RecB ki, bool) const {
         const float2 v = vstar[i];
         if (SOLVER == 0)
             vstar[i] = v - inv_dt * a * c.mass;  // dfsph.rs:159,191
@@ -386,50 +421,49 @@ struct OpJacobiB {
 // ---------------------------------------------------------------------------------------------------------------------
 // WCSPH accelerations
 // ---------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float tait_pressure(float stiffness, float rho0, float rho) {  // wscsph.rs:52-57
-    return stiffness * (powi_f(fmaxf(rho / rho0, 1.0f), 7) - 1.0f);
-}
 struct OpWcsphAccel {
-    typedef float4 Payload;  // vx, vy, rho, p
-    static constexpr bool HAS_PAYLOAD = true;
+    typedef float4 RecA;  // px, py, vx, vy
+    typedef float2 RecB;  // rho, p
+    static constexpr bool HAS_B = true;
     static constexpr bool USES_STATIC = true;
     static constexpr int REDUCE = REDUCE_MAX;
     static constexpr int TICKET = 1;
     typedef float2 Acc;
     const float2* vel;
     const float* dens;
+    const float* pressure;
     float2* accel;
     float2 gravity;
     ViscParams vp;
-    float stiffness, boundary_force_factor;
+    float boundary_force_factor;
     float dt;
     __device__ __forceinline__ bool skip(const Control*) const { return false; }
     __device__ __forceinline__ void prepare(const SweepCommon& c) { dt = c.ctl->dt_prev; }
-    __device__ __forceinline__ Payload load(const SweepCommon& c, uint32_t g) const {
-        const float2 v = vel[g];
-        const float rho = dens[g];
-        return make_float4(v.x, v.y, rho, tait_pressure(stiffness, c.rho0, rho));
+    __device__ __forceinline__ RecA load_a(const SweepCommon& c, uint32_t g) const {
+        const float2 p = c.pos[g], v = vel[g];
+        return make_float4(p.x, p.y, v.x, v.y);
     }
-    __device__ __forceinline__ bool init(const SweepCommon&, Acc& a, uint32_t, float2, Payload, uint32_t) const {
+    __device__ __forceinline__ RecB load_b(const SweepCommon&, uint32_t g) const { return f2(dens[g], pressure[g]); }
+    __device__ __forceinline__ bool init(const SweepCommon&, Acc& a, uint32_t, RecA, RecB, uint32_t) const {
         a = gravity;  // wscsph.rs:84
         return true;
     }
-    __device__ __forceinline__ void dyn(const SweepCommon& c, Acc& a, float2 pi, Payload self, float2 pj, Payload nb) const {
-        const float2 rij = pj - pi;
+    __device__ __forceinline__ void dyn(const SweepCommon& c, Acc& a, RecA self, RecB sb, RecA nb, RecB nbb) const {
+        const float2 rij = f2(nb.x - self.x, nb.y - self.y);
         const float r_sq = mag2(rij);
         const float r = sqrtf(r_sq);
-        const float pu = -c.mass * (self.w + nb.w) / (2.0f * self.z * nb.z);  // wscsph.rs:101
-        a = a + pu * (spiky_grad_scalar(c.kc, r) * rij);                      // wscsph.rs:102
-        a = a + visc_scalar(c.kc, vp, dt, r_sq, r, nb.z) * f2(nb.x - self.x, nb.y - self.y);  // wscsph.rs:104-106
+        const float pu = -c.mass * (sb.y + nbb.y) / (2.0f * sb.x * nbb.x);  // wscsph.rs:101
+        a = a + pu * (spiky_grad_scalar(c.kc, r) * rij);                    // wscsph.rs:102
+        a = a + visc_scalar(c.kc, vp, dt, r_sq, r, nbb.x) * f2(nb.z - self.z, nb.w - self.w);  // wscsph.rs:104-106
     }
-    __device__ __forceinline__ void stat(const SweepCommon& c, Acc& a, float2 pi, Payload, float2 pb) const {
-        const float2 rij = pb - pi;
+    __device__ __forceinline__ void stat(const SweepCommon& c, Acc& a, RecA self, RecB, float2 pb) const {
+        const float2 rij = pb - rec_pos(self);
         const float r_sq = mag2(rij);
         a = a - (boundary_force_factor * spiky_w(c.kc, sqrtf(r_sq)) / r_sq) * rij;  // wscsph.rs:113-115
     }
-    __device__ __forceinline__ double finish(const SweepCommon&, Acc& a, uint32_t i, float2, Payload self, bool) const {
+    __device__ __forceinline__ double finish(const SweepCommon&, Acc& a, uint32_t i, RecA self, RecB, bool) const {
         accel[i] = a;
-        return (double)mag2(f2(self.x, self.y) + a * dt);  // wscsph.rs:162
+        return (double)mag2(f2(self.z, self.w) + a * dt);  // wscsph.rs:162
     }
     __device__ __forceinline__ void finalize(const SweepCommon& c, double mx) const { c.ctl->max_v2_bits = __float_as_uint((float)mx); }
 };

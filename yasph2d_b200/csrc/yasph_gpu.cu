@@ -29,7 +29,11 @@ struct yasph_ctx {
     int device = 0, num_sms = YASPH_NUM_SMS_B200;
     cudaStream_t stream = nullptr;
     uint32_t n = 0, m = 0;
-    uint32_t cap_n = 0, cap_m = 0, max_tiles = 0, cap_dyn = 0, cap_stat = 0;
+    uint32_t cap_n = 0, cap_m = 0, max_tiles = 0;
+    uint32_t lim_dyn = 0, lim_stat = 0;      // configured upper limits for a tile's staged candidates (0 = what shared memory allows)
+    uint32_t cap_dyn = 0, cap_stat = 0;      // staging capacity of the current neighbourhood structure (largest tile, rounded up)
+    uint32_t num_tiles = 0;                  // host copy of Control::num_tiles for the current structure == grid of the tile kernels
+    size_t smem_optin = 0;
     float mass = 0, radius = 0;
     GridParams grid;
     KernelConsts kc;
@@ -38,14 +42,13 @@ struct yasph_ctx {
     float2 *pos = nullptr, *pos_alt = nullptr, *vel = nullptr, *vel_alt = nullptr, *vstar = nullptr, *vstar_alt = nullptr, *accel = nullptr;
     float *dens = nullptr, *alpha = nullptr, *kappa = nullptr, *stiff = nullptr, *err_buf = nullptr, *f_alt0 = nullptr, *f_alt1 = nullptr;
     uint32_t *keys[2] = {nullptr, nullptr}, *idx[2] = {nullptr, nullptr};
-    uint32_t *cell_key = nullptr, *cell_start = nullptr, *tile_key = nullptr, *tile_pstart = nullptr;
+    uint32_t *cell_key = nullptr, *cell_start = nullptr, *tile_key = nullptr, *tile_pstart = nullptr, *tile_cstart = nullptr;
     // boundary
     float2 *bpos = nullptr, *bpos_alt = nullptr;
-    uint32_t *scell_key = nullptr, *scell_start = nullptr;
+    uint32_t *scell_key = nullptr, *scell_start = nullptr, *stile_key = nullptr, *stile_cstart = nullptr;
     // tiles and lists
-    TileHeader* tile_hdr = nullptr;
-    TileCell *tile_dyn = nullptr, *tile_stat = nullptr;
-    uint8_t* tile_rank = nullptr;
+    TileRuns* tile_runs = nullptr;
+    uint32_t *cslot_d = nullptr, *cslot_s = nullptr;
     unsigned long long* lists = nullptr;
     uchar2* counts = nullptr;
     // scratch
@@ -63,7 +66,6 @@ struct yasph_ctx {
     // state flags
     bool have_particles = false, lists_valid = false, dfsph_ready = false;
     uint64_t launches = 0;
-    int grid_tiles = 0;  // persistent grid for tile kernels
     // profiling
     std::vector<PassEvent> events;
     std::vector<cudaEvent_t> event_pool;
@@ -190,19 +192,29 @@ extern "C" int32_t yasph_config_default(yasph_config* cfg, float smoothing_facto
 // ---------------------------------------------------------------------------------------------------------------------
 // create / destroy
 // ---------------------------------------------------------------------------------------------------------------------
-static size_t sweep_smem_bytes(const yasph_ctx* c, size_t payload_bytes) {
-    return sizeof(TileSmem) + (size_t)c->cap_dyn * (payload_bytes + sizeof(float2)) + (size_t)c->cap_stat * sizeof(float2);
+// every tile kernel may use up to the device's opt-in shared memory; the actual size is chosen per launch
+template <class K>
+static cudaError_t allow_max_smem(yasph_ctx* c, K kernel) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->smem_optin + 1024 - fa.sharedSizeBytes));
 }
 template <class Op>
 static cudaError_t prepare_sweep(yasph_ctx* c) {
-    const size_t bytes = sweep_smem_bytes(c, Op::HAS_PAYLOAD ? sizeof(typename Op::Payload) : 0);
-    return cudaFuncSetAttribute(k_sweep<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    return allow_max_smem(c, k_sweep<Op>);
+}
+// the most shared-memory-hungry tile kernels for given capacities: the list build and the WCSPH sweep (24 B per candidate)
+static size_t worst_smem_bytes(uint32_t cap_dyn, uint32_t cap_stat) {
+    const size_t a = list_smem_bytes(cap_dyn, cap_stat), b = sweep_smem_bytes<OpWcsphAccel>(cap_dyn, cap_stat);
+    return a > b ? a : b;
 }
 
 static void free_all(yasph_ctx* c) {
     void* ptrs[] = {c->pos, c->pos_alt, c->vel, c->vel_alt, c->vstar, c->vstar_alt, c->accel, c->dens, c->alpha, c->kappa, c->stiff, c->err_buf,
                     c->f_alt0, c->f_alt1, c->keys[0], c->keys[1], c->idx[0], c->idx[1], c->cell_key, c->cell_start, c->tile_key, c->tile_pstart,
-                    c->bpos, c->bpos_alt, c->scell_key, c->scell_start, c->tile_hdr, c->tile_dyn, c->tile_stat, c->tile_rank, c->lists, c->counts,
+                    c->tile_cstart, c->bpos, c->bpos_alt, c->scell_key, c->scell_start, c->stile_key, c->stile_cstart, c->tile_runs, c->cslot_d,
+                    c->cslot_s, c->lists, c->counts,
                     c->radix_table, c->radix_chunks, c->scan_chunks, c->scan_total, c->partials, c->ctl, c->exp_cd, c->exp_ct, c->exp_lists};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -257,18 +269,15 @@ extern "C" int32_t yasph_create(const yasph_config* cfg, yasph_ctx** out) {
     c->cap_n = cfg->max_particles;
     c->cap_m = cfg->max_boundary;
     c->max_tiles = cfg->max_tiles ? cfg->max_tiles : cfg->max_particles / 32 + 4096;
-    c->cap_dyn = cfg->tile_dynamic_capacity ? cfg->tile_dynamic_capacity : 2048;
-    c->cap_stat = cfg->tile_static_capacity ? cfg->tile_static_capacity : 1024;
-    c->cap_dyn = (c->cap_dyn + 15u) & ~15u;
-    c->cap_stat = (c->cap_stat + 15u) & ~15u;
-    if (c->cap_dyn > 16384 || c->cap_stat > 16384) CREATE_FAIL(YASPH_ERR_INVALID_ARGUMENT, "tile capacities must be <= 16384 slots");
-    if (sweep_smem_bytes(c, sizeof(float4)) > (size_t)prop.sharedMemPerBlockOptin)
-        CREATE_FAIL(YASPH_ERR_CAPACITY, "tile capacities %u/%u need %zu bytes of shared memory per CTA, the device allows %zu", c->cap_dyn, c->cap_stat,
-                    sweep_smem_bytes(c, sizeof(float4)), (size_t)prop.sharedMemPerBlockOptin);
+    c->smem_optin = (size_t)prop.sharedMemPerBlockOptin - 1024;  // dynamic part; 1 KB is kept for the kernels' static shared memory
+    c->lim_dyn = cfg->tile_dynamic_capacity;
+    c->lim_stat = cfg->tile_static_capacity;
+    if (c->lim_dyn > 65535u || c->lim_stat > 65535u) CREATE_FAIL(YASPH_ERR_INVALID_ARGUMENT, "tile capacities must be <= 65535 slots (16-bit slot indices)");
+    if ((c->lim_dyn || c->lim_stat) && worst_smem_bytes(c->lim_dyn, c->lim_stat) > c->smem_optin)
+        CREATE_FAIL(YASPH_ERR_CAPACITY, "tile capacities %u/%u need %zu bytes of shared memory per CTA, the device allows %zu", c->lim_dyn, c->lim_stat,
+                    worst_smem_bytes(c->lim_dyn, c->lim_stat), c->smem_optin);
     if (c->cfg.speculative_iterations == 0) c->cfg.speculative_iterations = 2;
     c->cfg.max_tiles = c->max_tiles;
-    c->cfg.tile_dynamic_capacity = c->cap_dyn;
-    c->cfg.tile_static_capacity = c->cap_stat;
 
     // ConstantFluidProperties
     c->mass = cfg->fluid_density / cfg->particle_density;   // fluidparticleworld.rs:74-76
@@ -307,14 +316,16 @@ extern "C" int32_t yasph_create(const yasph_config* cfg, yasph_ctx** out) {
     CUC(dmalloc(&c->cell_start, N + 2));
     CUC(dmalloc(&c->tile_key, (size_t)c->max_tiles + 1));
     CUC(dmalloc(&c->tile_pstart, (size_t)c->max_tiles + 2));
+    CUC(dmalloc(&c->tile_cstart, (size_t)c->max_tiles + 2));
     CUC(dmalloc(&c->bpos, M));
     CUC(dmalloc(&c->bpos_alt, M));
     CUC(dmalloc(&c->scell_key, M + 1));
     CUC(dmalloc(&c->scell_start, M + 2));
-    CUC(dmalloc(&c->tile_hdr, (size_t)c->max_tiles));
-    CUC(dmalloc(&c->tile_dyn, (size_t)c->max_tiles * YASPH_REGION_CELLS));
-    CUC(dmalloc(&c->tile_stat, (size_t)c->max_tiles * YASPH_REGION_CELLS));
-    CUC(dmalloc(&c->tile_rank, (size_t)c->max_tiles * 128));
+    CUC(dmalloc(&c->stile_key, M + 1));
+    CUC(dmalloc(&c->stile_cstart, M + 2));
+    CUC(dmalloc(&c->tile_runs, (size_t)c->max_tiles));
+    CUC(dmalloc(&c->cslot_d, (size_t)c->max_tiles * REGION_CELLS));
+    CUC(dmalloc(&c->cslot_s, (size_t)c->max_tiles * REGION_CELLS));
     CUC(dmalloc(&c->lists, N * (YASPH_MAXN / 4)));
     CUC(dmalloc(&c->counts, N));
     const size_t rtiles = radix_num_tiles((uint32_t)NM);
@@ -328,11 +339,13 @@ extern "C" int32_t yasph_create(const yasph_config* cfg, yasph_ctx** out) {
     CUC(cudaMemsetAsync(c->accel, 0, N * sizeof(float2), c->stream));  // WCSPHSolver: accellerations start at zero (wscsph.rs:128)
     CUC(cudaMemsetAsync(c->scell_key, 0xFF, sizeof(uint32_t), c->stream));  // empty static grid: sentinel only
     CUC(cudaMemsetAsync(c->scell_start, 0, 2 * sizeof(uint32_t), c->stream));
+    CUC(cudaMemsetAsync(c->stile_cstart, 0, 2 * sizeof(uint32_t), c->stream));
 
     // shared-memory opt-in for every tile kernel and the persistent grid size
     CUC((prepare_sweep<OpDensityAlpha<0, true>>(c)));
     CUC((prepare_sweep<OpDensityAlpha<0, false>>(c)));
     CUC((prepare_sweep<OpDensityAlpha<1, false>>(c)));
+    CUC((prepare_sweep<OpDensityAlpha<1, false, true>>(c)));
     CUC((prepare_sweep<OpDensityAlpha<2, false>>(c)));
     CUC((prepare_sweep<OpDensityAlpha<3, false>>(c)));
     CUC((prepare_sweep<OpAlphaOnly>(c)));
@@ -344,15 +357,8 @@ extern "C" int32_t yasph_create(const yasph_config* cfg, yasph_ctx** out) {
     CUC((prepare_sweep<OpJacobiB<1, false>>(c)));
     CUC((prepare_sweep<OpJacobiB<1, true>>(c)));
     CUC((prepare_sweep<OpWcsphAccel>(c)));
-    CUC(cudaFuncSetAttribute(k_build_lists, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes(c, 0)));
-    {
-        // size the persistent grid from the most shared-memory-hungry sweep (float4 payload)
-        int per_sm = 0;
-        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep<OpViscosity>, SW_THREADS, sweep_smem_bytes(c, sizeof(float4))));
-        if (per_sm < 1) CREATE_FAIL(YASPH_ERR_CAPACITY, "tile capacities %u/%u need more shared memory than one SM has", c->cap_dyn, c->cap_stat);
-        c->grid_tiles = c->num_sms * per_sm;
-    }
-    CUC(dmalloc(&c->partials, (size_t)c->grid_tiles));
+    CUC(allow_max_smem(c, k_build_lists));
+    CUC(dmalloc(&c->partials, (size_t)c->max_tiles + 1));
 
     // TimeManager::new: initial step = timestep_min / fixed (timemanager.rs:106-109); DFSPHSolver::new iteration counts (dfsph.rs:51,55)
     memset(c->h_ctl, 0, sizeof(Control));
@@ -450,7 +456,8 @@ static int32_t build_cells(yasph_ctx* c, uint32_t n, bool is_static) {
     if (n) {
         const uint32_t nch = scan_num_chunks(n);
         HeadFlagsIn in{c->keys[0]};
-        HeadCompactOut out{c->keys[0], ck, cs, c->tile_key, c->tile_pstart, is_static ? 0u : c->max_tiles};
+        HeadCompactOut out{c->keys[0], ck, cs, is_static ? c->stile_key : c->tile_key, is_static ? nullptr : c->tile_pstart,
+                           is_static ? c->stile_cstart : c->tile_cstart, is_static ? c->cap_m : c->max_tiles};
         k_scan_reduce<unsigned long long, HeadFlagsIn><<<nch, SCAN_THREADS, 0, c->stream>>>(in, n, c->scan_chunks);
         CHECK_LAUNCH();
         k_scan_chunks<unsigned long long><<<1, SCAN_THREADS, 0, c->stream>>>(c->scan_chunks, nch, c->scan_total);
@@ -458,12 +465,13 @@ static int32_t build_cells(yasph_ctx* c, uint32_t n, bool is_static) {
         k_scan_apply<unsigned long long, HeadFlagsIn, HeadCompactOut><<<nch, SCAN_THREADS, 0, c->stream>>>(in, n, c->scan_chunks, out);
         CHECK_LAUNCH();
     }
-    k_finish_cells<<<1, 32, 0, c->stream>>>(c->scan_total, n, ck, cs, c->tile_pstart, c->max_tiles, c->ctl, is_static ? 1 : 0);
+    k_finish_cells<<<1, 32, 0, c->stream>>>(c->scan_total, n, ck, cs, c->tile_pstart, is_static ? c->stile_cstart : c->tile_cstart,
+                                            is_static ? c->cap_m : c->max_tiles, c->ctl, is_static ? 1 : 0);
     CHECK_LAUNCH();
     return YASPH_OK;
 }
 
-static TileTables tile_tables(const yasph_ctx* c) { return TileTables{c->tile_hdr, c->tile_dyn, c->tile_stat, c->tile_rank}; }
+static TileTables tile_tables(const yasph_ctx* c) { return TileTables{c->tile_runs, c->cslot_d, c->cslot_s}; }
 
 static SweepCommon sweep_common(const yasph_ctx* c) {
     SweepCommon s;
@@ -484,8 +492,8 @@ static SweepCommon sweep_common(const yasph_ctx* c) {
 }
 template <class Op>
 static int32_t launch_sweep(yasph_ctx* c, Op op) {
-    const size_t bytes = sweep_smem_bytes(c, Op::HAS_PAYLOAD ? sizeof(typename Op::Payload) : 0);
-    k_sweep<Op><<<c->grid_tiles, SW_THREADS, bytes, c->stream>>>(sweep_common(c), op);
+    if (c->num_tiles == 0) return YASPH_OK;
+    k_sweep<Op><<<c->num_tiles, SW_THREADS, sweep_smem_bytes<Op>(c->cap_dyn, c->cap_stat), c->stream>>>(sweep_common(c), op);
     CHECK_LAUNCH();
     return YASPH_OK;
 }
@@ -500,7 +508,7 @@ static int32_t check_capacity_flags(yasph_ctx* c) {
     if (c->h_ctl->err_tile_count)
         return fail(c, YASPH_ERR_CAPACITY, "%u non-empty tiles exceed max_tiles=%u (particles too sparse for the configured capacity)", c->h_ctl->err_tile_count, c->max_tiles);
     if (c->h_ctl->err_tile_capacity)
-        return fail(c, YASPH_ERR_CAPACITY, "a tile stages %u candidates, above tile_dynamic_capacity=%u / tile_static_capacity=%u", c->h_ctl->err_tile_capacity, c->cap_dyn, c->cap_stat);
+        return fail(c, YASPH_ERR_CAPACITY, "a tile stages %u candidates; slots are 16-bit (<= 65535)", c->h_ctl->err_tile_capacity);
     return YASPH_OK;
 }
 
@@ -549,15 +557,29 @@ static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp
     TRY(build_cells(c, n, false));
     CU(cudaMemsetAsync(&c->ctl->total_neighbors, 0, sizeof(unsigned long long) + 2 * sizeof(unsigned int), c->stream));
     if (n) {
-        k_tile_tables<<<c->num_sms * 8, 128, 0, c->stream>>>(c->tile_key, c->tile_pstart, c->cell_key, c->cell_start, c->scell_key, c->scell_start, c->ctl,
-                                                            c->tile_hdr, c->tile_dyn, c->tile_stat, c->tile_rank, c->cap_dyn, c->cap_stat);
+        TileTableArgs ta{c->tile_key, c->tile_pstart, c->tile_cstart, c->cell_key, c->cell_start, c->stile_key, c->stile_cstart,
+                         c->scell_key, c->scell_start, c->tile_runs, c->cslot_d, c->cslot_s};
+        k_tile_tables<<<c->num_sms * 16, TT_WARPS * 32, 0, c->stream>>>(ta, c->ctl);
         CHECK_LAUNCH();
     }
     pass_end(c);
+    // The one host round trip of the neighbourhood update: tile count (grid of every tile kernel until the next update) and
+    // the largest tile (their shared-memory size).
+    TRY(read_control(c));
+    TRY(check_capacity_flags(c));
+    c->num_tiles = n ? c->h_ctl->num_tiles : 0u;
+    c->cap_dyn = (c->h_ctl->max_dyn_total + 15u) & ~15u;
+    c->cap_stat = (c->h_ctl->max_stat_total + 15u) & ~15u;
+    if ((c->lim_dyn && c->h_ctl->max_dyn_total > c->lim_dyn) || (c->lim_stat && c->h_ctl->max_stat_total > c->lim_stat))
+        return fail(c, YASPH_ERR_CAPACITY, "a tile stages %u dynamic / %u static candidates, above tile_dynamic_capacity=%u / tile_static_capacity=%u",
+                    c->h_ctl->max_dyn_total, c->h_ctl->max_stat_total, c->lim_dyn, c->lim_stat);
+    if (worst_smem_bytes(c->cap_dyn, c->cap_stat) > c->smem_optin)
+        return fail(c, YASPH_ERR_CAPACITY, "a tile stages %u dynamic / %u static candidates: %zu bytes of shared memory per CTA, the device allows %zu",
+                    c->h_ctl->max_dyn_total, c->h_ctl->max_stat_total, worst_smem_bytes(c->cap_dyn, c->cap_stat), c->smem_optin);
     pass_begin(c, YASPH_PASS_LISTS);
-    if (n) {
-        k_build_lists<<<c->grid_tiles, NB_THREADS, sweep_smem_bytes(c, 0), c->stream>>>(tile_tables(c), c->pos, c->bpos, c->keys[0], c->grid, c->ctl, c->lists,
-                                                                                      c->counts, c->cap_dyn, c->cap_stat);
+    if (c->num_tiles) {
+        k_build_lists<<<c->num_tiles, NB_THREADS, list_smem_bytes(c->cap_dyn, c->cap_stat), c->stream>>>(
+            tile_tables(c), c->pos, c->bpos, c->keys[0], c->grid, c->ctl, c->lists, c->counts, c->cap_dyn, c->cap_stat);
         CHECK_LAUNCH();
     }
     pass_end(c);
@@ -731,7 +753,7 @@ extern "C" int32_t yasph_neighbors_download(yasph_ctx* c, uint16_t* count_dynami
         CU(dmalloc(&c->exp_ct, (size_t)c->cap_n));
     }
     if (lists64 && !c->exp_lists) CU(dmalloc(&c->exp_lists, (size_t)c->cap_n * YASPH_MAXN));
-    k_export_lists<<<c->grid_tiles, NB_THREADS, 0, c->stream>>>(tile_tables(c), c->ctl, c->lists, c->counts, c->exp_cd, c->exp_ct, lists64 ? c->exp_lists : nullptr);
+    k_export_lists<<<c->num_tiles ? c->num_tiles : 1, 256, 0, c->stream>>>(tile_tables(c), c->ctl, c->lists, c->counts, c->exp_cd, c->exp_ct, lists64 ? c->exp_lists : nullptr);
     CHECK_LAUNCH();
     CU(cudaMemcpyAsync(count_dynamic, c->exp_cd, n * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(count_total, c->exp_ct, n * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream));
@@ -740,11 +762,13 @@ extern "C" int32_t yasph_neighbors_download(yasph_ctx* c, uint16_t* count_dynami
     return YASPH_OK;
 }
 
-template <int KERNEL>
+template <int KERNEL, bool WITH_PRESSURE = false>
 static int32_t launch_density(yasph_ctx* c) {
-    OpDensityAlpha<KERNEL, false> op;
+    OpDensityAlpha<KERNEL, false, WITH_PRESSURE> op;
     op.dens = c->dens;
     op.alpha = nullptr;
+    op.pressure = c->err_buf;  // WCSPH: Tait pressure per particle, in the buffer the (unused) Jacobi scratch occupies
+    op.stiffness = c->cfg.wcsph_stiffness;
     return launch_sweep(c, op);
 }
 extern "C" int32_t yasph_update_densities(yasph_ctx* c, int32_t kernel) {
@@ -771,6 +795,8 @@ extern "C" int32_t yasph_compute_alpha(yasph_ctx* c) {
         OpAlphaOnly op;
         op.dens = nullptr;
         op.alpha = c->alpha;
+        op.pressure = nullptr;
+        op.stiffness = 0.f;
         TRY(launch_sweep(c, op));
     }
     CU(cudaStreamSynchronize(c->stream));
@@ -809,8 +835,7 @@ static int32_t jacobi_solve(yasph_ctx* c) {
     {
         OpJacobiB<SOLVER, true> w;
         w.vstar = c->vstar;
-        w.err = nullptr;
-        w.alpha = nullptr;
+        w.kfac = nullptr;
         w.warm = warm_arr;
         w.clamp_min = -0.5f * rho0 * rho0;
         w.iter_index = 0;
@@ -828,14 +853,14 @@ static int32_t jacobi_solve(yasph_ctx* c) {
             OpJacobiA<SOLVER> a;
             a.vstar = c->vstar;
             a.dens = c->dens;
-            a.err = c->err_buf;
+            a.alpha = c->alpha;
+            a.kfac = c->err_buf;
             a.sp = sp;
             a.iter_index = it;
             TRY(launch_sweep(c, a));
             OpJacobiB<SOLVER, false> b;
             b.vstar = c->vstar;
-            b.err = c->err_buf;
-            b.alpha = c->alpha;
+            b.kfac = c->err_buf;
             b.warm = warm_arr;
             b.clamp_min = 0.f;
             b.iter_index = it;
@@ -866,6 +891,8 @@ static int32_t dfsph_step(yasph_ctx* c) {
         OpDensityAlpha<0, true> da;
         da.dens = c->dens;
         da.alpha = c->alpha;
+        da.pressure = nullptr;
+        da.stiffness = 0.f;
         TRY(launch_sweep(c, da));
         pass_end(c);
         c->dfsph_ready = true;
@@ -919,6 +946,8 @@ static int32_t dfsph_step(yasph_ctx* c) {
         OpDensityAlpha<0, true> da;  // dfsph.rs:516-518
         da.dens = c->dens;
         da.alpha = c->alpha;
+        da.pressure = nullptr;
+        da.stiffness = 0.f;
         TRY(launch_sweep(c, da));
     }
     k_begin_divergence<<<1, 32, 0, c->stream>>>(c->ctl);
@@ -946,17 +975,17 @@ static int32_t wcsph_step(yasph_ctx* c) {
     gp.alt2[1] = &c->vel_alt;
     TRY(neighborhood_update(c, true, gp));  // wscsph.rs:153
     pass_begin(c, YASPH_PASS_DENSITY_ALPHA);
-    TRY(launch_density<1>(c));  // Poly6, wscsph.rs:154
+    TRY((launch_density<1, true>(c)));  // Poly6, wscsph.rs:154; + Tait pressure per particle (wscsph.rs:91-92)
     pass_end(c);
     pass_begin(c, YASPH_PASS_WCSPH_ACCEL);
     {
         OpWcsphAccel a;  // wscsph.rs:155
         a.vel = c->vel;
         a.dens = c->dens;
+        a.pressure = c->err_buf;
         a.accel = c->accel;
         a.gravity = make_float2(c->cfg.gravity[0], c->cfg.gravity[1]);
         a.vp = visc_params(c);
-        a.stiffness = c->cfg.wcsph_stiffness;
         a.boundary_force_factor = c->cfg.wcsph_boundary_force_factor;
         a.dt = 0.f;
         TRY(launch_sweep(c, a));
