@@ -57,7 +57,7 @@ def test_static_neighbors_and_cap():
     rng = np.random.default_rng(5)
     pos = (rng.random((3000, 2)) * 9.0).astype(np.float32)
     bnd = (rng.random((4000, 2)) * 9.0).astype(np.float32)
-    ns, w = run_pair(pos, 1.0, bnd, tile_dynamic_capacity=4096, tile_static_capacity=6144)
+    ns, w = run_pair(pos, 1.0, bnd)
     assert w.neighbor_stats()["capped"] > 0
 
 
@@ -77,7 +77,7 @@ def test_clustered_points_many_per_cell():
     rng = np.random.default_rng(11)
     centers = rng.random((40, 2)) * 30.0
     pos = (centers[rng.integers(0, 40, 20000)] + rng.normal(0, 0.8, (20000, 2))).astype(np.float32)
-    run_pair(pos, 1.0, tile_dynamic_capacity=8192, tile_static_capacity=16)
+    run_pair(pos, 1.0)
 
 
 def test_oversized_tile_capacity_is_rejected():

@@ -22,7 +22,7 @@
 // and the maxima over all tiles (Control::max_*), which the host reads back once per neighbourhood update to size the
 // shared memory of the tile kernels exactly (no worst-case capacity, so many CTAs fit on an SM).
 #pragma once
-#include "common.cuh"
+#include "sort.cuh"
 
 namespace yasph {
 
@@ -60,39 +60,62 @@ struct TileTables {
 };
 
 // ---- keys ---------------------------------------------------------------------------------------------------------
+// All three key-generating kernels run RS_THREADS threads per block and feed the radix sort's global digit histograms
+// (sort.cuh) while they have the key in a register.
 // neighborhood_search.rs:111-114 (sequential in the reference)
-__global__ void k_keygen(const float2* __restrict__ pos, uint32_t n, GridParams g, uint32_t* __restrict__ keys, uint32_t* __restrict__ idx) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(RS_THREADS)
+    k_keygen(const float2* __restrict__ pos, uint32_t n, GridParams g, uint32_t* __restrict__ keys, uint32_t* __restrict__ idx, uint32_t* __restrict__ sort_scratch) {
+    __shared__ RadixHistSmem sh;
+    radix_hist_init(sh);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t key = 0;
     if (i < n) {
-        keys[i] = position_to_cidx(g, pos[i]);
+        key = position_to_cidx(g, pos[i]);
+        keys[i] = key;
         idx[i] = i;
     }
+    radix_hist_add(sh, key, i < n);
+    radix_hist_flush(sh, sort_scratch);
 }
 // dfsph.rs:502-509 (advect) fused with the key generation of the following re-sort
-__global__ void k_advect_keygen(float2* __restrict__ pos, const float2* __restrict__ vstar, uint32_t n, const Control* __restrict__ ctl,
-                                GridParams g, uint32_t* __restrict__ keys, uint32_t* __restrict__ idx) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(RS_THREADS)
+    k_advect_keygen(float2* __restrict__ pos, const float2* __restrict__ vstar, uint32_t n, const Control* __restrict__ ctl, GridParams g,
+                    uint32_t* __restrict__ keys, uint32_t* __restrict__ idx, uint32_t* __restrict__ sort_scratch) {
+    __shared__ RadixHistSmem sh;
+    radix_hist_init(sh);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t key = 0;
     if (i < n) {
         const float dt = ctl->dt;
         float2 p = pos[i] + vstar[i] * dt;
         pos[i] = p;
-        keys[i] = position_to_cidx(g, p);
+        key = position_to_cidx(g, p);
+        keys[i] = key;
         idx[i] = i;
     }
+    radix_hist_add(sh, key, i < n);
+    radix_hist_flush(sh, sort_scratch);
 }
 // wscsph.rs:141-150 (leap frog 1) fused with key generation
-__global__ void k_kickdrift_keygen(float2* __restrict__ pos, float2* __restrict__ vel, const float2* __restrict__ acc, uint32_t n,
-                                   const Control* __restrict__ ctl, GridParams g, uint32_t* __restrict__ keys, uint32_t* __restrict__ idx) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(RS_THREADS)
+    k_kickdrift_keygen(float2* __restrict__ pos, float2* __restrict__ vel, const float2* __restrict__ acc, uint32_t n, const Control* __restrict__ ctl,
+                       GridParams g, uint32_t* __restrict__ keys, uint32_t* __restrict__ idx, uint32_t* __restrict__ sort_scratch) {
+    __shared__ RadixHistSmem sh;
+    radix_hist_init(sh);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t key = 0;
     if (i < n) {
         const float dt = ctl->dt_prev;
         float2 v = vel[i] + 0.5f * dt * acc[i];
         float2 p = pos[i] + v * dt;
         vel[i] = v;
         pos[i] = p;
-        keys[i] = position_to_cidx(g, p);
+        key = position_to_cidx(g, p);
+        keys[i] = key;
         idx[i] = i;
     }
+    radix_hist_add(sh, key, i < n);
+    radix_hist_flush(sh, sort_scratch);
 }
 
 // apply_sorting (neighborhood_search.rs:71-78): out[k] = in[perm[k]] for up to three float2 and two float arrays
@@ -447,115 +470,167 @@ __device__ __forceinline__ void cswap(uint32_t& a, uint32_t& b) {
     b = hi;
 }
 
+// ---- cp.async staging (shared with sweeps.cuh) ---------------------------------------------------------------------------
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc) {
+    static_assert(BYTES == 4 || BYTES == 8 || BYTES == 16, "cp.async.ca copies 4, 8 or 16 bytes");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+constexpr int TILE_THREADS = 256;  // CTA size of every tile kernel
+// the copy-run table of a tile travels global -> registers -> shared memory two tiles ahead of its use
+struct RunsPrefetch {
+    uint4 v;
+    __device__ __forceinline__ void load(const TileRuns* __restrict__ src, bool valid) {
+        static_assert(sizeof(TileRuns) / 16 <= TILE_THREADS, "one uint4 per thread");
+        if (valid && threadIdx.x < sizeof(TileRuns) / 16) v = reinterpret_cast<const uint4*>(src)[threadIdx.x];
+    }
+    __device__ __forceinline__ void store(TileRuns& dst, bool valid) const {
+        if (valid && threadIdx.x < sizeof(TileRuns) / 16) reinterpret_cast<uint4*>(&dst)[threadIdx.x] = v;
+    }
+};
+
 // ---- neighbour lists: NeighborLists::try_update (neighborhood_search.rs:312-397) ---------------------------------------
-// One CTA per tile.  Phase 1 stages the candidate positions; meanwhile one thread per own cell turns the 3x3 box of its
-// cell into <= 9 slot runs in ascending slot order (the role of get_particle_runs_in_neighborbox, :191-259).  Phase 2:
-// one thread per particle walks its cell's runs with a branch-free inner loop -- every candidate's slot is stored to the
-// thread's column of a shared-memory list at row min(count, 64) and the count advances by the hit predicate -- so the
-// first 64 hits survive exactly as the reference's early exit leaves them.  Phase 3 packs the column into 8-byte words.
-constexpr int NB_THREADS = 256;
+// Persistent CTAs over tiles, staging double-buffered with cp.async like the sweeps (sweeps.cuh).  Per tile: one thread
+// per own cell turns the 3x3 box of its cell into <= 9 slot runs in ascending slot order (the role of
+// get_particle_runs_in_neighborbox, :191-259); then one thread per particle walks its cell's candidates in ONE flat loop
+// (all lanes of a warp iterate about the same number of times, whatever their cells' run structure) whose body is
+// branch-free: the candidate's slot is stored to the thread's column of a shared-memory list at row min(count, 64) and the
+// count advances by the hit predicate, so the first 64 hits survive exactly as the reference's early exit leaves them.
+// The column is then packed into 8-byte words of four u16 slots.
+constexpr int NB_THREADS = TILE_THREADS;
 constexpr int NB_ROWS = YASPH_MAXN + 1;  // row 64 absorbs everything past the cap
 struct ListSmem {
-    TileRuns tr;
-    uint32_t cs[2][REGION_CELLS];
+    TileRuns runs[3];
+    uint32_t cs[2][2][REGION_CELLS];  // [buffer][dynamic | static][region cell]: slot_start << 16 | count
     uint32_t crun[2][TILE_CELLS][9];  // per own cell: slot_start << 16 | count, ascending, merged
-    uint32_t ncrun[2][TILE_CELLS];
-    unsigned long long total;
+    uint32_t ncand[2][TILE_CELLS];    // per own cell: total candidates
+    unsigned long long wtotal[NB_THREADS / 32];
     uint16_t sl[NB_ROWS][NB_THREADS];
 };
-inline size_t list_smem_bytes(uint32_t cap_dyn, uint32_t cap_stat) { return sizeof(ListSmem) + ((size_t)cap_dyn + cap_stat) * sizeof(float2); }
+inline size_t list_smem_bytes(uint32_t cap_dyn, uint32_t cap_stat) { return sizeof(ListSmem) + 2 * ((size_t)cap_dyn + cap_stat) * sizeof(float2); }
 
-__global__ void __launch_bounds__(NB_THREADS)
-    k_build_lists(TileTables tt, const float2* __restrict__ pos, const float2* __restrict__ bpos, const uint32_t* __restrict__ keys,
-                  GridParams g, Control* ctl, unsigned long long* __restrict__ lists, uchar2* __restrict__ counts, uint32_t cap_dyn,
-                  uint32_t cap_stat) {
+struct ListArgs {
+    TileTables tt;
+    const float2* pos;
+    const float2* bpos;
+    const uint32_t* keys;
+    GridParams g;
+    Control* ctl;
+    unsigned long long* lists;
+    uchar2* counts;
+    uint32_t cap_dyn, cap_stat;
+};
+__device__ __forceinline__ void list_issue_stage(const ListArgs& a, uint32_t t, const TileRuns& tr, float2* sdyn, float2* sstat, uint32_t (*cs)[REGION_CELLS]) {
+    const TileHeader& h = tr.hdr;
+    for (uint32_t q = threadIdx.x; q < 2 * REGION_CELLS; q += NB_THREADS)
+        cp_async<4>(&cs[q / REGION_CELLS][q % REGION_CELLS], (q < REGION_CELLS ? a.tt.cslot_d : a.tt.cslot_s) + (size_t)t * REGION_CELLS + q % REGION_CELLS);
+    if (h.dyn_total > a.cap_dyn || h.stat_total > a.cap_stat) return;  // cannot happen: capacities are the maxima over all tiles
+    for (uint32_t s = threadIdx.x; s < h.dyn_total; s += NB_THREADS) cp_async<8>(&sdyn[s], &a.pos[dyn_slot_to_global(tr, s)]);
+    for (uint32_t s = threadIdx.x; s < h.stat_total; s += NB_THREADS) cp_async<8>(&sstat[s], &a.bpos[run_slot_to_global(tr.rs, s)]);
+}
+// candidates of one kind (dynamic / static) for one particle; returns the advanced hit count
+__device__ __forceinline__ uint32_t list_scan_candidates(const float2* __restrict__ cand, const uint32_t* __restrict__ cruns, uint32_t ncand, float2 q,
+                                                         float radius_sq, uint16_t* col, uint32_t c) {
+    uint32_t r = 0, rem = 0, s = 0;
+    for (uint32_t j = 0; j < ncand; ++j) {
+        if (rem == 0) {
+            const uint32_t run = cruns[r++];
+            s = run >> 16;
+            rem = run & 0xFFFFu;
+        }
+        const float2 d = cand[s] - q;
+        const float d2 = d.x * d.x + d.y * d.y;
+        col[min(c, (uint32_t)YASPH_MAXN) * NB_THREADS] = (uint16_t)s;
+        c += (d2 <= radius_sq && d2 > YASPH_MIN_DISTANCE) ? 1u : 0u;
+        ++s;
+        --rem;
+    }
+    return c;
+}
+__global__ void __launch_bounds__(NB_THREADS) k_build_lists(ListArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ListSmem& S = *reinterpret_cast<ListSmem*>(smem_raw);
-    float2* sdyn = reinterpret_cast<float2*>(smem_raw + sizeof(ListSmem));
-    float2* sstat = sdyn + cap_dyn;
-    const uint32_t ntiles = ctl->num_tiles;
-    const uint32_t tid = threadIdx.x;
+    float2* const sdyn[2] = {reinterpret_cast<float2*>(smem_raw + sizeof(ListSmem)),
+                             reinterpret_cast<float2*>(smem_raw + sizeof(ListSmem)) + a.cap_dyn + a.cap_stat};
+    const uint32_t ntiles = a.ctl->num_tiles;
+    const uint32_t tid = threadIdx.x, G = gridDim.x;
     unsigned long long my_total = 0;
     uint32_t my_capped = 0, my_dropped = 0;
-    for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        load_tile_runs(S.tr, tt.runs + t);
-        for (uint32_t q = tid; q < 2 * REGION_CELLS; q += NB_THREADS)
-            S.cs[q / REGION_CELLS][q % REGION_CELLS] = (q < REGION_CELLS ? tt.cslot_d : tt.cslot_s)[(size_t)t * REGION_CELLS + q % REGION_CELLS];
+    {
+        const uint32_t t0 = blockIdx.x, t1 = blockIdx.x + G;
+        if (t0 < ntiles) load_tile_runs(S.runs[0], a.tt.runs + t0);
+        if (t1 < ntiles) load_tile_runs(S.runs[1], a.tt.runs + t1);
         __syncthreads();
-        const TileHeader h = S.tr.hdr;
-        if (h.dyn_total <= cap_dyn && h.stat_total <= cap_stat) {
-            for (uint32_t s = tid; s < h.dyn_total; s += NB_THREADS) sdyn[s] = pos[dyn_slot_to_global(S.tr, s)];
-            for (uint32_t s = tid; s < h.stat_total; s += NB_THREADS) sstat[s] = bpos[run_slot_to_global(S.tr.rs, s)];
-            if (tid < 2 * TILE_CELLS) {
-                const uint32_t which = tid / TILE_CELLS, lc = tid % TILE_CELLS;
-                const uint32_t lx = morton_x(lc) + 1u, ly = morton_y(lc) + 1u;
-                uint32_t v[9];
+        if (t0 < ntiles) list_issue_stage(a, t0, S.runs[0], sdyn[0], sdyn[0] + a.cap_dyn, S.cs[0]);
+        cp_async_commit();
+    }
+    uint32_t k = 0;
+    for (uint32_t t = blockIdx.x; t < ntiles; t += G, ++k) {
+        const uint32_t b = k & 1u;
+        const float2* cdyn = sdyn[b];
+        const float2* cstat = sdyn[b] + a.cap_dyn;
+        const TileRuns& tr = S.runs[k % 3u];
+        RunsPrefetch pre;
+        const bool have2 = t + 2 * G < ntiles;
+        pre.load(a.tt.runs + t + 2 * G, have2);
+        cp_async_wait_all();
+        __syncthreads();  // this tile's copies have landed; everybody is done with the previous tile
+        if (t + G < ntiles) list_issue_stage(a, t + G, S.runs[(k + 1) % 3u], sdyn[b ^ 1u], sdyn[b ^ 1u] + a.cap_dyn, S.cs[b ^ 1u]);
+        cp_async_commit();
+        const TileHeader h = tr.hdr;
+        const bool fits = h.dyn_total <= a.cap_dyn && h.stat_total <= a.cap_stat;
+        if (tid < 2 * TILE_CELLS) {
+            const uint32_t which = tid / TILE_CELLS, lc = tid % TILE_CELLS;
+            const uint32_t lx = morton_x(lc) + 1u, ly = morton_y(lc) + 1u;
+            uint32_t v[9];
 #pragma unroll
-                for (int dy = 0; dy < 3; ++dy)
+            for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-                    for (int dx = 0; dx < 3; ++dx) {
-                        const uint32_t e = S.cs[which][(ly + dy - 1) * REGION_AXIS + lx + dx - 1];
-                        v[dy * 3 + dx] = (e & 0xFFFFu) ? e : 0xFFFFFFFFu;  // empty cells sort last
-                    }
-                // 25-exchange sorting network for 9 keys (slot_start in the high half: ascending slot order)
-                cswap(v[0], v[1]); cswap(v[3], v[4]); cswap(v[6], v[7]);
-                cswap(v[1], v[2]); cswap(v[4], v[5]); cswap(v[7], v[8]);
-                cswap(v[0], v[1]); cswap(v[3], v[4]); cswap(v[6], v[7]);
-                cswap(v[0], v[3]); cswap(v[3], v[6]); cswap(v[0], v[3]);
-                cswap(v[1], v[4]); cswap(v[4], v[7]); cswap(v[1], v[4]);
-                cswap(v[2], v[5]); cswap(v[5], v[8]); cswap(v[2], v[5]);
-                cswap(v[1], v[3]); cswap(v[5], v[7]); cswap(v[2], v[6]);
-                cswap(v[4], v[6]); cswap(v[2], v[4]); cswap(v[2], v[3]);
-                cswap(v[5], v[6]);
-                uint32_t nr = 0, cur = 0xFFFFFFFFu;
+                for (int dx = 0; dx < 3; ++dx) {
+                    const uint32_t e = S.cs[b][which][(ly + dy - 1) * REGION_AXIS + lx + dx - 1];
+                    v[dy * 3 + dx] = (e & 0xFFFFu) ? e : 0xFFFFFFFFu;  // empty cells sort last
+                }
+            // 25-exchange sorting network for 9 keys (slot_start in the high half: ascending slot order)
+            cswap(v[0], v[1]); cswap(v[3], v[4]); cswap(v[6], v[7]);
+            cswap(v[1], v[2]); cswap(v[4], v[5]); cswap(v[7], v[8]);
+            cswap(v[0], v[1]); cswap(v[3], v[4]); cswap(v[6], v[7]);
+            cswap(v[0], v[3]); cswap(v[3], v[6]); cswap(v[0], v[3]);
+            cswap(v[1], v[4]); cswap(v[4], v[7]); cswap(v[1], v[4]);
+            cswap(v[2], v[5]); cswap(v[5], v[8]); cswap(v[2], v[5]);
+            cswap(v[1], v[3]); cswap(v[5], v[7]); cswap(v[2], v[6]);
+            cswap(v[4], v[6]); cswap(v[2], v[4]); cswap(v[2], v[3]);
+            cswap(v[5], v[6]);
+            uint32_t nr = 0, cur = 0xFFFFFFFFu, tot = 0;
 #pragma unroll
-                for (int q = 0; q < 9; ++q) {
-                    if (v[q] != 0xFFFFFFFFu) {
-                        if (cur != 0xFFFFFFFFu && (cur >> 16) + (cur & 0xFFFFu) == (v[q] >> 16)) {
-                            cur += v[q] & 0xFFFFu;  // contiguous slots: extend (the sum stays <= 65535, checked by k_tile_tables)
-                        } else {
-                            if (cur != 0xFFFFFFFFu) S.crun[which][lc][nr++] = cur;
-                            cur = v[q];
-                        }
+            for (int q = 0; q < 9; ++q) {
+                if (v[q] != 0xFFFFFFFFu) {
+                    tot += v[q] & 0xFFFFu;
+                    if (cur != 0xFFFFFFFFu && (cur >> 16) + (cur & 0xFFFFu) == (v[q] >> 16)) {
+                        cur += v[q] & 0xFFFFu;  // contiguous slots: extend (the sum stays <= 65535, checked by k_tile_tables)
+                    } else {
+                        if (cur != 0xFFFFFFFFu) S.crun[which][lc][nr++] = cur;
+                        cur = v[q];
                     }
                 }
-                if (cur != 0xFFFFFFFFu) S.crun[which][lc][nr++] = cur;
-                S.ncrun[which][lc] = nr;
             }
-            __syncthreads();
+            if (cur != 0xFFFFFFFFu) S.crun[which][lc][nr++] = cur;
+            S.ncand[which][lc] = tot;
+        }
+        __syncthreads();
+        if (fits) {
             for (uint32_t tl = tid; tl < h.pcount; tl += NB_THREADS) {
                 const uint32_t i = h.pstart + tl;
-                const float2 q = sdyn[h.own_lo + tl];
-                const uint32_t lc = keys[i] & (TILE_CELLS - 1);
+                const float2 q = cdyn[h.own_lo + tl];
+                const uint32_t lc = a.keys[i] & (TILE_CELLS - 1);
                 uint16_t* col = &S.sl[0][tid];
-                uint32_t c = 0;
                 // dynamic candidates, ascending slot == ascending sorted index (neighborhood_search.rs:353-366)
-                const uint32_t nrd = S.ncrun[0][lc];
-                for (uint32_t r = 0; r < nrd; ++r) {
-                    const uint32_t run = S.crun[0][lc][r];
-                    const uint32_t s1 = (run >> 16) + (run & 0xFFFFu);
-                    for (uint32_t s = run >> 16; s < s1; ++s) {
-                        const float2 d = sdyn[s] - q;
-                        const float d2 = d.x * d.x + d.y * d.y;
-                        col[min(c, (uint32_t)YASPH_MAXN) * NB_THREADS] = (uint16_t)s;
-                        c += (d2 <= g.radius_sq && d2 > YASPH_MIN_DISTANCE) ? 1u : 0u;
-                    }
-                }
-                const uint32_t hits_d = c;
-                const uint32_t cd = min(c, (uint32_t)YASPH_MAXN);
-                c = cd;
+                const uint32_t hits_d = list_scan_candidates(cdyn, S.crun[0][lc], S.ncand[0][lc], q, a.g.radius_sq, col, 0u);
+                const uint32_t cd = min(hits_d, (uint32_t)YASPH_MAXN);
                 // static candidates (neighborhood_search.rs:367-381)
-                const uint32_t nrs = S.ncrun[1][lc];
-                for (uint32_t r = 0; r < nrs; ++r) {
-                    const uint32_t run = S.crun[1][lc][r];
-                    const uint32_t s1 = (run >> 16) + (run & 0xFFFFu);
-                    for (uint32_t s = run >> 16; s < s1; ++s) {
-                        const float2 d = sstat[s] - q;
-                        const float d2 = d.x * d.x + d.y * d.y;
-                        col[min(c, (uint32_t)YASPH_MAXN) * NB_THREADS] = (uint16_t)s;
-                        c += (d2 <= g.radius_sq && d2 > YASPH_MIN_DISTANCE) ? 1u : 0u;
-                    }
-                }
+                const uint32_t c = list_scan_candidates(cstat, S.crun[1][lc], S.ncand[1][lc], q, a.g.radius_sq, col, cd);
                 const uint32_t ct = min(c, (uint32_t)YASPH_MAXN);
                 // the reference's bookkeeping: "too many neighbors" when the 64th entry is written (:360,375); a static hit
                 // with all 64 slots taken by dynamic neighbours indexes neighbor_set[64] and panics (:373) -- dropped here
@@ -571,22 +646,33 @@ __global__ void __launch_bounds__(NB_THREADS)
 #pragma unroll
                     for (uint32_t e = 0; e < 4; ++e)
                         if (kb * 4 + e < ct) w |= (unsigned long long)col[(kb * 4 + e) * NB_THREADS] << (16 * e);
-                    lists[list_word_index(h.pstart, h.pcount, kb, tl)] = w;
+                    a.lists[list_word_index(h.pstart, h.pcount, kb, tl)] = w;
                 }
-                counts[i] = make_uchar2((unsigned char)cd, (unsigned char)ct);
+                a.counts[i] = make_uchar2((unsigned char)cd, (unsigned char)ct);
                 my_total += ct;
             }
         }
-        __syncthreads();
+        pre.store(S.runs[(k + 2) % 3u], have2);
     }
-    // statistics: one atomic per CTA
-    if (tid == 0) S.total = 0ull;
+    cp_async_wait_all();
+    // statistics: warp reduce, one global atomic per CTA
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        my_total += __shfl_xor_sync(0xffffffffu, my_total, o);
+        my_capped += __shfl_xor_sync(0xffffffffu, my_capped, o);
+        my_dropped += __shfl_xor_sync(0xffffffffu, my_dropped, o);
+    }
+    if (lane_id() == 0) {
+        S.wtotal[tid >> 5] = my_total;
+        if (my_capped) atomicAdd(&a.ctl->capped, my_capped);
+        if (my_dropped) atomicAdd(&a.ctl->dropped, my_dropped);
+    }
     __syncthreads();
-    if (my_total) atomicAdd(&S.total, my_total);
-    if (my_capped) atomicAdd(&ctl->capped, my_capped);
-    if (my_dropped) atomicAdd(&ctl->dropped, my_dropped);
-    __syncthreads();
-    if (tid == 0 && S.total) atomicAdd(&ctl->total_neighbors, S.total);
+    if (tid == 0) {
+        unsigned long long tot = 0;
+        for (int w = 0; w < NB_THREADS / 32; ++w) tot += S.wtotal[w];
+        if (tot) atomicAdd(&a.ctl->total_neighbors, tot);
+    }
 }
 
 // Export to the reference's layout (neighborhood_search.rs:268-273,433-449): u16 counts + u32 global indices, stride 64.

@@ -1,92 +1,210 @@
-// sort.cuh -- stable LSD radix sort of (cell key, particle index) pairs, 8 bits per pass.
+// sort.cuh -- stable LSD radix sort of (cell key, particle index) pairs, 8 bits per pass, one kernel per pass.
 // Replaces `particle_indices.par_sort_unstable_by_key(cell key)` (src/sph/neighborhood_search.rs:111-118).
 // Stability gives the canonical tie order (ties keep their previous relative order), see DESIGN.md "tie order".
 //
-// Per pass: k_radix_count (per-tile digit histogram -> table[digit][tile]), exclusive scan of the table in
-// digit-major order (scan.cuh), k_radix_scatter (warp match-any ranking, stable).
+// Structure ("onesweep"): the four global digit histograms are accumulated by the kernel that generates the keys
+// (radix_hist_* below, called from k_keygen / k_advect_keygen / k_kickdrift_keygen), so the keys are never read just to be
+// counted.  Each pass is then ONE kernel: a CTA takes the next tile of 4096 pairs (ticket order), ranks its keys per
+// warp with match.any, publishes the tile's digit counts, obtains the counts of all earlier tiles by decoupled look-back
+// over the published status words (count and state share one 32-bit word, so no fence pairs are needed), reorders the
+// tile by digit in shared memory and writes each digit's run contiguously.  Per pass every pair is read once and written
+// once.  A pass whose digit is the same for every key (high digits of a small domain) degenerates to a plain copy.
 #pragma once
-#include "scan.cuh"
+#include "common.cuh"
 
 namespace yasph {
 
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_ITEMS = 16;
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 keys per block
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 pairs per tile
 constexpr int RS_BINS = 256;
+constexpr int RS_PASSES = 4;
+constexpr uint32_t RS_FLAG_LOCAL = 1u << 30, RS_FLAG_GLOBAL = 2u << 30, RS_VALUE_MASK = (1u << 30) - 1u;
 
 inline uint32_t radix_num_tiles(uint32_t n) { return (n + RS_TILE - 1) / RS_TILE; }
+// scratch layout (uint32): [RS_PASSES] tile tickets | [RS_PASSES][RS_BINS] global histograms | [RS_PASSES][ntiles][RS_BINS] status
+inline size_t radix_scratch_words(uint32_t n) { return RS_PASSES + (size_t)RS_PASSES * RS_BINS + (size_t)RS_PASSES * radix_num_tiles(n) * RS_BINS; }
 
-__global__ void __launch_bounds__(RS_THREADS) k_radix_count(const uint32_t* __restrict__ keys, uint32_t n, int shift,
-                                                           uint32_t* __restrict__ table, uint32_t ntiles) {
-    __shared__ uint32_t hist[RS_BINS];
-    hist[threadIdx.x] = 0;
+// ---- global digit histograms, fused into the key-generating kernels ------------------------------------------------------
+// Call pattern inside a kernel of RS_THREADS threads: radix_hist_init(sh); ... radix_hist_add(sh, key) for each key ...;
+// radix_hist_flush(sh, scratch).
+struct RadixHistSmem {
+    uint32_t h[RS_PASSES][RS_BINS];
+};
+__device__ __forceinline__ void radix_hist_init(RadixHistSmem& sh) {
+    for (uint32_t q = threadIdx.x; q < RS_PASSES * RS_BINS; q += blockDim.x) (&sh.h[0][0])[q] = 0u;
     __syncthreads();
-    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
-    const uint32_t base = blockIdx.x * RS_TILE + warp * (32 * RS_ITEMS);
-#pragma unroll 4
-    for (int r = 0; r < RS_ITEMS; ++r) {
-        uint32_t i = base + r * 32 + lane;
-        bool valid = i < n;
-        uint32_t d = valid ? ((keys[i] >> shift) & 0xFFu) : 0x100u;
-        unsigned mask = __match_any_sync(0xffffffffu, d);
-        if (valid && lane == (unsigned)(__ffs(mask) - 1)) atomicAdd(&hist[d], (uint32_t)__popc(mask));
+}
+// Every thread of the warp calls this (valid == false for threads past the end).  The input is nearly sorted, so the lanes
+// of a warp form a few runs of equal digits (one run for the high digits): each run's first lane adds the run length.  One
+// shuffle, one ballot and a handful of integer instructions per digit; no lane pair ever hits the same counter at once
+// unless the same digit recurs in separate runs.
+__device__ __forceinline__ void radix_hist_add(RadixHistSmem& sh, uint32_t key, bool valid) {
+    const uint32_t lane = lane_id();
+#pragma unroll
+    for (int p = 0; p < RS_PASSES; ++p) {
+        const uint32_t d = valid ? ((key >> (8 * p)) & 0xFFu) : 0x1FFu;
+        const uint32_t prev = __shfl_up_sync(0xffffffffu, d, 1);
+        const bool head = lane == 0 || d != prev;
+        const unsigned hm = __ballot_sync(0xffffffffu, head);
+        if (head && valid) {
+            const unsigned later = lane == 31 ? 0u : (hm & (0xFFFFFFFEu << lane));
+            const uint32_t len = (later ? (uint32_t)__ffs(later) - 1u : 32u) - lane;
+            atomicAdd(&sh.h[p][d], len);
+        }
     }
+}
+__device__ __forceinline__ void radix_hist_flush(RadixHistSmem& sh, uint32_t* __restrict__ scratch) {
     __syncthreads();
-    table[(size_t)threadIdx.x * ntiles + blockIdx.x] = hist[threadIdx.x];
+    uint32_t* ghist = scratch + RS_PASSES;
+    for (uint32_t q = threadIdx.x; q < RS_PASSES * RS_BINS; q += blockDim.x) {
+        const uint32_t v = (&sh.h[0][0])[q];
+        if (v) atomicAdd(&ghist[q], v);
+    }
 }
 
+// ---- one pass -------------------------------------------------------------------------------------------------------------
+struct RadixPassSmem {
+    uint32_t cnt[RS_WARPS][RS_BINS];  // per-warp digit counts, then exclusive prefix over the warps
+    uint32_t lbin[RS_BINS];           // first position of the digit in the tile's digit-sorted order
+    uint32_t gbin[RS_BINS];           // global position of the tile's first key of the digit, minus lbin
+    uint32_t skey[RS_TILE];
+    uint32_t sval[RS_TILE];
+    uint32_t wsum[RS_WARPS];
+    uint32_t tile;
+    uint32_t trivial;
+};
 __global__ void __launch_bounds__(RS_THREADS)
-    k_radix_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
-                    uint32_t* __restrict__ vals_out, uint32_t n, int shift, const uint32_t* __restrict__ table_scanned, uint32_t ntiles) {
-    __shared__ uint32_t cnt[RS_WARPS][RS_BINS];
-    __shared__ uint32_t gbase[RS_BINS];
-    for (int w = 0; w < RS_WARPS; ++w) cnt[w][threadIdx.x] = 0;
-    __syncthreads();
-    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
-    const uint32_t base = blockIdx.x * RS_TILE + warp * (32 * RS_ITEMS);
+    k_radix_pass(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
+                 uint32_t* __restrict__ vals_out, uint32_t n, int pass, uint32_t* __restrict__ scratch, uint32_t ntiles) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RadixPassSmem& S = *reinterpret_cast<RadixPassSmem*>(smem_raw);
+    const int shift = pass * 8;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = lane_id();
     const unsigned lt = lanemask_lt();
+    const uint32_t* ghist = scratch + RS_PASSES + pass * RS_BINS;
+    volatile uint32_t* status = scratch + RS_PASSES + RS_PASSES * RS_BINS + (size_t)pass * ntiles * RS_BINS;
+    if (tid == 0) {
+        S.tile = atomicAdd(&scratch[pass], 1u);
+        S.trivial = 0u;
+    }
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) S.cnt[w][tid] = 0u;
+    __syncthreads();
+    const uint32_t tile = S.tile;
+    const uint32_t gh = ghist[tid];
+    if (gh == n) S.trivial = 1u;  // every key has this digit: the pass is the identity
+    const uint32_t base = tile * RS_TILE + warp * (32 * RS_ITEMS);
     uint32_t key[RS_ITEMS], val[RS_ITEMS], rank[RS_ITEMS];
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; ++r) {
-        uint32_t i = base + r * 32 + lane;
-        bool valid = i < n;
+        const uint32_t i = base + r * 32 + lane;
+        const bool valid = i < n;
         key[r] = valid ? keys_in[i] : 0xFFFFFFFFu;
         val[r] = valid ? vals_in[i] : 0u;
     }
+    __syncthreads();
+    if (S.trivial) {
+#pragma unroll
+        for (int r = 0; r < RS_ITEMS; ++r) {
+            const uint32_t i = base + r * 32 + lane;
+            if (i < n) {
+                keys_out[i] = key[r];
+                vals_out[i] = val[r];
+            }
+        }
+        return;
+    }
+    // 1. rank inside the warp (stable: rows in order, lanes in order)
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; ++r) {
-        uint32_t i = base + r * 32 + lane;
-        bool valid = i < n;
-        uint32_t d = valid ? ((key[r] >> shift) & 0xFFu) : 0x100u;
-        unsigned mask = __match_any_sync(0xffffffffu, d);
-        uint32_t b = valid ? cnt[warp][d] : 0u;
+        const uint32_t i = base + r * 32 + lane;
+        const bool valid = i < n;
+        const uint32_t d = valid ? ((key[r] >> shift) & 0xFFu) : 0x100u;
+        const unsigned mask = __match_any_sync(0xffffffffu, d);
+        const uint32_t b = valid ? S.cnt[warp][d] : 0u;
         __syncwarp();
-        if (valid && lane == (unsigned)(__ffs(mask) - 1)) cnt[warp][d] = b + (uint32_t)__popc(mask);
+        if (valid && lane == (unsigned)(__ffs(mask) - 1)) S.cnt[warp][d] = b + (uint32_t)__popc(mask);
         __syncwarp();
         rank[r] = b + (uint32_t)__popc(mask & lt);
     }
     __syncthreads();
-    {  // per digit: exclusive scan over the warps, plus the tile's global base
-        const uint32_t d = threadIdx.x;
-        uint32_t run = 0;
+    // 2. per digit (thread == digit): prefix over the warps, tile count, publish, look back
+    uint32_t tcount = 0;
+    {
 #pragma unroll
         for (int w = 0; w < RS_WARPS; ++w) {
-            uint32_t t = cnt[w][d];
-            cnt[w][d] = run;
-            run += t;
+            const uint32_t t = S.cnt[w][tid];
+            S.cnt[w][tid] = tcount;
+            tcount += t;
         }
-        gbase[d] = table_scanned[(size_t)d * ntiles + blockIdx.x];
+        status[(size_t)tile * RS_BINS + tid] = tcount | RS_FLAG_LOCAL;
+    }
+    // exclusive scan of the tile counts over the digits (position of each digit in the tile's sorted order) and of the
+    // global histogram (position of each digit in the output)
+    uint32_t lex, gex;
+    {
+        uint32_t a = tcount, g = gh;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t ua = __shfl_up_sync(0xffffffffu, a, o), ug = __shfl_up_sync(0xffffffffu, g, o);
+            if (lane >= (uint32_t)o) {
+                a += ua;
+                g += ug;
+            }
+        }
+        if (lane == 31) {
+            S.wsum[warp] = a;
+            S.lbin[warp] = g;  // borrowed until the sync below
+        }
+        __syncthreads();
+        uint32_t wa = 0, wg = 0;
+        for (uint32_t w = 0; w < warp; ++w) {
+            wa += S.wsum[w];
+            wg += S.lbin[w];
+        }
+        __syncthreads();
+        lex = wa + a - tcount;
+        gex = wg + g - gh;
+    }
+    {
+        uint32_t excl = 0;
+        for (int j = (int)tile - 1; j >= 0; --j) {
+            uint32_t s;
+            do {
+                s = status[(size_t)j * RS_BINS + tid];
+            } while ((s & ~RS_VALUE_MASK) == 0u);
+            excl += s & RS_VALUE_MASK;
+            if (s & RS_FLAG_GLOBAL) break;
+        }
+        status[(size_t)tile * RS_BINS + tid] = (excl + tcount) | RS_FLAG_GLOBAL;
+        S.lbin[tid] = lex;
+        S.gbin[tid] = gex + excl - lex;
     }
     __syncthreads();
+    // 3. reorder the tile by digit in shared memory
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; ++r) {
-        uint32_t i = base + r * 32 + lane;
+        const uint32_t i = base + r * 32 + lane;
         if (i < n) {
-            uint32_t d = (key[r] >> shift) & 0xFFu;
-            uint32_t pos = gbase[d] + cnt[warp][d] + rank[r];
-            keys_out[pos] = key[r];
-            vals_out[pos] = val[r];
+            const uint32_t d = (key[r] >> shift) & 0xFFu;
+            const uint32_t lp = S.lbin[d] + S.cnt[warp][d] + rank[r];
+            S.skey[lp] = key[r];
+            S.sval[lp] = val[r];
+        }
+    }
+    __syncthreads();
+    // 4. write every digit's run contiguously
+    const uint32_t tile_n = min((uint32_t)RS_TILE, n - tile * RS_TILE);
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        const uint32_t lp = r * RS_THREADS + tid;
+        if (lp < tile_n) {
+            const uint32_t k = S.skey[lp];
+            const uint32_t gp = S.gbin[(k >> shift) & 0xFFu] + lp;
+            keys_out[gp] = k;
+            vals_out[gp] = S.sval[lp];
         }
     }
 }

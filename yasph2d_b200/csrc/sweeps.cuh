@@ -1,10 +1,13 @@
 // sweeps.cuh -- every neighbour-dependent per-particle pass of the WCSPH / DFSPH solvers as one tile-staged kernel.
 //
-// Skeleton (k_sweep): one CTA per 8x8-cell tile.  The tile's own particles plus the 1-cell apron are staged into shared
-// memory once (a record per candidate: position + the per-pass neighbour payload; boundary positions), then one thread
-// per particle walks its compact neighbour list (u16 shared-memory slots, dynamic first, then static) in the reference's
-// order.  Shared memory is sized from the largest tile of the current neighbourhood structure (Control::max_*), a few KB,
-// so 4-8 CTAs are resident per SM and the staging latency of one tile hides behind the arithmetic of the others.
+// Skeleton (k_sweep): persistent CTAs, each walking tiles blockIdx.x, blockIdx.x + gridDim.x, ...  A tile's own particles
+// plus the 1-cell apron are staged into shared memory (positions, up to two per-pass payload arrays, boundary positions)
+// with cp.async, DOUBLE-BUFFERED: while the CTA computes tile k from buffer k&1 the copies for tile k+1 are in flight into
+// the other buffer and the copy-run table of tile k+2 is on its way through registers, so the global-memory latency of the
+// staging never sits between two barriers (one __syncthreads per tile).  One thread per particle then walks its compact
+// neighbour list (u16 shared-memory slots, dynamic first, then static) in the reference's order; the four slots of an
+// 8-byte list word are evaluated branch-free (select on the accumulator) so the compiler interleaves four independent
+// pair evaluations.  Shared memory is sized from the largest tile of the current neighbourhood structure (Control::max_*).
 // Reductions (Jacobi residual sum, CFL max) are fused: per-thread accumulation, block reduce, per-CTA partial, the
 // last-arriving CTA combines the partials in fixed order and takes the convergence decision on the device (no host round
 // trip inside a Jacobi iteration).
@@ -23,7 +26,7 @@
 
 namespace yasph {
 
-constexpr int SW_THREADS = 256;
+constexpr int SW_THREADS = TILE_THREADS;
 
 struct SweepCommon {
     TileTables tt;
@@ -41,53 +44,99 @@ struct SweepCommon {
 
 enum ReduceKind { REDUCE_NONE = 0, REDUCE_SUM = 1, REDUCE_MAX = 2 };
 
-struct NoRec {};
-__device__ __forceinline__ float2 rec_pos(float2 r) { return r; }
-__device__ __forceinline__ float2 rec_pos(float4 r) { return f2(r.x, r.y); }
+struct NoPay {};
 
-// shared memory of a sweep: TileRuns | RecA[cap_dyn] | RecB[cap_dyn] | float2[cap_stat]  (capacities are multiples of 2)
+// per-buffer shared-memory layout of a sweep: float2 pos[cap_dyn] | P0[cap_dyn] | P1[cap_dyn] | float2 stat[cap_stat]
+template <class Op>
+struct SweepLayout {
+    static constexpr size_t P0 = Op::NPAY >= 1 ? sizeof(typename Op::P0) : 0;
+    static constexpr size_t P1 = Op::NPAY >= 2 ? sizeof(typename Op::P1) : 0;
+    __host__ __device__ static size_t buffer_bytes(uint32_t cap_dyn, uint32_t cap_stat) {
+        return (size_t)cap_dyn * (sizeof(float2) + P0 + P1) + (Op::USES_STATIC ? (size_t)cap_stat * sizeof(float2) : 0);
+    }
+    __host__ __device__ static size_t total_bytes(uint32_t cap_dyn, uint32_t cap_stat) { return 3 * sizeof(TileRuns) + 2 * buffer_bytes(cap_dyn, cap_stat); }
+};
 template <class Op>
 inline size_t sweep_smem_bytes(uint32_t cap_dyn, uint32_t cap_stat) {
-    return sizeof(TileRuns) + (size_t)cap_dyn * (sizeof(typename Op::RecA) + (Op::HAS_B ? sizeof(typename Op::RecB) : 0)) +
-           (Op::USES_STATIC ? (size_t)cap_stat * sizeof(float2) : 0);
+    return SweepLayout<Op>::total_bytes(cap_dyn, cap_stat);
+}
+
+template <class Op>
+struct SweepBuffer {
+    float2* pos;
+    typename Op::P0* p0;
+    typename Op::P1* p1;
+    float2* stat;
+    __device__ __forceinline__ SweepBuffer(unsigned char* base, uint32_t cap_dyn) {
+        pos = reinterpret_cast<float2*>(base);
+        p0 = reinterpret_cast<typename Op::P0*>(base + (size_t)cap_dyn * sizeof(float2));
+        p1 = reinterpret_cast<typename Op::P1*>(base + (size_t)cap_dyn * (sizeof(float2) + SweepLayout<Op>::P0));
+        stat = reinterpret_cast<float2*>(base + (size_t)cap_dyn * (sizeof(float2) + SweepLayout<Op>::P0 + SweepLayout<Op>::P1));
+    }
+};
+
+template <class Op>
+__device__ __forceinline__ void sweep_issue_stage(const SweepCommon& c, const Op& op, const TileRuns& tr, const SweepBuffer<Op>& b) {
+    const TileHeader& h = tr.hdr;
+    if (h.dyn_total > c.cap_dyn || h.stat_total > c.cap_stat) return;  // cannot happen: capacities are the maxima over all tiles
+    for (uint32_t s = threadIdx.x; s < h.dyn_total; s += SW_THREADS) {
+        const uint32_t g = dyn_slot_to_global(tr, s);
+        cp_async<8>(&b.pos[s], &c.pos[g]);
+        if constexpr (Op::NPAY >= 1) cp_async<sizeof(typename Op::P0)>(&b.p0[s], &op.pay0()[g]);
+        if constexpr (Op::NPAY >= 2) cp_async<sizeof(typename Op::P1)>(&b.p1[s], &op.pay1()[g]);
+    }
+    if (Op::USES_STATIC)
+        for (uint32_t s = threadIdx.x; s < h.stat_total; s += SW_THREADS) cp_async<8>(&b.stat[s], &c.bpos[run_slot_to_global(tr.rs, s)]);
 }
 
 template <class Op>
 __global__ void __launch_bounds__(SW_THREADS) k_sweep(SweepCommon c, Op op) {
-    typedef typename Op::RecA RecA;
-    typedef typename Op::RecB RecB;
+    typedef typename Op::P0 P0;
+    typedef typename Op::P1 P1;
     if (op.skip(c.ctl)) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    TileRuns& tr = *reinterpret_cast<TileRuns*>(smem_raw);
-    RecA* sa = reinterpret_cast<RecA*>(smem_raw + sizeof(TileRuns));
-    RecB* sb = reinterpret_cast<RecB*>(smem_raw + sizeof(TileRuns) + sizeof(RecA) * (size_t)c.cap_dyn);
-    float2* sstat = reinterpret_cast<float2*>(smem_raw + sizeof(TileRuns) + (sizeof(RecA) + (Op::HAS_B ? sizeof(RecB) : 0)) * (size_t)c.cap_dyn);
+    TileRuns* runs = reinterpret_cast<TileRuns*>(smem_raw);  // [3]
+    const size_t bbytes = SweepLayout<Op>::buffer_bytes(c.cap_dyn, c.cap_stat);
+    const SweepBuffer<Op> buf0(smem_raw + 3 * sizeof(TileRuns), c.cap_dyn), buf1(smem_raw + 3 * sizeof(TileRuns) + bbytes, c.cap_dyn);
     op.prepare(c);
     const uint32_t ntiles = c.ctl->num_tiles;
+    const uint32_t G = gridDim.x;
     double racc = 0.0;
-    for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        load_tile_runs(tr, c.tt.runs + t);
+    // prologue: tables of the first two tiles, copies of the first
+    {
+        const uint32_t t0 = blockIdx.x, t1 = blockIdx.x + G;
+        if (t0 < ntiles) load_tile_runs(runs[0], c.tt.runs + t0);
+        if (t1 < ntiles) load_tile_runs(runs[1], c.tt.runs + t1);
         __syncthreads();
+        if (t0 < ntiles) sweep_issue_stage(c, op, runs[0], buf0);
+        cp_async_commit();
+    }
+    uint32_t k = 0;
+    for (uint32_t t = blockIdx.x; t < ntiles; t += G, ++k) {
+        const SweepBuffer<Op>& cur = (k & 1u) ? buf1 : buf0;
+        const SweepBuffer<Op>& nxt = (k & 1u) ? buf0 : buf1;
+        const TileRuns& tr = runs[k % 3u];
+        RunsPrefetch pre;
+        const bool have2 = t + 2 * G < ntiles;
+        pre.load(c.tt.runs + t + 2 * G, have2);
+        cp_async_wait_all();
+        __syncthreads();  // this tile's copies have landed; everybody is done with the previous tile's buffers
+        if (t + G < ntiles) sweep_issue_stage(c, op, runs[(k + 1) % 3u], nxt);
+        cp_async_commit();
         const TileHeader h = tr.hdr;
         if (h.dyn_total <= c.cap_dyn && h.stat_total <= c.cap_stat) {
-            for (uint32_t s = threadIdx.x; s < h.dyn_total; s += SW_THREADS) {
-                const uint32_t g = dyn_slot_to_global(tr, s);
-                sa[s] = op.load_a(c, g);
-                if (Op::HAS_B) sb[s] = op.load_b(c, g);
-            }
-            if (Op::USES_STATIC)
-                for (uint32_t s = threadIdx.x; s < h.stat_total; s += SW_THREADS) sstat[s] = c.bpos[run_slot_to_global(tr.rs, s)];
-            __syncthreads();
             for (uint32_t tl = threadIdx.x; tl < h.pcount; tl += SW_THREADS) {
                 const uint32_t i = h.pstart + tl;
                 const uint32_t own = h.own_lo + tl;
-                const RecA self_a = sa[own];
-                RecB self_b;
-                if (Op::HAS_B) self_b = sb[own];
+                const float2 pi = cur.pos[own];
+                P0 s0;
+                P1 s1;
+                if (Op::NPAY >= 1) s0 = cur.p0[own];
+                if (Op::NPAY >= 2) s1 = cur.p1[own];
                 const uchar2 cnt = c.counts[i];
                 const uint32_t cd = cnt.x, ct = Op::USES_STATIC ? cnt.y : cnt.x;
                 typename Op::Acc acc;
-                const bool active = op.init(c, acc, i, self_a, self_b, cnt.y);
+                const bool active = op.init(c, acc, i, pi, s0, s1, cnt.y);
                 if (active) {
                     // dynamic neighbours: entries [0, cd), four per 8-byte word, next word prefetched
                     const uint32_t nkb = (cd + 3u) >> 2;
@@ -96,30 +145,34 @@ __global__ void __launch_bounds__(SW_THREADS) k_sweep(SweepCommon c, Op op) {
                         const unsigned long long wn = (kb + 1 < nkb) ? c.lists[list_word_index(h.pstart, h.pcount, kb + 1, tl)] : 0ull;
 #pragma unroll
                         for (uint32_t q = 0; q < 4; ++q) {
-                            if (kb * 4 + q < cd) {
-                                const uint32_t slot = (uint32_t)(w >> (16 * q)) & 0xFFFFu;
-                                RecB nb_b;
-                                if (Op::HAS_B) nb_b = sb[slot];
-                                op.dyn(c, acc, self_a, self_b, sa[slot], nb_b);
-                            }
+                            const bool valid = kb * 4 + q < cd;
+                            const uint32_t slot = valid ? ((uint32_t)(w >> (16 * q)) & 0xFFFFu) : own;
+                            P0 n0;
+                            P1 n1;
+                            if (Op::NPAY >= 1) n0 = cur.p0[slot];
+                            if (Op::NPAY >= 2) n1 = cur.p1[slot];
+                            typename Op::Acc trial = acc;
+                            op.dyn(c, trial, pi, s0, s1, cur.pos[slot], n0, n1);
+                            if (valid) acc = trial;
                         }
                         w = wn;
                     }
                     // static neighbours: entries [cd, ct) of the same list (only near boundaries)
                     if (Op::USES_STATIC) {
-                        for (uint32_t k = cd; k < ct; ++k) {
-                            const uint32_t slot = unpack_slot(c.lists[list_word_index(h.pstart, h.pcount, k >> 2, tl)], k);
-                            op.stat(c, acc, self_a, self_b, sstat[slot]);
+                        for (uint32_t kk = cd; kk < ct; ++kk) {
+                            const uint32_t slot = unpack_slot(c.lists[list_word_index(h.pstart, h.pcount, kk >> 2, tl)], kk);
+                            op.stat(c, acc, pi, s0, s1, cur.stat[slot]);
                         }
                     }
                 }
-                const double r = op.finish(c, acc, i, self_a, self_b, active);
+                const double r = op.finish(c, acc, i, pi, s0, s1, active);
                 if (Op::REDUCE == REDUCE_SUM) racc += r;
                 if (Op::REDUCE == REDUCE_MAX) racc = fmax(racc, r);
             }
         }
-        if (t + gridDim.x < ntiles) __syncthreads();
+        pre.store(runs[(k + 2) % 3u], have2);  // last read before this iteration's barrier; next read after the next one
     }
+    cp_async_wait_all();
     if (Op::REDUCE != REDUCE_NONE) {
         __shared__ double wred[SW_THREADS / 32];
         __shared__ bool is_last;
@@ -172,9 +225,9 @@ __device__ __forceinline__ float tait_pressure(float stiffness, float rho0, floa
 }
 template <int KERNEL, bool WITH_ALPHA, bool WITH_PRESSURE = false>
 struct OpDensityAlpha {
-    typedef float2 RecA;
-    typedef NoRec RecB;
-    static constexpr bool HAS_B = false;
+    typedef NoPay P0;
+    typedef NoPay P1;
+    static constexpr int NPAY = 0;
     static constexpr bool USES_STATIC = true;
     static constexpr int REDUCE = REDUCE_NONE;
     static constexpr int TICKET = 0;
@@ -185,19 +238,19 @@ struct OpDensityAlpha {
     };
     float* dens;
     float* alpha;
-    float* pressure;
+    float2* rho_p;  // WCSPH: (rho, Tait pressure) per particle
     float stiffness;
+    __device__ __forceinline__ const P0* pay0() const { return nullptr; }
+    __device__ __forceinline__ const P1* pay1() const { return nullptr; }
     __device__ __forceinline__ bool skip(const Control*) const { return false; }
     __device__ __forceinline__ void prepare(const SweepCommon&) {}
-    __device__ __forceinline__ RecA load_a(const SweepCommon& c, uint32_t g) const { return c.pos[g]; }
-    __device__ __forceinline__ RecB load_b(const SweepCommon&, uint32_t) const { return RecB(); }
     __device__ __forceinline__ float w(const KernelConsts& k, float r_sq, float r) const {
         if (KERNEL == 0) return wendland_w(k, r);
         if (KERNEL == 1) return poly6_w(k, r_sq);
         if (KERNEL == 2) return spiky_w(k, r);
         return cubic_w(k, r);
     }
-    __device__ __forceinline__ bool init(const SweepCommon& c, Acc& a, uint32_t, RecA, RecB, uint32_t) const {
+    __device__ __forceinline__ bool init(const SweepCommon& c, Acc& a, uint32_t, float2, P0, P1, uint32_t) const {
         a.dens = w(c.kc, 0.0f, 0.0f) * c.mass;  // self contribution, fluidparticleworld.rs:213
         a.gsum = f2(0.0f, 0.0f);
         a.gsq = 0.0f;
@@ -206,7 +259,7 @@ struct OpDensityAlpha {
     __device__ __forceinline__ void pair(const SweepCommon& c, Acc& a, float2 pi, float2 pj) const {
         const float2 rij = pj - pi;
         const float r_sq = mag2(rij);
-        const float r = sqrtf(r_sq);
+        const float r = (KERNEL == 1 && !WITH_ALPHA) ? 0.0f : sqrtf(r_sq);  // Poly6 needs r^2 only (poly6.rs:28-31)
         a.dens += w(c.kc, r_sq, r) * c.mass;
         if (WITH_ALPHA) {
             const float2 g = (wendland_grad_scalar(c.kc, r) * rij) * c.mass;
@@ -214,13 +267,13 @@ struct OpDensityAlpha {
             a.gsq += mag2(g);
         }
     }
-    __device__ __forceinline__ void dyn(const SweepCommon& c, Acc& a, RecA pi, RecB, RecA pj, RecB) const { pair(c, a, pi, pj); }
-    __device__ __forceinline__ void stat(const SweepCommon& c, Acc& a, RecA pi, RecB, float2 pb) const { pair(c, a, pi, pb); }
-    __device__ __forceinline__ double finish(const SweepCommon& c, Acc& a, uint32_t i, RecA, RecB, bool) const {
+    __device__ __forceinline__ void dyn(const SweepCommon& c, Acc& a, float2 pi, P0, P1, float2 pj, P0, P1) const { pair(c, a, pi, pj); }
+    __device__ __forceinline__ void stat(const SweepCommon& c, Acc& a, float2 pi, P0, P1, float2 pb) const { pair(c, a, pi, pb); }
+    __device__ __forceinline__ double finish(const SweepCommon& c, Acc& a, uint32_t i, float2, P0, P1, bool) const {
         const float rho = fmaxf(a.dens, c.rho0);  // fluidparticleworld.rs:229
         dens[i] = rho;
         if (WITH_ALPHA) alpha[i] = 1.0f / fmaxf(mag2(a.gsum) + a.gsq, 1e-6f);  // dfsph.rs:94
-        if (WITH_PRESSURE) pressure[i] = tait_pressure(stiffness, c.rho0, rho);  // wscsph.rs:91-92, once per particle
+        if (WITH_PRESSURE) rho_p[i] = f2(rho, tait_pressure(stiffness, c.rho0, rho));  // wscsph.rs:91-92, once per particle
         return 0.0;
     }
     __device__ __forceinline__ void finalize(const SweepCommon&, double) const {}
@@ -228,7 +281,7 @@ struct OpDensityAlpha {
 
 // alpha only (yasph_compute_alpha: dfsph.rs:68-97 on its own)
 struct OpAlphaOnly : OpDensityAlpha<0, true> {
-    __device__ __forceinline__ double finish(const SweepCommon&, Acc& a, uint32_t i, RecA, RecB, bool) const {
+    __device__ __forceinline__ double finish(const SweepCommon&, Acc& a, uint32_t i, float2, P0, P1, bool) const {
         alpha[i] = 1.0f / fmaxf(mag2(a.gsum) + a.gsq, 1e-6f);
         return 0.0;
     }
@@ -247,9 +300,9 @@ __device__ __forceinline__ float visc_scalar(const KernelConsts& k, const ViscPa
 }
 
 struct OpViscosity {
-    typedef float4 RecA;  // px, py, vx, vy
-    typedef float RecB;   // rho
-    static constexpr bool HAS_B = true;
+    typedef float2 P0;  // velocity
+    typedef float P1;   // density
+    static constexpr int NPAY = 2;
     static constexpr bool USES_STATIC = false;
     static constexpr int REDUCE = REDUCE_MAX;
     static constexpr int TICKET = 1;
@@ -260,28 +313,25 @@ struct OpViscosity {
     float2 base_accel;  // (gravity * m) / m, dfsph.rs:442-444
     ViscParams vp;
     float dt;
+    __device__ __forceinline__ const P0* pay0() const { return vel; }
+    __device__ __forceinline__ const P1* pay1() const { return dens; }
     __device__ __forceinline__ bool skip(const Control*) const { return false; }
     __device__ __forceinline__ void prepare(const SweepCommon& c) { dt = c.ctl->dt_prev; }
-    __device__ __forceinline__ RecA load_a(const SweepCommon& c, uint32_t g) const {
-        const float2 p = c.pos[g], v = vel[g];
-        return make_float4(p.x, p.y, v.x, v.y);
-    }
-    __device__ __forceinline__ RecB load_b(const SweepCommon&, uint32_t g) const { return dens[g]; }
-    __device__ __forceinline__ bool init(const SweepCommon&, Acc& a, uint32_t, RecA, RecB, uint32_t) const {
+    __device__ __forceinline__ bool init(const SweepCommon&, Acc& a, uint32_t, float2, P0, P1, uint32_t) const {
         a = base_accel;
         return true;
     }
-    __device__ __forceinline__ void dyn(const SweepCommon& c, Acc& a, RecA self, RecB, RecA nb, RecB rhoj) const {
-        const float2 rij = f2(nb.x - self.x, nb.y - self.y);
+    __device__ __forceinline__ void dyn(const SweepCommon& c, Acc& a, float2 pi, P0 vi, P1, float2 pj, P0 vj, P1 rhoj) const {
+        const float2 rij = pj - pi;
         const float r_sq = mag2(rij);
         const float r = vp.kind == 0 ? 0.0f : sqrtf(r_sq);  // XSPH needs r^2 only (xsph.rs:19-24)
         const float s = visc_scalar(c.kc, vp, dt, r_sq, r, rhoj);
-        a = a + s * f2(nb.z - self.z, nb.w - self.w);
+        a = a + s * (vj - vi);
     }
-    __device__ __forceinline__ void stat(const SweepCommon&, Acc&, RecA, RecB, float2) const {}
-    __device__ __forceinline__ double finish(const SweepCommon&, Acc& a, uint32_t i, RecA self, RecB, bool) const {
+    __device__ __forceinline__ void stat(const SweepCommon&, Acc&, float2, P0, P1, float2) const {}
+    __device__ __forceinline__ double finish(const SweepCommon&, Acc& a, uint32_t i, float2, P0 vi, P1, bool) const {
         accel[i] = a;
-        return (double)mag2(f2(self.z, self.w) + a * dt);  // dfsph.rs:476
+        return (double)mag2(vi + a * dt);  // dfsph.rs:476
     }
     __device__ __forceinline__ void finalize(const SweepCommon& c, double mx) const { c.ctl->max_v2_bits = __float_as_uint((float)mx); }
 };
@@ -295,9 +345,9 @@ struct SolverParams {
 };
 template <int SOLVER>
 struct OpJacobiA {
-    typedef float4 RecA;  // px, py, predicted velocity
-    typedef NoRec RecB;
-    static constexpr bool HAS_B = false;
+    typedef float2 P0;  // predicted velocity
+    typedef NoPay P1;
+    static constexpr int NPAY = 1;
     static constexpr bool USES_STATIC = true;
     static constexpr int REDUCE = REDUCE_SUM;
     static constexpr int TICKET = 2;
@@ -309,24 +359,21 @@ struct OpJacobiA {
     SolverParams sp;
     uint32_t iter_index;
     float dt;
+    __device__ __forceinline__ const P0* pay0() const { return vstar; }
+    __device__ __forceinline__ const P1* pay1() const { return nullptr; }
     __device__ __forceinline__ bool skip(const Control* ctl) const { return iter_index >= ctl->stop_iter[SOLVER]; }
     __device__ __forceinline__ void prepare(const SweepCommon& c) { dt = c.ctl->dt; }
-    __device__ __forceinline__ RecA load_a(const SweepCommon& c, uint32_t g) const {
-        const float2 p = c.pos[g], v = vstar[g];
-        return make_float4(p.x, p.y, v.x, v.y);
-    }
-    __device__ __forceinline__ RecB load_b(const SweepCommon&, uint32_t) const { return RecB(); }
-    __device__ __forceinline__ bool init(const SweepCommon&, Acc& a, uint32_t, RecA, RecB, uint32_t ct) const {
+    __device__ __forceinline__ bool init(const SweepCommon&, Acc& a, uint32_t, float2, P0, P1, uint32_t ct) const {
         a = 0.0f;
         return SOLVER == 0 ? true : ct >= 9u;  // particle deficiency, dfsph.rs:261
     }
-    __device__ __forceinline__ void dyn(const SweepCommon& c, Acc& a, RecA self, RecB, RecA nb, RecB) const {
-        a += dot2(f2(self.z - nb.z, self.w - nb.w), wendland_grad_from_positions(c.kc, rec_pos(self), rec_pos(nb)));
+    __device__ __forceinline__ void dyn(const SweepCommon& c, Acc& a, float2 pi, P0 vi, P1, float2 pj, P0 vj, P1) const {
+        a += dot2(vi - vj, wendland_grad_from_positions(c.kc, pi, pj));
     }
-    __device__ __forceinline__ void stat(const SweepCommon& c, Acc& a, RecA self, RecB, float2 pb) const {
-        a += dot2(f2(self.z, self.w), wendland_grad_from_positions(c.kc, rec_pos(self), pb));
+    __device__ __forceinline__ void stat(const SweepCommon& c, Acc& a, float2 pi, P0 vi, P1, float2 pb) const {
+        a += dot2(vi, wendland_grad_from_positions(c.kc, pi, pb));
     }
-    __device__ __forceinline__ double finish(const SweepCommon& c, Acc& a, uint32_t i, RecA, RecB, bool active) const {
+    __device__ __forceinline__ double finish(const SweepCommon& c, Acc& a, uint32_t i, float2, P0, P1, bool active) const {
         float e;
         if (SOLVER == 0) {
             e = dens[i] + a * c.mass * dt;       // dfsph.rs:121
@@ -371,9 +418,9 @@ struct OpJacobiA {
 // ---------------------------------------------------------------------------------------------------------------------
 template <int SOLVER, bool WARM>
 struct OpJacobiB {
-    typedef float2 RecA;  // position
-    typedef float RecB;   // k_j
-    static constexpr bool HAS_B = true;
+    typedef float P0;  // k_j (Jacobi B) / raw warm-start value (warm start; the clamp is applied on use)
+    typedef NoPay P1;
+    static constexpr int NPAY = 1;
     static constexpr bool USES_STATIC = true;
     static constexpr int REDUCE = REDUCE_NONE;
     static constexpr int TICKET = 0;
@@ -384,6 +431,8 @@ struct OpJacobiB {
     float clamp_min;  // -0.5 * rho0 * rho0
     uint32_t iter_index;
     float dt, inv_dt;
+    __device__ __forceinline__ const P0* pay0() const { return WARM ? warm : kfac; }
+    __device__ __forceinline__ const P1* pay1() const { return nullptr; }
     __device__ __forceinline__ bool skip(const Control* ctl) const {
         return WARM ? ctl->warm[SOLVER] == 0u : iter_index >= ctl->stop_iter[SOLVER];
     }
@@ -391,28 +440,28 @@ struct OpJacobiB {
         dt = c.ctl->dt;
         inv_dt = 1.0f / dt;  // dfsph.rs:132,167
     }
-    __device__ __forceinline__ RecA load_a(const SweepCommon& c, uint32_t g) const { return c.pos[g]; }
-    __device__ __forceinline__ RecB load_b(const SweepCommon&, uint32_t g) const {
-        if (WARM) return 0.5f * fmaxf(warm[g], clamp_min);  // dfsph.rs:201-203 / 356-358
-        return kfac[g];
+    __device__ __forceinline__ float kval(float raw) const {
+        return WARM ? 0.5f * fmaxf(raw, clamp_min) : raw;  // dfsph.rs:201-203 / 356-358
     }
-    __device__ __forceinline__ bool init(const SweepCommon&, Acc& a, uint32_t, RecA, RecB, uint32_t) const {
+    __device__ __forceinline__ bool init(const SweepCommon&, Acc& a, uint32_t, float2, P0, P1, uint32_t) const {
         a = f2(0.0f, 0.0f);
         return true;
     }
-    __device__ __forceinline__ void dyn(const SweepCommon& c, Acc& a, RecA pi, RecB ki, RecA pj, RecB kj) const {
-        a = a + (ki + kj) * wendland_grad_from_positions(c.kc, pi, pj);
+    __device__ __forceinline__ void dyn(const SweepCommon& c, Acc& a, float2 pi, P0 ki, P1, float2 pj, P0 kj, P1) const {
+        a = a + (kval(ki) + kval(kj)) * wendland_grad_from_positions(c.kc, pi, pj);
     }
-    __device__ __forceinline__ void stat(const SweepCommon& c, Acc& a, RecA pi, RecB ki, float2 pb) const {
-        a = a + ki * wendland_grad_from_positions(c.kc, pi, pb);
+    __device__ __forceinline__ void stat(const SweepCommon& c, Acc& a, float2 pi, P0 ki, P1, float2 pb) const {
+        a = a + kval(ki) * wendland_grad_from_positions(c.kc, pi, pb);
     }
-    __device__ __forceinline__ double finish(const SweepCommon& c, Acc& a, uint32_t i, RecA, RecB ki, bool) const {
+    __device__ __forceinline__ double finish(const SweepCommon& c, Acc& a, uint32_t i, float2, P0 ki, P1, bool) const {
         const float2 v = vstar[i];
         if (SOLVER == 0)
             vstar[i] = v - inv_dt * a * c.mass;  // dfsph.rs:159,191
         else
             vstar[i] = v - a * c.mass;           // dfsph.rs:312,342
-        if (!WARM) warm[i] = (iter_index == 0 ? 0.0f : warm[i]) + ki;  // zeroing (dfsph.rs:206-208) fused into iteration 0
+        // The warm start never stores its clamped values: other tiles are still reading the raw array, and iteration 0 of the
+        // solve that always follows overwrites it (zeroing, dfsph.rs:206-208, fused into that iteration).
+        if (!WARM) warm[i] = (iter_index == 0 ? 0.0f : warm[i]) + ki;
         return 0.0;
     }
     __device__ __forceinline__ void finalize(const SweepCommon&, double) const {}
@@ -422,48 +471,44 @@ struct OpJacobiB {
 // WCSPH accelerations
 // ---------------------------------------------------------------------------------------------------------------------
 struct OpWcsphAccel {
-    typedef float4 RecA;  // px, py, vx, vy
-    typedef float2 RecB;  // rho, p
-    static constexpr bool HAS_B = true;
+    typedef float2 P0;  // velocity
+    typedef float2 P1;  // (rho, p), written by the density pass
+    static constexpr int NPAY = 2;
     static constexpr bool USES_STATIC = true;
     static constexpr int REDUCE = REDUCE_MAX;
     static constexpr int TICKET = 1;
     typedef float2 Acc;
     const float2* vel;
-    const float* dens;
-    const float* pressure;
+    const float2* rho_p;
     float2* accel;
     float2 gravity;
     ViscParams vp;
     float boundary_force_factor;
     float dt;
+    __device__ __forceinline__ const P0* pay0() const { return vel; }
+    __device__ __forceinline__ const P1* pay1() const { return rho_p; }
     __device__ __forceinline__ bool skip(const Control*) const { return false; }
     __device__ __forceinline__ void prepare(const SweepCommon& c) { dt = c.ctl->dt_prev; }
-    __device__ __forceinline__ RecA load_a(const SweepCommon& c, uint32_t g) const {
-        const float2 p = c.pos[g], v = vel[g];
-        return make_float4(p.x, p.y, v.x, v.y);
-    }
-    __device__ __forceinline__ RecB load_b(const SweepCommon&, uint32_t g) const { return f2(dens[g], pressure[g]); }
-    __device__ __forceinline__ bool init(const SweepCommon&, Acc& a, uint32_t, RecA, RecB, uint32_t) const {
+    __device__ __forceinline__ bool init(const SweepCommon&, Acc& a, uint32_t, float2, P0, P1, uint32_t) const {
         a = gravity;  // wscsph.rs:84
         return true;
     }
-    __device__ __forceinline__ void dyn(const SweepCommon& c, Acc& a, RecA self, RecB sb, RecA nb, RecB nbb) const {
-        const float2 rij = f2(nb.x - self.x, nb.y - self.y);
+    __device__ __forceinline__ void dyn(const SweepCommon& c, Acc& a, float2 pi, P0 vi, P1 rpi, float2 pj, P0 vj, P1 rpj) const {
+        const float2 rij = pj - pi;
         const float r_sq = mag2(rij);
         const float r = sqrtf(r_sq);
-        const float pu = -c.mass * (sb.y + nbb.y) / (2.0f * sb.x * nbb.x);  // wscsph.rs:101
-        a = a + pu * (spiky_grad_scalar(c.kc, r) * rij);                    // wscsph.rs:102
-        a = a + visc_scalar(c.kc, vp, dt, r_sq, r, nbb.x) * f2(nb.z - self.z, nb.w - self.w);  // wscsph.rs:104-106
+        const float pu = -c.mass * (rpi.y + rpj.y) / (2.0f * rpi.x * rpj.x);  // wscsph.rs:101
+        a = a + pu * (spiky_grad_scalar(c.kc, r) * rij);                      // wscsph.rs:102
+        a = a + visc_scalar(c.kc, vp, dt, r_sq, r, rpj.x) * (vj - vi);        // wscsph.rs:104-106
     }
-    __device__ __forceinline__ void stat(const SweepCommon& c, Acc& a, RecA self, RecB, float2 pb) const {
-        const float2 rij = pb - rec_pos(self);
+    __device__ __forceinline__ void stat(const SweepCommon& c, Acc& a, float2 pi, P0, P1, float2 pb) const {
+        const float2 rij = pb - pi;
         const float r_sq = mag2(rij);
         a = a - (boundary_force_factor * spiky_w(c.kc, sqrtf(r_sq)) / r_sq) * rij;  // wscsph.rs:113-115
     }
-    __device__ __forceinline__ double finish(const SweepCommon&, Acc& a, uint32_t i, RecA self, RecB, bool) const {
+    __device__ __forceinline__ double finish(const SweepCommon&, Acc& a, uint32_t i, float2, P0 vi, P1, bool) const {
         accel[i] = a;
-        return (double)mag2(f2(self.z, self.w) + a * dt);  // wscsph.rs:162
+        return (double)mag2(vi + a * dt);  // wscsph.rs:162
     }
     __device__ __forceinline__ void finalize(const SweepCommon& c, double mx) const { c.ctl->max_v2_bits = __float_as_uint((float)mx); }
 };

@@ -11,7 +11,7 @@
 #include <string>
 #include <vector>
 
-#include "sort.cuh"
+#include "scan.cuh"
 #include "sweeps.cuh"
 
 using namespace yasph;
@@ -52,7 +52,7 @@ struct yasph_ctx {
     unsigned long long* lists = nullptr;
     uchar2* counts = nullptr;
     // scratch
-    uint32_t *radix_table = nullptr, *radix_chunks = nullptr;
+    uint32_t* radix_scratch = nullptr;
     unsigned long long *scan_chunks = nullptr, *scan_total = nullptr;
     double* partials = nullptr;
     Control* ctl = nullptr;
@@ -215,7 +215,7 @@ static void free_all(yasph_ctx* c) {
                     c->f_alt0, c->f_alt1, c->keys[0], c->keys[1], c->idx[0], c->idx[1], c->cell_key, c->cell_start, c->tile_key, c->tile_pstart,
                     c->tile_cstart, c->bpos, c->bpos_alt, c->scell_key, c->scell_start, c->stile_key, c->stile_cstart, c->tile_runs, c->cslot_d,
                     c->cslot_s, c->lists, c->counts,
-                    c->radix_table, c->radix_chunks, c->scan_chunks, c->scan_total, c->partials, c->ctl, c->exp_cd, c->exp_ct, c->exp_lists};
+                    c->radix_scratch, c->scan_chunks, c->scan_total, c->partials, c->ctl, c->exp_cd, c->exp_ct, c->exp_lists};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (c->h_ctl) cudaFreeHost(c->h_ctl);
@@ -328,9 +328,7 @@ extern "C" int32_t yasph_create(const yasph_config* cfg, yasph_ctx** out) {
     CUC(dmalloc(&c->cslot_s, (size_t)c->max_tiles * REGION_CELLS));
     CUC(dmalloc(&c->lists, N * (YASPH_MAXN / 4)));
     CUC(dmalloc(&c->counts, N));
-    const size_t rtiles = radix_num_tiles((uint32_t)NM);
-    CUC(dmalloc(&c->radix_table, rtiles * RS_BINS));
-    CUC(dmalloc(&c->radix_chunks, (size_t)scan_num_chunks((uint32_t)(rtiles * RS_BINS)) + 1));
+    CUC(dmalloc(&c->radix_scratch, radix_scratch_words((uint32_t)NM)));
     CUC(dmalloc(&c->scan_chunks, (size_t)scan_num_chunks((uint32_t)NM) + 1));
     CUC(dmalloc(&c->scan_total, 1));
     CUC(dmalloc(&c->ctl, 1));
@@ -425,24 +423,19 @@ extern "C" int32_t yasph_pass_times(yasph_ctx* c, float* out_us) {
 // ---------------------------------------------------------------------------------------------------------------------
 static inline uint32_t blocks_for(uint32_t n, uint32_t threads) { return (n + threads - 1) / threads; }
 
-// stable LSD radix sort of (keys[0], idx[0]) over n elements; result back in buffer 0 (4 passes)
+// Stable LSD radix sort of (keys[0], idx[0]) over n elements; result back in buffer 0 (4 passes).  radix_prepare must be
+// enqueued BEFORE the kernel that generates the keys, because that kernel accumulates the digit histograms.
+static int32_t radix_prepare(yasph_ctx* c, uint32_t n) {
+    if (n) CU(cudaMemsetAsync(c->radix_scratch, 0, radix_scratch_words(n) * sizeof(uint32_t), c->stream));
+    return YASPH_OK;
+}
 static int32_t radix_sort(yasph_ctx* c, uint32_t n) {
     if (n == 0) return YASPH_OK;
     const uint32_t ntiles = radix_num_tiles(n);
-    const uint32_t tab = ntiles * RS_BINS;
-    const uint32_t nch = scan_num_chunks(tab);
     int src = 0;
-    for (int pass = 0; pass < 4; ++pass) {
-        const int shift = pass * 8;
-        k_radix_count<<<ntiles, RS_THREADS, 0, c->stream>>>(c->keys[src], n, shift, c->radix_table, ntiles);
-        CHECK_LAUNCH();
-        k_scan_reduce<uint32_t, U32In><<<nch, SCAN_THREADS, 0, c->stream>>>(U32In{c->radix_table}, tab, c->radix_chunks);
-        CHECK_LAUNCH();
-        k_scan_chunks<uint32_t><<<1, SCAN_THREADS, 0, c->stream>>>(c->radix_chunks, nch, nullptr);
-        CHECK_LAUNCH();
-        k_scan_apply<uint32_t, U32In, U32Out><<<nch, SCAN_THREADS, 0, c->stream>>>(U32In{c->radix_table}, tab, c->radix_chunks, U32Out{c->radix_table});
-        CHECK_LAUNCH();
-        k_radix_scatter<<<ntiles, RS_THREADS, 0, c->stream>>>(c->keys[src], c->idx[src], c->keys[src ^ 1], c->idx[src ^ 1], n, shift, c->radix_table, ntiles);
+    for (int pass = 0; pass < RS_PASSES; ++pass) {
+        k_radix_pass<<<ntiles, RS_THREADS, sizeof(RadixPassSmem), c->stream>>>(c->keys[src], c->idx[src], c->keys[src ^ 1], c->idx[src ^ 1], n, pass,
+                                                                             c->radix_scratch, ntiles);
         CHECK_LAUNCH();
         src ^= 1;
     }
@@ -490,10 +483,19 @@ static SweepCommon sweep_common(const yasph_ctx* c) {
     s.partials = c->partials;
     return s;
 }
+// persistent grid of a tile kernel: every SM filled to the kernel's occupancy at this shared-memory size, at most one CTA per tile
+template <class K>
+static uint32_t persistent_grid(const yasph_ctx* c, K kernel, size_t smem_bytes) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TILE_THREADS, smem_bytes) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const uint32_t g = (uint32_t)(c->num_sms * per_sm);
+    return g < c->num_tiles ? g : (c->num_tiles ? c->num_tiles : 1u);
+}
 template <class Op>
 static int32_t launch_sweep(yasph_ctx* c, Op op) {
     if (c->num_tiles == 0) return YASPH_OK;
-    k_sweep<Op><<<c->num_tiles, SW_THREADS, sweep_smem_bytes<Op>(c->cap_dyn, c->cap_stat), c->stream>>>(sweep_common(c), op);
+    const size_t bytes = sweep_smem_bytes<Op>(c->cap_dyn, c->cap_stat);
+    k_sweep<Op><<<persistent_grid(c, k_sweep<Op>, bytes), SW_THREADS, bytes, c->stream>>>(sweep_common(c), op);
     CHECK_LAUNCH();
     return YASPH_OK;
 }
@@ -528,7 +530,8 @@ static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp
     c->lists_valid = false;
     pass_begin(c, YASPH_PASS_SORT);
     if (!keys_ready && n) {
-        k_keygen<<<blocks_for(n, 256), 256, 0, c->stream>>>(c->pos, n, c->grid, c->keys[0], c->idx[0]);
+        TRY(radix_prepare(c, n));
+        k_keygen<<<blocks_for(n, RS_THREADS), RS_THREADS, 0, c->stream>>>(c->pos, n, c->grid, c->keys[0], c->idx[0], c->radix_scratch);
         CHECK_LAUNCH();
     }
     TRY(radix_sort(c, n));
@@ -578,8 +581,9 @@ static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp
                     c->h_ctl->max_dyn_total, c->h_ctl->max_stat_total, worst_smem_bytes(c->cap_dyn, c->cap_stat), c->smem_optin);
     pass_begin(c, YASPH_PASS_LISTS);
     if (c->num_tiles) {
-        k_build_lists<<<c->num_tiles, NB_THREADS, list_smem_bytes(c->cap_dyn, c->cap_stat), c->stream>>>(
-            tile_tables(c), c->pos, c->bpos, c->keys[0], c->grid, c->ctl, c->lists, c->counts, c->cap_dyn, c->cap_stat);
+        const size_t bytes = list_smem_bytes(c->cap_dyn, c->cap_stat);
+        ListArgs la{tile_tables(c), c->pos, c->bpos, c->keys[0], c->grid, c->ctl, c->lists, c->counts, c->cap_dyn, c->cap_stat};
+        k_build_lists<<<persistent_grid(c, k_build_lists, bytes), NB_THREADS, bytes, c->stream>>>(la);
         CHECK_LAUNCH();
     }
     pass_end(c);
@@ -621,7 +625,8 @@ extern "C" int32_t yasph_set_boundary(yasph_ctx* c, const float* xy, uint32_t m)
     if (m) {
         CU(cudaMemcpyAsync(c->bpos, xy, (size_t)m * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
         // update_static (neighborhood_search.rs:488-491): sort the boundary particles in place, build the static cells
-        k_keygen<<<blocks_for(m, 256), 256, 0, c->stream>>>(c->bpos, m, c->grid, c->keys[0], c->idx[0]);
+        TRY(radix_prepare(c, m));
+        k_keygen<<<blocks_for(m, RS_THREADS), RS_THREADS, 0, c->stream>>>(c->bpos, m, c->grid, c->keys[0], c->idx[0], c->radix_scratch);
         CHECK_LAUNCH();
         TRY(radix_sort(c, m));
         GatherArgs ga;
@@ -767,7 +772,7 @@ static int32_t launch_density(yasph_ctx* c) {
     OpDensityAlpha<KERNEL, false, WITH_PRESSURE> op;
     op.dens = c->dens;
     op.alpha = nullptr;
-    op.pressure = c->err_buf;  // WCSPH: Tait pressure per particle, in the buffer the (unused) Jacobi scratch occupies
+    op.rho_p = c->vstar;  // WCSPH: (rho, Tait pressure) per particle, in the buffer DFSPH uses for the predicted velocities
     op.stiffness = c->cfg.wcsph_stiffness;
     return launch_sweep(c, op);
 }
@@ -795,7 +800,7 @@ extern "C" int32_t yasph_compute_alpha(yasph_ctx* c) {
         OpAlphaOnly op;
         op.dens = nullptr;
         op.alpha = c->alpha;
-        op.pressure = nullptr;
+        op.rho_p = nullptr;
         op.stiffness = 0.f;
         TRY(launch_sweep(c, op));
     }
@@ -813,6 +818,7 @@ extern "C" int32_t yasph_clear_cached(yasph_ctx* c) {
     c->dfsph_ready = false;
     unsigned int zero2[2] = {0u, 0u};
     CU(cudaMemcpyAsync(&c->ctl->iters[0], zero2, sizeof(zero2), cudaMemcpyHostToDevice, c->stream));
+    c->h_ctl->iters[0] = c->h_ctl->iters[1] = 0u;
     CU(cudaMemsetAsync(c->accel, 0, (size_t)c->cap_n * sizeof(float2), c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return YASPH_OK;
@@ -832,7 +838,10 @@ static int32_t jacobi_solve(yasph_ctx* c) {
     const float rho0 = c->cfg.fluid_density;
     float* warm_arr = SOLVER == 0 ? c->kappa : c->stiff;
     pass_begin(c, SOLVER == 0 ? YASPH_PASS_DENSITY_WARM : YASPH_PASS_DIVERGENCE_WARM);
-    {
+    // The warm start runs iff the previous solve took more than one iteration (dfsph.rs:199,354).  The host mirror of the
+    // control block still holds that count (it is refreshed at every read-back and this solve has not started), so the
+    // launch is skipped altogether when it would be a no-op; the kernel checks the device-side flag as well.
+    if (c->h_ctl->iters[SOLVER] > 1u) {
         OpJacobiB<SOLVER, true> w;
         w.vstar = c->vstar;
         w.kfac = nullptr;
@@ -891,7 +900,7 @@ static int32_t dfsph_step(yasph_ctx* c) {
         OpDensityAlpha<0, true> da;
         da.dens = c->dens;
         da.alpha = c->alpha;
-        da.pressure = nullptr;
+        da.rho_p = nullptr;
         da.stiffness = 0.f;
         TRY(launch_sweep(c, da));
         pass_end(c);
@@ -921,7 +930,8 @@ static int32_t dfsph_step(yasph_ctx* c) {
     TRY(jacobi_solve<0>(c));  // dfsph.rs:496
     // advect (dfsph.rs:502-509) fused with the key generation of the re-sort (dfsph.rs:512)
     pass_begin(c, YASPH_PASS_ADVECT_KEYGEN);
-    k_advect_keygen<<<blocks_for(n, 256), 256, 0, c->stream>>>(c->pos, c->vstar, n, c->ctl, c->grid, c->keys[0], c->idx[0]);
+    TRY(radix_prepare(c, n));
+    k_advect_keygen<<<blocks_for(n, RS_THREADS), RS_THREADS, 0, c->stream>>>(c->pos, c->vstar, n, c->ctl, c->grid, c->keys[0], c->idx[0], c->radix_scratch);
     CHECK_LAUNCH();
     pass_end(c);
     {
@@ -946,7 +956,7 @@ static int32_t dfsph_step(yasph_ctx* c) {
         OpDensityAlpha<0, true> da;  // dfsph.rs:516-518
         da.dens = c->dens;
         da.alpha = c->alpha;
-        da.pressure = nullptr;
+        da.rho_p = nullptr;
         da.stiffness = 0.f;
         TRY(launch_sweep(c, da));
     }
@@ -964,7 +974,8 @@ static int32_t wcsph_step(yasph_ctx* c) {
     CHECK_LAUNCH();
     // leap frog 1 (wscsph.rs:141-150) fused with key generation
     pass_begin(c, YASPH_PASS_ADVECT_KEYGEN);
-    k_kickdrift_keygen<<<blocks_for(n, 256), 256, 0, c->stream>>>(c->pos, c->vel, c->accel, n, c->ctl, c->grid, c->keys[0], c->idx[0]);
+    TRY(radix_prepare(c, n));
+    k_kickdrift_keygen<<<blocks_for(n, RS_THREADS), RS_THREADS, 0, c->stream>>>(c->pos, c->vel, c->accel, n, c->ctl, c->grid, c->keys[0], c->idx[0], c->radix_scratch);
     CHECK_LAUNCH();
     pass_end(c);
     GatherPlan gp;
@@ -981,8 +992,7 @@ static int32_t wcsph_step(yasph_ctx* c) {
     {
         OpWcsphAccel a;  // wscsph.rs:155
         a.vel = c->vel;
-        a.dens = c->dens;
-        a.pressure = c->err_buf;
+        a.rho_p = c->vstar;
         a.accel = c->accel;
         a.gravity = make_float2(c->cfg.gravity[0], c->cfg.gravity[1]);
         a.vp = visc_params(c);
