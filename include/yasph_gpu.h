@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define YASPH_ABI_VERSION 1u
+#define YASPH_ABI_VERSION 2u
 #define YASPH_MAX_NEIGHBORS 64u /* neighborhood_search.rs:322 */
 
 typedef struct yasph_ctx yasph_ctx;
@@ -64,13 +64,18 @@ typedef enum yasph_field {
     YASPH_FIELD_ACCELERATION = 6, /* float2[N]  WCSPH accellerations (wscsph.rs:22) / DFSPH non-pressure accel of the last step */
     YASPH_FIELD_CELL_KEY = 7,     /* uint32[N]  Morton cell index of each sorted particle */
     YASPH_FIELD_SORT_PERMUTATION = 8, /* uint32[N] permutation applied by the last re-sort: new[k] = old[perm[k]] */
-    YASPH_FIELD_BOUNDARY = 9      /* float2[M]  boundary particles in their sorted order (fluidparticleworld.rs:247-252) */
+    YASPH_FIELD_BOUNDARY = 9,     /* float2[M]  boundary particles in their sorted order (fluidparticleworld.rs:247-252) */
+    YASPH_FIELD_ID = 10,          /* uint32[N]  caller-visible particle id: index in the last yasph_upload_particles (+ id_base); needs YASPH_FLAG_TRACK_IDS */
+    YASPH_FIELD_GHOST = 11        /* uint8[N_local] 1 = ghost copy of a particle another rank owns (slab mode; only with YASPH_FIELD_LOCAL_BIT) */
 } yasph_field;
+/* Slab mode: OR into the field id to read the rank's whole local array (owned + ghost particles, sorted order, the
+ * indexing yasph_neighbors_download uses) instead of the owned particles only; *n_local of yasph_slab_get sizes it. */
+#define YASPH_FIELD_LOCAL_BIT 0x100
 
 typedef struct yasph_config {
     uint32_t abi_version;         /* = YASPH_ABI_VERSION */
     int32_t device;               /* CUDA device ordinal */
-    uint32_t max_particles;       /* capacity for dynamic particles (incl. halo copies on multi-GPU runs) */
+    uint32_t max_particles;       /* capacity for dynamic particles (slab mode: owned + ghosts + one step's migrants) */
     uint32_t max_boundary;        /* capacity for boundary particles */
     /* ConstantFluidProperties, fluidparticleworld.rs:46-90 */
     float smoothing_length;       /* h == neighbour search radius == cell size (neighborhood_search.rs:466) */
@@ -101,10 +106,13 @@ typedef struct yasph_config {
     uint32_t tile_static_capacity;       /* staged boundary candidates per tile (default 1024) */
     uint32_t speculative_iterations;     /* Jacobi iterations launched between two convergence read-backs (default 2) */
     uint32_t flags;                      /* YASPH_FLAG_* */
+    uint32_t max_halo;                   /* slab mode: capacity (particles per side) of the ghost / migrant buffers; default max(65536, max_particles / 8) */
+    uint32_t reserved;
 } yasph_config;
 
 #define YASPH_FLAG_PERMUTE_WARMSTART 1u /* permute kappa/stiffness with the particles; default off = reference behaviour (quirk Q1: dfsph.rs:512 passes only v*) */
 #define YASPH_FLAG_PROFILE_PASSES 2u    /* record a CUDA event pair per pass (see yasph_pass_times) */
+#define YASPH_FLAG_TRACK_IDS 4u         /* carry a uint32 id with every particle through re-sorts and migration (YASPH_FIELD_ID) */
 
 /* Fills every field with the reference's defaults for the given world parameters
  * (FluidParticleWorld::new(smoothing_factor, particle_density, fluid_density), main.rs:85-89). */
@@ -175,6 +183,49 @@ int32_t yasph_neighbors_download(yasph_ctx* ctx, uint16_t* count_dynamic, uint16
 int32_t yasph_update_densities(yasph_ctx* ctx, int32_t kernel);
 /* DFSPH compute_alpha_factors (dfsph.rs:68-97) on the current lists; result readable via YASPH_FIELD_ALPHA */
 int32_t yasph_compute_alpha(yasph_ctx* ctx);
+
+/* ---- multi-GPU: 1-D slab decomposition over cell columns (one process per GPU, NCCL over NVLink) ----------------- */
+/* The reference is single-address-space; this group has no counterpart there.  Every rank owns the
+ * particles whose cell column (x index of neighborhood_search.rs:45-64) lies in [col_lo, col_hi); the slabs of ranks
+ * 0..world-1 are adjacent and ascending in x.  Each neighbourhood update migrates particles that left the slab to the
+ * adjacent rank and receives the neighbours' boundary columns as ghost particles; every neighbour-dependent pass is
+ * followed by a halo exchange of the field the next pass gathers, the Jacobi residual and the CFL maximum are
+ * all-reduced.  Boundary particles are replicated on every rank.  Slab mode implies YASPH_FLAG_PERMUTE_WARMSTART (the
+ * reference's index-stale warm-start arrays, quirk Q1, have no meaning across address spaces).
+ * In slab mode yasph_upload_particles takes this rank's particles only, and yasph_download_particles /
+ * yasph_download_field / yasph_num_particles report the owned particles only (ghosts are internal). */
+#define YASPH_COMM_ID_BYTES 128u
+/* ncclGetUniqueId: call on one rank, hand the bytes to every rank over any host channel */
+int32_t yasph_comm_unique_id(void* out_id, uint64_t bytes);
+/* ncclCommInitRank on the context's device; collective over all ranks */
+int32_t yasph_comm_init(yasph_ctx* ctx, int32_t rank, int32_t world, const void* id, uint64_t bytes);
+/* Loopback transport: all ranks are contexts of ONE process (one host thread per rank, on one or several devices); the
+ * messages of the NCCL transport travel as device-to-device copies.  It exists so that the complete slab logic can be
+ * tested on a single GPU.  Every rank's calls must come from its own thread (they rendezvous). */
+int32_t yasph_loopback_create(int32_t world, void** fabric);
+int32_t yasph_loopback_destroy(void* fabric);
+int32_t yasph_comm_init_loopback(yasph_ctx* ctx, void* fabric, int32_t rank);
+/* Owned cell-column range of this rank and the global number of dynamic particles (the N of dfsph.rs:221,376).
+ * id_base is added to the upload index to form YASPH_FIELD_ID.  Call before yasph_upload_particles. */
+int32_t yasph_slab_set(yasph_ctx* ctx, uint32_t col_lo, uint32_t col_hi, uint64_t n_global, uint32_t id_base);
+typedef struct yasph_slab_info {
+    int32_t rank, world;
+    uint32_t col_lo, col_hi;
+    uint32_t n_own;                 /* particles this rank owns after the last neighbourhood update */
+    uint32_t n_local;               /* owned + ghost particles */
+    uint32_t n_ghost_left, n_ghost_right;
+    uint32_t migrated_out_left, migrated_out_right, migrated_in;  /* of the last neighbourhood update */
+    uint64_t n_global;
+    uint64_t halo_exchanges;        /* halo exchanges (NCCL send/recv groups) since creation */
+    uint64_t allreduces;            /* NCCL all-reduces since creation */
+} yasph_slab_info;
+int32_t yasph_slab_get(yasph_ctx* ctx, yasph_slab_info* out);
+/* cell column of an x coordinate under the context's grid (neighborhood_search.rs:52-58), for host-side partitioning */
+int32_t yasph_cell_column(const yasph_config* cfg, float x, uint32_t* column);
+/* yasph_step_host for a slab: n_in particles in (this rank's, in the order of the last download), one step, the owned
+ * particles after migration out (*n_out <= capacity). */
+int32_t yasph_step_host_slab(yasph_ctx* ctx, float* pos_xy, float* vel_xy, float* densities, uint32_t n_in, uint32_t capacity,
+                             uint32_t* n_out, yasph_step_report* report);
 
 /* ---- measurement ----------------------------------------------------------------------------------------------- */
 #define YASPH_NUM_PASSES 16

@@ -9,14 +9,16 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libyasph_gpu.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_NEIGHBORS = 64
 SOLVER_DFSPH, SOLVER_WCSPH = 0, 1
 VISCOSITY_XSPH, VISCOSITY_PHYSICAL = 0, 1
 KERNEL_WENDLAND_C2, KERNEL_POLY6, KERNEL_SPIKY, KERNEL_CUBIC = 0, 1, 2, 3
 (FIELD_POSITION, FIELD_VELOCITY, FIELD_DENSITY, FIELD_ALPHA, FIELD_KAPPA, FIELD_STIFFNESS, FIELD_ACCELERATION, FIELD_CELL_KEY,
- FIELD_SORT_PERMUTATION, FIELD_BOUNDARY) = range(10)
-FLAG_PERMUTE_WARMSTART, FLAG_PROFILE_PASSES = 1, 2
+ FIELD_SORT_PERMUTATION, FIELD_BOUNDARY, FIELD_ID, FIELD_GHOST) = range(12)
+FIELD_LOCAL_BIT = 0x100
+FLAG_PERMUTE_WARMSTART, FLAG_PROFILE_PASSES, FLAG_TRACK_IDS = 1, 2, 4
+COMM_ID_BYTES = 128
 NUM_PASSES = 16
 PASS_NAMES = ["viscosity", "predict", "density_warm", "density_solve", "advect_keygen", "sort", "gather", "cells_tiles", "lists",
               "density_alpha", "divergence_warm", "divergence_solve", "wcsph_accel", "wcsph_kick", "halo", "total"]
@@ -30,6 +32,8 @@ EXPORTED_SYMBOLS = [
     "yasph_neighborhood_update", "yasph_neighbors_download", "yasph_update_densities", "yasph_compute_alpha", "yasph_pass_times",
     "yasph_launch_count", "yasph_stream", "yasph_scene_fluid_rect", "yasph_scene_boundary_line", "yasph_scene_boundary_thick_line",
     "yasph_duration_from_secs_f32", "yasph_duration_as_secs_f32",
+    "yasph_comm_unique_id", "yasph_comm_init", "yasph_slab_set", "yasph_slab_get", "yasph_cell_column", "yasph_step_host_slab",
+    "yasph_loopback_create", "yasph_loopback_destroy", "yasph_comm_init_loopback",
 ]
 
 
@@ -45,7 +49,7 @@ class Config(C.Structure):
         ("adaptive_timestep", C.c_int32), ("timestep_fixed_ns", C.c_uint64), ("timestep_min_ns", C.c_uint64),
         ("timestep_max_ns", C.c_uint64), ("cfl_factor", C.c_float),
         ("max_tiles", C.c_uint32), ("tile_dynamic_capacity", C.c_uint32), ("tile_static_capacity", C.c_uint32),
-        ("speculative_iterations", C.c_uint32), ("flags", C.c_uint32),
+        ("speculative_iterations", C.c_uint32), ("flags", C.c_uint32), ("max_halo", C.c_uint32), ("reserved", C.c_uint32),
     ]
 
 
@@ -60,6 +64,18 @@ class StepReport(C.Structure):
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
+
+
+class SlabInfo(C.Structure):
+    _fields_ = [
+        ("rank", C.c_int32), ("world", C.c_int32), ("col_lo", C.c_uint32), ("col_hi", C.c_uint32), ("n_own", C.c_uint32), ("n_local", C.c_uint32),
+        ("n_ghost_left", C.c_uint32), ("n_ghost_right", C.c_uint32), ("migrated_out_left", C.c_uint32),
+        ("migrated_out_right", C.c_uint32), ("migrated_in", C.c_uint32), ("n_global", C.c_uint64),
+        ("halo_exchanges", C.c_uint64), ("allreduces", C.c_uint64),
+    ]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
 
 
 class YasphError(RuntimeError):
@@ -121,6 +137,15 @@ def lib():
         C.c_uint32, u32p)
     sig("yasph_duration_from_secs_f32", C.c_uint64, C.c_float)
     sig("yasph_duration_as_secs_f32", C.c_float, C.c_uint64)
+    sig("yasph_comm_unique_id", C.c_int32, vp, C.c_uint64)
+    sig("yasph_comm_init", C.c_int32, vp, C.c_int32, C.c_int32, vp, C.c_uint64)
+    sig("yasph_slab_set", C.c_int32, vp, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32)
+    sig("yasph_slab_get", C.c_int32, vp, C.POINTER(SlabInfo))
+    sig("yasph_cell_column", C.c_int32, C.POINTER(Config), C.c_float, u32p)
+    sig("yasph_loopback_create", C.c_int32, C.c_int32, C.POINTER(vp))
+    sig("yasph_loopback_destroy", C.c_int32, vp)
+    sig("yasph_comm_init_loopback", C.c_int32, vp, vp, C.c_int32)
+    sig("yasph_step_host_slab", C.c_int32, vp, f32p, f32p, f32p, C.c_uint32, C.c_uint32, u32p, rp)
     _lib = L
     return L
 

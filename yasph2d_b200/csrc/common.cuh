@@ -186,6 +186,7 @@ struct Control {
     // time
     unsigned long long step_ns;       // TimeManager::simulation_step
     unsigned long long step_prev_ns;  // value at step entry
+    double resid_sum;                 // Jacobi residual sum of the running iteration (slab mode: all-reduced in place over the ranks)
     float dt;                         // step_ns as_secs_f32 (after update) -- the dt of this step
     float dt_prev;                    // dt at step entry (viscosity, CFL estimate)
     unsigned int max_v2_bits;         // max |v + a dt|^2 as uint bits (value >= 0 so uint order == float order)
@@ -210,7 +211,38 @@ struct Control {
     unsigned int err_tile_count;      // more tiles than max_tiles
     // last-block tickets
     unsigned int ticket[4];
+    // slab mode (multi-GPU): counts of the ordered selections of a neighbourhood update
+    unsigned long long slab_migrants;    // low word: migrants to the left rank, high word: to the right rank
+    unsigned long long slab_ghost_send;  // own particles in the first / last owned column (sent as ghosts)
+    unsigned long long slab_send;        // per-pass halo send lists (left | right), in sorted order
+    unsigned long long slab_ghost;       // ghosts from the left | right rank, in sorted order
+    unsigned long long slab_own;         // owned particles (low word)
+    unsigned int err_slab;               // a particle arrived that this rank does not own (moved more than one slab in a step)
+    unsigned int pad_slab;
 };
+
+// slab decomposition parameters handed to the key-generating kernels (active == 0: single GPU)
+struct SlabParams {
+    uint32_t col_lo, col_hi;
+    uint8_t* pflag;  // in: 1 = ghost of the current structure; out: 0 stays, 1 / 2 migrates left / right, 3 dropped ghost
+    int active;
+};
+enum { SLAB_STAY = 0, SLAB_MIG_LEFT = 1, SLAB_MIG_RIGHT = 2, SLAB_DROP_GHOST = 3 };
+#define YASPH_KEY_DROPPED 0xFFFFFFFFu  // sort key of particles that leave the local set (they sort to the end and are cut off)
+// classification of a local particle with (new) cell key `key`; returns the key to sort by
+__device__ __forceinline__ uint32_t slab_classify(const SlabParams& sp, uint32_t i, uint32_t key) {
+    if (!sp.active) return key;
+    const uint32_t col = compact_1by1(key);
+    uint8_t out = SLAB_STAY;
+    if (sp.pflag[i])
+        out = SLAB_DROP_GHOST;
+    else if (col < sp.col_lo)
+        out = SLAB_MIG_LEFT;
+    else if (col >= sp.col_hi)
+        out = SLAB_MIG_RIGHT;
+    sp.pflag[i] = out;
+    return out ? YASPH_KEY_DROPPED : key;
+}
 
 // warp helpers
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }

@@ -64,13 +64,14 @@ struct TileTables {
 // (sort.cuh) while they have the key in a register.
 // neighborhood_search.rs:111-114 (sequential in the reference)
 __global__ void __launch_bounds__(RS_THREADS)
-    k_keygen(const float2* __restrict__ pos, uint32_t n, GridParams g, uint32_t* __restrict__ keys, uint32_t* __restrict__ idx, uint32_t* __restrict__ sort_scratch) {
+    k_keygen(const float2* __restrict__ pos, uint32_t first, uint32_t n, GridParams g, uint32_t* __restrict__ keys, uint32_t* __restrict__ idx,
+             uint32_t* __restrict__ sort_scratch, SlabParams sp) {
     __shared__ RadixHistSmem sh;
     radix_hist_init(sh);
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t key = 0;
     if (i < n) {
-        key = position_to_cidx(g, pos[i]);
+        key = slab_classify(sp, i, position_to_cidx(g, pos[i]));
         keys[i] = key;
         idx[i] = i;
     }
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(RS_THREADS)
 // dfsph.rs:502-509 (advect) fused with the key generation of the following re-sort
 __global__ void __launch_bounds__(RS_THREADS)
     k_advect_keygen(float2* __restrict__ pos, const float2* __restrict__ vstar, uint32_t n, const Control* __restrict__ ctl, GridParams g,
-                    uint32_t* __restrict__ keys, uint32_t* __restrict__ idx, uint32_t* __restrict__ sort_scratch) {
+                    uint32_t* __restrict__ keys, uint32_t* __restrict__ idx, uint32_t* __restrict__ sort_scratch, SlabParams sp) {
     __shared__ RadixHistSmem sh;
     radix_hist_init(sh);
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(RS_THREADS)
         const float dt = ctl->dt;
         float2 p = pos[i] + vstar[i] * dt;
         pos[i] = p;
-        key = position_to_cidx(g, p);
+        key = slab_classify(sp, i, position_to_cidx(g, p));
         keys[i] = key;
         idx[i] = i;
     }
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(RS_THREADS)
 // wscsph.rs:141-150 (leap frog 1) fused with key generation
 __global__ void __launch_bounds__(RS_THREADS)
     k_kickdrift_keygen(float2* __restrict__ pos, float2* __restrict__ vel, const float2* __restrict__ acc, uint32_t n, const Control* __restrict__ ctl,
-                       GridParams g, uint32_t* __restrict__ keys, uint32_t* __restrict__ idx, uint32_t* __restrict__ sort_scratch) {
+                       GridParams g, uint32_t* __restrict__ keys, uint32_t* __restrict__ idx, uint32_t* __restrict__ sort_scratch, SlabParams sp) {
     __shared__ RadixHistSmem sh;
     radix_hist_init(sh);
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(RS_THREADS)
         float2 p = pos[i] + v * dt;
         vel[i] = v;
         pos[i] = p;
-        key = position_to_cidx(g, p);
+        key = slab_classify(sp, i, position_to_cidx(g, p));
         keys[i] = key;
         idx[i] = i;
     }
@@ -118,12 +119,12 @@ __global__ void __launch_bounds__(RS_THREADS)
     radix_hist_flush(sh, sort_scratch);
 }
 
-// apply_sorting (neighborhood_search.rs:71-78): out[k] = in[perm[k]] for up to three float2 and two float arrays
+// apply_sorting (neighborhood_search.rs:71-78): out[k] = in[perm[k]] for up to three float2 and three 4-byte arrays
 struct GatherArgs {
     const float2* in2[3];
     float2* out2[3];
-    const float* in1[2];
-    float* out1[2];
+    const float* in1[3];
+    float* out1[3];
     int n2, n1;
 };
 __global__ void k_gather(const uint32_t* __restrict__ perm, uint32_t n, GatherArgs a) {
@@ -134,7 +135,7 @@ __global__ void k_gather(const uint32_t* __restrict__ perm, uint32_t n, GatherAr
         for (int q = 0; q < 3; ++q)
             if (q < a.n2) a.out2[q][k] = a.in2[q][s];
 #pragma unroll
-        for (int q = 0; q < 2; ++q)
+        for (int q = 0; q < 3; ++q)
             if (q < a.n1) a.out1[q][k] = a.in1[q][s];
     }
 }

@@ -40,6 +40,10 @@ struct SweepCommon {
     uint32_t n;
     float mass, rho0;
     double* partials;  // [gridDim.x]
+    // slab mode (multi-GPU): ghosts are excluded from the reductions, the residual average runs over the global particle count
+    // and the convergence decision is taken after the all-reduce (k_jacobi_decide)
+    const uint8_t* ghost;  // null on a single GPU
+    float n_avg;           // particle count of dfsph.rs:221,376 as f32
 };
 
 enum ReduceKind { REDUCE_NONE = 0, REDUCE_SUM = 1, REDUCE_MAX = 2 };
@@ -165,7 +169,8 @@ __global__ void __launch_bounds__(SW_THREADS) k_sweep(SweepCommon c, Op op) {
                         }
                     }
                 }
-                const double r = op.finish(c, acc, i, pi, s0, s1, active);
+                double r = op.finish(c, acc, i, pi, s0, s1, active);
+                if (Op::REDUCE != REDUCE_NONE && c.ghost != nullptr && c.ghost[i]) r = 0.0;
                 if (Op::REDUCE == REDUCE_SUM) racc += r;
                 if (Op::REDUCE == REDUCE_MAX) racc = fmax(racc, r);
             }
@@ -343,6 +348,36 @@ struct SolverParams {
     float max_error;
     uint32_t max_iters;
 };
+// iteration bookkeeping and the loop decision of correct_density_error / correct_divergence_error (dfsph.rs:219-245, 374-400)
+// from the residual sum in ctl->resid_sum
+template <int SOLVER>
+__device__ __forceinline__ void jacobi_decide(Control* ctl, const SolverParams& sp, uint32_t iter_index, float n_avg, float rho0) {
+    const float dt = ctl->dt;
+    const float s = (float)ctl->resid_sum;  // f64 accumulation rounded once (DESIGN.md "residual sums")
+    const uint32_t it = iter_index + 1;
+    ctl->iters[SOLVER] = it;
+    bool conv;
+    float avg;
+    if (SOLVER == 0) {
+        avg = s / n_avg;                      // dfsph.rs:221
+        const float rel = avg / rho0;         // dfsph.rs:222
+        conv = rel * dt < sp.max_error;       // dfsph.rs:226
+    } else {
+        avg = s / n_avg / rho0;               // dfsph.rs:376-377
+        conv = avg * dt < sp.max_error;       // dfsph.rs:381
+    }
+    ctl->avg[SOLVER] = avg;
+    if (!isfinite(avg)) {  // the reference asserts (dfsph.rs:223,378); stop and report
+        ctl->nonfinite |= 1u << SOLVER;
+        conv = true;
+    }
+    if (conv) {
+        ctl->stop_iter[SOLVER] = it;
+    } else if (it > sp.max_iters) {  // dfsph.rs:236,391
+        ctl->stop_iter[SOLVER] = it;
+        ctl->not_converged |= 1u << SOLVER;
+    }
+}
 template <int SOLVER>
 struct OpJacobiA {
     typedef float2 P0;  // predicted velocity
@@ -385,33 +420,14 @@ struct OpJacobiA {
         return (double)e;
     }
     __device__ __forceinline__ void finalize(const SweepCommon& c, double sum) const {
-        Control* ctl = c.ctl;
-        const float s = (float)sum;  // f64 accumulation rounded once (DESIGN.md "residual sums")
-        const uint32_t it = iter_index + 1;
-        ctl->iters[SOLVER] = it;
-        bool conv;
-        float avg;
-        if (SOLVER == 0) {
-            avg = s / (float)c.n;                 // dfsph.rs:221
-            const float rel = avg / c.rho0;       // dfsph.rs:222
-            conv = rel * dt < sp.max_error;       // dfsph.rs:226
-        } else {
-            avg = s / (float)c.n / c.rho0;        // dfsph.rs:376-377
-            conv = avg * dt < sp.max_error;       // dfsph.rs:381
-        }
-        ctl->avg[SOLVER] = avg;
-        if (!isfinite(avg)) {  // the reference asserts (dfsph.rs:223,378); stop and report
-            ctl->nonfinite |= 1u << SOLVER;
-            conv = true;
-        }
-        if (conv) {
-            ctl->stop_iter[SOLVER] = it;
-        } else if (it > sp.max_iters) {  // dfsph.rs:236,391
-            ctl->stop_iter[SOLVER] = it;
-            ctl->not_converged |= 1u << SOLVER;
-        }
+        c.ctl->resid_sum = sum;
+        if (c.ghost == nullptr) jacobi_decide<SOLVER>(c.ctl, sp, iter_index, c.n_avg, c.rho0);  // slab mode: after the all-reduce
     }
 };
+template <int SOLVER>
+__global__ void k_jacobi_decide(Control* ctl, SolverParams sp, uint32_t iter_index, float n_avg, float rho0) {
+    if (threadIdx.x == 0 && blockIdx.x == 0 && iter_index < ctl->stop_iter[SOLVER]) jacobi_decide<SOLVER>(ctl, sp, iter_index, n_avg, rho0);
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Jacobi B and warm starts

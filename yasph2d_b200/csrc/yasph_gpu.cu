@@ -5,13 +5,18 @@
 // YASPH_ERR_NO_DEVICE.
 #include "../../include/yasph_gpu.h"
 
+#include <dlfcn.h>
+
 #include <cstdarg>
 #include <cstdio>
+#include <condition_variable>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
 #include "scan.cuh"
+#include "slab.cuh"
 #include "sweeps.cuh"
 
 using namespace yasph;
@@ -63,6 +68,31 @@ struct yasph_ctx {
     // pinned staging for yasph_step_host
     float *h_stage = nullptr;
     size_t h_stage_bytes = 0;
+    // particle ids (YASPH_FLAG_TRACK_IDS) and the slab decomposition (multi-GPU)
+    uint32_t *ids = nullptr, *ids_alt = nullptr;
+    struct Slab {
+        bool active = false;
+        int rank = 0, world = 1;
+        uint32_t col_lo = 0, col_hi = 65536, id_base = 0;
+        uint64_t n_global = 0;
+        void* comm = nullptr;            // ncclComm_t
+        struct Fabric* fabric = nullptr; // loopback transport (all ranks in one process) instead of NCCL
+        cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+        uint64_t link_seq[2] = {0, 0};
+        uint8_t* pflag = nullptr;        // [cap_n] ghost flag of the current structure / classification during an update
+        uint32_t* sel[2] = {nullptr, nullptr};    // scratch index lists of the ordered selections (migrants, ghost sends) [max_halo]
+        uint32_t* send_idx[2] = {nullptr, nullptr};   // per-pass halo send lists (left, right), sorted order [max_halo]
+        uint32_t* ghost_idx[2] = {nullptr, nullptr};  // ghosts from the left / right rank, sorted order [max_halo]
+        uint32_t* own_idx = nullptr;     // owned particles, sorted order [cap_n] (built on demand)
+        unsigned char* sbuf[2] = {nullptr, nullptr};  // send buffers (left, right) [max_halo * RECORD_MAX]
+        unsigned char* rbuf[2] = {nullptr, nullptr};  // receive buffers
+        uint32_t *d_cnt = nullptr, *h_cnt = nullptr;  // [4]: send left/right, recv left/right
+        uint32_t max_halo = 0;
+        uint32_t n_own = 0, n_ghost[2] = {0, 0}, n_send[2] = {0, 0};
+        uint32_t mig_out[2] = {0, 0}, mig_in = 0;
+        bool own_idx_valid = false;
+        uint64_t halo_exchanges = 0, allreduces = 0;
+    } slab;
     // state flags
     bool have_particles = false, lists_valid = false, dfsph_ready = false;
     uint64_t launches = 0;
@@ -77,16 +107,19 @@ struct yasph_ctx {
 // ---------------------------------------------------------------------------------------------------------------------
 // error helpers
 // ---------------------------------------------------------------------------------------------------------------------
+static void fabric_mark_failed(yasph_ctx* c);
 static int32_t fail(yasph_ctx* c, int32_t code, const char* fmt, ...) {
     char buf[512];
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(buf, sizeof(buf), fmt, ap);
     va_end(ap);
-    if (c)
+    if (c) {
         c->err = buf;
-    else
+        fabric_mark_failed(c);  // loopback transport: wake the peer ranks of this process instead of leaving them waiting
+    } else {
         g_create_error = buf;
+    }
     return code;
 }
 #define CU(call)                                                                                                     \
@@ -109,6 +142,105 @@ static int32_t fail(yasph_ctx* c, int32_t code, const char* fmt, ...) {
 template <typename T>
 static cudaError_t dmalloc(T** p, size_t count) {
     return cudaMalloc((void**)p, (count ? count : 1) * sizeof(T));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Loopback transport: every rank is a context of THIS process (one host thread per rank, any mix of devices).  It carries
+// the same messages as the NCCL transport through device-to-device copies and exists so that the whole slab logic
+// (migration, ghosts, halo exchange, all-reduce) can be exercised on a single GPU.
+// ---------------------------------------------------------------------------------------------------------------------
+struct Fabric {
+    int world = 0;
+    std::mutex m;
+    std::condition_variable cv;
+    struct Post {
+        const void* buf = nullptr;
+        size_t bytes = 0;
+        cudaEvent_t ready = nullptr;
+        uint64_t seq = 0;
+    };
+    struct Ack {
+        cudaEvent_t done = nullptr;
+        uint64_t seq = 0;
+    };
+    std::vector<Post> post;  // [rank * 2 + side]: what `rank` offers to its neighbour on `side`
+    std::vector<Ack> ack;    // [rank * 2 + side]: `rank` has enqueued the copy of what its neighbour on `side` offered
+    // all-reduce rendezvous
+    std::vector<double> ar_val;
+    uint64_t ar_gen = 0;
+    int ar_count = 0;
+    double ar_result = 0.0;
+    bool failed = false;
+};
+static void fabric_mark_failed(yasph_ctx* c) {
+    Fabric* f = c->slab.fabric;
+    if (!f || !c->slab.active) return;
+    {
+        std::lock_guard<std::mutex> lk(f->m);
+        f->failed = true;
+    }
+    f->cv.notify_all();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// NCCL, bound at run time (dlopen) so that single-GPU use has no dependency on it.  If the process already holds a
+// libnccl.so.2 (e.g. the one PyTorch ships) the dynamic loader hands back that instance.
+// ---------------------------------------------------------------------------------------------------------------------
+#include <nccl.h>
+struct NcclApi {
+    void* handle = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclSend) Send = nullptr;
+    decltype(&ncclRecv) Recv = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
+    std::string error;
+};
+static NcclApi g_nccl;
+static bool nccl_load() {
+    if (g_nccl.handle) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* nm : names) {
+        h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) {
+        g_nccl.error = std::string("dlopen(libnccl.so.2) failed: ") + (dlerror() ? dlerror() : "?");
+        return false;
+    }
+#define NCCL_SYM(field, name)                                                   \
+    g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(h, name));    \
+    if (!g_nccl.field) {                                                        \
+        g_nccl.error = std::string("NCCL symbol missing: ") + name;             \
+        dlclose(h);                                                             \
+        return false;                                                           \
+    }
+    NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+    NCCL_SYM(CommInitRank, "ncclCommInitRank")
+    NCCL_SYM(CommDestroy, "ncclCommDestroy")
+    NCCL_SYM(GetErrorString, "ncclGetErrorString")
+    NCCL_SYM(GroupStart, "ncclGroupStart")
+    NCCL_SYM(GroupEnd, "ncclGroupEnd")
+    NCCL_SYM(Send, "ncclSend")
+    NCCL_SYM(Recv, "ncclRecv")
+    NCCL_SYM(AllReduce, "ncclAllReduce")
+#undef NCCL_SYM
+    g_nccl.handle = h;
+    return true;
+}
+#define NC(call)                                                                                                          \
+    do {                                                                                                                  \
+        ncclResult_t r_ = (call);                                                                                         \
+        if (r_ != ncclSuccess) return fail(c, YASPH_ERR_COMM, "%s failed: %s (%s:%d)", #call, g_nccl.GetErrorString(r_), __FILE__, __LINE__); \
+    } while (0)
+static void comm_destroy(yasph_ctx* c) {
+    if (c->slab.comm && g_nccl.handle) g_nccl.CommDestroy((ncclComm_t)c->slab.comm);
+    c->slab.comm = nullptr;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -215,11 +347,20 @@ static void free_all(yasph_ctx* c) {
                     c->f_alt0, c->f_alt1, c->keys[0], c->keys[1], c->idx[0], c->idx[1], c->cell_key, c->cell_start, c->tile_key, c->tile_pstart,
                     c->tile_cstart, c->bpos, c->bpos_alt, c->scell_key, c->scell_start, c->stile_key, c->stile_cstart, c->tile_runs, c->cslot_d,
                     c->cslot_s, c->lists, c->counts,
-                    c->radix_scratch, c->scan_chunks, c->scan_total, c->partials, c->ctl, c->exp_cd, c->exp_ct, c->exp_lists};
+                    c->radix_scratch, c->scan_chunks, c->scan_total, c->partials, c->ctl, c->exp_cd, c->exp_ct, c->exp_lists,
+                    c->ids, c->ids_alt, c->slab.pflag, c->slab.sel[0], c->slab.sel[1], c->slab.send_idx[0], c->slab.send_idx[1],
+                    c->slab.ghost_idx[0], c->slab.ghost_idx[1], c->slab.own_idx, c->slab.sbuf[0], c->slab.sbuf[1], c->slab.rbuf[0],
+                    c->slab.rbuf[1], c->slab.d_cnt};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (c->h_ctl) cudaFreeHost(c->h_ctl);
     if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->slab.h_cnt) cudaFreeHost(c->slab.h_cnt);
+    for (int sd = 0; sd < 2; ++sd) {
+        if (c->slab.ev_ready[sd]) cudaEventDestroy(c->slab.ev_ready[sd]);
+        if (c->slab.ev_done[sd]) cudaEventDestroy(c->slab.ev_done[sd]);
+    }
+    comm_destroy(c);
     for (auto e : c->event_pool) cudaEventDestroy(e);
     for (auto& e : c->events) {
         cudaEventDestroy(e.a);
@@ -278,6 +419,8 @@ extern "C" int32_t yasph_create(const yasph_config* cfg, yasph_ctx** out) {
                     worst_smem_bytes(c->lim_dyn, c->lim_stat), c->smem_optin);
     if (c->cfg.speculative_iterations == 0) c->cfg.speculative_iterations = 2;
     c->cfg.max_tiles = c->max_tiles;
+    if (c->cfg.max_halo == 0) c->cfg.max_halo = cfg->max_particles / 8 > 65536u ? cfg->max_particles / 8 : 65536u;
+    if (c->cfg.max_halo > cfg->max_particles) c->cfg.max_halo = cfg->max_particles;
 
     // ConstantFluidProperties
     c->mass = cfg->fluid_density / cfg->particle_density;   // fluidparticleworld.rs:74-76
@@ -398,7 +541,7 @@ extern "C" int32_t yasph_get_properties(const yasph_ctx* c, float* out2) {
 }
 extern "C" int32_t yasph_num_particles(const yasph_ctx* c, uint32_t* n, uint32_t* m) {
     if (!c) return YASPH_ERR_INVALID_ARGUMENT;
-    if (n) *n = c->n;
+    if (n) *n = c->slab.active ? c->slab.n_own : c->n;
     if (m) *m = c->m;
     return YASPH_OK;
 }
@@ -481,6 +624,8 @@ static SweepCommon sweep_common(const yasph_ctx* c) {
     s.mass = c->mass;
     s.rho0 = c->cfg.fluid_density;
     s.partials = c->partials;
+    s.ghost = c->slab.active ? c->slab.pflag : nullptr;
+    s.n_avg = c->slab.active ? (float)c->slab.n_global : (float)c->n;
     return s;
 }
 // persistent grid of a tile kernel: every SM filled to the kernel's occupancy at this shared-memory size, at most one CTA per tile
@@ -514,27 +659,343 @@ static int32_t check_capacity_flags(yasph_ctx* c) {
     return YASPH_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// slab mode (multi-GPU) plumbing
+// ---------------------------------------------------------------------------------------------------------------------
+static SlabParams slab_params(const yasph_ctx* c) { return SlabParams{c->slab.col_lo, c->slab.col_hi, c->slab.pflag, c->slab.active ? 1 : 0}; }
+static bool has_left(const yasph_ctx* c) { return c->slab.active && c->slab.rank > 0; }
+static bool has_right(const yasph_ctx* c) { return c->slab.active && c->slab.rank + 1 < c->slab.world; }
+constexpr size_t RECORD_MAX_BYTES = 3 * 8 + 3 * 4;
+
+// ordered selection of two index lists over [0, n): *total_out (device) receives count A | count B << 32
+template <class In>
+static int32_t select_pair(yasph_ctx* c, In in, uint32_t n, uint32_t* out_a, uint32_t* out_b, uint8_t* pflag_out, uint32_t cap, unsigned long long* total_out) {
+    if (n == 0) {
+        CU(cudaMemsetAsync(total_out, 0, sizeof(unsigned long long), c->stream));
+        return YASPH_OK;
+    }
+    const uint32_t nch = scan_num_chunks(n);
+    IndexPairOut out{out_a, out_b, pflag_out, cap};
+    k_scan_reduce<unsigned long long, In><<<nch, SCAN_THREADS, 0, c->stream>>>(in, n, c->scan_chunks);
+    CHECK_LAUNCH();
+    k_scan_chunks<unsigned long long><<<1, SCAN_THREADS, 0, c->stream>>>(c->scan_chunks, nch, total_out);
+    CHECK_LAUNCH();
+    k_scan_apply<unsigned long long, In, IndexPairOut><<<nch, SCAN_THREADS, 0, c->stream>>>(in, n, c->scan_chunks, out);
+    CHECK_LAUNCH();
+    return YASPH_OK;
+}
+
+// one NCCL group: send `sbytes[side]` bytes of sbuf[side] to / receive `rbytes[side]` bytes into rbuf[side] from the left
+// (side 0) and the right (side 1) neighbour rank
+static int32_t loopback_sendrecv(yasph_ctx* c, const void* const sbuf[2], const size_t sbytes[2], void* const rbuf[2], const size_t rbytes[2]) {
+    auto& sl = c->slab;
+    Fabric* f = sl.fabric;
+    // like the NCCL transport, a link with nothing to move in either direction is skipped (both ends know both sizes)
+    const bool side_on[2] = {sl.rank > 0 && (sbytes[0] || rbytes[0]), sl.rank + 1 < sl.world && (sbytes[1] || rbytes[1])};
+    const int peer[2] = {sl.rank - 1, sl.rank + 1};
+    uint64_t seq[2] = {0, 0};
+    // offer my buffers
+    for (int sd = 0; sd < 2; ++sd)
+        if (side_on[sd]) {
+            seq[sd] = ++sl.link_seq[sd];
+            CU(cudaEventRecord(sl.ev_ready[sd], c->stream));
+        }
+    {
+        std::lock_guard<std::mutex> lk(f->m);
+        for (int sd = 0; sd < 2; ++sd)
+            if (side_on[sd]) f->post[sl.rank * 2 + sd] = Fabric::Post{sbuf[sd], sbytes[sd], sl.ev_ready[sd], seq[sd]};
+    }
+    f->cv.notify_all();
+    // take what the neighbours offer (the neighbour on my side sd offers on its side 1 - sd)
+    for (int sd = 0; sd < 2; ++sd) {
+        if (!side_on[sd]) continue;
+        Fabric::Post p;
+        bool failed;
+        {
+            std::unique_lock<std::mutex> lk(f->m);
+            f->cv.wait(lk, [&] { return f->failed || f->post[peer[sd] * 2 + (1 - sd)].seq >= seq[sd]; });
+            failed = f->failed;
+            p = f->post[peer[sd] * 2 + (1 - sd)];
+        }
+        if (failed) return fail(c, YASPH_ERR_COMM, "loopback transport: a peer rank failed");
+        if (p.seq != seq[sd] || p.bytes != rbytes[sd])
+            return fail(c, YASPH_ERR_COMM, "loopback transport: rank %d expected %zu bytes (seq %llu) from rank %d, which offers %zu (seq %llu)", sl.rank,
+                        rbytes[sd], (unsigned long long)seq[sd], peer[sd], p.bytes, (unsigned long long)p.seq);
+        CU(cudaStreamWaitEvent(c->stream, p.ready, 0));
+        if (p.bytes) CU(cudaMemcpyAsync(rbuf[sd], p.buf, p.bytes, cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaEventRecord(sl.ev_done[sd], c->stream));
+        {
+            std::lock_guard<std::mutex> lk(f->m);
+            f->ack[sl.rank * 2 + sd] = Fabric::Ack{sl.ev_done[sd], seq[sd]};
+        }
+        f->cv.notify_all();
+    }
+    // my send buffers may be rewritten once the neighbours' copies have run
+    for (int sd = 0; sd < 2; ++sd) {
+        if (!side_on[sd]) continue;
+        Fabric::Ack a;
+        bool failed;
+        {
+            std::unique_lock<std::mutex> lk(f->m);
+            f->cv.wait(lk, [&] { return f->failed || f->ack[peer[sd] * 2 + (1 - sd)].seq >= seq[sd]; });
+            failed = f->failed;
+            a = f->ack[peer[sd] * 2 + (1 - sd)];
+        }
+        if (failed) return fail(c, YASPH_ERR_COMM, "loopback transport: a peer rank failed");
+        CU(cudaStreamWaitEvent(c->stream, a.done, 0));
+    }
+    sl.halo_exchanges++;
+    return YASPH_OK;
+}
+static int32_t loopback_allreduce(yasph_ctx* c, void* dev_ptr, bool is_double_sum) {
+    auto& sl = c->slab;
+    Fabric* f = sl.fabric;
+    double v = 0.0;
+    if (is_double_sum) {
+        CU(cudaMemcpyAsync(&v, dev_ptr, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    } else {
+        float x = 0.f;
+        CU(cudaMemcpyAsync(&x, dev_ptr, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        v = (double)x;
+    }
+    double result;
+    bool peer_failed;
+    {
+        std::unique_lock<std::mutex> lk(f->m);
+        const uint64_t gen = f->ar_gen;
+        f->ar_val[sl.rank] = v;
+        if (++f->ar_count == f->world) {
+            double r = is_double_sum ? 0.0 : f->ar_val[0];
+            for (int k = 0; k < f->world; ++k) r = is_double_sum ? r + f->ar_val[k] : (f->ar_val[k] > r ? f->ar_val[k] : r);
+            f->ar_result = r;
+            f->ar_count = 0;
+            f->ar_gen++;
+            f->cv.notify_all();
+        } else {
+            f->cv.wait(lk, [&] { return f->failed || f->ar_gen != gen; });
+        }
+        result = f->ar_result;
+        peer_failed = f->failed;
+    }
+    if (peer_failed) return fail(c, YASPH_ERR_COMM, "loopback transport: a peer rank failed");
+    if (is_double_sum) {
+        CU(cudaMemcpyAsync(dev_ptr, &result, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    } else {
+        const float x = (float)result;
+        CU(cudaMemcpyAsync(dev_ptr, &x, sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));  // the source is a stack variable
+    sl.allreduces++;
+    return YASPH_OK;
+}
+
+static int32_t neighbor_sendrecv(yasph_ctx* c, const void* const sbuf[2], const size_t sbytes[2], void* const rbuf[2], const size_t rbytes[2]) {
+    if (c->slab.fabric) return loopback_sendrecv(c, sbuf, sbytes, rbuf, rbytes);
+    ncclComm_t comm = (ncclComm_t)c->slab.comm;
+    const bool side_on[2] = {has_left(c), has_right(c)};
+    const int peer[2] = {c->slab.rank - 1, c->slab.rank + 1};
+    NC(g_nccl.GroupStart());
+    for (int sd = 0; sd < 2; ++sd) {
+        if (!side_on[sd]) continue;
+        if (sbytes[sd]) NC(g_nccl.Send(sbuf[sd], sbytes[sd], ncclChar, peer[sd], comm, c->stream));
+        if (rbytes[sd]) NC(g_nccl.Recv(rbuf[sd], rbytes[sd], ncclChar, peer[sd], comm, c->stream));
+    }
+    NC(g_nccl.GroupEnd());
+    c->slab.halo_exchanges++;
+    return YASPH_OK;
+}
+
+// exchanges the pair of counts in `packed` (device: left | right << 32) with the neighbours; afterwards h_cnt[0..1] = sent
+// left / right, h_cnt[2..3] = received from left / right (synchronises the stream)
+static int32_t exchange_counts(yasph_ctx* c, const unsigned long long* packed) {
+    uint32_t* d = c->slab.d_cnt;
+    CU(cudaMemcpyAsync(d, packed, 2 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemsetAsync(d + 2, 0, 2 * sizeof(uint32_t), c->stream));
+    const void* sb[2] = {d, d + 1};
+    void* rb[2] = {d + 2, d + 3};
+    const size_t by[2] = {sizeof(uint32_t), sizeof(uint32_t)};
+    TRY(neighbor_sendrecv(c, sb, by, rb, by));
+    CU(cudaMemcpyAsync(c->slab.h_cnt, d, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return YASPH_OK;
+}
+
+// halo exchange of one per-particle field of the current structure: owners' values overwrite the ghosts'
+template <typename T>
+static int32_t halo_exchange(yasph_ctx* c, T* field) {
+    if (!c->slab.active || c->slab.world < 2) return YASPH_OK;
+    pass_begin(c, YASPH_PASS_HALO);
+    auto& sl = c->slab;
+    const uint32_t ns = sl.n_send[0] + sl.n_send[1], ng = sl.n_ghost[0] + sl.n_ghost[1];
+    if (ns) {
+        k_halo_pack<T><<<blocks_for(ns, 256), 256, 0, c->stream>>>(field, sl.send_idx[0], sl.n_send[0], sl.send_idx[1], sl.n_send[1],
+                                                                   reinterpret_cast<T*>(sl.sbuf[0]), reinterpret_cast<T*>(sl.sbuf[1]));
+        CHECK_LAUNCH();
+    }
+    const void* sb[2] = {sl.sbuf[0], sl.sbuf[1]};
+    void* rb[2] = {sl.rbuf[0], sl.rbuf[1]};
+    const size_t sby[2] = {sl.n_send[0] * sizeof(T), sl.n_send[1] * sizeof(T)};
+    const size_t rby[2] = {sl.n_ghost[0] * sizeof(T), sl.n_ghost[1] * sizeof(T)};
+    TRY(neighbor_sendrecv(c, sb, sby, rb, rby));
+    if (ng) {
+        k_halo_unpack<T><<<blocks_for(ng, 256), 256, 0, c->stream>>>(field, sl.ghost_idx[0], sl.n_ghost[0], sl.ghost_idx[1], sl.n_ghost[1],
+                                                                     reinterpret_cast<const T*>(sl.rbuf[0]), reinterpret_cast<const T*>(sl.rbuf[1]));
+        CHECK_LAUNCH();
+    }
+    pass_end(c);
+    return YASPH_OK;
+}
+
+// in-place all-reduce of one scalar of the control block over the ranks
+static int32_t allreduce_scalar(yasph_ctx* c, void* dev_ptr, ncclDataType_t type, ncclRedOp_t op) {
+    if (!c->slab.active || c->slab.world < 2) return YASPH_OK;
+    if (c->slab.fabric) return loopback_allreduce(c, dev_ptr, type == ncclDouble && op == ncclSum);
+    NC(g_nccl.AllReduce(dev_ptr, dev_ptr, 1, type, op, (ncclComm_t)c->slab.comm, c->stream));
+    c->slab.allreduces++;
+    return YASPH_OK;
+}
+
 // CompactMortonCellGrid::update for the dynamic particles + NeighborLists::update.
 // `keys_ready`: keys[0]/idx[0] were already produced by a fused advect / kick kernel.
-// gather2: float2 arrays permuted with the particles (pointer to the ctx member pair), gather1 likewise for float arrays.
+// gather2: float2 arrays permuted with the particles (pointer to the ctx member pair), gather1 likewise for 4-byte arrays.
 struct GatherPlan {
     float2** a2[3];
     float2** alt2[3];
     int n2 = 0;
-    float** a1[2];
-    float** alt1[2];
+    float** a1[3];
+    float** alt1[3];
     int n1 = 0;
 };
+static RecordArrays record_arrays(const GatherPlan& gp) {
+    RecordArrays r;
+    memset(&r, 0, sizeof(r));
+    r.n2 = gp.n2;
+    r.n1 = gp.n1;
+    for (int q = 0; q < gp.n2; ++q) r.a2[q] = *gp.a2[q];
+    for (int q = 0; q < gp.n1; ++q) r.a1[q] = *gp.a1[q];
+    return r;
+}
+
+// Slab mode, between key generation and the sort: particles that left the slab migrate to the adjacent rank, the ghosts of
+// the previous structure are dropped, and the first / last owned columns are exchanged as the new ghosts.  On return
+// *n_sort particles (old local + arrivals) carry sort keys (dropped ones YASPH_KEY_DROPPED) and *n_keep of them survive.
+static int32_t slab_exchange_particles(yasph_ctx* c, const GatherPlan& gp, uint32_t n_old, uint32_t* n_sort, uint32_t* n_keep) {
+    auto& sl = c->slab;
+    const RecordArrays ra = record_arrays(gp);
+    const size_t rec = record_bytes(gp.n2, gp.n1);
+    const SlabParams sp = slab_params(c);
+    const uint32_t ghosts_old = sl.n_ghost[0] + sl.n_ghost[1];
+    // (1) migrants: ordered selection by classification flag, counts to both neighbours
+    TRY(select_pair(c, FlagSelIn{sl.pflag, (uint8_t)SLAB_MIG_LEFT, (uint8_t)SLAB_MIG_RIGHT}, n_old, sl.sel[0], sl.sel[1], nullptr, sl.max_halo, &c->ctl->slab_migrants));
+    TRY(exchange_counts(c, &c->ctl->slab_migrants));
+    uint32_t out[2] = {sl.h_cnt[0], sl.h_cnt[1]}, in[2] = {sl.h_cnt[2], sl.h_cnt[3]};
+    // a particle that leaves through an end of the domain has no rank to go to
+    if ((out[0] && !has_left(c)) || (out[1] && !has_right(c)))
+        return fail(c, YASPH_ERR_STATE, "rank %d: %u / %u particles left the domain's first / last slab [%u, %u)", sl.rank, out[0], out[1], sl.col_lo, sl.col_hi);
+    sl.mig_out[0] = out[0];
+    sl.mig_out[1] = out[1];
+    for (int sd = 0; sd < 2; ++sd)
+        if (out[sd] > sl.max_halo || in[sd] > sl.max_halo)
+            return fail(c, YASPH_ERR_CAPACITY, "rank %d: %u migrants out / %u in on side %d exceed max_halo=%u", sl.rank, out[sd], in[sd], sd, sl.max_halo);
+    uint32_t n1 = n_old + in[0] + in[1];
+    if (n1 > c->cap_n) return fail(c, YASPH_ERR_CAPACITY, "rank %d: %u local particles after migration > max_particles=%u", sl.rank, n1, c->cap_n);
+    if (out[0] + out[1] + in[0] + in[1]) {
+        for (int sd = 0; sd < 2; ++sd)
+            if (out[sd]) {
+                k_pack_records<<<blocks_for(out[sd], 256), 256, 0, c->stream>>>(ra, sl.sel[sd], out[sd], sl.sbuf[sd]);
+                CHECK_LAUNCH();
+            }
+        const void* sb[2] = {sl.sbuf[0], sl.sbuf[1]};
+        void* rb[2] = {sl.rbuf[0], sl.rbuf[1]};
+        const size_t sby[2] = {out[0] * rec, out[1] * rec}, rby[2] = {in[0] * rec, in[1] * rec};
+        TRY(neighbor_sendrecv(c, sb, sby, rb, rby));
+        uint32_t first = n_old;
+        for (int sd = 0; sd < 2; ++sd)
+            if (in[sd]) {
+                k_unpack_records<<<blocks_for(in[sd], 256), 256, 0, c->stream>>>(ra, first, in[sd], sl.rbuf[sd], sl.pflag);
+                CHECK_LAUNCH();
+                first += in[sd];
+            }
+        const uint32_t nin = in[0] + in[1];
+        if (nin) {
+            k_keygen<<<blocks_for(nin, RS_THREADS), RS_THREADS, 0, c->stream>>>(c->pos, n_old, n1, c->grid, c->keys[0], c->idx[0], c->radix_scratch, sp);
+            CHECK_LAUNCH();
+            k_check_arrivals<<<blocks_for(nin, 256), 256, 0, c->stream>>>(sl.pflag, n_old, n1, c->ctl);
+            CHECK_LAUNCH();
+        }
+    }
+    sl.mig_in = in[0] + in[1];
+    // (2) ghosts: the owned particles of the first / last owned column, in pre-sort order, to the left / right rank
+    const uint32_t ca = has_left(c) ? sl.col_lo : 0xFFFFFFFFu, cb = has_right(c) ? sl.col_hi - 1u : 0xFFFFFFFFu;
+    TRY(select_pair(c, ColumnSelIn{c->keys[0], sl.pflag, ca, cb}, n1, sl.sel[0], sl.sel[1], nullptr, sl.max_halo, &c->ctl->slab_ghost_send));
+    TRY(exchange_counts(c, &c->ctl->slab_ghost_send));
+    uint32_t gout[2] = {sl.h_cnt[0], sl.h_cnt[1]}, gin[2] = {sl.h_cnt[2], sl.h_cnt[3]};
+    for (int sd = 0; sd < 2; ++sd)
+        if (gout[sd] > sl.max_halo || gin[sd] > sl.max_halo)
+            return fail(c, YASPH_ERR_CAPACITY, "rank %d: %u ghosts out / %u in on side %d exceed max_halo=%u", sl.rank, gout[sd], gin[sd], sd, sl.max_halo);
+    const uint32_t n2 = n1 + gin[0] + gin[1];
+    if (n2 > c->cap_n) return fail(c, YASPH_ERR_CAPACITY, "rank %d: %u local particles with ghosts > max_particles=%u", sl.rank, n2, c->cap_n);
+    if (gout[0] + gout[1] + gin[0] + gin[1]) {
+        for (int sd = 0; sd < 2; ++sd)
+            if (gout[sd]) {
+                k_pack_records<<<blocks_for(gout[sd], 256), 256, 0, c->stream>>>(ra, sl.sel[sd], gout[sd], sl.sbuf[sd]);
+                CHECK_LAUNCH();
+            }
+        const void* sb[2] = {sl.sbuf[0], sl.sbuf[1]};
+        void* rb[2] = {sl.rbuf[0], sl.rbuf[1]};
+        const size_t sby[2] = {gout[0] * rec, gout[1] * rec}, rby[2] = {gin[0] * rec, gin[1] * rec};
+        TRY(neighbor_sendrecv(c, sb, sby, rb, rby));
+        uint32_t first = n1;
+        for (int sd = 0; sd < 2; ++sd)
+            if (gin[sd]) {
+                k_unpack_records<<<blocks_for(gin[sd], 256), 256, 0, c->stream>>>(ra, first, gin[sd], sl.rbuf[sd], sl.pflag);
+                CHECK_LAUNCH();
+                first += gin[sd];
+            }
+        const uint32_t ngin = gin[0] + gin[1];
+        if (ngin) {  // ghosts keep their keys (they lie outside the slab by construction): no classification
+            k_keygen<<<blocks_for(ngin, RS_THREADS), RS_THREADS, 0, c->stream>>>(c->pos, n1, n2, c->grid, c->keys[0], c->idx[0], c->radix_scratch,
+                                                                               SlabParams{0u, 0u, nullptr, 0});
+            CHECK_LAUNCH();
+        }
+    }
+    sl.n_send[0] = gout[0];
+    sl.n_send[1] = gout[1];
+    sl.n_ghost[0] = gin[0];
+    sl.n_ghost[1] = gin[1];
+    *n_sort = n2;
+    *n_keep = n2 - ghosts_old - sl.mig_out[0] - sl.mig_out[1];
+    return YASPH_OK;
+}
+
 static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp) {
-    const uint32_t n = c->n;
+    uint32_t n = c->n;
     c->lists_valid = false;
+    c->slab.own_idx_valid = false;
+    if (c->cfg.flags & YASPH_FLAG_TRACK_IDS) {  // ids travel with the particles
+        if (gp.n1 >= 3) return fail(c, YASPH_ERR_STATE, "neighborhood_update: too many permuted arrays");
+        gp.a1[gp.n1] = reinterpret_cast<float**>(&c->ids);
+        gp.alt1[gp.n1] = reinterpret_cast<float**>(&c->ids_alt);
+        gp.n1++;
+    }
     pass_begin(c, YASPH_PASS_SORT);
     if (!keys_ready && n) {
         TRY(radix_prepare(c, n));
-        k_keygen<<<blocks_for(n, RS_THREADS), RS_THREADS, 0, c->stream>>>(c->pos, n, c->grid, c->keys[0], c->idx[0], c->radix_scratch);
+        k_keygen<<<blocks_for(n, RS_THREADS), RS_THREADS, 0, c->stream>>>(c->pos, 0u, n, c->grid, c->keys[0], c->idx[0], c->radix_scratch, slab_params(c));
         CHECK_LAUNCH();
     }
-    TRY(radix_sort(c, n));
+    uint32_t n_sort = n;
+    if (c->slab.active) {
+        pass_end(c);
+        pass_begin(c, YASPH_PASS_HALO);
+        TRY(slab_exchange_particles(c, gp, n, &n_sort, &n));
+        pass_end(c);
+        pass_begin(c, YASPH_PASS_SORT);
+        c->n = n;
+    }
+    TRY(radix_sort(c, n_sort));
     pass_end(c);
     pass_begin(c, YASPH_PASS_GATHER);
     if (n) {
@@ -565,11 +1026,30 @@ static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp
         k_tile_tables<<<c->num_sms * 16, TT_WARPS * 32, 0, c->stream>>>(ta, c->ctl);
         CHECK_LAUNCH();
     }
+    if (c->slab.active) {
+        // per-pass halo lists of the new structure, in sorted order: what this rank sends (its first / last owned column) and
+        // where its ghosts sit; the ghost flags; counts come back with the control block below
+        auto& sl = c->slab;
+        const uint32_t ca = has_left(c) ? sl.col_lo : 0xFFFFFFFFu, cb = has_right(c) ? sl.col_hi - 1u : 0xFFFFFFFFu;
+        TRY(select_pair(c, ColumnSelIn{c->keys[0], nullptr, ca, cb}, n, sl.send_idx[0], sl.send_idx[1], nullptr, sl.max_halo, &c->ctl->slab_send));
+        TRY(select_pair(c, GhostSelIn{c->keys[0], sl.col_lo, sl.col_hi}, n, sl.ghost_idx[0], sl.ghost_idx[1], sl.pflag, sl.max_halo, &c->ctl->slab_ghost));
+    }
     pass_end(c);
     // The one host round trip of the neighbourhood update: tile count (grid of every tile kernel until the next update) and
     // the largest tile (their shared-memory size).
     TRY(read_control(c));
     TRY(check_capacity_flags(c));
+    if (c->slab.active) {
+        auto& sl = c->slab;
+        const Control& h = *c->h_ctl;
+        const uint32_t s0 = (uint32_t)(h.slab_send & 0xFFFFFFFFull), s1 = (uint32_t)(h.slab_send >> 32);
+        const uint32_t g0 = (uint32_t)(h.slab_ghost & 0xFFFFFFFFull), g1 = (uint32_t)(h.slab_ghost >> 32);
+        if (h.err_slab) return fail(c, YASPH_ERR_STATE, "rank %d: %u migrants arrived outside the slab [%u, %u) (a particle crossed more than one slab in a step)", sl.rank, h.err_slab, sl.col_lo, sl.col_hi);
+        if (s0 != sl.n_send[0] || s1 != sl.n_send[1] || g0 != sl.n_ghost[0] || g1 != sl.n_ghost[1])
+            return fail(c, YASPH_ERR_STATE, "rank %d: halo lists (%u,%u | %u,%u) disagree with the exchanged ghosts (%u,%u | %u,%u)", sl.rank, s0, s1, g0, g1,
+                        sl.n_send[0], sl.n_send[1], sl.n_ghost[0], sl.n_ghost[1]);
+        sl.n_own = n - g0 - g1;
+    }
     c->num_tiles = n ? c->h_ctl->num_tiles : 0u;
     c->cap_dyn = (c->h_ctl->max_dyn_total + 15u) & ~15u;
     c->cap_stat = (c->h_ctl->max_stat_total + 15u) & ~15u;
@@ -613,6 +1093,65 @@ static void fill_report(const yasph_ctx* c, yasph_step_report* r) {
     r->total_neighbors = h.total_neighbors;
 }
 
+// a new particle set of n particles is about to be copied into pos / vel (all owned, no ghosts, no lists)
+static int32_t reset_particle_set(yasph_ctx* c, uint32_t n) {
+    const uint32_t n_prev = c->slab.active ? c->slab.n_own : c->n;
+    if (n != n_prev) c->dfsph_ready = false;  // dfsph.rs:419: alpha_values.len() != positions.len() -> re-initialise
+    c->n = n;
+    c->lists_valid = false;
+    c->have_particles = true;
+    if (c->slab.active) {
+        auto& sl = c->slab;
+        sl.n_own = n;
+        sl.n_ghost[0] = sl.n_ghost[1] = sl.n_send[0] = sl.n_send[1] = 0;
+        sl.own_idx_valid = false;
+        c->dfsph_ready = false;  // the ghosts are gone: the structure must be rebuilt
+        if (n) CU(cudaMemsetAsync(sl.pflag, 0, n, c->stream));
+    }
+    if (c->cfg.flags & YASPH_FLAG_TRACK_IDS) {
+        if (!c->ids) {
+            CU(dmalloc(&c->ids, (size_t)c->cap_n));
+            CU(dmalloc(&c->ids_alt, (size_t)c->cap_n));
+        }
+        if (n) {
+            k_iota<<<blocks_for(n, 256), 256, 0, c->stream>>>(c->ids, n, c->slab.id_base);
+            CHECK_LAUNCH();
+        }
+    }
+    return YASPH_OK;
+}
+
+// slab mode: sorted positions of the owned particles (built on demand, valid until the next neighbourhood update)
+static int32_t ensure_own_index(yasph_ctx* c) {
+    auto& sl = c->slab;
+    if (!sl.active || sl.own_idx_valid) return YASPH_OK;
+    if (!sl.own_idx) CU(dmalloc(&sl.own_idx, (size_t)c->cap_n));
+    TRY(select_pair(c, OwnSelIn{sl.pflag}, c->n, sl.own_idx, sl.own_idx, nullptr, c->cap_n, &c->ctl->slab_own));
+    unsigned long long cnt = 0;
+    CU(cudaMemcpyAsync(&cnt, &c->ctl->slab_own, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if ((uint32_t)(cnt & 0xFFFFFFFFull) != sl.n_own)
+        return fail(c, YASPH_ERR_STATE, "rank %d: %llu owned particles flagged, %u expected", sl.rank, cnt & 0xFFFFFFFFull, sl.n_own);
+    sl.own_idx_valid = true;
+    return YASPH_OK;
+}
+// device -> host copy of a per-particle array: owned particles only in slab mode (compacted through `scratch`)
+template <typename T>
+static int32_t download_array(yasph_ctx* c, const T* src, T* scratch, void* host_out) {
+    if (!c->slab.active || (c->slab.n_ghost[0] + c->slab.n_ghost[1] == 0)) {
+        const size_t n = c->slab.active ? c->slab.n_own : c->n;
+        if (n) CU(cudaMemcpyAsync(host_out, src, n * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+        return YASPH_OK;
+    }
+    TRY(ensure_own_index(c));
+    const uint32_t n = c->slab.n_own;
+    if (!n) return YASPH_OK;
+    k_own_compact<T><<<blocks_for(n, 256), 256, 0, c->stream>>>(src, c->slab.own_idx, n, scratch);
+    CHECK_LAUNCH();
+    CU(cudaMemcpyAsync(host_out, scratch, (size_t)n * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+    return YASPH_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // particle state
 // ---------------------------------------------------------------------------------------------------------------------
@@ -626,7 +1165,7 @@ extern "C" int32_t yasph_set_boundary(yasph_ctx* c, const float* xy, uint32_t m)
         CU(cudaMemcpyAsync(c->bpos, xy, (size_t)m * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
         // update_static (neighborhood_search.rs:488-491): sort the boundary particles in place, build the static cells
         TRY(radix_prepare(c, m));
-        k_keygen<<<blocks_for(m, RS_THREADS), RS_THREADS, 0, c->stream>>>(c->bpos, m, c->grid, c->keys[0], c->idx[0], c->radix_scratch);
+        k_keygen<<<blocks_for(m, RS_THREADS), RS_THREADS, 0, c->stream>>>(c->bpos, 0u, m, c->grid, c->keys[0], c->idx[0], c->radix_scratch, SlabParams{0u, 0u, nullptr, 0});
         CHECK_LAUNCH();
         TRY(radix_sort(c, m));
         GatherArgs ga;
@@ -647,10 +1186,7 @@ extern "C" int32_t yasph_upload_particles(yasph_ctx* c, const float* pos_xy, con
     if (!c || (n && !pos_xy)) return YASPH_ERR_INVALID_ARGUMENT;
     if (n > c->cap_n) return fail(c, YASPH_ERR_CAPACITY, "yasph_upload_particles: %u particles > max_particles=%u", n, c->cap_n);
     CU(cudaSetDevice(c->device));
-    if (n != c->n) c->dfsph_ready = false;  // dfsph.rs:419: alpha_values.len() != positions.len() -> re-initialise
-    c->n = n;
-    c->lists_valid = false;
-    c->have_particles = true;
+    TRY(reset_particle_set(c, n));
     if (n) {
         CU(cudaMemcpyAsync(c->pos, pos_xy, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
         if (vel_xy)
@@ -666,12 +1202,9 @@ extern "C" int32_t yasph_download_particles(yasph_ctx* c, float* pos_xy, float* 
     if (!c) return YASPH_ERR_INVALID_ARGUMENT;
     if (!c->have_particles) return fail(c, YASPH_ERR_STATE, "yasph_download_particles: no particles uploaded");
     CU(cudaSetDevice(c->device));
-    const size_t n = c->n;
-    if (n) {
-        if (pos_xy) CU(cudaMemcpyAsync(pos_xy, c->pos, n * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
-        if (vel_xy) CU(cudaMemcpyAsync(vel_xy, c->vel, n * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
-        if (densities) CU(cudaMemcpyAsync(densities, c->dens, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    }
+    if (pos_xy) TRY(download_array(c, c->pos, c->pos_alt, pos_xy));
+    if (vel_xy) TRY(download_array(c, c->vel, c->vel_alt, vel_xy));
+    if (densities) TRY(download_array(c, c->dens, c->f_alt0, densities));
     CU(cudaStreamSynchronize(c->stream));
     return YASPH_OK;
 }
@@ -679,24 +1212,53 @@ extern "C" int32_t yasph_download_particles(yasph_ctx* c, float* pos_xy, float* 
 extern "C" int32_t yasph_download_field(yasph_ctx* c, int32_t field, void* out, uint64_t out_bytes) {
     if (!c || !out) return YASPH_ERR_INVALID_ARGUMENT;
     CU(cudaSetDevice(c->device));
-    const void* src = nullptr;
-    size_t bytes = 0;
-    const size_t n = c->n, m = c->m;
+    const bool local = (field & YASPH_FIELD_LOCAL_BIT) != 0;  // slab mode: owned + ghosts, uncompacted
+    field &= ~YASPH_FIELD_LOCAL_BIT;
+    const size_t n = (c->slab.active && !local) ? c->slab.n_own : c->n, m = c->m;
+    const float2* src2 = nullptr;
+    const float* src1 = nullptr;
     switch (field) {
-        case YASPH_FIELD_POSITION: src = c->pos; bytes = n * sizeof(float2); break;
-        case YASPH_FIELD_VELOCITY: src = c->vel; bytes = n * sizeof(float2); break;
-        case YASPH_FIELD_DENSITY: src = c->dens; bytes = n * sizeof(float); break;
-        case YASPH_FIELD_ALPHA: src = c->alpha; bytes = n * sizeof(float); break;
-        case YASPH_FIELD_KAPPA: src = c->kappa; bytes = n * sizeof(float); break;
-        case YASPH_FIELD_STIFFNESS: src = c->stiff; bytes = n * sizeof(float); break;
-        case YASPH_FIELD_ACCELERATION: src = c->accel; bytes = n * sizeof(float2); break;
-        case YASPH_FIELD_CELL_KEY: src = c->keys[0]; bytes = n * sizeof(uint32_t); break;
-        case YASPH_FIELD_SORT_PERMUTATION: src = c->idx[0]; bytes = n * sizeof(uint32_t); break;
-        case YASPH_FIELD_BOUNDARY: src = c->bpos; bytes = m * sizeof(float2); break;
+        case YASPH_FIELD_GHOST: {
+            if (!local) return fail(c, YASPH_ERR_INVALID_ARGUMENT, "yasph_download_field: YASPH_FIELD_GHOST needs YASPH_FIELD_LOCAL_BIT");
+            if (out_bytes < c->n) return fail(c, YASPH_ERR_INVALID_ARGUMENT, "yasph_download_field: buffer too small");
+            if (c->slab.active) {
+                if (c->n) CU(cudaMemcpyAsync(out, c->slab.pflag, c->n, cudaMemcpyDeviceToHost, c->stream));
+                CU(cudaStreamSynchronize(c->stream));
+            } else {
+                memset(out, 0, c->n);
+            }
+            return YASPH_OK;
+        }
+        case YASPH_FIELD_POSITION: src2 = c->pos; break;
+        case YASPH_FIELD_VELOCITY: src2 = c->vel; break;
+        case YASPH_FIELD_ACCELERATION: src2 = c->accel; break;
+        case YASPH_FIELD_DENSITY: src1 = c->dens; break;
+        case YASPH_FIELD_ALPHA: src1 = c->alpha; break;
+        case YASPH_FIELD_KAPPA: src1 = c->kappa; break;
+        case YASPH_FIELD_STIFFNESS: src1 = c->stiff; break;
+        case YASPH_FIELD_CELL_KEY: src1 = reinterpret_cast<const float*>(c->keys[0]); break;
+        case YASPH_FIELD_SORT_PERMUTATION: src1 = reinterpret_cast<const float*>(c->idx[0]); break;
+        case YASPH_FIELD_ID:
+            if (!c->ids) return fail(c, YASPH_ERR_STATE, "yasph_download_field: ids are not tracked (YASPH_FLAG_TRACK_IDS)");
+            src1 = reinterpret_cast<const float*>(c->ids);
+            break;
+        case YASPH_FIELD_BOUNDARY: {
+            if (out_bytes < m * sizeof(float2)) return fail(c, YASPH_ERR_INVALID_ARGUMENT, "yasph_download_field: buffer too small");
+            if (m) CU(cudaMemcpyAsync(out, c->bpos, m * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            return YASPH_OK;
+        }
         default: return fail(c, YASPH_ERR_INVALID_ARGUMENT, "yasph_download_field: unknown field %d", field);
     }
+    const size_t bytes = n * (src2 ? sizeof(float2) : sizeof(float));
     if (out_bytes < bytes) return fail(c, YASPH_ERR_INVALID_ARGUMENT, "yasph_download_field: buffer of %llu bytes < %zu", (unsigned long long)out_bytes, bytes);
-    if (bytes) CU(cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (local) {
+        if (bytes) CU(cudaMemcpyAsync(out, src2 ? (const void*)src2 : (const void*)src1, bytes, cudaMemcpyDeviceToHost, c->stream));
+    } else if (src2) {
+        TRY(download_array(c, src2, c->pos_alt, out));
+    } else {
+        TRY(download_array(c, src1, c->f_alt0, out));
+    }
     CU(cudaStreamSynchronize(c->stream));
     return YASPH_OK;
 }
@@ -849,6 +1411,8 @@ static int32_t jacobi_solve(yasph_ctx* c) {
         w.clamp_min = -0.5f * rho0 * rho0;
         w.iter_index = 0;
         TRY(launch_sweep(c, w));
+        pass_end(c);
+        TRY(halo_exchange(c, c->vstar));  // slab mode: the warm start moved the owners' v*
     }
     pass_end(c);
     pass_begin(c, SOLVER == 0 ? YASPH_PASS_DENSITY_SOLVE : YASPH_PASS_DIVERGENCE_SOLVE);
@@ -856,7 +1420,10 @@ static int32_t jacobi_solve(yasph_ctx* c) {
     sp.max_error = SOLVER == 0 ? c->cfg.dfsph_max_avg_density_error : c->cfg.dfsph_max_divergence_error;
     sp.max_iters = SOLVER == 0 ? c->cfg.dfsph_max_density_iters : c->cfg.dfsph_max_divergence_iters;
     uint32_t it = 0;
-    const uint32_t chunk = c->cfg.speculative_iterations;
+    // slab mode: every iteration carries collectives that cannot be skipped on the device, so nothing is launched speculatively
+    const bool slab = c->slab.active && c->slab.world > 1;
+    const uint32_t chunk = slab ? 1u : c->cfg.speculative_iterations;
+    const int solve_pass = SOLVER == 0 ? YASPH_PASS_DENSITY_SOLVE : YASPH_PASS_DIVERGENCE_SOLVE;
     while (true) {
         for (uint32_t q = 0; q < chunk; ++q, ++it) {
             OpJacobiA<SOLVER> a;
@@ -867,6 +1434,17 @@ static int32_t jacobi_solve(yasph_ctx* c) {
             a.sp = sp;
             a.iter_index = it;
             TRY(launch_sweep(c, a));
+            if (c->slab.active) {
+                // global residual: sum over the ranks, then the loop decision every rank takes identically
+                TRY(allreduce_scalar(c, &c->ctl->resid_sum, ncclDouble, ncclSum));
+                k_jacobi_decide<SOLVER><<<1, 32, 0, c->stream>>>(c->ctl, sp, it, (float)c->slab.n_global, c->cfg.fluid_density);
+                CHECK_LAUNCH();
+                if (slab) {
+                    pass_end(c);
+                    TRY(halo_exchange(c, c->err_buf));  // k_j of the ghosts for pass B
+                    pass_begin(c, solve_pass);
+                }
+            }
             OpJacobiB<SOLVER, false> b;
             b.vstar = c->vstar;
             b.kfac = c->err_buf;
@@ -874,6 +1452,11 @@ static int32_t jacobi_solve(yasph_ctx* c) {
             b.clamp_min = 0.f;
             b.iter_index = it;
             TRY(launch_sweep(c, b));
+            if (slab) {
+                pass_end(c);
+                TRY(halo_exchange(c, c->vstar));  // v* of the ghosts for the next pass A / the advection
+                pass_begin(c, solve_pass);
+            }
         }
         TRY(read_control(c));
         if (c->h_ctl->stop_iter[SOLVER] != 0xFFFFFFFFu) break;
@@ -884,7 +1467,6 @@ static int32_t jacobi_solve(yasph_ctx* c) {
 }
 
 static int32_t dfsph_step(yasph_ctx* c) {
-    const uint32_t n = c->n;
     if (!c->dfsph_ready) {
         // dfsph.rs:419-428: first call (or particle count changed): zero the warm-start arrays, sort, densities, alpha
         CU(cudaMemsetAsync(c->kappa, 0, (size_t)c->cap_n * sizeof(float), c->stream));
@@ -904,8 +1486,10 @@ static int32_t dfsph_step(yasph_ctx* c) {
         da.stiffness = 0.f;
         TRY(launch_sweep(c, da));
         pass_end(c);
+        TRY(halo_exchange(c, c->dens));  // rho_j of the ghosts for the viscosity pass
         c->dfsph_ready = true;
     }
+    const uint32_t n = c->n;  // local particles (slab mode: owned + ghosts); the neighbourhood update below changes it
     k_begin_step<<<1, 32, 0, c->stream>>>(c->ctl);
     CHECK_LAUNCH();
     // non-pressure forces + CFL maximum (dfsph.rs:436-477)
@@ -922,16 +1506,19 @@ static int32_t dfsph_step(yasph_ctx* c) {
         TRY(launch_sweep(c, v));
     }
     pass_end(c);
+    TRY(allreduce_scalar(c, &c->ctl->max_v2_bits, ncclFloat, ncclMax));  // CFL maximum over all ranks (values are >= 0)
     // update timestep + velocity prediction (dfsph.rs:478-491)
     pass_begin(c, YASPH_PASS_PREDICT);
     k_timestep_apply<0><<<blocks_for(n, 256), 256, 0, c->stream>>>(c->ctl, c->tp, c->radius * 2.0f, c->vel, c->accel, c->vstar, n);
     CHECK_LAUNCH();
     pass_end(c);
+    TRY(halo_exchange(c, c->vstar));  // ghosts: v* of their owners (their own accelerations are incomplete)
     TRY(jacobi_solve<0>(c));  // dfsph.rs:496
     // advect (dfsph.rs:502-509) fused with the key generation of the re-sort (dfsph.rs:512)
     pass_begin(c, YASPH_PASS_ADVECT_KEYGEN);
     TRY(radix_prepare(c, n));
-    k_advect_keygen<<<blocks_for(n, RS_THREADS), RS_THREADS, 0, c->stream>>>(c->pos, c->vstar, n, c->ctl, c->grid, c->keys[0], c->idx[0], c->radix_scratch);
+    k_advect_keygen<<<blocks_for(n, RS_THREADS), RS_THREADS, 0, c->stream>>>(c->pos, c->vstar, n, c->ctl, c->grid, c->keys[0], c->idx[0], c->radix_scratch,
+                                                                            slab_params(c));
     CHECK_LAUNCH();
     pass_end(c);
     {
@@ -942,7 +1529,7 @@ static int32_t dfsph_step(yasph_ctx* c) {
         gp.alt2[0] = &c->pos_alt;
         gp.a2[1] = &c->vstar;
         gp.alt2[1] = &c->vstar_alt;
-        if (c->cfg.flags & YASPH_FLAG_PERMUTE_WARMSTART) {
+        if ((c->cfg.flags & YASPH_FLAG_PERMUTE_WARMSTART) || c->slab.active) {
             gp.n1 = 2;
             gp.a1[0] = &c->kappa;
             gp.alt1[0] = &c->f_alt0;
@@ -963,19 +1550,21 @@ static int32_t dfsph_step(yasph_ctx* c) {
     k_begin_divergence<<<1, 32, 0, c->stream>>>(c->ctl);
     CHECK_LAUNCH();
     pass_end(c);
+    TRY(halo_exchange(c, c->dens));  // rho_j of the ghosts for the next step's viscosity pass
     TRY(jacobi_solve<1>(c));        // dfsph.rs:521
     std::swap(c->vel, c->vstar);    // dfsph.rs:524
     return YASPH_OK;
 }
 
 static int32_t wcsph_step(yasph_ctx* c) {
-    const uint32_t n = c->n;
+    uint32_t n = c->n;
     k_begin_step<<<1, 32, 0, c->stream>>>(c->ctl);
     CHECK_LAUNCH();
     // leap frog 1 (wscsph.rs:141-150) fused with key generation
     pass_begin(c, YASPH_PASS_ADVECT_KEYGEN);
     TRY(radix_prepare(c, n));
-    k_kickdrift_keygen<<<blocks_for(n, RS_THREADS), RS_THREADS, 0, c->stream>>>(c->pos, c->vel, c->accel, n, c->ctl, c->grid, c->keys[0], c->idx[0], c->radix_scratch);
+    k_kickdrift_keygen<<<blocks_for(n, RS_THREADS), RS_THREADS, 0, c->stream>>>(c->pos, c->vel, c->accel, n, c->ctl, c->grid, c->keys[0], c->idx[0],
+                                                                               c->radix_scratch, slab_params(c));
     CHECK_LAUNCH();
     pass_end(c);
     GatherPlan gp;
@@ -985,9 +1574,11 @@ static int32_t wcsph_step(yasph_ctx* c) {
     gp.a2[1] = &c->vel;
     gp.alt2[1] = &c->vel_alt;
     TRY(neighborhood_update(c, true, gp));  // wscsph.rs:153
+    n = c->n;
     pass_begin(c, YASPH_PASS_DENSITY_ALPHA);
     TRY((launch_density<1, true>(c)));  // Poly6, wscsph.rs:154; + Tait pressure per particle (wscsph.rs:91-92)
     pass_end(c);
+    TRY(halo_exchange(c, c->vstar));  // (rho, p) of the ghosts
     pass_begin(c, YASPH_PASS_WCSPH_ACCEL);
     {
         OpWcsphAccel a;  // wscsph.rs:155
@@ -1001,6 +1592,7 @@ static int32_t wcsph_step(yasph_ctx* c) {
         TRY(launch_sweep(c, a));
     }
     pass_end(c);
+    TRY(allreduce_scalar(c, &c->ctl->max_v2_bits, ncclFloat, ncclMax));
     // update timestep + leap frog 2 (wscsph.rs:160-177)
     pass_begin(c, YASPH_PASS_WCSPH_KICK);
     k_timestep_apply<1><<<blocks_for(n, 256), 256, 0, c->stream>>>(c->ctl, c->tp, c->radius * 2.0f, c->vel, c->accel, c->vel, n);
@@ -1011,7 +1603,7 @@ static int32_t wcsph_step(yasph_ctx* c) {
 
 extern "C" int32_t yasph_step(yasph_ctx* c, yasph_step_report* report) {
     if (!c) return YASPH_ERR_INVALID_ARGUMENT;
-    if (!c->have_particles || c->n == 0) return fail(c, YASPH_ERR_STATE, "yasph_step: no particles uploaded");
+    if (!c->have_particles || (c->n == 0 && !c->slab.active)) return fail(c, YASPH_ERR_STATE, "yasph_step: no particles uploaded");
     CU(cudaSetDevice(c->device));
     if (c->cfg.solver == YASPH_SOLVER_WCSPH)
         TRY(wcsph_step(c));
@@ -1028,10 +1620,9 @@ extern "C" int32_t yasph_step(yasph_ctx* c, yasph_step_report* report) {
 extern "C" int32_t yasph_step_host(yasph_ctx* c, float* pos_xy, float* vel_xy, float* densities, uint32_t n, yasph_step_report* report) {
     if (!c || !pos_xy || !vel_xy) return YASPH_ERR_INVALID_ARGUMENT;
     if (n == 0 || n > c->cap_n) return fail(c, YASPH_ERR_CAPACITY, "yasph_step_host: n=%u out of range (max_particles=%u)", n, c->cap_n);
+    if (c->slab.active) return fail(c, YASPH_ERR_STATE, "yasph_step_host: the particle count of a slab changes with migration, use yasph_step_host_slab");
     CU(cudaSetDevice(c->device));
-    if (n != c->n) c->dfsph_ready = false;
-    c->n = n;
-    c->have_particles = true;
+    if (n != c->n) TRY(reset_particle_set(c, n));
     CU(cudaMemcpyAsync(c->pos, pos_xy, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->vel, vel_xy, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
     int32_t rc = yasph_step(c, report);
@@ -1039,6 +1630,176 @@ extern "C" int32_t yasph_step_host(yasph_ctx* c, float* pos_xy, float* vel_xy, f
     CU(cudaMemcpyAsync(pos_xy, c->pos, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(vel_xy, c->vel, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
     if (densities) CU(cudaMemcpyAsync(densities, c->dens, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return YASPH_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// multi-GPU surface
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" int32_t yasph_comm_unique_id(void* out_id, uint64_t bytes) {
+    yasph_ctx* c = nullptr;
+    if (!out_id || bytes < YASPH_COMM_ID_BYTES) return fail(c, YASPH_ERR_INVALID_ARGUMENT, "yasph_comm_unique_id: need a %u-byte buffer", YASPH_COMM_ID_BYTES);
+    static_assert(sizeof(ncclUniqueId) == YASPH_COMM_ID_BYTES, "ncclUniqueId size");
+    if (!nccl_load()) return fail(c, YASPH_ERR_COMM, "%s", g_nccl.error.c_str());
+    ncclUniqueId id;
+    NC(g_nccl.GetUniqueId(&id));
+    memcpy(out_id, &id, sizeof(id));
+    return YASPH_OK;
+}
+
+extern "C" int32_t yasph_comm_init(yasph_ctx* c, int32_t rank, int32_t world, const void* id_bytes, uint64_t bytes) {
+    if (!c || !id_bytes || bytes < YASPH_COMM_ID_BYTES || world < 1 || rank < 0 || rank >= world)
+        return fail(c, YASPH_ERR_INVALID_ARGUMENT, "yasph_comm_init: bad arguments (rank %d of %d)", rank, world);
+    if (c->slab.comm) return fail(c, YASPH_ERR_STATE, "yasph_comm_init: communicator already initialised");
+    if (!nccl_load()) return fail(c, YASPH_ERR_COMM, "%s", g_nccl.error.c_str());
+    CU(cudaSetDevice(c->device));
+    ncclUniqueId id;
+    memcpy(&id, id_bytes, sizeof(id));
+    ncclComm_t comm = nullptr;
+    NC(g_nccl.CommInitRank(&comm, world, id, rank));
+    c->slab.comm = comm;
+    c->slab.rank = rank;
+    c->slab.world = world;
+    return YASPH_OK;
+}
+
+extern "C" int32_t yasph_loopback_create(int32_t world, void** fabric) {
+    if (!fabric || world < 1) return YASPH_ERR_INVALID_ARGUMENT;
+    Fabric* f = new Fabric();
+    f->world = world;
+    f->post.resize((size_t)world * 2);
+    f->ack.resize((size_t)world * 2);
+    f->ar_val.resize(world);
+    *fabric = f;
+    return YASPH_OK;
+}
+extern "C" int32_t yasph_loopback_destroy(void* fabric) {
+    if (!fabric) return YASPH_ERR_INVALID_ARGUMENT;
+    delete static_cast<Fabric*>(fabric);
+    return YASPH_OK;
+}
+extern "C" int32_t yasph_comm_init_loopback(yasph_ctx* c, void* fabric, int32_t rank) {
+    if (!c || !fabric) return YASPH_ERR_INVALID_ARGUMENT;
+    Fabric* f = static_cast<Fabric*>(fabric);
+    if (rank < 0 || rank >= f->world) return fail(c, YASPH_ERR_INVALID_ARGUMENT, "yasph_comm_init_loopback: rank %d of %d", rank, f->world);
+    if (c->slab.comm || c->slab.fabric) return fail(c, YASPH_ERR_STATE, "yasph_comm_init_loopback: communicator already initialised");
+    CU(cudaSetDevice(c->device));
+    for (int sd = 0; sd < 2; ++sd) {
+        CU(cudaEventCreateWithFlags(&c->slab.ev_ready[sd], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->slab.ev_done[sd], cudaEventDisableTiming));
+    }
+    c->slab.fabric = f;
+    c->slab.rank = rank;
+    c->slab.world = f->world;
+    return YASPH_OK;
+}
+
+extern "C" int32_t yasph_slab_set(yasph_ctx* c, uint32_t col_lo, uint32_t col_hi, uint64_t n_global, uint32_t id_base) {
+    if (!c) return YASPH_ERR_INVALID_ARGUMENT;
+    auto& sl = c->slab;
+    if (sl.world > 1 && !sl.comm && !sl.fabric) return fail(c, YASPH_ERR_STATE, "yasph_slab_set: call yasph_comm_init first");
+    if (sl.rank == 0) col_lo = 0;                  // the end slabs extend to the ends of the grid
+    if (sl.rank == sl.world - 1) col_hi = 65536u;
+    if (col_lo >= col_hi || col_hi > 65536u) return fail(c, YASPH_ERR_INVALID_ARGUMENT, "yasph_slab_set: empty or invalid column range [%u, %u)", col_lo, col_hi);
+    CU(cudaSetDevice(c->device));
+    sl.col_lo = col_lo;
+    sl.col_hi = col_hi;
+    sl.n_global = n_global;
+    sl.id_base = id_base;
+    sl.max_halo = c->cfg.max_halo;
+    if (!sl.pflag) {
+        CU(dmalloc(&sl.pflag, (size_t)c->cap_n));
+        CU(cudaMemsetAsync(sl.pflag, 0, c->cap_n, c->stream));
+        for (int sd = 0; sd < 2; ++sd) {
+            CU(dmalloc(&sl.sel[sd], (size_t)sl.max_halo));
+            CU(dmalloc(&sl.send_idx[sd], (size_t)sl.max_halo));
+            CU(dmalloc(&sl.ghost_idx[sd], (size_t)sl.max_halo));
+            CU(dmalloc(&sl.sbuf[sd], (size_t)sl.max_halo * RECORD_MAX_BYTES));
+            CU(dmalloc(&sl.rbuf[sd], (size_t)sl.max_halo * RECORD_MAX_BYTES));
+        }
+        CU(dmalloc(&sl.d_cnt, 4));
+        CU(cudaMallocHost((void**)&sl.h_cnt, 4 * sizeof(uint32_t)));
+    }
+    sl.active = true;
+    sl.n_own = 0;
+    sl.n_ghost[0] = sl.n_ghost[1] = sl.n_send[0] = sl.n_send[1] = 0;
+    c->n = 0;
+    c->have_particles = false;
+    c->lists_valid = false;
+    c->dfsph_ready = false;
+    CU(cudaStreamSynchronize(c->stream));
+    return YASPH_OK;
+}
+
+extern "C" int32_t yasph_slab_get(yasph_ctx* c, yasph_slab_info* out) {
+    if (!c || !out) return YASPH_ERR_INVALID_ARGUMENT;
+    const auto& sl = c->slab;
+    memset(out, 0, sizeof(*out));
+    out->rank = sl.rank;
+    out->world = sl.world;
+    out->col_lo = sl.col_lo;
+    out->col_hi = sl.col_hi;
+    out->n_own = sl.active ? sl.n_own : c->n;
+    out->n_local = c->n;
+    out->n_ghost_left = sl.n_ghost[0];
+    out->n_ghost_right = sl.n_ghost[1];
+    out->migrated_out_left = sl.mig_out[0];
+    out->migrated_out_right = sl.mig_out[1];
+    out->migrated_in = sl.mig_in;
+    out->n_global = sl.active ? sl.n_global : c->n;
+    out->halo_exchanges = sl.halo_exchanges;
+    out->allreduces = sl.allreduces;
+    return YASPH_OK;
+}
+
+extern "C" int32_t yasph_cell_column(const yasph_config* cfg, float x, uint32_t* column) {
+    if (!cfg || !column || !(cfg->smoothing_length > 0.f)) return YASPH_ERR_INVALID_ARGUMENT;
+    const float inv = 1.0f / cfg->smoothing_length;  // neighborhood_search.rs:475
+    *column = f32_as_u16((x - cfg->grid_min[0]) * inv);
+    return YASPH_OK;
+}
+
+extern "C" int32_t yasph_step_host_slab(yasph_ctx* c, float* pos_xy, float* vel_xy, float* densities, uint32_t n_in, uint32_t capacity, uint32_t* n_out,
+                                        yasph_step_report* report) {
+    if (!c || !pos_xy || !vel_xy || !n_out) return YASPH_ERR_INVALID_ARGUMENT;
+    if (!c->slab.active) return fail(c, YASPH_ERR_STATE, "yasph_step_host_slab: yasph_slab_set has not been called");
+    if (n_in > c->cap_n || n_in > capacity) return fail(c, YASPH_ERR_CAPACITY, "yasph_step_host_slab: n_in=%u out of range", n_in);
+    CU(cudaSetDevice(c->device));
+    auto& sl = c->slab;
+    if (c->have_particles && c->lists_valid && n_in == sl.n_own) {
+        // the arrays are the owned particles in the order of the last download: put them back between the ghosts
+        TRY(ensure_own_index(c));
+        if (n_in) {
+            CU(cudaMemcpyAsync(c->pos_alt, pos_xy, (size_t)n_in * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+            CU(cudaMemcpyAsync(c->vel_alt, vel_xy, (size_t)n_in * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+            k_own_scatter<float2><<<blocks_for(n_in, 256), 256, 0, c->stream>>>(c->pos, sl.own_idx, n_in, c->pos_alt);
+            CHECK_LAUNCH();
+            k_own_scatter<float2><<<blocks_for(n_in, 256), 256, 0, c->stream>>>(c->vel, sl.own_idx, n_in, c->vel_alt);
+            CHECK_LAUNCH();
+        }
+    } else {
+        TRY(reset_particle_set(c, n_in));
+        if (n_in) {
+            CU(cudaMemcpyAsync(c->pos, pos_xy, (size_t)n_in * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+            CU(cudaMemcpyAsync(c->vel, vel_xy, (size_t)n_in * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+        }
+    }
+    // every rank steps, also one that currently owns no particle (the collectives are matched)
+    if (c->cfg.solver == YASPH_SOLVER_WCSPH)
+        TRY(wcsph_step(c));
+    else
+        TRY(dfsph_step(c));
+    TRY(read_control(c));
+    pass_resolve(c);
+    TRY(check_capacity_flags(c));
+    fill_report(c, report);
+    if (c->h_ctl->nonfinite) return fail(c, YASPH_ERR_NONFINITE, "non-finite Jacobi residual (solver mask %u)", c->h_ctl->nonfinite);
+    *n_out = sl.n_own;
+    if (sl.n_own > capacity) return fail(c, YASPH_ERR_CAPACITY, "yasph_step_host_slab: %u owned particles after the step > capacity %u", sl.n_own, capacity);
+    TRY(download_array(c, c->pos, c->pos_alt, pos_xy));
+    TRY(download_array(c, c->vel, c->vel_alt, vel_xy));
+    if (densities) TRY(download_array(c, c->dens, c->f_alt0, densities));
     CU(cudaStreamSynchronize(c->stream));
     return YASPH_OK;
 }

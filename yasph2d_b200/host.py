@@ -113,7 +113,7 @@ class GpuContext:
             out = np.empty((n, 2), np.float32)
         elif field == capi.FIELD_BOUNDARY:
             out = np.empty((m, 2), np.float32)
-        elif field in (capi.FIELD_CELL_KEY, capi.FIELD_SORT_PERMUTATION):
+        elif field in (capi.FIELD_CELL_KEY, capi.FIELD_SORT_PERMUTATION, capi.FIELD_ID):
             out = np.empty(n, np.uint32)
         else:
             out = np.empty(n, np.float32)
