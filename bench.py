@@ -4,8 +4,9 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload tank|dam_break]
 
 A "step" is one Solver::simulation_step (dfsph.rs:414-525) over the whole particle set.  Default workload: the DFSPH
-dam-break tank of BASELINE.json configs[3] at its per-GPU size (2 000 x 1 000 = 2 M fluid particles per GPU; 8 GPUs =
-the 16 M-particle tank), advanced `--presteps` steps before anything is timed so the column is collapsing.
+dam-break tank of BASELINE.json configs[3] at 2 000 x 1 000 = 2 M fluid particles per GPU (8 GPUs = the 16 M-particle
+tank), ONE tank slab-decomposed over the ranks along x (migration, ghost columns and per-pass halo exchange over NCCL, all-
+reduced Jacobi residual and CFL maximum), advanced `--presteps` steps before anything is timed so the column is collapsing.
 `value` is timed with the state resident in HBM; `e2e` goes through yasph_step_host with pinned HOST buffers
 (upload pos+vel, step, download pos+vel+densities every step) -- what the reference's `simulation_step(&mut world, ..)`
 does to the Vecs the Rust host owns.  `--impl reference` times the CPU restatement of the reference (oracle/, C++/OpenMP,
@@ -168,26 +169,41 @@ def main():
         if dist is not None:
             dist.barrier()
 
-    # ---- scene (host) ----
+    # ---- scene (host): every rank builds the whole scene (the jitter stream is sequential), then keeps its slab ----
     hw = y.FluidParticleWorld(2.0, 10000.0, 100.0)
     if args.workload == "tank":
-        y.tank_scene(hw, args.columns_per_gpu, args.rows)
-        workload = "DFSPH dam-break tank (BASELINE configs[3] per-GPU share): %d x %d fluid particles per GPU" % (args.columns_per_gpu, args.rows)
+        y.tank_scene(hw, args.columns_per_gpu * world, args.rows)
+        workload = "DFSPH dam-break tank (BASELINE configs[3]): %d x %d fluid particles per GPU, %d in total" % (
+            args.columns_per_gpu, args.rows, args.columns_per_gpu * world * args.rows)
     else:
         y.dam_break_scene(hw)
         workload = "DFSPH application dam-break scene (BASELINE configs[1], main.rs:177-196)"
-    n, m = hw.particles.num_dynamic_particles(), hw.particles.num_boundary_particles()
+    n_global, m = hw.particles.num_dynamic_particles(), hw.particles.num_boundary_particles()
 
     cfg = capi.default_config(2.0, 10000.0, 100.0, capi.SOLVER_DFSPH)
     cfg.device = local_rank
-    cfg.max_particles, cfg.max_boundary = n, m
-    ctx = y.GpuContext(cfg)
-    ctx.set_boundary(hw.particles.boundary_particles)
-    ctx.upload_particles(hw.particles.positions, hw.particles.velocities)
+    if world == 1:
+        n = n_global
+        cfg.max_particles, cfg.max_boundary = n, m
+        ctx = y.GpuContext(cfg)
+        ctx.set_boundary(hw.particles.boundary_particles)
+        ctx.upload_particles(hw.particles.positions, hw.particles.velocities)
+        ranges = None
+    else:
+        from yasph2d_b200 import slab
+
+        # 1-D slab decomposition over cell columns: migration + ghost columns + per-pass halo exchange over NCCL
+        cfg.max_particles, cfg.max_boundary = int(n_global / world * 1.3) + 65536, m
+        uid = slab.broadcast_unique_id(dist)
+        ctx, ranges, _ = slab.make_slab_context(cfg, rank, world, uid, hw.particles.positions, hw.particles.velocities, hw.particles.boundary_particles)
+        n = ctx.counts()[0]
+    del hw
     stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=torch.device("cuda", local_rank))
 
     for _ in range(args.presteps):
         ctx.step()
+    if world > 1:
+        n = ctx.counts()[0]
 
     def timed(step_fn, steps, warmup):
         for _ in range(warmup):
@@ -218,7 +234,14 @@ def main():
     ms, reps, launches = timed(ctx.step, args.steps, args.warmup)
     stop.set()
     th.join(timeout=3)
-    value = n * world * args.steps / (ms * 1e-3)
+    if world == 1:
+        n_total = n
+    else:
+        t = torch.tensor([ctx.counts()[0]], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t)
+        n_total = int(t.item())
+        assert n_total == n_global, (n_total, n_global)
+    value = n_total * args.steps / (ms * 1e-3)
     it_rho = float(np.mean([r.iters_density for r in reps]))
     it_div = float(np.mean([r.iters_divergence for r in reps]))
     w_rho = float(np.mean([r.warm_density for r in reps]))
@@ -267,23 +290,37 @@ def main():
     roofline = {
         "bound": "hbm", "kernel": dominant + " (k_sweep)", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
         "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_kind,
-        "whole_step": {"alg_bytes_per_particle_step": round(step_bytes, 1), "GBps": round(step_bytes * n * world * args.steps / (ms * 1e-3) / 1e9, 1),
-                       "frac": round(step_bytes * n * args.steps / (ms * 1e-3) / 1e9 / peak, 4)},
+        "whole_step": {"alg_bytes_per_particle_step": round(step_bytes, 1), "GBps": round(step_bytes * n_total * args.steps / (ms * 1e-3) / 1e9, 1),
+                       "frac_per_gpu": round(step_bytes * n_total / world * args.steps / (ms * 1e-3) / 1e9 / peak, 4)},
         "passes": passes, "pass_us_per_step": {k: round(v, 2) for k, v in pt.items()},
     }
 
     # ---- end to end through the reference-facing call with pinned HOST buffers ----
     e2e = None
     if not args.no_e2e:
-        pos_t = torch.empty((n, 2), dtype=torch.float32, pin_memory=True)
-        vel_t = torch.empty((n, 2), dtype=torch.float32, pin_memory=True)
-        den_t = torch.empty((n,), dtype=torch.float32, pin_memory=True)
+        cap = int(cfg.max_particles)
+        pos_t = torch.empty((cap, 2), dtype=torch.float32, pin_memory=True)
+        vel_t = torch.empty((cap, 2), dtype=torch.float32, pin_memory=True)
+        den_t = torch.empty((cap,), dtype=torch.float32, pin_memory=True)
         pos, vel, den = pos_t.numpy(), vel_t.numpy(), den_t.numpy()
         p0, v0, _ = ctx.download_particles()
-        pos[:], vel[:] = p0, v0
-        ems, ereps, _ = timed(lambda: ctx.step_host(pos, vel, den), args.steps, args.warmup)
-        e2e = {"value": n * world * args.steps / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(n * 16), "d2h_bytes_per_step": int(n * 20),
-               "ms_per_step": ems / args.steps, "api": "yasph_step_host (upload pos+vel, simulation_step, download pos+vel+densities)"}
+        n_cur = [len(p0)]
+        pos[: n_cur[0]], vel[: n_cur[0]] = p0, v0
+        moved = [0, 0]
+
+        def host_step():
+            if world == 1:
+                return ctx.step_host(pos[: n_cur[0]], vel[: n_cur[0]], den[: n_cur[0]])
+            moved[0] += n_cur[0] * 16
+            rep, n_out = ctx.step_host_slab(pos, vel, den, n_cur[0])
+            n_cur[0] = n_out
+            moved[1] += n_out * 20
+            return rep
+
+        ems, ereps, _ = timed(host_step, args.steps, args.warmup)
+        e2e = {"value": n_total * args.steps / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(n_total * 16), "d2h_bytes_per_step": int(n_total * 20),
+               "ms_per_step": ems / args.steps,
+               "api": "yasph_step_host%s (upload pos+vel, simulation_step, download pos+vel+densities; bytes summed over ranks)" % ("" if world == 1 else "_slab")}
 
     # ---- CPU baseline (rank 0, single-GPU run only) ----
     cpu = None
@@ -297,7 +334,8 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
                 "workload": workload, "particles_per_gpu": n, "boundary_particles": m, "presteps": args.presteps,
-                "parallelism": "1 GPU" if world == 1 else "%d independent per-GPU tanks (slab halo exchange not built yet)" % world,
+                "parallelism": "1 GPU" if world == 1 else "1-D slab decomposition over cell columns, %d ranks, NCCL migration / ghost / halo exchange + all-reduced residual" % world,
+                "slab_ranges": ranges, "slab_info_rank0": (ctx.info().as_dict() if world > 1 else None),
                 "l2": "working set %.0f MB per GPU > 126 MB L2 (no explicit flush)" % (n * 240 / 1e6) if n * 240 > 126e6 else "working set fits L2 (small scene)",
                 "mean_neighbors": round(K, 2), "iters_density": it_rho, "iters_divergence": it_div, "warm_density": w_rho, "warm_divergence": w_div,
                 "arithmetic": "strict f32, no FMA contraction, IEEE div/sqrt (bit-exact vs oracle)",

@@ -101,3 +101,21 @@ def test_slab_world_one_equals_plain_context():
     results, merged = run_slabs_loopback(1, pos, vel, boundary, 30, [29])
     for k in ("pos", "vel", "dens"):
         assert np.array_equal(snaps1[29][k], merged[29][k])
+
+
+def test_nccl_transport_two_gpus():
+    """The same equivalence through the NCCL transport, one process per GPU (needs >= 2 GPUs on the box)."""
+    import os
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29517",
+           os.path.join(root, "tests", "slab_nccl_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
+    assert '"result": "ok"' in r.stdout, r.stdout[-2000:]
