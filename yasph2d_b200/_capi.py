@@ -96,7 +96,7 @@ def lib():
         raise RuntimeError(
             "libyasph_gpu.so is missing at %s: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
             "yasph2d_b200 has no CPU fallback." % LIB_PATH)
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(os.environ.get("YASPH_GPU_LIB", LIB_PATH))  # the override serves A/B timing of kernel variants (still this library)
     vp, f32p, u32p, u16p, u64p = C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_uint16), C.POINTER(C.c_uint64)
     rp = C.POINTER(StepReport)
 

@@ -18,15 +18,18 @@ def sources():
     return [os.path.join(d, f) for f in sorted(os.listdir(d))] + [os.path.join(_HERE, "..", "include", "yasph_gpu.h")]
 
 
-def build(force=False, verbose=False):
-    if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(s) for s in sources()):
-        return OUT
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+def build(force=False, verbose=False, defines=(), out=OUT):
+    """defines / out: build a variant of the library (e.g. -DYASPH_SWEEP_MIN_CTAS=5) next to the default one for A/B timing."""
+    if not force and not defines and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(s) for s in sources()):
+        return out
+    cmd = [NVCC] + FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, SRC]
     subprocess.check_call(cmd)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
     import sys
 
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[2:] for a in sys.argv[1:] if a.startswith("-o")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=os.path.abspath(outs[0]) if outs else OUT))

@@ -195,7 +195,8 @@ struct Control {
     unsigned int num_cells, num_tiles;
     unsigned int num_cells_static, num_tiles_static;
     // per-tile maxima of the last tile-table build: they size the shared memory of every tile kernel
-    unsigned int max_dyn_total, max_stat_total, max_pcount, pad_max;
+    unsigned int max_dyn_total, max_stat_total, max_pcount;
+    unsigned int max_nk;              // most list words of any particle (written by the list build; sizes the list staging of the NEXT sweeps)
     // list-build statistics: 16 contiguous bytes, zeroed together before every list build
     unsigned long long total_neighbors;
     unsigned int capped, dropped;

@@ -43,8 +43,20 @@ struct TileHeader {       // 32 bytes
     uint32_t stat_total;  // staged boundary candidates
     uint32_t own_lo;      // slot of the tile's first own particle in the staged dynamic array
     uint32_t nruns_d, nruns_s;
-    uint32_t pad;
+    uint32_t pad;         // unused slots before | after << 8 the tile's own particles (see k_tile_tables step 4)
 };
+// The own particles of a tile sit at slots [own_lo, own_lo + pcount) with own_lo == pstart (mod 4) and are surrounded by
+// pad slots such that the 4-element-aligned global range [pstart & ~3, roundup4(pstart + pcount)) maps onto the
+// 4-slot-aligned range [own_lo - (pstart & 3), ...): every per-particle array can then be staged with ONE 16-byte aligned bulk
+// copy, whose leading / trailing surplus elements land in the pad slots.
+__host__ __device__ __forceinline__ uint32_t tile_pad_before(const TileHeader& h) { return h.pad & 0xFFu; }
+__host__ __device__ __forceinline__ uint32_t tile_pad_after(const TileHeader& h) { return (h.pad >> 8) & 0xFFu; }
+// the a-th staged dynamic candidate that is NOT one of the tile's own particles or a pad slot (a < tile_apron_count)
+__host__ __device__ __forceinline__ uint32_t tile_apron_count(const TileHeader& h) { return h.dyn_total - h.pcount - tile_pad_before(h) - tile_pad_after(h); }
+__host__ __device__ __forceinline__ uint32_t tile_apron_slot(const TileHeader& h, uint32_t a) {
+    const uint32_t lo = h.own_lo - tile_pad_before(h);
+    return a < lo ? a : a - lo + h.own_lo + h.pcount + tile_pad_after(h);
+}
 // copy run: .x = first global index, .y = first slot; unused entries carry .y = 0xFFFFFFFF
 struct TileRuns {
     TileHeader hdr;
@@ -199,6 +211,7 @@ __global__ void k_finish_cells(const unsigned long long* __restrict__ total, uin
             ctl->max_dyn_total = 0u;
             ctl->max_stat_total = 0u;
             ctl->max_pcount = 0u;
+            ctl->max_nk = 0u;
         }
     }
 }
@@ -360,10 +373,19 @@ __global__ void __launch_bounds__(TT_WARPS * 32) k_tile_tables(TileTableArgs a, 
         // 4. walk the cells in slot order: slot starts (exclusive prefix of the counts) and copy runs
         uint32_t totals[2], nruns[2];
         TileRuns* out = a.truns + t;
+        // pad slots around the own block (dynamic candidates only), see TileHeader
+        const uint32_t ownB = S.blk_seq[4], ownE = ownB + TILE_CELLS;  // the own block's region cells in slot order: [ownB, ownE)
+        uint32_t slotB = 0;
+        for (uint32_t q = lane; q < ownB; q += 32) slotB += S.cnt[0][S.seq[q]];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) slotB += __shfl_xor_sync(0xffffffffu, slotB, o);
+        const uint32_t pad_before = ((slotB + 3u) & ~3u) - slotB + (pstart & 3u);
+        const uint32_t own_hi = slotB + pad_before + (pend - pstart);
+        const uint32_t pad_after = ((own_hi + 3u) & ~3u) - own_hi;
 #pragma unroll
         for (int which = 0; which < 2; ++which) {
             uint2* runs = which ? out->rs : out->rd;
-            uint32_t carry = 0, carry_runs = 0, carry_end = 0;
+            uint32_t carry = 0, carry_runs = 0, carry_end = 0, carry_q = 0;
             bool carry_valid = false;
             for (uint32_t q0 = 0; q0 < REGION_CELLS; q0 += 32) {
                 const uint32_t q = q0 + lane;
@@ -371,7 +393,8 @@ __global__ void __launch_bounds__(TT_WARPS * 32) k_tile_tables(TileTableArgs a, 
                 const uint32_t r = in ? S.seq[q] : 0u;
                 const uint32_t cn = in ? S.cnt[which][r] : 0u;
                 const uint32_t g = in ? S.gs[which][r] : 0u;
-                uint32_t inc = cn;
+                const uint32_t ex = which == 0 ? (q == ownB ? pad_before : 0u) + (q == ownE ? pad_after : 0u) : 0u;  // pads precede the cell
+                uint32_t inc = cn + ex;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
                     const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
@@ -385,7 +408,10 @@ __global__ void __launch_bounds__(TT_WARPS * 32) k_tile_tables(TileTableArgs a, 
                 const uint32_t pend_g = __shfl_sync(0xffffffffu, g + cn, pl);
                 const bool has_prev = before ? true : carry_valid;
                 const uint32_t prev_end = before ? pend_g : carry_end;
-                const bool head = cn > 0 && !(has_prev && prev_end == g);
+                const uint32_t prev_q = before ? q0 + (uint32_t)pl : carry_q;
+                // a copy run never spans the pad slots on either side of the own block
+                const bool crosses = which == 0 && ((prev_q < ownB && q >= ownB) || (prev_q < ownE && q >= ownE));
+                const bool head = cn > 0 && !(has_prev && prev_end == g && !crosses);
                 const unsigned hm = __ballot_sync(0xffffffffu, head);
                 if (head) {
                     const uint32_t ri = carry_runs + (uint32_t)__popc(hm & lt);
@@ -396,9 +422,11 @@ __global__ void __launch_bounds__(TT_WARPS * 32) k_tile_tables(TileTableArgs a, 
                 if (ne) {
                     const int ll = 31 - __clz((int)ne);
                     carry_end = __shfl_sync(0xffffffffu, g + cn, ll);
+                    carry_q = q0 + (uint32_t)ll;
                     carry_valid = true;
                 }
             }
+            if (which == 0 && ownE >= (uint32_t)REGION_CELLS) carry += pad_after;  // the own block is last in slot order
             totals[which] = carry;
             nruns[which] = carry_runs < (uint32_t)MAX_RUNS ? carry_runs : (uint32_t)MAX_RUNS;
             for (uint32_t q = nruns[which] + lane; q < (uint32_t)MAX_RUNS; q += 32) runs[q] = make_uint2(0u, 0xFFFFFFFFu);
@@ -414,7 +442,7 @@ __global__ void __launch_bounds__(TT_WARPS * 32) k_tile_tables(TileTableArgs a, 
             h.own_lo = S.slot[0][REGION_AXIS + 1];  // region cell (1,1) == the tile's first cell
             h.nruns_d = nruns[0];
             h.nruns_s = nruns[1];
-            h.pad = 0;
+            h.pad = pad_before | (pad_after << 8);
             out->hdr = h;
             if (totals[0] > 0xFFFFu || totals[1] > 0xFFFFu) atomicMax(&ctl->err_tile_capacity, max(totals[0], totals[1]));
         }
@@ -458,9 +486,13 @@ __device__ __forceinline__ uint32_t dyn_slot_to_global(const TileRuns& tr, uint3
     return run_slot_to_global(tr.rd, s);
 }
 
-// list storage: per tile, base = pstart * 16 words; entry (k, tl) lives in 8-byte word (k/4)*pcount + tl, lane k%4
+// list storage: per tile, base = pstart * LIST_WORDS words; word kb of particle tl lives at kb * pcount + tl (a warp reads 256
+// contiguous bytes).  A word holds four u16 slots.  Dynamic neighbours fill words [0, ceil(cd / 4)), the last one PADDED with the
+// particle's own slot (a pair of a particle with itself contributes an exact zero to every pass but the density sum, so the
+// sweeps need no per-entry validity test); static neighbours follow from the next word on.
+constexpr int LIST_WORDS = YASPH_MAXN / 4 + 2;  // ceil(cd / 4) + ceil(cs / 4) <= 17 for cd + cs <= 64; even, so a tile's block is 16-byte aligned (bulk copies)
 __device__ __forceinline__ size_t list_word_index(uint32_t pstart, uint32_t pcount, uint32_t kb, uint32_t tl) {
-    return (size_t)pstart * (YASPH_MAXN / 4) + (size_t)kb * pcount + tl;
+    return (size_t)pstart * LIST_WORDS + (size_t)kb * pcount + tl;
 }
 __device__ __forceinline__ uint32_t unpack_slot(unsigned long long w, uint32_t k) { return (uint32_t)(w >> ((k & 3u) * 16)) & 0xFFFFu; }
 
@@ -509,6 +541,9 @@ struct ListSmem {
     uint32_t crun[2][TILE_CELLS][9];  // per own cell: slot_start << 16 | count, ascending, merged
     uint32_t ncand[2][TILE_CELLS];    // per own cell: total candidates
     unsigned long long wtotal[NB_THREADS / 32];
+    uint32_t nk_max;
+    uint32_t wk[NB_THREADS / 32][LIST_WORDS];  // particles per (warp, list-word count): the tile's work order
+    uint32_t wk_bin[LIST_WORDS];
     uint16_t sl[NB_ROWS][NB_THREADS];
 };
 inline size_t list_smem_bytes(uint32_t cap_dyn, uint32_t cap_stat) { return sizeof(ListSmem) + 2 * ((size_t)cap_dyn + cap_stat) * sizeof(float2); }
@@ -521,7 +556,8 @@ struct ListArgs {
     GridParams g;
     Control* ctl;
     unsigned long long* lists;
-    uchar2* counts;
+    uint32_t* counts;   // low half: count_dynamic | count_total << 8 of particle i; high half: work order of i's tile (see k_build_lists)
+    uint32_t* tile_nk;  // [tile] most list words of any particle of the tile
     uint32_t cap_dyn, cap_stat;
 };
 __device__ __forceinline__ void list_issue_stage(const ListArgs& a, uint32_t t, const TileRuns& tr, float2* sdyn, float2* sstat, uint32_t (*cs)[REGION_CELLS]) {
@@ -529,7 +565,11 @@ __device__ __forceinline__ void list_issue_stage(const ListArgs& a, uint32_t t, 
     for (uint32_t q = threadIdx.x; q < 2 * REGION_CELLS; q += NB_THREADS)
         cp_async<4>(&cs[q / REGION_CELLS][q % REGION_CELLS], (q < REGION_CELLS ? a.tt.cslot_d : a.tt.cslot_s) + (size_t)t * REGION_CELLS + q % REGION_CELLS);
     if (h.dyn_total > a.cap_dyn || h.stat_total > a.cap_stat) return;  // cannot happen: capacities are the maxima over all tiles
-    for (uint32_t s = threadIdx.x; s < h.dyn_total; s += NB_THREADS) cp_async<8>(&sdyn[s], &a.pos[dyn_slot_to_global(tr, s)]);
+    for (uint32_t s = threadIdx.x; s < h.pcount; s += NB_THREADS) cp_async<8>(&sdyn[h.own_lo + s], &a.pos[h.pstart + s]);
+    for (uint32_t q = threadIdx.x, na = tile_apron_count(h); q < na; q += NB_THREADS) {
+        const uint32_t s = tile_apron_slot(h, q);
+        cp_async<8>(&sdyn[s], &a.pos[run_slot_to_global(tr.rd, s)]);
+    }
     for (uint32_t s = threadIdx.x; s < h.stat_total; s += NB_THREADS) cp_async<8>(&sstat[s], &a.bpos[run_slot_to_global(tr.rs, s)]);
 }
 // candidates of one kind (dynamic / static) for one particle; returns the advanced hit count
@@ -559,7 +599,7 @@ __global__ void __launch_bounds__(NB_THREADS) k_build_lists(ListArgs a) {
     const uint32_t ntiles = a.ctl->num_tiles;
     const uint32_t tid = threadIdx.x, G = gridDim.x;
     unsigned long long my_total = 0;
-    uint32_t my_capped = 0, my_dropped = 0;
+    uint32_t my_capped = 0, my_dropped = 0, cta_nk = 0;
     {
         const uint32_t t0 = blockIdx.x, t1 = blockIdx.x + G;
         if (t0 < ntiles) load_tile_runs(S.runs[0], a.tt.runs + t0);
@@ -620,7 +660,11 @@ __global__ void __launch_bounds__(NB_THREADS) k_build_lists(ListArgs a) {
             if (cur != 0xFFFFFFFFu) S.crun[which][lc][nr++] = cur;
             S.ncand[which][lc] = tot;
         }
+        if (tid == 0) S.nk_max = 0u;
+        if (tid < (NB_THREADS / 32) * LIST_WORDS) (&S.wk[0][0])[tid] = 0u;
         __syncthreads();
+        uint32_t my_nk = 0, my_words = 0xFFu;
+        uint16_t* const counts16 = reinterpret_cast<uint16_t*>(a.counts);
         if (fits) {
             for (uint32_t tl = tid; tl < h.pcount; tl += NB_THREADS) {
                 const uint32_t i = h.pstart + tl;
@@ -641,17 +685,66 @@ __global__ void __launch_bounds__(NB_THREADS) k_build_lists(ListArgs a) {
                 } else if (c >= YASPH_MAXN) {
                     ++my_capped;
                 }
-                const uint32_t nkb = (ct + 3u) >> 2;
-                for (uint32_t kb = 0; kb < nkb; ++kb) {
+                const uint32_t nkd = (cd + 3u) >> 2, nks = (ct - cd + 3u) >> 2;
+                const unsigned long long own = h.own_lo + tl;
+                for (uint32_t kb = 0; kb < nkd; ++kb) {  // dynamic words, padded with the own slot
+                    unsigned long long w = 0ull;
+#pragma unroll
+                    for (uint32_t e = 0; e < 4; ++e) w |= (kb * 4 + e < cd ? (unsigned long long)col[(kb * 4 + e) * NB_THREADS] : own) << (16 * e);
+                    a.lists[list_word_index(h.pstart, h.pcount, kb, tl)] = w;
+                }
+                for (uint32_t kb = 0; kb < nks; ++kb) {  // static words
                     unsigned long long w = 0ull;
 #pragma unroll
                     for (uint32_t e = 0; e < 4; ++e)
-                        if (kb * 4 + e < ct) w |= (unsigned long long)col[(kb * 4 + e) * NB_THREADS] << (16 * e);
-                    a.lists[list_word_index(h.pstart, h.pcount, kb, tl)] = w;
+                        if (cd + kb * 4 + e < ct) w |= (unsigned long long)col[(cd + kb * 4 + e) * NB_THREADS] << (16 * e);
+                    a.lists[list_word_index(h.pstart, h.pcount, nkd + kb, tl)] = w;
                 }
-                a.counts[i] = make_uchar2((unsigned char)cd, (unsigned char)ct);
+                counts16[2 * (size_t)i] = (uint16_t)(cd | (ct << 8));
+                my_words = nkd + nks;
+                my_nk = max(my_nk, my_words);
                 my_total += ct;
             }
+        }
+        my_nk = __reduce_max_sync(0xffffffffu, my_nk);
+        if (lane_id() == 0 && my_nk) atomicMax(&S.nk_max, my_nk);
+        // Work order of the tile: its particles sorted (stably) by their number of list words.  The sweeps hand 32 consecutive
+        // entries of this order to one warp, so the lanes of a warp walk lists of (nearly) equal length.  Stored in the high
+        // half of counts[pstart + position].  Tiles of more than NB_THREADS particles keep the identity order.
+        const bool sortable = fits && h.pcount <= NB_THREADS;
+        const unsigned same = __match_any_sync(0xffffffffu, my_words);
+        if (sortable && my_words != 0xFFu && lane_id() == (unsigned)(__ffs(same) - 1)) S.wk[tid >> 5][my_words] = (uint32_t)__popc(same);
+        __syncthreads();  // also orders this tile's reads of S.crun / S.ncand before the next tile's writes
+        if (tid < 32) {
+            uint32_t tot = 0;
+            if (tid < LIST_WORDS) {
+#pragma unroll
+                for (int w = 0; w < NB_THREADS / 32; ++w) {
+                    const uint32_t v = S.wk[w][tid];
+                    S.wk[w][tid] = tot;  // exclusive over the warps
+                    tot += v;
+                }
+            }
+            uint32_t inc = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+                if (tid >= (uint32_t)o) inc += u;
+            }
+            if (tid < LIST_WORDS) S.wk_bin[tid] = inc - tot;
+        }
+        __syncthreads();
+        if (sortable) {
+            if (my_words != 0xFFu) {
+                const uint32_t position = S.wk_bin[my_words] + S.wk[tid >> 5][my_words] + (uint32_t)__popc(same & lanemask_lt());
+                counts16[2 * (size_t)(h.pstart + position) + 1] = (uint16_t)tid;
+            }
+        } else if (fits) {
+            for (uint32_t tl = tid; tl < h.pcount; tl += NB_THREADS) counts16[2 * (size_t)(h.pstart + tl) + 1] = (uint16_t)tl;
+        }
+        if (tid == 0) {
+            a.tile_nk[t] = S.nk_max;
+            cta_nk = max(cta_nk, S.nk_max);
         }
         pre.store(S.runs[(k + 2) % 3u], have2);
     }
@@ -673,12 +766,13 @@ __global__ void __launch_bounds__(NB_THREADS) k_build_lists(ListArgs a) {
         unsigned long long tot = 0;
         for (int w = 0; w < NB_THREADS / 32; ++w) tot += S.wtotal[w];
         if (tot) atomicAdd(&a.ctl->total_neighbors, tot);
+        if (cta_nk > *(volatile unsigned int*)&a.ctl->max_nk) atomicMax(&a.ctl->max_nk, cta_nk);
     }
 }
 
 // Export to the reference's layout (neighborhood_search.rs:268-273,433-449): u16 counts + u32 global indices, stride 64.
 __global__ void __launch_bounds__(256)
-    k_export_lists(TileTables tt, const Control* __restrict__ ctl, const unsigned long long* __restrict__ lists, const uchar2* __restrict__ counts,
+    k_export_lists(TileTables tt, const Control* __restrict__ ctl, const unsigned long long* __restrict__ lists, const uint32_t* __restrict__ counts,
                    uint16_t* __restrict__ out_cd, uint16_t* __restrict__ out_ct, uint32_t* __restrict__ out_lists) {
     __shared__ TileRuns tr;
     const uint32_t ntiles = ctl->num_tiles;
@@ -688,12 +782,15 @@ __global__ void __launch_bounds__(256)
         const TileHeader h = tr.hdr;
         for (uint32_t tl = threadIdx.x; tl < h.pcount; tl += blockDim.x) {
             const uint32_t i = h.pstart + tl;
-            const uchar2 c = counts[i];
-            out_cd[i] = c.x;
-            out_ct[i] = c.y;
+            const uint32_t cw = counts[i];
+            const uint2 c = make_uint2(cw & 0xFFu, (cw >> 8) & 0xFFu);
+            out_cd[i] = (uint16_t)c.x;
+            out_ct[i] = (uint16_t)c.y;
             if (out_lists) {
+                const uint32_t nkd = (c.x + 3u) >> 2;
                 for (uint32_t k = 0; k < c.y; ++k) {
-                    const uint32_t s = unpack_slot(lists[list_word_index(h.pstart, h.pcount, k >> 2, tl)], k);
+                    const uint32_t e = k < c.x ? k : nkd * 4u + (k - c.x);  // static entries start at a word boundary
+                    const uint32_t s = unpack_slot(lists[list_word_index(h.pstart, h.pcount, e >> 2, tl)], e);
                     out_lists[(size_t)i * YASPH_MAXN + k] = k < c.x ? dyn_slot_to_global(tr, s) : run_slot_to_global(tr.rs, s);
                 }
             }

@@ -26,17 +26,37 @@
 
 namespace yasph {
 
-constexpr int SW_THREADS = TILE_THREADS;
+#ifndef YASPH_SWEEP_PRODUCERS
+#define YASPH_SWEEP_PRODUCERS 2
+#endif
+#ifndef YASPH_SWEEP_CONSUMERS
+#define YASPH_SWEEP_CONSUMERS 8
+#endif
+constexpr int SW_PRODUCER_WARPS = YASPH_SWEEP_PRODUCERS;  // warps 0.. stage tiles into shared memory
+constexpr int SW_CONSUMER_WARPS = YASPH_SWEEP_CONSUMERS;  // the other warps compute
+constexpr int SW_THREADS = 32 * (SW_PRODUCER_WARPS + SW_CONSUMER_WARPS);
+#ifndef YASPH_SWEEP_MIN_CTAS
+#define YASPH_SWEEP_MIN_CTAS 1
+#endif
+#ifndef YASPH_SWEEP_STAGES
+#define YASPH_SWEEP_STAGES 3
+#endif
+constexpr int SW_STAGES = YASPH_SWEEP_STAGES;  // stages of the shared-memory ring (fewer at run time when tiles are very large)
+constexpr uint32_t SW_MAX_STAGED_WORDS = 8;  // list words per particle staged in shared memory (the rest, if any, is read from global memory)
 
 struct SweepCommon {
     TileTables tt;
+    const uint32_t* tile_nk;  // [tile] most list words of any particle of the tile
     const unsigned long long* lists;
-    const uchar2* counts;
+    const uint32_t* counts;   // per particle: count_dynamic | count_total << 8
     const float2* pos;
     const float2* bpos;
     Control* ctl;
     KernelConsts kc;
-    uint32_t cap_dyn, cap_stat;
+    uint32_t cap_dyn, cap_stat;  // staged candidates of the largest tile (multiples of 16)
+    uint32_t cap_pc;             // particles of the largest tile (multiple of 16)
+    uint32_t nk_stage;           // list words per particle that fit the stage (<= SW_MAX_STAGED_WORDS)
+    uint32_t nstages;            // ring depth, 1..SW_STAGES
     uint32_t n;
     float mass, rho0;
     double* partials;  // [gridDim.x]
@@ -50,134 +70,299 @@ enum ReduceKind { REDUCE_NONE = 0, REDUCE_SUM = 1, REDUCE_MAX = 2 };
 
 struct NoPay {};
 
-// per-buffer shared-memory layout of a sweep: float2 pos[cap_dyn] | P0[cap_dyn] | P1[cap_dyn] | float2 stat[cap_stat]
+// ---- mbarrier / bulk-copy primitives (sm_90+ PTX) ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(void* bar) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(void* bar, uint32_t bytes) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// the calling thread's earlier cp.async copies arrive on the barrier when they have landed (does not raise the pending count)
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(void* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        " .reg .pred p;\n"
+        "MBAR_WAIT:\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x10000;\n"  // suspend-time hint (ns): the warp sleeps instead of spinning
+        " @p bra MBAR_DONE;\n"
+        " bra MBAR_WAIT;\n"
+        "MBAR_DONE:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA unit; completion is counted in bytes on the barrier.  16-byte aligned, 16 | bytes.
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, void* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---- shared-memory layout -------------------------------------------------------------------------------------------------
+// [ full[SW_STAGES] | empty[SW_STAGES] mbarriers ][ TileRuns x2 (producer) ][ stage 0 ][ stage 1 ] ...
+// stage: TileHeader | nk | float2 pos[cap_dyn] | P0[cap_dyn] | P1[cap_dyn] | float2 stat[cap_stat] | u32 cnt[cap_pc] | O0[cap_pc] |
+//        O1[cap_pc] | u64 lists[nk_stage * cap_pc]
 template <class Op>
 struct SweepLayout {
     static constexpr size_t P0 = Op::NPAY >= 1 ? sizeof(typename Op::P0) : 0;
     static constexpr size_t P1 = Op::NPAY >= 2 ? sizeof(typename Op::P1) : 0;
-    __host__ __device__ static size_t buffer_bytes(uint32_t cap_dyn, uint32_t cap_stat) {
-        return (size_t)cap_dyn * (sizeof(float2) + P0 + P1) + (Op::USES_STATIC ? (size_t)cap_stat * sizeof(float2) : 0);
+    static constexpr size_t O0 = Op::NOWN >= 1 ? sizeof(typename Op::O0) : 0;
+    static constexpr size_t O1 = Op::NOWN >= 2 ? sizeof(typename Op::O1) : 0;
+    static constexpr size_t HEAD = 128;                                   // barriers
+    static constexpr size_t RUNS = 2 * SW_PRODUCER_WARPS * sizeof(TileRuns);  // every producer warp's copy-run tables
+    static constexpr size_t STAGE_HDR = 48;                               // TileHeader + nk, padded to 16
+    __host__ __device__ static size_t stage_bytes(uint32_t cap_dyn, uint32_t cap_stat, uint32_t cap_pc, uint32_t nk_stage) {
+        return STAGE_HDR + (size_t)cap_dyn * (sizeof(float2) + P0 + P1) + (Op::USES_STATIC ? (size_t)cap_stat * sizeof(float2) : 0) +
+               (size_t)cap_pc * (4 + O0 + O1) + (size_t)nk_stage * cap_pc * 8;
     }
-    __host__ __device__ static size_t total_bytes(uint32_t cap_dyn, uint32_t cap_stat) { return 3 * sizeof(TileRuns) + 2 * buffer_bytes(cap_dyn, cap_stat); }
+    __host__ __device__ static size_t total_bytes(uint32_t cap_dyn, uint32_t cap_stat, uint32_t cap_pc, uint32_t nk_stage, uint32_t nstages) {
+        return HEAD + RUNS + nstages * stage_bytes(cap_dyn, cap_stat, cap_pc, nk_stage);
+    }
 };
 template <class Op>
-inline size_t sweep_smem_bytes(uint32_t cap_dyn, uint32_t cap_stat) {
-    return SweepLayout<Op>::total_bytes(cap_dyn, cap_stat);
-}
-
-template <class Op>
-struct SweepBuffer {
+struct SweepStage {
+    TileHeader* hdr;
+    uint32_t* nk;
     float2* pos;
     typename Op::P0* p0;
     typename Op::P1* p1;
     float2* stat;
-    __device__ __forceinline__ SweepBuffer(unsigned char* base, uint32_t cap_dyn) {
-        pos = reinterpret_cast<float2*>(base);
-        p0 = reinterpret_cast<typename Op::P0*>(base + (size_t)cap_dyn * sizeof(float2));
-        p1 = reinterpret_cast<typename Op::P1*>(base + (size_t)cap_dyn * (sizeof(float2) + SweepLayout<Op>::P0));
-        stat = reinterpret_cast<float2*>(base + (size_t)cap_dyn * (sizeof(float2) + SweepLayout<Op>::P0 + SweepLayout<Op>::P1));
+    uint32_t* cnt;
+    typename Op::O0* o0;
+    typename Op::O1* o1;
+    unsigned long long* lists;
+    __device__ __forceinline__ SweepStage(unsigned char* b, uint32_t cap_dyn, uint32_t cap_stat, uint32_t cap_pc) {
+        typedef SweepLayout<Op> L;
+        hdr = reinterpret_cast<TileHeader*>(b);
+        nk = reinterpret_cast<uint32_t*>(b + sizeof(TileHeader));
+        b += L::STAGE_HDR;
+        pos = reinterpret_cast<float2*>(b);
+        b += (size_t)cap_dyn * sizeof(float2);
+        p0 = reinterpret_cast<typename Op::P0*>(b);
+        b += (size_t)cap_dyn * L::P0;
+        p1 = reinterpret_cast<typename Op::P1*>(b);
+        b += (size_t)cap_dyn * L::P1;
+        stat = reinterpret_cast<float2*>(b);
+        b += Op::USES_STATIC ? (size_t)cap_stat * sizeof(float2) : 0;
+        cnt = reinterpret_cast<uint32_t*>(b);
+        b += (size_t)cap_pc * 4;
+        o0 = reinterpret_cast<typename Op::O0*>(b);
+        b += (size_t)cap_pc * L::O0;
+        o1 = reinterpret_cast<typename Op::O1*>(b);
+        b += (size_t)cap_pc * L::O1;
+        lists = reinterpret_cast<unsigned long long*>(b);
     }
 };
-
+// list words per particle that fit a stage when the whole kernel may use `budget` bytes of shared memory
 template <class Op>
-__device__ __forceinline__ void sweep_issue_stage(const SweepCommon& c, const Op& op, const TileRuns& tr, const SweepBuffer<Op>& b) {
-    const TileHeader& h = tr.hdr;
-    if (h.dyn_total > c.cap_dyn || h.stat_total > c.cap_stat) return;  // cannot happen: capacities are the maxima over all tiles
-    for (uint32_t s = threadIdx.x; s < h.dyn_total; s += SW_THREADS) {
-        const uint32_t g = dyn_slot_to_global(tr, s);
-        cp_async<8>(&b.pos[s], &c.pos[g]);
-        if constexpr (Op::NPAY >= 1) cp_async<sizeof(typename Op::P0)>(&b.p0[s], &op.pay0()[g]);
-        if constexpr (Op::NPAY >= 2) cp_async<sizeof(typename Op::P1)>(&b.p1[s], &op.pay1()[g]);
+inline uint32_t sweep_nk_stage(uint32_t cap_dyn, uint32_t cap_stat, uint32_t cap_pc, uint32_t nk_max, uint32_t nstages, size_t budget) {
+    uint32_t nk = nk_max < SW_MAX_STAGED_WORDS ? nk_max : SW_MAX_STAGED_WORDS;
+    while (nk > 0 && SweepLayout<Op>::total_bytes(cap_dyn, cap_stat, cap_pc, nk, nstages) > budget) --nk;
+    return nk;
+}
+
+// slot of entry q of a list word, from constant shifts
+__device__ __forceinline__ uint32_t word_slot(unsigned long long w, uint32_t q) {
+    const uint32_t half = q < 2 ? (uint32_t)w : (uint32_t)(w >> 32);
+    return (q & 1u) ? (half >> 16) : (half & 0xFFFFu);
+}
+
+// ---- producer warps: stage one tile ---------------------------------------------------------------------------------------
+// Contiguous pieces travel as 16-byte aligned bulk copies (TMA unit, one instruction each, issued by one lane): the own
+// particles' positions and payloads into their slots (TileHeader: pad slots absorb the alignment surplus), their counts and
+// per-particle operands, and the tile's block of list words.  Only the apron (candidates from the eight surrounding tiles,
+// ~36 short runs) and the boundary candidates are copied element-wise with cp.async, spread over the producer warps.
+template <class Op>
+__device__ __forceinline__ void sweep_stage_tile(const SweepCommon& c, const Op& op, const TileRuns& tr, uint32_t nk_tile, const SweepStage<Op>& st, void* full_bar,
+                                                 uint32_t pw) {
+    typedef SweepLayout<Op> L;
+    const uint32_t lane = lane_id();
+    const uint32_t first = pw * 32u + lane, stride = 32u * SW_PRODUCER_WARPS;  // the producer warps interleave
+    const TileHeader h = tr.hdr;
+    const uint32_t d = h.pstart & 3u;
+    const uint32_t nel = (d + h.pcount + 3u) & ~3u;  // elements of the aligned own range [pstart - d, roundup4(pstart + pcount))
+    const bool fits = h.dyn_total <= c.cap_dyn && h.stat_total <= c.cap_stat && nel <= c.cap_pc;  // always: capacities are the maxima over all tiles
+    const uint32_t nk = nk_tile < c.nk_stage ? nk_tile : c.nk_stage;
+    if (lane == 0 && pw == 0) {
+        *st.hdr = h;
+        *st.nk = fits ? nk : 0xFFFFFFFFu;
     }
-    if (Op::USES_STATIC)
-        for (uint32_t s = threadIdx.x; s < h.stat_total; s += SW_THREADS) cp_async<8>(&b.stat[s], &c.bpos[run_slot_to_global(tr.rs, s)]);
+    if (fits) {
+        for (uint32_t a = first, na = tile_apron_count(h); a < na; a += stride) {
+            const uint32_t s = tile_apron_slot(h, a);
+            const uint32_t g = run_slot_to_global(tr.rd, s);
+            cp_async<8>(&st.pos[s], &c.pos[g]);
+            if constexpr (Op::NPAY >= 1) cp_async<sizeof(typename Op::P0)>(&st.p0[s], &op.pay0()[g]);
+            if constexpr (Op::NPAY >= 2) cp_async<sizeof(typename Op::P1)>(&st.p1[s], &op.pay1()[g]);
+        }
+        if (Op::USES_STATIC)
+            for (uint32_t s = first; s < h.stat_total; s += stride) cp_async<8>(&st.stat[s], &c.bpos[run_slot_to_global(tr.rs, s)]);
+    }
+    cp_async_mbar_arrive_noinc(full_bar);  // 32 arrivals per producer warp: this lane's copies have landed
+    __syncwarp();                          // lane 0's header stores are ordered before its arrival below
+    if (lane == 0 && pw == 0) {
+        if (fits) {
+            const uint32_t lbytes = (nk * h.pcount * 8u + 15u) & ~15u;  // the first nk list words of every particle: one contiguous block
+            mbar_arrive_expect_tx(full_bar, nel * (uint32_t)(sizeof(float2) + L::P0 + L::P1 + 4 + L::O0 + L::O1) + lbytes);
+            const size_t g0 = h.pstart - d;
+            const uint32_t s0 = h.own_lo - d;
+            bulk_copy_g2s(st.pos + s0, c.pos + g0, nel * (uint32_t)sizeof(float2), full_bar);
+            if constexpr (Op::NPAY >= 1) bulk_copy_g2s(st.p0 + s0, op.pay0() + g0, nel * (uint32_t)L::P0, full_bar);
+            if constexpr (Op::NPAY >= 2) bulk_copy_g2s(st.p1 + s0, op.pay1() + g0, nel * (uint32_t)L::P1, full_bar);
+            bulk_copy_g2s(st.cnt, c.counts + g0, nel * 4u, full_bar);
+            if constexpr (Op::NOWN >= 1) bulk_copy_g2s(st.o0, op.own0() + g0, nel * (uint32_t)L::O0, full_bar);
+            if constexpr (Op::NOWN >= 2) bulk_copy_g2s(st.o1, op.own1() + g0, nel * (uint32_t)L::O1, full_bar);
+            if (lbytes) bulk_copy_g2s(st.lists, c.lists + (size_t)h.pstart * LIST_WORDS, lbytes, full_bar);
+        } else {
+            mbar_arrive(full_bar);
+        }
+    }
 }
 
 template <class Op>
-__global__ void __launch_bounds__(SW_THREADS) k_sweep(SweepCommon c, Op op) {
+__global__ void __launch_bounds__(SW_THREADS, YASPH_SWEEP_MIN_CTAS) k_sweep(SweepCommon c, Op op) {
     typedef typename Op::P0 P0;
     typedef typename Op::P1 P1;
+    typedef SweepLayout<Op> L;
     if (op.skip(c.ctl)) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    TileRuns* runs = reinterpret_cast<TileRuns*>(smem_raw);  // [3]
-    const size_t bbytes = SweepLayout<Op>::buffer_bytes(c.cap_dyn, c.cap_stat);
-    const SweepBuffer<Op> buf0(smem_raw + 3 * sizeof(TileRuns), c.cap_dyn), buf1(smem_raw + 3 * sizeof(TileRuns) + bbytes, c.cap_dyn);
+    unsigned long long* full_bar = reinterpret_cast<unsigned long long*>(smem_raw);
+    unsigned long long* empty_bar = full_bar + SW_STAGES;
+    const uint32_t NS = c.nstages;
+    TileRuns* runs = reinterpret_cast<TileRuns*>(smem_raw + L::HEAD) + 2 * (threadIdx.x >> 5);  // [2] per producer warp
+    const size_t sbytes = L::stage_bytes(c.cap_dyn, c.cap_stat, c.cap_pc, c.nk_stage);
+    unsigned char* stage0 = smem_raw + L::HEAD + L::RUNS;
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < NS; ++s) {
+            mbar_init(&full_bar[s], 32 * SW_PRODUCER_WARPS + 1);  // cp.async arrivals of every producer lane + the bulk-copy / plain arrival
+            mbar_init(&empty_bar[s], SW_CONSUMER_WARPS);  // every consumer warp releases the stage
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     op.prepare(c);
+    __syncthreads();
     const uint32_t ntiles = c.ctl->num_tiles;
     const uint32_t G = gridDim.x;
     double racc = 0.0;
-    // prologue: tables of the first two tiles, copies of the first
-    {
-        const uint32_t t0 = blockIdx.x, t1 = blockIdx.x + G;
-        if (t0 < ntiles) load_tile_runs(runs[0], c.tt.runs + t0);
-        if (t1 < ntiles) load_tile_runs(runs[1], c.tt.runs + t1);
-        __syncthreads();
-        if (t0 < ntiles) sweep_issue_stage(c, op, runs[0], buf0);
-        cp_async_commit();
-    }
-    uint32_t k = 0;
-    for (uint32_t t = blockIdx.x; t < ntiles; t += G, ++k) {
-        const SweepBuffer<Op>& cur = (k & 1u) ? buf1 : buf0;
-        const SweepBuffer<Op>& nxt = (k & 1u) ? buf0 : buf1;
-        const TileRuns& tr = runs[k % 3u];
-        RunsPrefetch pre;
-        const bool have2 = t + 2 * G < ntiles;
-        pre.load(c.tt.runs + t + 2 * G, have2);
-        cp_async_wait_all();
-        __syncthreads();  // this tile's copies have landed; everybody is done with the previous tile's buffers
-        if (t + G < ntiles) sweep_issue_stage(c, op, runs[(k + 1) % 3u], nxt);
-        cp_async_commit();
-        const TileHeader h = tr.hdr;
-        if (h.dyn_total <= c.cap_dyn && h.stat_total <= c.cap_stat) {
-            for (uint32_t tl = threadIdx.x; tl < h.pcount; tl += SW_THREADS) {
-                const uint32_t i = h.pstart + tl;
-                const uint32_t own = h.own_lo + tl;
-                const float2 pi = cur.pos[own];
-                P0 s0;
-                P1 s1;
-                if (Op::NPAY >= 1) s0 = cur.p0[own];
-                if (Op::NPAY >= 2) s1 = cur.p1[own];
-                const uchar2 cnt = c.counts[i];
-                const uint32_t cd = cnt.x, ct = Op::USES_STATIC ? cnt.y : cnt.x;
-                typename Op::Acc acc;
-                const bool active = op.init(c, acc, i, pi, s0, s1, cnt.y);
-                if (active) {
-                    // dynamic neighbours: entries [0, cd), four per 8-byte word, next word prefetched
-                    const uint32_t nkb = (cd + 3u) >> 2;
-                    unsigned long long w = nkb ? c.lists[list_word_index(h.pstart, h.pcount, 0, tl)] : 0ull;
-                    for (uint32_t kb = 0; kb < nkb; ++kb) {
-                        const unsigned long long wn = (kb + 1 < nkb) ? c.lists[list_word_index(h.pstart, h.pcount, kb + 1, tl)] : 0ull;
-#pragma unroll
-                        for (uint32_t q = 0; q < 4; ++q) {
-                            const bool valid = kb * 4 + q < cd;
-                            const uint32_t slot = valid ? ((uint32_t)(w >> (16 * q)) & 0xFFFFu) : own;
-                            P0 n0;
-                            P1 n1;
-                            if (Op::NPAY >= 1) n0 = cur.p0[slot];
-                            if (Op::NPAY >= 2) n1 = cur.p1[slot];
-                            typename Op::Acc trial = acc;
-                            op.dyn(c, trial, pi, s0, s1, cur.pos[slot], n0, n1);
-                            if (valid) acc = trial;
-                        }
-                        w = wn;
-                    }
-                    // static neighbours: entries [cd, ct) of the same list (only near boundaries)
-                    if (Op::USES_STATIC) {
-                        for (uint32_t kk = cd; kk < ct; ++kk) {
-                            const uint32_t slot = unpack_slot(c.lists[list_word_index(h.pstart, h.pcount, kk >> 2, tl)], kk);
-                            op.stat(c, acc, pi, s0, s1, cur.stat[slot]);
-                        }
-                    }
-                }
-                double r = op.finish(c, acc, i, pi, s0, s1, active);
-                if (Op::REDUCE != REDUCE_NONE && c.ghost != nullptr && c.ghost[i]) r = 0.0;
-                if (Op::REDUCE == REDUCE_SUM) racc += r;
-                if (Op::REDUCE == REDUCE_MAX) racc = fmax(racc, r);
+    if (warp < SW_PRODUCER_WARPS) {
+        // ---------------- producers ----------------
+        uint4 pre[2];
+        uint32_t pre_nk = 0;
+        const uint32_t NV = sizeof(TileRuns) / 16;
+        static_assert(sizeof(TileRuns) / 16 <= 64, "two uint4 per lane");
+        auto prefetch = [&](uint32_t t) {
+            if (t < ntiles) {
+                const uint4* src = reinterpret_cast<const uint4*>(c.tt.runs + t);
+                if (lane < NV) pre[0] = src[lane];
+                if (lane + 32 < NV) pre[1] = src[lane + 32];
+                pre_nk = c.tile_nk[t];
+            }
+        };
+        prefetch(blockIdx.x);
+        uint32_t k = 0, stage = 0, round = 0;  // round: completed passes over the ring
+        for (uint32_t t = blockIdx.x; t < ntiles; t += G, ++k) {
+            TileRuns& tr = runs[k & 1u];
+            uint4* dst = reinterpret_cast<uint4*>(&tr);
+            if (lane < NV) dst[lane] = pre[0];
+            if (lane + 32 < NV) dst[lane + 32] = pre[1];
+            const uint32_t nk_tile = pre_nk;
+            __syncwarp();
+            prefetch(t + G);  // in flight while this tile is staged
+            if (round) mbar_wait(&empty_bar[stage], (round - 1u) & 1u);  // every consumer warp has released the stage
+            const SweepStage<Op> st(stage0 + stage * sbytes, c.cap_dyn, c.cap_stat, c.cap_pc);
+            sweep_stage_tile(c, op, tr, nk_tile, st, &full_bar[stage], warp);
+            if (++stage == NS) {
+                stage = 0;
+                ++round;
             }
         }
-        pre.store(runs[(k + 2) % 3u], have2);  // last read before this iteration's barrier; next read after the next one
+    } else {
+        // ---------------- consumers ----------------
+        const uint32_t cw = warp - SW_PRODUCER_WARPS;
+        uint32_t chunk_base = 0;  // chunks (32 particles) of all earlier tiles of this CTA: chunks are dealt round-robin to the warps
+        uint32_t stage = 0, round = 0;
+        for (uint32_t t = blockIdx.x; t < ntiles; t += G) {
+            const SweepStage<Op> st(stage0 + stage * sbytes, c.cap_dyn, c.cap_stat, c.cap_pc);
+            mbar_wait(&full_bar[stage], round & 1u);
+            const TileHeader h = *st.hdr;
+            const uint32_t nk_st = *st.nk;
+            const uint32_t nchunks = (h.pcount + 31u) >> 5;
+            const uint32_t od = h.pstart & 3u;  // the per-particle operand arrays are staged from the 4-element-aligned index below pstart
+            if (nk_st != 0xFFFFFFFFu) {
+                for (uint32_t j = (cw + SW_CONSUMER_WARPS - chunk_base % SW_CONSUMER_WARPS) % SW_CONSUMER_WARPS; j < nchunks; j += SW_CONSUMER_WARPS) {
+                    const uint32_t wo = j * 32u + lane;  // entry of the tile's work order: its particles sorted by list length
+                    if (wo < h.pcount) {
+                        const uint32_t tl = st.cnt[od + wo] >> 16;
+                        const uint32_t i = h.pstart + tl;
+                        const uint32_t own = h.own_lo + tl;
+                        const float2 pi = st.pos[own];
+                        P0 s0;
+                        P1 s1;
+                        if (Op::NPAY >= 1) s0 = st.p0[own];
+                        if (Op::NPAY >= 2) s1 = st.p1[own];
+                        const uint32_t cnt = st.cnt[od + tl] & 0xFFFFu;
+                        const uint32_t cd = cnt & 0xFFu, ct = (cnt >> 8) & 0xFFu;
+                        typename Op::O0 w0;
+                        typename Op::O1 w1;
+                        if (Op::NOWN >= 1) w0 = st.o0[od + tl];
+                        if (Op::NOWN >= 2) w1 = st.o1[od + tl];
+                        typename Op::Acc acc;
+                        const bool active = op.init(c, acc, i, pi, s0, s1, ct);
+                        const uint32_t nkd = (cd + 3u) >> 2;
+                        if (active) {
+                            // dynamic neighbours: nkd words of four slots; the last word is padded with the particle's own slot, whose
+                            // pair contributes an exact zero unless the pass says otherwise (PAD_IS_ZERO == false: density)
+                            for (uint32_t kb = 0; kb < nkd; ++kb) {
+                                const unsigned long long w = kb < nk_st ? st.lists[kb * h.pcount + tl] : c.lists[list_word_index(h.pstart, h.pcount, kb, tl)];
+#pragma unroll
+                                for (uint32_t q = 0; q < 4; ++q) {
+                                    const uint32_t slot = word_slot(w, q);
+                                    P0 n0;
+                                    P1 n1;
+                                    if (Op::NPAY >= 1) n0 = st.p0[slot];
+                                    if (Op::NPAY >= 2) n1 = st.p1[slot];
+                                    if (Op::PAD_IS_ZERO) {
+                                        op.dyn(c, acc, pi, s0, s1, st.pos[slot], n0, n1);
+                                    } else {
+                                        typename Op::Acc trial = acc;
+                                        op.dyn(c, trial, pi, s0, s1, st.pos[slot], n0, n1);
+                                        if (kb * 4 + q < cd) acc = trial;
+                                    }
+                                }
+                            }
+                            // static neighbours: ct - cd entries from word nkd on (only near boundaries)
+                            if (Op::USES_STATIC) {
+                                for (uint32_t e = 0; e < ct - cd; ++e) {
+                                    const uint32_t kb = nkd + (e >> 2);
+                                    const unsigned long long w = kb < nk_st ? st.lists[kb * h.pcount + tl] : c.lists[list_word_index(h.pstart, h.pcount, kb, tl)];
+                                    op.stat(c, acc, pi, s0, s1, st.stat[unpack_slot(w, e)]);
+                                }
+                            }
+                        }
+                        double r = op.finish(c, acc, i, pi, s0, s1, active, w0, w1);
+                        if (Op::REDUCE != REDUCE_NONE && c.ghost != nullptr && c.ghost[i]) r = 0.0;
+                        if (Op::REDUCE == REDUCE_SUM) racc += r;
+                        if (Op::REDUCE == REDUCE_MAX) racc = fmax(racc, r);
+                    }
+                }
+            }
+            chunk_base += nchunks;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[stage]);  // this warp is done with the stage
+            if (++stage == NS) {
+                stage = 0;
+                ++round;
+            }
+        }
     }
-    cp_async_wait_all();
     if (Op::REDUCE != REDUCE_NONE) {
         __shared__ double wred[SW_THREADS / 32];
         __shared__ bool is_last;
@@ -186,7 +371,7 @@ __global__ void __launch_bounds__(SW_THREADS) k_sweep(SweepCommon c, Op op) {
             double u = __shfl_xor_sync(0xffffffffu, racc, o);
             racc = Op::REDUCE == REDUCE_SUM ? racc + u : fmax(racc, u);
         }
-        if (lane_id() == 0) wred[threadIdx.x >> 5] = racc;
+        if (lane == 0) wred[warp] = racc;  // the producer warp contributes the neutral 0 (all reduced quantities are >= 0)
         __syncthreads();
         if (threadIdx.x == 0) {
             double tsum = wred[0];
@@ -210,7 +395,7 @@ __global__ void __launch_bounds__(SW_THREADS) k_sweep(SweepCommon c, Op op) {
                 v = Op::REDUCE == REDUCE_SUM ? v + u : fmax(v, u);
             }
             __syncthreads();
-            if (lane_id() == 0) wred[threadIdx.x >> 5] = v;
+            if (lane == 0) wred[warp] = v;
             __syncthreads();
             if (threadIdx.x == 0) {
                 double tot = wred[0];
@@ -236,6 +421,12 @@ struct OpDensityAlpha {
     static constexpr bool USES_STATIC = true;
     static constexpr int REDUCE = REDUCE_NONE;
     static constexpr int TICKET = 0;
+    static constexpr bool PAD_IS_ZERO = false;  // W(0) * m is not zero: padded entries are masked
+    typedef NoPay O0;
+    typedef NoPay O1;
+    static constexpr int NOWN = 0;
+    __device__ __forceinline__ const O0* own0() const { return nullptr; }
+    __device__ __forceinline__ const O1* own1() const { return nullptr; }
     struct Acc {
         float dens;
         float2 gsum;
@@ -274,7 +465,7 @@ struct OpDensityAlpha {
     }
     __device__ __forceinline__ void dyn(const SweepCommon& c, Acc& a, float2 pi, P0, P1, float2 pj, P0, P1) const { pair(c, a, pi, pj); }
     __device__ __forceinline__ void stat(const SweepCommon& c, Acc& a, float2 pi, P0, P1, float2 pb) const { pair(c, a, pi, pb); }
-    __device__ __forceinline__ double finish(const SweepCommon& c, Acc& a, uint32_t i, float2, P0, P1, bool) const {
+    __device__ __forceinline__ double finish(const SweepCommon& c, Acc& a, uint32_t i, float2, P0, P1, bool, O0, O1) const {
         const float rho = fmaxf(a.dens, c.rho0);  // fluidparticleworld.rs:229
         dens[i] = rho;
         if (WITH_ALPHA) alpha[i] = 1.0f / fmaxf(mag2(a.gsum) + a.gsq, 1e-6f);  // dfsph.rs:94
@@ -286,7 +477,7 @@ struct OpDensityAlpha {
 
 // alpha only (yasph_compute_alpha: dfsph.rs:68-97 on its own)
 struct OpAlphaOnly : OpDensityAlpha<0, true> {
-    __device__ __forceinline__ double finish(const SweepCommon&, Acc& a, uint32_t i, float2, P0, P1, bool) const {
+    __device__ __forceinline__ double finish(const SweepCommon&, Acc& a, uint32_t i, float2, P0, P1, bool, O0, O1) const {
         alpha[i] = 1.0f / fmaxf(mag2(a.gsum) + a.gsq, 1e-6f);
         return 0.0;
     }
@@ -311,6 +502,12 @@ struct OpViscosity {
     static constexpr bool USES_STATIC = false;
     static constexpr int REDUCE = REDUCE_MAX;
     static constexpr int TICKET = 1;
+    static constexpr bool PAD_IS_ZERO = true;  // s * (v_i - v_i) == 0
+    typedef NoPay O0;
+    typedef NoPay O1;
+    static constexpr int NOWN = 0;
+    __device__ __forceinline__ const O0* own0() const { return nullptr; }
+    __device__ __forceinline__ const O1* own1() const { return nullptr; }
     typedef float2 Acc;
     const float2* vel;
     const float* dens;
@@ -334,7 +531,7 @@ struct OpViscosity {
         a = a + s * (vj - vi);
     }
     __device__ __forceinline__ void stat(const SweepCommon&, Acc&, float2, P0, P1, float2) const {}
-    __device__ __forceinline__ double finish(const SweepCommon&, Acc& a, uint32_t i, float2, P0 vi, P1, bool) const {
+    __device__ __forceinline__ double finish(const SweepCommon&, Acc& a, uint32_t i, float2, P0 vi, P1, bool, O0, O1) const {
         accel[i] = a;
         return (double)mag2(vi + a * dt);  // dfsph.rs:476
     }
@@ -386,6 +583,12 @@ struct OpJacobiA {
     static constexpr bool USES_STATIC = true;
     static constexpr int REDUCE = REDUCE_SUM;
     static constexpr int TICKET = 2;
+    static constexpr bool PAD_IS_ZERO = true;  // (v_i - v_i) . grad == 0
+    typedef float O0;  // rho_i
+    typedef float O1;  // alpha_i
+    static constexpr int NOWN = 2;
+    __device__ __forceinline__ const O0* own0() const { return dens; }
+    __device__ __forceinline__ const O1* own1() const { return alpha; }
     typedef float Acc;
     const float2* vstar;
     const float* dens;
@@ -408,15 +611,15 @@ struct OpJacobiA {
     __device__ __forceinline__ void stat(const SweepCommon& c, Acc& a, float2 pi, P0 vi, P1, float2 pb) const {
         a += dot2(vi, wendland_grad_from_positions(c.kc, pi, pb));
     }
-    __device__ __forceinline__ double finish(const SweepCommon& c, Acc& a, uint32_t i, float2, P0, P1, bool active) const {
+    __device__ __forceinline__ double finish(const SweepCommon& c, Acc& a, uint32_t i, float2, P0, P1, bool active, O0 rho_i, O1 alpha_i) const {
         float e;
         if (SOLVER == 0) {
-            e = dens[i] + a * c.mass * dt;       // dfsph.rs:121
+            e = rho_i + a * c.mass * dt;         // dfsph.rs:121
             e = fmaxf(c.rho0, e) - c.rho0;       // dfsph.rs:124
         } else {
             e = active ? fmaxf(a * c.mass, 0.0f) : 0.0f;  // dfsph.rs:262,277-278
         }
-        kfac[i] = e * alpha[i];
+        kfac[i] = e * alpha_i;
         return (double)e;
     }
     __device__ __forceinline__ void finalize(const SweepCommon& c, double sum) const {
@@ -430,6 +633,77 @@ __global__ void k_jacobi_decide(Control* ctl, SolverParams sp, uint32_t iter_ind
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// densities + alpha factors + the first density-change pass of the divergence solver in ONE sweep
+// ---------------------------------------------------------------------------------------------------------------------
+// update_densities (fluidparticleworld.rs:197-231), compute_alpha_factors (dfsph.rs:68-97) and iteration 0 of
+// compute_density_change (dfsph.rs:249-280) walk the same neighbours with the same r_ij and the same gradient and need
+// nothing from the neighbours that an earlier pass of this step has to produce (positions and v* only), so the step runs
+// them as one sweep whenever the divergence warm start -- which would move v* first (dfsph.rs:354-360) -- does not run.
+// Every accumulator keeps its own reference order, so each result is bit-identical to the three separate passes.
+struct OpDensityAlphaDiv {
+    typedef float2 P0;  // predicted velocity
+    typedef NoPay P1;
+    static constexpr int NPAY = 1;
+    static constexpr bool USES_STATIC = true;
+    static constexpr int REDUCE = REDUCE_SUM;
+    static constexpr int TICKET = 2;
+    static constexpr bool PAD_IS_ZERO = false;
+    typedef NoPay O0;
+    typedef NoPay O1;
+    static constexpr int NOWN = 0;
+    __device__ __forceinline__ const O0* own0() const { return nullptr; }
+    __device__ __forceinline__ const O1* own1() const { return nullptr; }
+    struct Acc {
+        float dens;
+        float2 gsum;
+        float gsq;
+        float div;
+        uint32_t ct;
+    };
+    const float2* vstar;
+    float* dens;
+    float* alpha;
+    float* kfac;
+    SolverParams sp;
+    __device__ __forceinline__ const P0* pay0() const { return vstar; }
+    __device__ __forceinline__ const P1* pay1() const { return nullptr; }
+    __device__ __forceinline__ bool skip(const Control*) const { return false; }
+    __device__ __forceinline__ void prepare(const SweepCommon&) {}
+    __device__ __forceinline__ bool init(const SweepCommon& c, Acc& a, uint32_t, float2, P0, P1, uint32_t ct) const {
+        a.dens = wendland_w(c.kc, 0.0f) * c.mass;  // fluidparticleworld.rs:213
+        a.gsum = f2(0.0f, 0.0f);
+        a.gsq = 0.0f;
+        a.div = 0.0f;
+        a.ct = ct;
+        return true;
+    }
+    __device__ __forceinline__ void pair(const SweepCommon& c, Acc& a, float2 pi, float2 vrel, float2 pj) const {
+        const float2 rij = pj - pi;
+        const float r = sqrtf(mag2(rij));
+        a.dens += wendland_w(c.kc, r) * c.mass;                  // fluidparticleworld.rs:218-219 / 224-225
+        const float2 grad = wendland_grad_scalar(c.kc, r) * rij;  // kernel.rs:22-28
+        const float2 g = grad * c.mass;                          // dfsph.rs:81-83 / 87-89
+        a.gsum = a.gsum + g;
+        a.gsq += mag2(g);
+        a.div += dot2(vrel, grad);                               // dfsph.rs:267 / 274
+    }
+    __device__ __forceinline__ void dyn(const SweepCommon& c, Acc& a, float2 pi, P0 vi, P1, float2 pj, P0 vj, P1) const { pair(c, a, pi, vi - vj, pj); }
+    __device__ __forceinline__ void stat(const SweepCommon& c, Acc& a, float2 pi, P0 vi, P1, float2 pb) const { pair(c, a, pi, vi, pb); }
+    __device__ __forceinline__ double finish(const SweepCommon& c, Acc& a, uint32_t i, float2, P0, P1, bool, O0, O1) const {
+        dens[i] = fmaxf(a.dens, c.rho0);                                   // fluidparticleworld.rs:229
+        const float al = 1.0f / fmaxf(mag2(a.gsum) + a.gsq, 1e-6f);       // dfsph.rs:94
+        alpha[i] = al;
+        const float e = a.ct >= 9u ? fmaxf(a.div * c.mass, 0.0f) : 0.0f;  // dfsph.rs:261-262,277-278
+        kfac[i] = e * al;                                                 // dfsph.rs:295
+        return (double)e;
+    }
+    __device__ __forceinline__ void finalize(const SweepCommon& c, double sum) const {
+        c.ctl->resid_sum = sum;
+        if (c.ghost == nullptr) jacobi_decide<1>(c.ctl, sp, 0u, c.n_avg, c.rho0);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Jacobi B and warm starts
 // ---------------------------------------------------------------------------------------------------------------------
 template <int SOLVER, bool WARM>
@@ -440,6 +714,12 @@ struct OpJacobiB {
     static constexpr bool USES_STATIC = true;
     static constexpr int REDUCE = REDUCE_NONE;
     static constexpr int TICKET = 0;
+    static constexpr bool PAD_IS_ZERO = true;  // (k_i + k_i) * grad(r = 0) == (0, 0)
+    typedef float2 O0;  // v*_i
+    typedef float O1;   // accumulated warm-start value of i
+    static constexpr int NOWN = 2;
+    __device__ __forceinline__ const O0* own0() const { return vstar; }
+    __device__ __forceinline__ const O1* own1() const { return warm; }
     typedef float2 Acc;
     float2* vstar;
     const float* kfac;
@@ -469,15 +749,14 @@ struct OpJacobiB {
     __device__ __forceinline__ void stat(const SweepCommon& c, Acc& a, float2 pi, P0 ki, P1, float2 pb) const {
         a = a + kval(ki) * wendland_grad_from_positions(c.kc, pi, pb);
     }
-    __device__ __forceinline__ double finish(const SweepCommon& c, Acc& a, uint32_t i, float2, P0 ki, P1, bool) const {
-        const float2 v = vstar[i];
+    __device__ __forceinline__ double finish(const SweepCommon& c, Acc& a, uint32_t i, float2, P0 ki, P1, bool, O0 v, O1 warm_i) const {
         if (SOLVER == 0)
             vstar[i] = v - inv_dt * a * c.mass;  // dfsph.rs:159,191
         else
             vstar[i] = v - a * c.mass;           // dfsph.rs:312,342
         // The warm start never stores its clamped values: other tiles are still reading the raw array, and iteration 0 of the
         // solve that always follows overwrites it (zeroing, dfsph.rs:206-208, fused into that iteration).
-        if (!WARM) warm[i] = (iter_index == 0 ? 0.0f : warm[i]) + ki;
+        if (!WARM) warm[i] = (iter_index == 0 ? 0.0f : warm_i) + ki;
         return 0.0;
     }
     __device__ __forceinline__ void finalize(const SweepCommon&, double) const {}
@@ -493,6 +772,12 @@ struct OpWcsphAccel {
     static constexpr bool USES_STATIC = true;
     static constexpr int REDUCE = REDUCE_MAX;
     static constexpr int TICKET = 1;
+    static constexpr bool PAD_IS_ZERO = true;  // spiky gradient times r_ij and the velocity difference of a particle with itself vanish
+    typedef NoPay O0;
+    typedef NoPay O1;
+    static constexpr int NOWN = 0;
+    __device__ __forceinline__ const O0* own0() const { return nullptr; }
+    __device__ __forceinline__ const O1* own1() const { return nullptr; }
     typedef float2 Acc;
     const float2* vel;
     const float2* rho_p;
@@ -522,7 +807,7 @@ struct OpWcsphAccel {
         const float r_sq = mag2(rij);
         a = a - (boundary_force_factor * spiky_w(c.kc, sqrtf(r_sq)) / r_sq) * rij;  // wscsph.rs:113-115
     }
-    __device__ __forceinline__ double finish(const SweepCommon&, Acc& a, uint32_t i, float2, P0 vi, P1, bool) const {
+    __device__ __forceinline__ double finish(const SweepCommon&, Acc& a, uint32_t i, float2, P0 vi, P1, bool, O0, O1) const {
         accel[i] = a;
         return (double)mag2(vi + a * dt);  // wscsph.rs:162
     }

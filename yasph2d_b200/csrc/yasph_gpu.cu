@@ -37,6 +37,7 @@ struct yasph_ctx {
     uint32_t cap_n = 0, cap_m = 0, max_tiles = 0;
     uint32_t lim_dyn = 0, lim_stat = 0;      // configured upper limits for a tile's staged candidates (0 = what shared memory allows)
     uint32_t cap_dyn = 0, cap_stat = 0;      // staging capacity of the current neighbourhood structure (largest tile, rounded up)
+    uint32_t cap_pc = 0;                     // particles of the largest tile, rounded up
     uint32_t num_tiles = 0;                  // host copy of Control::num_tiles for the current structure == grid of the tile kernels
     size_t smem_optin = 0;
     float mass = 0, radius = 0;
@@ -55,7 +56,8 @@ struct yasph_ctx {
     TileRuns* tile_runs = nullptr;
     uint32_t *cslot_d = nullptr, *cslot_s = nullptr;
     unsigned long long* lists = nullptr;
-    uchar2* counts = nullptr;
+    uint32_t* counts = nullptr;   // per particle: count_dynamic | count_total << 8
+    uint32_t* tile_nk = nullptr;  // per tile: most list words of any of its particles
     // scratch
     uint32_t* radix_scratch = nullptr;
     unsigned long long *scan_chunks = nullptr, *scan_total = nullptr;
@@ -141,7 +143,8 @@ static int32_t fail(yasph_ctx* c, int32_t code, const char* fmt, ...) {
 
 template <typename T>
 static cudaError_t dmalloc(T** p, size_t count) {
-    return cudaMalloc((void**)p, (count ? count : 1) * sizeof(T));
+    // 64 bytes of slack: the sweeps' 16-byte aligned bulk copies may read up to three elements past the last particle
+    return cudaMalloc((void**)p, (count ? count : 1) * sizeof(T) + 64);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -337,8 +340,9 @@ static cudaError_t prepare_sweep(yasph_ctx* c) {
     return allow_max_smem(c, k_sweep<Op>);
 }
 // the most shared-memory-hungry tile kernels for given capacities: the list build and the WCSPH sweep (24 B per candidate)
-static size_t worst_smem_bytes(uint32_t cap_dyn, uint32_t cap_stat) {
-    const size_t a = list_smem_bytes(cap_dyn, cap_stat), b = sweep_smem_bytes<OpWcsphAccel>(cap_dyn, cap_stat);
+static size_t worst_smem_bytes(uint32_t cap_dyn, uint32_t cap_stat, uint32_t cap_pc) {
+    // the sweep's list staging is optional (sweep_nk_stage shrinks it to what fits), so its floor is the size without it
+    const size_t a = list_smem_bytes(cap_dyn, cap_stat), b = SweepLayout<OpWcsphAccel>::total_bytes(cap_dyn, cap_stat, cap_pc, 0, 1);
     return a > b ? a : b;
 }
 
@@ -346,7 +350,7 @@ static void free_all(yasph_ctx* c) {
     void* ptrs[] = {c->pos, c->pos_alt, c->vel, c->vel_alt, c->vstar, c->vstar_alt, c->accel, c->dens, c->alpha, c->kappa, c->stiff, c->err_buf,
                     c->f_alt0, c->f_alt1, c->keys[0], c->keys[1], c->idx[0], c->idx[1], c->cell_key, c->cell_start, c->tile_key, c->tile_pstart,
                     c->tile_cstart, c->bpos, c->bpos_alt, c->scell_key, c->scell_start, c->stile_key, c->stile_cstart, c->tile_runs, c->cslot_d,
-                    c->cslot_s, c->lists, c->counts,
+                    c->cslot_s, c->lists, c->counts, c->tile_nk,
                     c->radix_scratch, c->scan_chunks, c->scan_total, c->partials, c->ctl, c->exp_cd, c->exp_ct, c->exp_lists,
                     c->ids, c->ids_alt, c->slab.pflag, c->slab.sel[0], c->slab.sel[1], c->slab.send_idx[0], c->slab.send_idx[1],
                     c->slab.ghost_idx[0], c->slab.ghost_idx[1], c->slab.own_idx, c->slab.sbuf[0], c->slab.sbuf[1], c->slab.rbuf[0],
@@ -414,9 +418,9 @@ extern "C" int32_t yasph_create(const yasph_config* cfg, yasph_ctx** out) {
     c->lim_dyn = cfg->tile_dynamic_capacity;
     c->lim_stat = cfg->tile_static_capacity;
     if (c->lim_dyn > 65535u || c->lim_stat > 65535u) CREATE_FAIL(YASPH_ERR_INVALID_ARGUMENT, "tile capacities must be <= 65535 slots (16-bit slot indices)");
-    if ((c->lim_dyn || c->lim_stat) && worst_smem_bytes(c->lim_dyn, c->lim_stat) > c->smem_optin)
+    if ((c->lim_dyn || c->lim_stat) && worst_smem_bytes(c->lim_dyn, c->lim_stat, 0) > c->smem_optin)
         CREATE_FAIL(YASPH_ERR_CAPACITY, "tile capacities %u/%u need %zu bytes of shared memory per CTA, the device allows %zu", c->lim_dyn, c->lim_stat,
-                    worst_smem_bytes(c->lim_dyn, c->lim_stat), c->smem_optin);
+                    worst_smem_bytes(c->lim_dyn, c->lim_stat, 0), c->smem_optin);
     if (c->cfg.speculative_iterations == 0) c->cfg.speculative_iterations = 2;
     c->cfg.max_tiles = c->max_tiles;
     if (c->cfg.max_halo == 0) c->cfg.max_halo = cfg->max_particles / 8 > 65536u ? cfg->max_particles / 8 : 65536u;
@@ -469,8 +473,9 @@ extern "C" int32_t yasph_create(const yasph_config* cfg, yasph_ctx** out) {
     CUC(dmalloc(&c->tile_runs, (size_t)c->max_tiles));
     CUC(dmalloc(&c->cslot_d, (size_t)c->max_tiles * REGION_CELLS));
     CUC(dmalloc(&c->cslot_s, (size_t)c->max_tiles * REGION_CELLS));
-    CUC(dmalloc(&c->lists, N * (YASPH_MAXN / 4)));
+    CUC(dmalloc(&c->lists, N * LIST_WORDS));
     CUC(dmalloc(&c->counts, N));
+    CUC(dmalloc(&c->tile_nk, (size_t)c->max_tiles + 1));
     CUC(dmalloc(&c->radix_scratch, radix_scratch_words((uint32_t)NM)));
     CUC(dmalloc(&c->scan_chunks, (size_t)scan_num_chunks((uint32_t)NM) + 1));
     CUC(dmalloc(&c->scan_total, 1));
@@ -490,6 +495,7 @@ extern "C" int32_t yasph_create(const yasph_config* cfg, yasph_ctx** out) {
     CUC((prepare_sweep<OpDensityAlpha<2, false>>(c)));
     CUC((prepare_sweep<OpDensityAlpha<3, false>>(c)));
     CUC((prepare_sweep<OpAlphaOnly>(c)));
+    CUC((prepare_sweep<OpDensityAlphaDiv>(c)));
     CUC((prepare_sweep<OpViscosity>(c)));
     CUC((prepare_sweep<OpJacobiA<0>>(c)));
     CUC((prepare_sweep<OpJacobiA<1>>(c)));
@@ -614,6 +620,9 @@ static SweepCommon sweep_common(const yasph_ctx* c) {
     s.tt = tile_tables(c);
     s.lists = c->lists;
     s.counts = c->counts;
+    s.tile_nk = c->tile_nk;
+    s.cap_pc = c->cap_pc;
+    s.nk_stage = 0;  // launch_sweep
     s.pos = c->pos;
     s.bpos = c->bpos;
     s.ctl = c->ctl;
@@ -630,17 +639,30 @@ static SweepCommon sweep_common(const yasph_ctx* c) {
 }
 // persistent grid of a tile kernel: every SM filled to the kernel's occupancy at this shared-memory size, at most one CTA per tile
 template <class K>
-static uint32_t persistent_grid(const yasph_ctx* c, K kernel, size_t smem_bytes) {
+static uint32_t persistent_grid(const yasph_ctx* c, K kernel, size_t smem_bytes, int threads = TILE_THREADS) {
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TILE_THREADS, smem_bytes) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem_bytes) != cudaSuccess || per_sm < 1) per_sm = 1;
     const uint32_t g = (uint32_t)(c->num_sms * per_sm);
     return g < c->num_tiles ? g : (c->num_tiles ? c->num_tiles : 1u);
 }
 template <class Op>
 static int32_t launch_sweep(yasph_ctx* c, Op op) {
     if (c->num_tiles == 0) return YASPH_OK;
-    const size_t bytes = sweep_smem_bytes<Op>(c->cap_dyn, c->cap_stat);
-    k_sweep<Op><<<persistent_grid(c, k_sweep<Op>, bytes), SW_THREADS, bytes, c->stream>>>(sweep_common(c), op);
+    SweepCommon sc = sweep_common(c);
+    // List words staged per particle: what the lists needed at the last read-back (+1: they change slowly), bounded by what
+    // lets three CTAs share an SM.  Any value is correct -- words beyond it are read from global memory.
+    const uint32_t hint = c->h_ctl->max_nk ? c->h_ctl->max_nk + 1u : 4u;
+    const size_t soft = std::min<size_t>(c->smem_optin, 74 * 1024);
+    typedef SweepLayout<Op> L;
+    sc.nstages = SW_STAGES;
+    if (L::total_bytes(c->cap_dyn, c->cap_stat, c->cap_pc, 0, SW_STAGES) <= soft) {
+        sc.nk_stage = sweep_nk_stage<Op>(c->cap_dyn, c->cap_stat, c->cap_pc, hint, SW_STAGES, soft);
+    } else {  // very large tiles: the deepest ring that fits the SM at all (neighborhood_update checked that one stage does)
+        while (sc.nstages > 1 && L::total_bytes(c->cap_dyn, c->cap_stat, c->cap_pc, 0, sc.nstages) > c->smem_optin) --sc.nstages;
+        sc.nk_stage = sweep_nk_stage<Op>(c->cap_dyn, c->cap_stat, c->cap_pc, hint, sc.nstages, c->smem_optin);
+    }
+    const size_t bytes = L::total_bytes(c->cap_dyn, c->cap_stat, c->cap_pc, sc.nk_stage, sc.nstages);
+    k_sweep<Op><<<persistent_grid(c, k_sweep<Op>, bytes, SW_THREADS), SW_THREADS, bytes, c->stream>>>(sc, op);
     CHECK_LAUNCH();
     return YASPH_OK;
 }
@@ -1052,17 +1074,18 @@ static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp
     }
     c->num_tiles = n ? c->h_ctl->num_tiles : 0u;
     c->cap_dyn = (c->h_ctl->max_dyn_total + 15u) & ~15u;
+    c->cap_pc = (c->h_ctl->max_pcount + 6u + 15u) & ~15u;  // + the alignment surplus of the bulk copies
     c->cap_stat = (c->h_ctl->max_stat_total + 15u) & ~15u;
     if ((c->lim_dyn && c->h_ctl->max_dyn_total > c->lim_dyn) || (c->lim_stat && c->h_ctl->max_stat_total > c->lim_stat))
         return fail(c, YASPH_ERR_CAPACITY, "a tile stages %u dynamic / %u static candidates, above tile_dynamic_capacity=%u / tile_static_capacity=%u",
                     c->h_ctl->max_dyn_total, c->h_ctl->max_stat_total, c->lim_dyn, c->lim_stat);
-    if (worst_smem_bytes(c->cap_dyn, c->cap_stat) > c->smem_optin)
+    if (worst_smem_bytes(c->cap_dyn, c->cap_stat, c->cap_pc) > c->smem_optin)
         return fail(c, YASPH_ERR_CAPACITY, "a tile stages %u dynamic / %u static candidates: %zu bytes of shared memory per CTA, the device allows %zu",
-                    c->h_ctl->max_dyn_total, c->h_ctl->max_stat_total, worst_smem_bytes(c->cap_dyn, c->cap_stat), c->smem_optin);
+                    c->h_ctl->max_dyn_total, c->h_ctl->max_stat_total, worst_smem_bytes(c->cap_dyn, c->cap_stat, c->cap_pc), c->smem_optin);
     pass_begin(c, YASPH_PASS_LISTS);
     if (c->num_tiles) {
         const size_t bytes = list_smem_bytes(c->cap_dyn, c->cap_stat);
-        ListArgs la{tile_tables(c), c->pos, c->bpos, c->keys[0], c->grid, c->ctl, c->lists, c->counts, c->cap_dyn, c->cap_stat};
+        ListArgs la{tile_tables(c), c->pos, c->bpos, c->keys[0], c->grid, c->ctl, c->lists, c->counts, c->tile_nk, c->cap_dyn, c->cap_stat};
         k_build_lists<<<persistent_grid(c, k_build_lists, bytes), NB_THREADS, bytes, c->stream>>>(la);
         CHECK_LAUNCH();
     }
@@ -1395,8 +1418,9 @@ static ViscParams visc_params(const yasph_ctx* c) {
 
 // Runs one Jacobi solve (density: SOLVER 0 / divergence: SOLVER 1): optional warm start, then A/B iterations launched in
 // chunks of `speculative_iterations`; kernels past the converged iteration exit immediately on the device-side stop_iter.
+// first_a_done: pass A of iteration 0 (with its reduction and decision) already ran fused into the density+alpha sweep.
 template <int SOLVER>
-static int32_t jacobi_solve(yasph_ctx* c) {
+static int32_t jacobi_solve(yasph_ctx* c, bool first_a_done = false) {
     const float rho0 = c->cfg.fluid_density;
     float* warm_arr = SOLVER == 0 ? c->kappa : c->stiff;
     pass_begin(c, SOLVER == 0 ? YASPH_PASS_DENSITY_WARM : YASPH_PASS_DIVERGENCE_WARM);
@@ -1426,14 +1450,16 @@ static int32_t jacobi_solve(yasph_ctx* c) {
     const int solve_pass = SOLVER == 0 ? YASPH_PASS_DENSITY_SOLVE : YASPH_PASS_DIVERGENCE_SOLVE;
     while (true) {
         for (uint32_t q = 0; q < chunk; ++q, ++it) {
-            OpJacobiA<SOLVER> a;
-            a.vstar = c->vstar;
-            a.dens = c->dens;
-            a.alpha = c->alpha;
-            a.kfac = c->err_buf;
-            a.sp = sp;
-            a.iter_index = it;
-            TRY(launch_sweep(c, a));
+            if (!(first_a_done && it == 0)) {
+                OpJacobiA<SOLVER> a;
+                a.vstar = c->vstar;
+                a.dens = c->dens;
+                a.alpha = c->alpha;
+                a.kfac = c->err_buf;
+                a.sp = sp;
+                a.iter_index = it;
+                TRY(launch_sweep(c, a));
+            }
             if (c->slab.active) {
                 // global residual: sum over the ranks, then the loop decision every rank takes identically
                 TRY(allreduce_scalar(c, &c->ctl->resid_sum, ncclDouble, ncclSum));
@@ -1539,7 +1565,22 @@ static int32_t dfsph_step(yasph_ctx* c) {
         TRY(neighborhood_update(c, true, gp));
     }
     pass_begin(c, YASPH_PASS_DENSITY_ALPHA);
-    {
+    k_begin_divergence<<<1, 32, 0, c->stream>>>(c->ctl);
+    CHECK_LAUNCH();
+    // The divergence warm start runs iff the previous divergence solve took more than one iteration (dfsph.rs:354); the
+    // host mirror still holds that count.  Without a warm start, iteration 0's density-change pass reads the same v* and
+    // positions as the density / alpha passes and is fused into their sweep.
+    const bool fuse_div_a0 = c->h_ctl->iters[1] <= 1u;
+    if (fuse_div_a0) {
+        OpDensityAlphaDiv f;  // dfsph.rs:516-518 + iteration 0 of dfsph.rs:372
+        f.vstar = c->vstar;
+        f.dens = c->dens;
+        f.alpha = c->alpha;
+        f.kfac = c->err_buf;
+        f.sp.max_error = c->cfg.dfsph_max_divergence_error;
+        f.sp.max_iters = c->cfg.dfsph_max_divergence_iters;
+        TRY(launch_sweep(c, f));
+    } else {
         OpDensityAlpha<0, true> da;  // dfsph.rs:516-518
         da.dens = c->dens;
         da.alpha = c->alpha;
@@ -1547,11 +1588,9 @@ static int32_t dfsph_step(yasph_ctx* c) {
         da.stiffness = 0.f;
         TRY(launch_sweep(c, da));
     }
-    k_begin_divergence<<<1, 32, 0, c->stream>>>(c->ctl);
-    CHECK_LAUNCH();
     pass_end(c);
     TRY(halo_exchange(c, c->dens));  // rho_j of the ghosts for the next step's viscosity pass
-    TRY(jacobi_solve<1>(c));        // dfsph.rs:521
+    TRY(jacobi_solve<1>(c, fuse_div_a0));  // dfsph.rs:521
     std::swap(c->vel, c->vstar);    // dfsph.rs:524
     return YASPH_OK;
 }
