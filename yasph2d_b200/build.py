@@ -24,6 +24,12 @@ def build(force=False, verbose=False, defines=(), out=OUT):
         return out
     cmd = [NVCC] + FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, SRC]
     subprocess.check_call(cmd)
+    # Bit-exactness guard: the path computes in strict f32 without contraction.  ptxas is known to contract
+    # packed mul.rn.f32x2 + add/sub.rn.f32x2 into FFMA2 despite -fmad=false; no kernel of this library may contain one.
+    sass = subprocess.run(["cuobjdump", "-sass", out], capture_output=True, text=True).stdout
+    if "FFMA2" in sass:
+        os.remove(out)
+        raise RuntimeError("libyasph_gpu.so: ptxas emitted FFMA2 (fused packed multiply-add): results would not match the reference bit for bit")
     return out
 
 

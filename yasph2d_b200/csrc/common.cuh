@@ -18,14 +18,57 @@
 namespace yasph {
 
 // ---- float2 helpers mirroring cgmath (component-wise, no contraction) ---------------------------------------------
+// On the device the two components travel through Blackwell's packed f32x2 pipe (add/sub/mul.rn.f32x2: one instruction,
+// two independently rounded IEEE results -- bit-identical to the scalar pair, half the issue slots).
+#ifndef YASPH_F32X2
+#define YASPH_F32X2 6  // bit 0: add, bit 1: sub, bit 2: mul.  Packed add stays off and products that feed a subtraction go through
+                       // sub_scalar(): ptxas contracts mul.rn.f32x2 + add/sub.rn.f32x2 into FFMA2 (one rounding), -fmad=false notwithstanding.
+                       // build.py rejects a library whose SASS contains FFMA2.
+#endif
 __host__ __device__ __forceinline__ float2 f2(float x, float y) { return make_float2(x, y); }
-__host__ __device__ __forceinline__ float2 operator+(float2 a, float2 b) { return f2(a.x + b.x, a.y + b.y); }
-__host__ __device__ __forceinline__ float2 operator-(float2 a, float2 b) { return f2(a.x - b.x, a.y - b.y); }
-__host__ __device__ __forceinline__ float2 operator*(float2 a, float s) { return f2(a.x * s, a.y * s); }
-__host__ __device__ __forceinline__ float2 operator*(float s, float2 a) { return f2(s * a.x, s * a.y); }
+#if defined(__CUDA_ARCH__) && YASPH_F32X2
+#define YASPH_PACKED2(op, a, b)                                                                                   \
+    unsigned long long r_;                                                                                        \
+    asm(op ".rn.f32x2 %0, %1, %2;"                                                                                \
+        : "=l"(r_)                                                                                                \
+        : "l"(((unsigned long long)__float_as_uint(a.y) << 32) | __float_as_uint(a.x)),                           \
+          "l"(((unsigned long long)__float_as_uint(b.y) << 32) | __float_as_uint(b.x)));                          \
+    return make_float2(__uint_as_float((uint32_t)r_), __uint_as_float((uint32_t)(r_ >> 32)));
+#endif
+__host__ __device__ __forceinline__ float2 operator+(float2 a, float2 b) {
+#if defined(YASPH_PACKED2) && (YASPH_F32X2 & 1)
+    YASPH_PACKED2("add", a, b)
+#else
+    return f2(a.x + b.x, a.y + b.y);
+#endif
+}
+__host__ __device__ __forceinline__ float2 operator-(float2 a, float2 b) {
+#if defined(YASPH_PACKED2) && (YASPH_F32X2 & 2)
+    YASPH_PACKED2("sub", a, b)
+#else
+    return f2(a.x - b.x, a.y - b.y);
+#endif
+}
+__host__ __device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+#if defined(YASPH_PACKED2) && (YASPH_F32X2 & 4)
+    YASPH_PACKED2("mul", a, b)
+#else
+    return f2(a.x * b.x, a.y * b.y);
+#endif
+}
+__host__ __device__ __forceinline__ float2 operator*(float2 a, float s) { return mul2(a, f2(s, s)); }
+__host__ __device__ __forceinline__ float2 operator*(float s, float2 a) { return mul2(f2(s, s), a); }
+__host__ __device__ __forceinline__ float dot2(float2 a, float2 b) {
+    const float2 p = mul2(a, b);
+    return p.x + p.y;
+}
+__host__ __device__ __forceinline__ float mag2(float2 a) {
+    const float2 p = mul2(a, a);
+    return p.x + p.y;
+}
 __host__ __device__ __forceinline__ float2 operator/(float2 a, float s) { return f2(a.x / s, a.y / s); }
-__host__ __device__ __forceinline__ float dot2(float2 a, float2 b) { return a.x * b.x + a.y * b.y; }
-__host__ __device__ __forceinline__ float mag2(float2 a) { return a.x * a.x + a.y * a.y; }
+// a - b with scalar instructions: for b = (packed product), see YASPH_F32X2
+__host__ __device__ __forceinline__ float2 sub_scalar(float2 a, float2 b) { return f2(a.x - b.x, a.y - b.y); }
 
 // Rust f32::powi == compiler-rt __powisf2
 __host__ __device__ inline float powi_f(float a, int b) {

@@ -72,62 +72,73 @@ struct TileTables {
 };
 
 // ---- keys ---------------------------------------------------------------------------------------------------------
-// All three key-generating kernels run RS_THREADS threads per block and feed the radix sort's global digit histograms
+// All three key-generating kernels run KG_THREADS threads per block and feed the radix sort's global digit histograms
 // (sort.cuh) while they have the key in a register.
+// grid of a key-generating kernel: a few CTAs per SM, each walking chunks of KG_THREADS particles
+inline uint32_t keygen_grid(uint32_t n, int num_sms) {
+    const uint32_t chunks = (n + KG_THREADS - 1) / KG_THREADS, cap = (uint32_t)num_sms * 8u;
+    return chunks < cap ? (chunks ? chunks : 1u) : cap;
+}
 // neighborhood_search.rs:111-114 (sequential in the reference)
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(KG_THREADS)
     k_keygen(const float2* __restrict__ pos, uint32_t first, uint32_t n, GridParams g, uint32_t* __restrict__ keys, uint32_t* __restrict__ idx,
              uint32_t* __restrict__ sort_scratch, SlabParams sp) {
     __shared__ RadixHistSmem sh;
     radix_hist_init(sh);
-    const uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t key = 0;
-    if (i < n) {
-        key = slab_classify(sp, i, position_to_cidx(g, pos[i]));
-        keys[i] = key;
-        idx[i] = i;
+    for (uint32_t base = first + blockIdx.x * KG_THREADS; base < n; base += gridDim.x * KG_THREADS) {
+        const uint32_t i = base + threadIdx.x;
+        uint32_t key = 0;
+        if (i < n) {
+            key = slab_classify(sp, i, position_to_cidx(g, pos[i]));
+            keys[i] = key;
+            idx[i] = i;
+        }
+        radix_hist_add(sh, key, i < n);
     }
-    radix_hist_add(sh, key, i < n);
     radix_hist_flush(sh, sort_scratch);
 }
 // dfsph.rs:502-509 (advect) fused with the key generation of the following re-sort
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(KG_THREADS)
     k_advect_keygen(float2* __restrict__ pos, const float2* __restrict__ vstar, uint32_t n, const Control* __restrict__ ctl, GridParams g,
                     uint32_t* __restrict__ keys, uint32_t* __restrict__ idx, uint32_t* __restrict__ sort_scratch, SlabParams sp) {
     __shared__ RadixHistSmem sh;
     radix_hist_init(sh);
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t key = 0;
-    if (i < n) {
-        const float dt = ctl->dt;
-        float2 p = pos[i] + vstar[i] * dt;
-        pos[i] = p;
-        key = slab_classify(sp, i, position_to_cidx(g, p));
-        keys[i] = key;
-        idx[i] = i;
+    const float dt = ctl->dt;
+    for (uint32_t base = blockIdx.x * KG_THREADS; base < n; base += gridDim.x * KG_THREADS) {
+        const uint32_t i = base + threadIdx.x;
+        uint32_t key = 0;
+        if (i < n) {
+            float2 p = pos[i] + vstar[i] * dt;
+            pos[i] = p;
+            key = slab_classify(sp, i, position_to_cidx(g, p));
+            keys[i] = key;
+            idx[i] = i;
+        }
+        radix_hist_add(sh, key, i < n);
     }
-    radix_hist_add(sh, key, i < n);
     radix_hist_flush(sh, sort_scratch);
 }
 // wscsph.rs:141-150 (leap frog 1) fused with key generation
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(KG_THREADS)
     k_kickdrift_keygen(float2* __restrict__ pos, float2* __restrict__ vel, const float2* __restrict__ acc, uint32_t n, const Control* __restrict__ ctl,
                        GridParams g, uint32_t* __restrict__ keys, uint32_t* __restrict__ idx, uint32_t* __restrict__ sort_scratch, SlabParams sp) {
     __shared__ RadixHistSmem sh;
     radix_hist_init(sh);
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t key = 0;
-    if (i < n) {
-        const float dt = ctl->dt_prev;
-        float2 v = vel[i] + 0.5f * dt * acc[i];
-        float2 p = pos[i] + v * dt;
-        vel[i] = v;
-        pos[i] = p;
-        key = slab_classify(sp, i, position_to_cidx(g, p));
-        keys[i] = key;
-        idx[i] = i;
+    const float dt = ctl->dt_prev;
+    for (uint32_t base = blockIdx.x * KG_THREADS; base < n; base += gridDim.x * KG_THREADS) {
+        const uint32_t i = base + threadIdx.x;
+        uint32_t key = 0;
+        if (i < n) {
+            float2 v = vel[i] + 0.5f * dt * acc[i];
+            float2 p = pos[i] + v * dt;
+            vel[i] = v;
+            pos[i] = p;
+            key = slab_classify(sp, i, position_to_cidx(g, p));
+            keys[i] = key;
+            idx[i] = i;
+        }
+        radix_hist_add(sh, key, i < n);
     }
-    radix_hist_add(sh, key, i < n);
     radix_hist_flush(sh, sort_scratch);
 }
 
@@ -583,7 +594,7 @@ __device__ __forceinline__ uint32_t list_scan_candidates(const float2* __restric
             rem = run & 0xFFFFu;
         }
         const float2 d = cand[s] - q;
-        const float d2 = d.x * d.x + d.y * d.y;
+        const float d2 = mag2(d);  // fl(fl(dx * dx) + fl(dy * dy)), neighborhood_search.rs:356
         col[min(c, (uint32_t)YASPH_MAXN) * NB_THREADS] = (uint16_t)s;
         c += (d2 <= radius_sq && d2 > YASPH_MIN_DISTANCE) ? 1u : 0u;
         ++s;

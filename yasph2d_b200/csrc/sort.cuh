@@ -14,12 +14,23 @@
 
 namespace yasph {
 
-constexpr int RS_THREADS = 256;
+#ifndef YASPH_RS_THREADS
+#define YASPH_RS_THREADS 512
+#endif
+#ifndef YASPH_RS_ITEMS
+#define YASPH_RS_ITEMS 12
+#endif
+constexpr int RS_THREADS = YASPH_RS_THREADS;  // threads of a radix pass CTA (>= RS_BINS: thread d < RS_BINS owns digit d)
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 16;
+constexpr int RS_ITEMS = YASPH_RS_ITEMS;
+constexpr int KG_THREADS = 256;              // threads of the key-generating kernels
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 pairs per tile
 constexpr int RS_BINS = 256;
 constexpr int RS_PASSES = 4;
+#ifndef YASPH_RS_LOOKBACK
+#define YASPH_RS_LOOKBACK 8
+#endif
+constexpr int RS_LOOKBACK = YASPH_RS_LOOKBACK;  // predecessor tiles inspected per look-back round trip
 constexpr uint32_t RS_FLAG_LOCAL = 1u << 30, RS_FLAG_GLOBAL = 2u << 30, RS_VALUE_MASK = (1u << 30) - 1u;
 
 inline uint32_t radix_num_tiles(uint32_t n) { return (n + RS_TILE - 1) / RS_TILE; }
@@ -27,8 +38,8 @@ inline uint32_t radix_num_tiles(uint32_t n) { return (n + RS_TILE - 1) / RS_TILE
 inline size_t radix_scratch_words(uint32_t n) { return RS_PASSES + (size_t)RS_PASSES * RS_BINS + (size_t)RS_PASSES * radix_num_tiles(n) * RS_BINS; }
 
 // ---- global digit histograms, fused into the key-generating kernels ------------------------------------------------------
-// Call pattern inside a kernel of RS_THREADS threads: radix_hist_init(sh); ... radix_hist_add(sh, key) for each key ...;
-// radix_hist_flush(sh, scratch).
+// Call pattern inside a kernel: radix_hist_init(sh); ... radix_hist_add(sh, key, valid) by whole warps for each key ...;
+// radix_hist_flush(sh, scratch).  The key-generating kernels are grid-stride loops, so a CTA flushes once for many keys.
 struct RadixHistSmem {
     uint32_t h[RS_PASSES][RS_BINS];
 };
@@ -36,23 +47,32 @@ __device__ __forceinline__ void radix_hist_init(RadixHistSmem& sh) {
     for (uint32_t q = threadIdx.x; q < RS_PASSES * RS_BINS; q += blockDim.x) (&sh.h[0][0])[q] = 0u;
     __syncthreads();
 }
-// Every thread of the warp calls this (valid == false for threads past the end).  The input is nearly sorted, so the lanes
-// of a warp form a few runs of equal digits (one run for the high digits): each run's first lane adds the run length.  One
-// shuffle, one ballot and a handful of integer instructions per digit; no lane pair ever hits the same counter at once
-// unless the same digit recurs in separate runs.
+// Every thread of the warp calls this (valid == false for threads past the end).  The input is nearly sorted: most warps
+// hold 32 keys that agree in everything but the lowest digit, and then one lane adds 32 to three counters.  Otherwise the
+// lanes of a warp form a few runs of equal digits and each run's first lane adds the run length: one shuffle, one ballot
+// and a handful of integer instructions per digit; no lane pair hits the same counter at once unless the same digit recurs
+// in separate runs.
+__device__ __forceinline__ void radix_hist_add_digit(RadixHistSmem& sh, int p, uint32_t key, bool valid, uint32_t lane) {
+    const uint32_t d = valid ? ((key >> (8 * p)) & 0xFFu) : 0x1FFu;
+    const uint32_t prev = __shfl_up_sync(0xffffffffu, d, 1);
+    const bool head = lane == 0 || d != prev;
+    const unsigned hm = __ballot_sync(0xffffffffu, head);
+    if (head && valid) {
+        const unsigned later = lane == 31 ? 0u : (hm & (0xFFFFFFFEu << lane));
+        const uint32_t len = (later ? (uint32_t)__ffs(later) - 1u : 32u) - lane;
+        atomicAdd(&sh.h[p][d], len);
+    }
+}
 __device__ __forceinline__ void radix_hist_add(RadixHistSmem& sh, uint32_t key, bool valid) {
     const uint32_t lane = lane_id();
+    radix_hist_add_digit(sh, 0, key, valid, lane);
+    const uint32_t hi = valid ? (key >> 8) : 0xFFFFFFFFu;  // a valid key has hi < 2^24
+    const uint32_t hi0 = __shfl_sync(0xffffffffu, hi, 0);
+    if (__all_sync(0xffffffffu, hi == hi0)) {
+        if (lane < 3 && hi0 != 0xFFFFFFFFu) atomicAdd(&sh.h[lane + 1][(hi0 >> (8 * lane)) & 0xFFu], 32u);
+    } else {
 #pragma unroll
-    for (int p = 0; p < RS_PASSES; ++p) {
-        const uint32_t d = valid ? ((key >> (8 * p)) & 0xFFu) : 0x1FFu;
-        const uint32_t prev = __shfl_up_sync(0xffffffffu, d, 1);
-        const bool head = lane == 0 || d != prev;
-        const unsigned hm = __ballot_sync(0xffffffffu, head);
-        if (head && valid) {
-            const unsigned later = lane == 31 ? 0u : (hm & (0xFFFFFFFEu << lane));
-            const uint32_t len = (later ? (uint32_t)__ffs(later) - 1u : 32u) - lane;
-            atomicAdd(&sh.h[p][d], len);
-        }
+        for (int p = 1; p < RS_PASSES; ++p) radix_hist_add_digit(sh, p, key, valid, lane);
     }
 }
 __device__ __forceinline__ void radix_hist_flush(RadixHistSmem& sh, uint32_t* __restrict__ scratch) {
@@ -85,16 +105,17 @@ __global__ void __launch_bounds__(RS_THREADS)
     const unsigned lt = lanemask_lt();
     const uint32_t* ghist = scratch + RS_PASSES + pass * RS_BINS;
     volatile uint32_t* status = scratch + RS_PASSES + RS_PASSES * RS_BINS + (size_t)pass * ntiles * RS_BINS;
+    static_assert(RS_THREADS >= RS_BINS && RS_BINS == 256, "thread d < RS_BINS owns digit d");
     if (tid == 0) {
         S.tile = atomicAdd(&scratch[pass], 1u);
         S.trivial = 0u;
     }
-#pragma unroll
-    for (int w = 0; w < RS_WARPS; ++w) S.cnt[w][tid] = 0u;
+    for (uint32_t q = tid; q < RS_WARPS * RS_BINS; q += RS_THREADS) (&S.cnt[0][0])[q] = 0u;
     __syncthreads();
     const uint32_t tile = S.tile;
-    const uint32_t gh = ghist[tid];
-    if (gh == n) S.trivial = 1u;  // every key has this digit: the pass is the identity
+    const bool owner = tid < RS_BINS;
+    const uint32_t gh = owner ? ghist[tid] : 0u;
+    if (owner && gh == n) S.trivial = 1u;  // every key has this digit: the pass is the identity
     const uint32_t base = tile * RS_TILE + warp * (32 * RS_ITEMS);
     uint32_t key[RS_ITEMS], val[RS_ITEMS], rank[RS_ITEMS];
 #pragma unroll
@@ -132,7 +153,7 @@ __global__ void __launch_bounds__(RS_THREADS)
     __syncthreads();
     // 2. per digit (thread == digit): prefix over the warps, tile count, publish, look back
     uint32_t tcount = 0;
-    {
+    if (owner) {
 #pragma unroll
         for (int w = 0; w < RS_WARPS; ++w) {
             const uint32_t t = S.cnt[w][tid];
@@ -154,13 +175,13 @@ __global__ void __launch_bounds__(RS_THREADS)
                 g += ug;
             }
         }
-        if (lane == 31) {
+        if (lane == 31 && owner) {
             S.wsum[warp] = a;
             S.lbin[warp] = g;  // borrowed until the sync below
         }
         __syncthreads();
         uint32_t wa = 0, wg = 0;
-        for (uint32_t w = 0; w < warp; ++w) {
+        for (uint32_t w = 0; w < warp && w < RS_BINS / 32; ++w) {
             wa += S.wsum[w];
             wg += S.lbin[w];
         }
@@ -168,15 +189,24 @@ __global__ void __launch_bounds__(RS_THREADS)
         lex = wa + a - tcount;
         gex = wg + g - gh;
     }
-    {
+    if (owner) {
+        // Decoupled look-back, RS_LOOKBACK predecessors per round trip: their status words are loaded together (independent
+        // loads in flight at once) and then consumed nearest first, so the prefix chain advances a window of tiles per L2 latency.
         uint32_t excl = 0;
-        for (int j = (int)tile - 1; j >= 0; --j) {
-            uint32_t s;
-            do {
-                s = status[(size_t)j * RS_BINS + tid];
-            } while ((s & ~RS_VALUE_MASK) == 0u);
-            excl += s & RS_VALUE_MASK;
-            if (s & RS_FLAG_GLOBAL) break;
+        for (int j = (int)tile - 1; j >= 0; j -= RS_LOOKBACK) {
+            uint32_t sw[RS_LOOKBACK];
+#pragma unroll
+            for (int u = 0; u < RS_LOOKBACK; ++u) sw[u] = j - u >= 0 ? (uint32_t)status[(size_t)(j - u) * RS_BINS + tid] : (uint32_t)(2u << 30);
+            bool done = false;
+#pragma unroll
+            for (int u = 0; u < RS_LOOKBACK; ++u) {
+                if (!done) {
+                    while ((sw[u] & ~RS_VALUE_MASK) == 0u) sw[u] = status[(size_t)(j - u) * RS_BINS + tid];  // not published yet
+                    excl += sw[u] & RS_VALUE_MASK;
+                    done = (sw[u] & RS_FLAG_GLOBAL) != 0u;
+                }
+            }
+            if (done) break;
         }
         status[(size_t)tile * RS_BINS + tid] = (excl + tcount) | RS_FLAG_GLOBAL;
         S.lbin[tid] = lex;

@@ -751,9 +751,9 @@ struct OpJacobiB {
     }
     __device__ __forceinline__ double finish(const SweepCommon& c, Acc& a, uint32_t i, float2, P0 ki, P1, bool, O0 v, O1 warm_i) const {
         if (SOLVER == 0)
-            vstar[i] = v - inv_dt * a * c.mass;  // dfsph.rs:159,191
+            vstar[i] = sub_scalar(v, inv_dt * a * c.mass);  // dfsph.rs:159,191
         else
-            vstar[i] = v - a * c.mass;           // dfsph.rs:312,342
+            vstar[i] = sub_scalar(v, a * c.mass);           // dfsph.rs:312,342
         // The warm start never stores its clamped values: other tiles are still reading the raw array, and iteration 0 of the
         // solve that always follows overwrites it (zeroing, dfsph.rs:206-208, fused into that iteration).
         if (!WARM) warm[i] = (iter_index == 0 ? 0.0f : warm_i) + ki;
@@ -805,7 +805,7 @@ struct OpWcsphAccel {
     __device__ __forceinline__ void stat(const SweepCommon& c, Acc& a, float2 pi, P0, P1, float2 pb) const {
         const float2 rij = pb - pi;
         const float r_sq = mag2(rij);
-        a = a - (boundary_force_factor * spiky_w(c.kc, sqrtf(r_sq)) / r_sq) * rij;  // wscsph.rs:113-115
+        a = sub_scalar(a, (boundary_force_factor * spiky_w(c.kc, sqrtf(r_sq)) / r_sq) * rij);  // wscsph.rs:113-115
     }
     __device__ __forceinline__ double finish(const SweepCommon&, Acc& a, uint32_t i, float2, P0 vi, P1, bool, O0, O1) const {
         accel[i] = a;

@@ -505,6 +505,7 @@ extern "C" int32_t yasph_create(const yasph_config* cfg, yasph_ctx** out) {
     CUC((prepare_sweep<OpJacobiB<1, true>>(c)));
     CUC((prepare_sweep<OpWcsphAccel>(c)));
     CUC(allow_max_smem(c, k_build_lists));
+    CUC(allow_max_smem(c, k_radix_pass));
     CUC(dmalloc(&c->partials, (size_t)c->max_tiles + 1));
 
     // TimeManager::new: initial step = timestep_min / fixed (timemanager.rs:106-109); DFSPHSolver::new iteration counts (dfsph.rs:51,55)
@@ -942,7 +943,7 @@ static int32_t slab_exchange_particles(yasph_ctx* c, const GatherPlan& gp, uint3
             }
         const uint32_t nin = in[0] + in[1];
         if (nin) {
-            k_keygen<<<blocks_for(nin, RS_THREADS), RS_THREADS, 0, c->stream>>>(c->pos, n_old, n1, c->grid, c->keys[0], c->idx[0], c->radix_scratch, sp);
+            k_keygen<<<keygen_grid(nin, c->num_sms), KG_THREADS, 0, c->stream>>>(c->pos, n_old, n1, c->grid, c->keys[0], c->idx[0], c->radix_scratch, sp);
             CHECK_LAUNCH();
             k_check_arrivals<<<blocks_for(nin, 256), 256, 0, c->stream>>>(sl.pflag, n_old, n1, c->ctl);
             CHECK_LAUNCH();
@@ -978,7 +979,7 @@ static int32_t slab_exchange_particles(yasph_ctx* c, const GatherPlan& gp, uint3
             }
         const uint32_t ngin = gin[0] + gin[1];
         if (ngin) {  // ghosts keep their keys (they lie outside the slab by construction): no classification
-            k_keygen<<<blocks_for(ngin, RS_THREADS), RS_THREADS, 0, c->stream>>>(c->pos, n1, n2, c->grid, c->keys[0], c->idx[0], c->radix_scratch,
+            k_keygen<<<keygen_grid(ngin, c->num_sms), KG_THREADS, 0, c->stream>>>(c->pos, n1, n2, c->grid, c->keys[0], c->idx[0], c->radix_scratch,
                                                                                SlabParams{0u, 0u, nullptr, 0});
             CHECK_LAUNCH();
         }
@@ -1005,7 +1006,7 @@ static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp
     pass_begin(c, YASPH_PASS_SORT);
     if (!keys_ready && n) {
         TRY(radix_prepare(c, n));
-        k_keygen<<<blocks_for(n, RS_THREADS), RS_THREADS, 0, c->stream>>>(c->pos, 0u, n, c->grid, c->keys[0], c->idx[0], c->radix_scratch, slab_params(c));
+        k_keygen<<<keygen_grid(n, c->num_sms), KG_THREADS, 0, c->stream>>>(c->pos, 0u, n, c->grid, c->keys[0], c->idx[0], c->radix_scratch, slab_params(c));
         CHECK_LAUNCH();
     }
     uint32_t n_sort = n;
@@ -1188,7 +1189,7 @@ extern "C" int32_t yasph_set_boundary(yasph_ctx* c, const float* xy, uint32_t m)
         CU(cudaMemcpyAsync(c->bpos, xy, (size_t)m * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
         // update_static (neighborhood_search.rs:488-491): sort the boundary particles in place, build the static cells
         TRY(radix_prepare(c, m));
-        k_keygen<<<blocks_for(m, RS_THREADS), RS_THREADS, 0, c->stream>>>(c->bpos, 0u, m, c->grid, c->keys[0], c->idx[0], c->radix_scratch, SlabParams{0u, 0u, nullptr, 0});
+        k_keygen<<<keygen_grid(m, c->num_sms), KG_THREADS, 0, c->stream>>>(c->bpos, 0u, m, c->grid, c->keys[0], c->idx[0], c->radix_scratch, SlabParams{0u, 0u, nullptr, 0});
         CHECK_LAUNCH();
         TRY(radix_sort(c, m));
         GatherArgs ga;
@@ -1543,7 +1544,7 @@ static int32_t dfsph_step(yasph_ctx* c) {
     // advect (dfsph.rs:502-509) fused with the key generation of the re-sort (dfsph.rs:512)
     pass_begin(c, YASPH_PASS_ADVECT_KEYGEN);
     TRY(radix_prepare(c, n));
-    k_advect_keygen<<<blocks_for(n, RS_THREADS), RS_THREADS, 0, c->stream>>>(c->pos, c->vstar, n, c->ctl, c->grid, c->keys[0], c->idx[0], c->radix_scratch,
+    k_advect_keygen<<<keygen_grid(n, c->num_sms), KG_THREADS, 0, c->stream>>>(c->pos, c->vstar, n, c->ctl, c->grid, c->keys[0], c->idx[0], c->radix_scratch,
                                                                             slab_params(c));
     CHECK_LAUNCH();
     pass_end(c);
@@ -1602,7 +1603,7 @@ static int32_t wcsph_step(yasph_ctx* c) {
     // leap frog 1 (wscsph.rs:141-150) fused with key generation
     pass_begin(c, YASPH_PASS_ADVECT_KEYGEN);
     TRY(radix_prepare(c, n));
-    k_kickdrift_keygen<<<blocks_for(n, RS_THREADS), RS_THREADS, 0, c->stream>>>(c->pos, c->vel, c->accel, n, c->ctl, c->grid, c->keys[0], c->idx[0],
+    k_kickdrift_keygen<<<keygen_grid(n, c->num_sms), KG_THREADS, 0, c->stream>>>(c->pos, c->vel, c->accel, n, c->ctl, c->grid, c->keys[0], c->idx[0],
                                                                                c->radix_scratch, slab_params(c));
     CHECK_LAUNCH();
     pass_end(c);
