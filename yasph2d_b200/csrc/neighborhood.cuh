@@ -583,9 +583,16 @@ __device__ __forceinline__ void list_issue_stage(const ListArgs& a, uint32_t t, 
     }
     for (uint32_t s = threadIdx.x; s < h.stat_total; s += NB_THREADS) cp_async<8>(&sstat[s], &a.bpos[run_slot_to_global(tr.rs, s)]);
 }
-// candidates of one kind (dynamic / static) for one particle; returns the advanced hit count
-__device__ __forceinline__ uint32_t list_scan_candidates(const float2* __restrict__ cand, const uint32_t* __restrict__ cruns, uint32_t ncand, float2 q,
-                                                         float radius_sq, uint16_t* col, uint32_t c) {
+// float2 at byte offset `off` of the CTA's dynamic shared memory (every `extern __shared__` array starts at its base): spelled
+// this way the compiler knows the address space and emits LDS instead of a generic load
+__device__ __forceinline__ float2 lds_f2(uint32_t off) {
+    extern __shared__ __align__(16) unsigned char dyn_smem_base[];
+    return *reinterpret_cast<const float2*>(dyn_smem_base + off);
+}
+// candidates of one kind (dynamic / static) for one particle; returns the advanced hit count.
+// cand = byte offset of the staged positions in the CTA's dynamic shared memory.
+__device__ __forceinline__ uint32_t list_scan_candidates(uint32_t cand, const uint32_t* __restrict__ cruns, uint32_t ncand, float2 q, float radius_sq,
+                                                         uint16_t* col, uint32_t c) {
     uint32_t r = 0, rem = 0, s = 0;
     for (uint32_t j = 0; j < ncand; ++j) {
         if (rem == 0) {
@@ -593,7 +600,7 @@ __device__ __forceinline__ uint32_t list_scan_candidates(const float2* __restric
             s = run >> 16;
             rem = run & 0xFFFFu;
         }
-        const float2 d = cand[s] - q;
+        const float2 d = lds_f2(cand + s * 8u) - q;
         const float d2 = mag2(d);  // fl(fl(dx * dx) + fl(dy * dy)), neighborhood_search.rs:356
         col[min(c, (uint32_t)YASPH_MAXN) * NB_THREADS] = (uint16_t)s;
         c += (d2 <= radius_sq && d2 > YASPH_MIN_DISTANCE) ? 1u : 0u;
@@ -623,7 +630,7 @@ __global__ void __launch_bounds__(NB_THREADS) k_build_lists(ListArgs a) {
     for (uint32_t t = blockIdx.x; t < ntiles; t += G, ++k) {
         const uint32_t b = k & 1u;
         const float2* cdyn = sdyn[b];
-        const float2* cstat = sdyn[b] + a.cap_dyn;
+        const uint32_t cdyn_s = (uint32_t)(reinterpret_cast<const unsigned char*>(cdyn) - smem_raw), cstat_s = cdyn_s + a.cap_dyn * (uint32_t)sizeof(float2);
         const TileRuns& tr = S.runs[k % 3u];
         RunsPrefetch pre;
         const bool have2 = t + 2 * G < ntiles;
@@ -683,10 +690,10 @@ __global__ void __launch_bounds__(NB_THREADS) k_build_lists(ListArgs a) {
                 const uint32_t lc = a.keys[i] & (TILE_CELLS - 1);
                 uint16_t* col = &S.sl[0][tid];
                 // dynamic candidates, ascending slot == ascending sorted index (neighborhood_search.rs:353-366)
-                const uint32_t hits_d = list_scan_candidates(cdyn, S.crun[0][lc], S.ncand[0][lc], q, a.g.radius_sq, col, 0u);
+                const uint32_t hits_d = list_scan_candidates(cdyn_s, S.crun[0][lc], S.ncand[0][lc], q, a.g.radius_sq, col, 0u);
                 const uint32_t cd = min(hits_d, (uint32_t)YASPH_MAXN);
                 // static candidates (neighborhood_search.rs:367-381)
-                const uint32_t c = list_scan_candidates(cstat, S.crun[1][lc], S.ncand[1][lc], q, a.g.radius_sq, col, cd);
+                const uint32_t c = list_scan_candidates(cstat_s, S.crun[1][lc], S.ncand[1][lc], q, a.g.radius_sq, col, cd);
                 const uint32_t ct = min(c, (uint32_t)YASPH_MAXN);
                 // the reference's bookkeeping: "too many neighbors" when the 64th entry is written (:360,375); a static hit
                 // with all 64 slots taken by dynamic neighbours indexes neighbor_set[64] and panics (:373) -- dropped here
