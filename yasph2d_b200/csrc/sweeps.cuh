@@ -36,7 +36,13 @@ constexpr int SW_PRODUCER_WARPS = YASPH_SWEEP_PRODUCERS;  // warps 0.. stage til
 constexpr int SW_CONSUMER_WARPS = YASPH_SWEEP_CONSUMERS;  // the other warps compute
 constexpr int SW_THREADS = 32 * (SW_PRODUCER_WARPS + SW_CONSUMER_WARPS);
 #ifndef YASPH_SWEEP_MIN_CTAS
-#define YASPH_SWEEP_MIN_CTAS 1
+#define YASPH_SWEEP_MIN_CTAS 3  // caps the registers so that three CTAs share an SM
+#endif
+#ifndef YASPH_SWEEP_PSLEEP
+#define YASPH_SWEEP_PSLEEP 200  // ns between a producer's polls of an empty barrier
+#endif
+#ifndef YASPH_SWEEP_CSLEEP
+#define YASPH_SWEEP_CSLEEP 40   // ns between a consumer's polls of a full barrier
 #endif
 #ifndef YASPH_SWEEP_STAGES
 #define YASPH_SWEEP_STAGES 3
@@ -85,18 +91,23 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(void* bar, uint32_t bytes)
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(void* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(void* bar, uint32_t parity) {
+    uint32_t ok;
     asm volatile(
         "{\n"
         " .reg .pred p;\n"
-        "MBAR_WAIT:\n"
-        " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x10000;\n"  // suspend-time hint (ns): the warp sleeps instead of spinning
-        " @p bra MBAR_DONE;\n"
-        " bra MBAR_WAIT;\n"
-        "MBAR_DONE:\n"
-        "}" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        " selp.u32 %0, 1, 0, p;\n"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
+    return ok != 0u;
+}
+// A waiting warp sleeps between polls so that its polling does not take issue slots from the warps that compute.
+template <unsigned SLEEP_NS>
+__device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(SLEEP_NS);
 }
 // 1-D bulk copy global -> shared through the TMA unit; completion is counted in bytes on the barrier.  16-byte aligned, 16 | bytes.
 __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, void* bar) {
@@ -276,7 +287,7 @@ __global__ void __launch_bounds__(SW_THREADS, YASPH_SWEEP_MIN_CTAS) k_sweep(Swee
             const uint32_t nk_tile = pre_nk;
             __syncwarp();
             prefetch(t + G);  // in flight while this tile is staged
-            if (round) mbar_wait(&empty_bar[stage], (round - 1u) & 1u);  // every consumer warp has released the stage
+            if (round) mbar_wait<YASPH_SWEEP_PSLEEP>(&empty_bar[stage], (round - 1u) & 1u);  // every consumer warp has released the stage
             const SweepStage<Op> st(stage0 + stage * sbytes, c.cap_dyn, c.cap_stat, c.cap_pc);
             sweep_stage_tile(c, op, tr, nk_tile, st, &full_bar[stage], warp);
             if (++stage == NS) {
@@ -291,7 +302,7 @@ __global__ void __launch_bounds__(SW_THREADS, YASPH_SWEEP_MIN_CTAS) k_sweep(Swee
         uint32_t stage = 0, round = 0;
         for (uint32_t t = blockIdx.x; t < ntiles; t += G) {
             const SweepStage<Op> st(stage0 + stage * sbytes, c.cap_dyn, c.cap_stat, c.cap_pc);
-            mbar_wait(&full_bar[stage], round & 1u);
+            mbar_wait<YASPH_SWEEP_CSLEEP>(&full_bar[stage], round & 1u);
             const TileHeader h = *st.hdr;
             const uint32_t nk_st = *st.nk;
             const uint32_t nchunks = (h.pcount + 31u) >> 5;
