@@ -168,6 +168,32 @@ def test_dfsph_step_host_equals_resident():
     assert np.array_equal(dens, w2.particles.densities)
 
 
+@pytest.mark.parametrize("solver", [capi.SOLVER_DFSPH, capi.SOLVER_WCSPH])
+def test_step_host_pinned_arrays_overlapped_download(solver):
+    """Pinned host arrays: positions and densities leave on the copy stream while the step still computes (yasph_step_host);
+    the arrays handed back must equal device-resident stepping bit for bit, every step."""
+    import torch
+
+    w, _ = make_worlds()
+    kw = dict(cfl_factor=0.2) if solver == capi.SOLVER_WCSPH else {}
+    ctx = gpu_ctx(w, solver, **kw)
+    ctx2 = gpu_ctx(w, solver, **kw)
+    n = len(w.particles.positions)
+    pos_t = torch.empty((n, 2), dtype=torch.float32, pin_memory=True)
+    vel_t = torch.empty((n, 2), dtype=torch.float32, pin_memory=True)
+    den_t = torch.empty((n,), dtype=torch.float32, pin_memory=True)
+    pos, vel, den = pos_t.numpy(), vel_t.numpy(), den_t.numpy()
+    pos[:] = w.particles.positions
+    vel[:] = w.particles.velocities
+    for s in range(25):
+        rep = ctx.step()
+        den[:] = -1.0
+        rep2 = ctx2.step_host(pos, vel, den)
+        assert rep.dt_ns == rep2.dt_ns
+        p1, v1, d1 = ctx.download_particles()
+        assert np.array_equal(p1, pos) and np.array_equal(v1, vel) and np.array_equal(d1, den), s
+
+
 def test_wcsph_trajectory_dam_break():
     """WCSPH (wscsph.rs:126-179), cfl 0.2 (main.rs:116): 300 steps identical to the oracle incl. accelerations."""
     w, ow = make_worlds()

@@ -79,6 +79,11 @@ struct yasph_ctx {
     // pinned staging for yasph_step_host
     float *h_stage = nullptr;
     size_t h_stage_bytes = 0;
+    // yasph_step_host: results that are final before the step ends (sorted positions after the gather, densities after the
+    // density sweep) leave on a second stream while the rest of the step computes; only the velocities wait for the last pass
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_early[2] = {nullptr, nullptr};
+    float *early_pos_out = nullptr, *early_dens_out = nullptr;  // pinned host destinations of the current yasph_step_host call
     // particle ids (YASPH_FLAG_TRACK_IDS) and the slab decomposition (multi-GPU)
     uint32_t *ids = nullptr, *ids_alt = nullptr;
     struct Slab {
@@ -380,6 +385,9 @@ static void free_all(yasph_ctx* c) {
         cudaEventDestroy(e.a);
         cudaEventDestroy(e.b);
     }
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    for (int i = 0; i < 2; ++i)
+        if (c->ev_early[i]) cudaEventDestroy(c->ev_early[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
 }
 
@@ -420,6 +428,8 @@ extern "C" int32_t yasph_create(const yasph_config* cfg, yasph_ctx** out) {
     } while (0)
     CUC(cudaSetDevice(c->device));
     CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) CUC(cudaEventCreateWithFlags(&c->ev_early[i], cudaEventDisableTiming));
 
     c->cap_n = cfg->max_particles;
     c->cap_m = cfg->max_boundary;
@@ -666,7 +676,7 @@ static int32_t launch_sweep(yasph_ctx* c, Op op) {
     // List words staged per particle: what the lists needed at the last read-back (+1: they change slowly), bounded by what
     // lets three CTAs share an SM.  Any value is correct -- words beyond it are read from global memory.
     const uint32_t hint = c->h_ctl->max_nk ? c->h_ctl->max_nk + 1u : 4u;
-    const size_t soft = std::min<size_t>(c->smem_optin, 74 * 1024);
+    const size_t soft = std::min<size_t>(c->smem_optin, YASPH_SWEEP_MIN_CTAS == 3 ? 74 * 1024 : (size_t)(227 * 1024) / YASPH_SWEEP_MIN_CTAS - 1536);
     typedef SweepLayout<Op> L;
     sc.nstages = SW_STAGES;
     if (L::total_bytes(c->cap_dyn, c->cap_stat, c->cap_pc, 0, SW_STAGES) <= soft) {
@@ -1459,6 +1469,16 @@ static ViscParams visc_params(const yasph_ctx* c) {
     return v;
 }
 
+// yasph_step_host: start the download of an array that no later pass of this step writes, behind everything queued so far
+static int32_t early_download(yasph_ctx* c, float** host_dst, const void* dev, size_t bytes, int which) {
+    if (!*host_dst) return YASPH_OK;
+    CU(cudaEventRecord(c->ev_early[which], c->stream));
+    CU(cudaStreamWaitEvent(c->copy_stream, c->ev_early[which], 0));
+    CU(cudaMemcpyAsync(*host_dst, dev, bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+    *host_dst = nullptr;  // done for this call
+    return YASPH_OK;
+}
+
 // Runs one Jacobi solve (density: SOLVER 0 / divergence: SOLVER 1): optional warm start, then A/B iterations launched in
 // chunks of `speculative_iterations`; kernels past the converged iteration exit immediately on the device-side stop_iter.
 // first_a_done: pass A of iteration 0 (with its reduction and decision) already ran fused into the density+alpha sweep.
@@ -1612,6 +1632,7 @@ static int32_t dfsph_step(yasph_ctx* c) {
         }
         TRY(neighborhood_update(c, true, gp));
     }
+    TRY(early_download(c, &c->early_pos_out, c->pos, (size_t)c->n * sizeof(float2), 0));  // positions are final (dfsph.rs:502-512)
     pass_begin(c, YASPH_PASS_DENSITY_ALPHA);
     k_begin_divergence<<<1, 32, 0, c->stream>>>(c->ctl);
     CHECK_LAUNCH();
@@ -1637,6 +1658,7 @@ static int32_t dfsph_step(yasph_ctx* c) {
         TRY(launch_sweep(c, da));
     }
     pass_end(c);
+    TRY(early_download(c, &c->early_dens_out, c->dens, (size_t)c->n * sizeof(float), 1));  // densities are final (dfsph.rs:516)
     TRY(halo_exchange(c, c->dens));  // rho_j of the ghosts for the next step's viscosity pass
     TRY(jacobi_solve<1>(c, fuse_div_a0));  // dfsph.rs:521
     std::swap(c->vel, c->vstar);    // dfsph.rs:524
@@ -1662,9 +1684,11 @@ static int32_t wcsph_step(yasph_ctx* c) {
     gp.alt2[1] = &c->vel_alt;
     TRY(neighborhood_update(c, true, gp));  // wscsph.rs:153
     n = c->n;
+    TRY(early_download(c, &c->early_pos_out, c->pos, (size_t)n * sizeof(float2), 0));  // positions are final (wscsph.rs:141-153)
     pass_begin(c, YASPH_PASS_DENSITY_ALPHA);
     TRY((launch_density<1, true>(c)));  // Poly6, wscsph.rs:154; + Tait pressure per particle (wscsph.rs:91-92)
     pass_end(c);
+    TRY(early_download(c, &c->early_dens_out, c->dens, (size_t)n * sizeof(float), 1));  // densities are final (wscsph.rs:154)
     TRY(halo_exchange(c, c->vstar));  // (rho, p) of the ghosts
     pass_begin(c, YASPH_PASS_WCSPH_ACCEL);
     {
@@ -1696,12 +1720,22 @@ extern "C" int32_t yasph_step(yasph_ctx* c, yasph_step_report* report) {
         TRY(wcsph_step(c));
     else
         TRY(dfsph_step(c));
-    TRY(read_control(c));
+    // the divergence solve ends with a read-back and launches nothing after it: the DFSPH step's control block is current
+    if (c->cfg.solver == YASPH_SOLVER_WCSPH) TRY(read_control(c));
     pass_resolve(c);
     TRY(check_capacity_flags(c));
     fill_report(c, report);
     if (c->h_ctl->nonfinite) return fail(c, YASPH_ERR_NONFINITE, "non-finite Jacobi residual (solver mask %u)", c->h_ctl->nonfinite);
     return YASPH_OK;
+}
+
+static bool is_pinned_host(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
 }
 
 extern "C" int32_t yasph_step_host(yasph_ctx* c, float* pos_xy, float* vel_xy, float* densities, uint32_t n, yasph_step_report* report) {
@@ -1712,12 +1746,25 @@ extern "C" int32_t yasph_step_host(yasph_ctx* c, float* pos_xy, float* vel_xy, f
     if (n != c->n) TRY(reset_particle_set(c, n));
     CU(cudaMemcpyAsync(c->pos, pos_xy, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->vel, vel_xy, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+    // Pinned (or registered) host arrays take their results as soon as they are final, on the copy stream, overlapped with the
+    // remaining passes; pageable arrays would block the launching thread in mid-step, so they are copied at the end as before.
+    const bool pin_pos = is_pinned_host(pos_xy), pin_dens = densities && is_pinned_host(densities);
+    c->early_pos_out = pin_pos ? pos_xy : nullptr;
+    c->early_dens_out = pin_dens ? densities : nullptr;
     int32_t rc = yasph_step(c, report);
-    if (rc != YASPH_OK) return rc;
-    CU(cudaMemcpyAsync(pos_xy, c->pos, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+    // still armed: the step did not pass the hand-over point
+    float* late_pos = (!pin_pos || c->early_pos_out) ? pos_xy : nullptr;
+    float* late_dens = densities && (!pin_dens || c->early_dens_out) ? densities : nullptr;
+    c->early_pos_out = c->early_dens_out = nullptr;
+    if (rc != YASPH_OK) {
+        cudaStreamSynchronize(c->copy_stream);  // nothing of this call stays in flight towards the caller's arrays
+        return rc;
+    }
     CU(cudaMemcpyAsync(vel_xy, c->vel, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
-    if (densities) CU(cudaMemcpyAsync(densities, c->dens, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (late_pos) CU(cudaMemcpyAsync(late_pos, c->pos, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+    if (late_dens) CU(cudaMemcpyAsync(late_dens, c->dens, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->copy_stream));
     return YASPH_OK;
 }
 
