@@ -287,9 +287,27 @@ def main():
     achieved = (d_bpp * n) / (d_us * 1e-6) / 1e9
     step_bytes = (B["viscosity"] + B["predict"] + it_rho * B["density_iter"] + w_rho * B["density_warm"] + 4 + B["advect_keygen"] + B["neighborhood"]
                   + B["density_alpha"] + it_div * B["divergence_iter"] + w_div * B["divergence_warm"] + 4)
+    # the kernel(s) behind each pass group, and the DRAM traffic ncu counted for one launch of them (committed capture)
+    pass_kernels = {
+        "viscosity": ["void k_sweep<OpViscosity>(SweepCommon, T1)"],
+        "density_solve": ["void k_sweep<OpJacobiA<0>>(SweepCommon, T1)", "void k_sweep<OpJacobiB<0, 0>>(SweepCommon, T1)"],
+        "divergence_solve": ["void k_sweep<OpJacobiB<1, 0>>(SweepCommon, T1)"],
+        "density_alpha": ["void k_sweep<OpDensityAlphaDiv>(SweepCommon, T1)"],
+        "lists": ["k_build_lists(ListArgs)"],
+    }
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01", "traffic_v5.json")))
+        if n == 2000000 and world == 1:  # the capture is of this workload
+            traffic = sum(tj["kernels"][k]["dram_bytes_read"] + tj["kernels"][k]["dram_bytes_write"] for k in pass_kernels[dominant])
+            traffic_src = tj["source"]
+    except Exception:
+        pass
     roofline = {
-        "bound": "hbm", "kernel": dominant + " (k_sweep)", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-        "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_kind,
+        "bound": "hbm", "kernel": "%s (%s)" % (dominant, " + ".join(k.replace("void ", "").split("(")[0] for k in pass_kernels[dominant])),
+        "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+        "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
+        "traffic_source": traffic_src, "alg_bytes_per_launch": round(d_bpp * n, 0), "peak_source": peak_kind,
         "whole_step": {"alg_bytes_per_particle_step": round(step_bytes, 1), "GBps": round(step_bytes * n_total * args.steps / (ms * 1e-3) / 1e9, 1),
                        "frac_per_gpu": round(step_bytes * n_total / world * args.steps / (ms * 1e-3) / 1e9 / peak, 4)},
         "passes": passes, "pass_us_per_step": {k: round(v, 2) for k, v in pt.items()},
@@ -318,8 +336,15 @@ def main():
             return rep
 
         ems, ereps, _ = timed(host_step, args.steps, args.warmup)
+        timeline = None
+        if world == 1:  # where the call's time goes: device timeline of a few more calls (events on the library's streams; the event
+            # records themselves queue behind the link traffic, so this run is slower than the timed one -- read it as an order)
+            ctx.set_flags(capi.FLAG_PROFILE_PASSES)
+            tl = [dict(host_step() and ctx.host_step_times_us()) for _ in range(5)][2:]
+            ctx.set_flags(0)
+            timeline = {k: round(float(np.mean([t[k] for t in tl])), 1) for k in tl[0]}
         e2e = {"value": n_total * args.steps / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(n_total * 16), "d2h_bytes_per_step": int(n_total * 20),
-               "ms_per_step": ems / args.steps,
+               "ms_per_step": ems / args.steps, "device_timeline_us": timeline,
                "api": "yasph_step_host%s (upload pos+vel, simulation_step, download pos+vel+densities; bytes summed over ranks)" % ("" if world == 1 else "_slab")}
 
     # ---- CPU baseline (rank 0, single-GPU run only) ----

@@ -237,6 +237,10 @@ typedef enum yasph_pass {
     YASPH_PASS_WCSPH_ACCEL = 12, YASPH_PASS_WCSPH_KICK = 13, YASPH_PASS_HALO = 14, YASPH_PASS_TOTAL = 15
 } yasph_pass;
 int32_t yasph_pass_times(yasph_ctx* ctx, float* out_us /* [YASPH_NUM_PASSES] */);
+/* Device timeline of the last yasph_step_host call in microseconds from its first upload (needs YASPH_FLAG_PROFILE_PASSES):
+ * [1] both uploads done, [2] positions on the host, [3] densities on the host, [4] last kernel done, [5] velocities on the host
+ * (= end of the call's device work); [0] is 0. */
+int32_t yasph_host_step_times(yasph_ctx* ctx, float* out_us /* [6] */);
 /* number of kernel launches issued by this context since creation */
 int32_t yasph_launch_count(const yasph_ctx* ctx, uint64_t* launches);
 /* raw CUDA stream (cudaStream_t) the context launches on, for event timing by the caller */

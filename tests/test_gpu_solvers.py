@@ -168,14 +168,16 @@ def test_dfsph_step_host_equals_resident():
     assert np.array_equal(dens, w2.particles.densities)
 
 
-@pytest.mark.parametrize("solver", [capi.SOLVER_DFSPH, capi.SOLVER_WCSPH])
-def test_step_host_pinned_arrays_overlapped_download(solver):
-    """Pinned host arrays: positions and densities leave on the copy stream while the step still computes (yasph_step_host);
-    the arrays handed back must equal device-resident stepping bit for bit, every step."""
+@pytest.mark.parametrize("solver,tight", [(capi.SOLVER_DFSPH, False), (capi.SOLVER_DFSPH, True), (capi.SOLVER_WCSPH, False)])
+def test_step_host_pinned_arrays_overlapped_download(solver, tight):
+    """Pinned host arrays: positions and densities leave on the copy stream while the step still computes and the velocities
+    ahead of the last read-back (yasph_step_host); the arrays handed back must equal device-resident stepping bit for bit."""
     import torch
 
     w, _ = make_worlds()
     kw = dict(cfl_factor=0.2) if solver == capi.SOLVER_WCSPH else {}
+    if tight:  # many Jacobi iterations over several speculative chunks: the early velocity download goes stale and is repeated
+        kw = dict(dfsph_max_avg_density_error=1e-6, dfsph_max_divergence_error=1e-5)
     ctx = gpu_ctx(w, solver, **kw)
     ctx2 = gpu_ctx(w, solver, **kw)
     n = len(w.particles.positions)

@@ -29,7 +29,7 @@ EXPORTED_SYMBOLS = [
     "yasph_config_default", "yasph_create", "yasph_destroy", "yasph_last_error", "yasph_get_config", "yasph_set_flags", "yasph_get_properties",
     "yasph_set_boundary", "yasph_upload_particles", "yasph_download_particles", "yasph_download_field", "yasph_num_particles",
     "yasph_clear_cached", "yasph_step", "yasph_step_host", "yasph_time_get_step_ns", "yasph_time_set_step_ns", "yasph_time_restart",
-    "yasph_neighborhood_update", "yasph_neighbors_download", "yasph_update_densities", "yasph_compute_alpha", "yasph_pass_times",
+    "yasph_neighborhood_update", "yasph_neighbors_download", "yasph_update_densities", "yasph_compute_alpha", "yasph_pass_times", "yasph_host_step_times",
     "yasph_launch_count", "yasph_stream", "yasph_scene_fluid_rect", "yasph_scene_boundary_line", "yasph_scene_boundary_thick_line",
     "yasph_duration_from_secs_f32", "yasph_duration_as_secs_f32",
     "yasph_comm_unique_id", "yasph_comm_init", "yasph_slab_set", "yasph_slab_get", "yasph_cell_column", "yasph_step_host_slab",
@@ -128,6 +128,7 @@ def lib():
     sig("yasph_update_densities", C.c_int32, vp, C.c_int32)
     sig("yasph_compute_alpha", C.c_int32, vp)
     sig("yasph_pass_times", C.c_int32, vp, f32p)
+    sig("yasph_host_step_times", C.c_int32, vp, f32p)
     sig("yasph_launch_count", C.c_int32, vp, u64p)
     sig("yasph_stream", C.c_int32, vp, C.POINTER(vp))
     sig("yasph_scene_fluid_rect", C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_uint64, f32p,

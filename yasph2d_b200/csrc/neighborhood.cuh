@@ -557,7 +557,6 @@ struct ListSmem {
     uint32_t wk_bin[LIST_WORDS];
     uint16_t sl[NB_ROWS][NB_THREADS];
 };
-static_assert((YASPH_MAXN + 1 - 48) * TILE_THREADS >= TILE_CELLS * 50, "the expanded candidate arrays fit the unused rows of the hit columns");
 inline size_t list_smem_bytes(uint32_t cap_dyn, uint32_t cap_stat) { return sizeof(ListSmem) + 2 * ((size_t)cap_dyn + cap_stat) * sizeof(float2); }
 
 struct ListArgs {
@@ -610,35 +609,6 @@ __device__ __forceinline__ uint32_t list_scan_candidates(uint32_t cand, const ui
     }
     return c;
 }
-// Fast path of the dynamic candidates.  When no cell of the tile has more than LIST_SEG_MAX candidates in its 3x3 box, the cell
-// threads expand each cell's runs into a flat array of slots (LIST_SEG_STRIDE entries apart: an odd number of words, so the
-// lanes of a warp, which sit in a handful of different cells, read different banks), and the particle's loop body shrinks
-// to: slot, position, distance test, store, count.  No run bookkeeping, and no clamp of the row: the count cannot pass
-// LIST_SEG_MAX < 64.  The array lives in the rows of the hit columns (ListSmem::sl) that such a tile cannot reach.
-constexpr uint32_t LIST_SEG_MAX = 48, LIST_SEG_STRIDE = 50;
-// the neighbour predicate of neighborhood_search.rs:356-357, d2 <= radius_sq && d2 > 1e-10, as ONE unsigned comparison of the
-// bit patterns: d2 is a sum of squares (never negative, never -0), and a NaN's pattern lies above every finite radius_sq
-struct HitTest {
-    uint32_t lo, range;
-    __device__ __forceinline__ HitTest(float radius_sq) {
-        lo = __float_as_uint(YASPH_MIN_DISTANCE) + 1u;
-        range = __float_as_uint(radius_sq) - lo;
-    }
-    __device__ __forceinline__ uint32_t operator()(float d2) const { return (__float_as_uint(d2) - lo) <= range ? 1u : 0u; }
-};
-__device__ __forceinline__ uint32_t list_scan_expanded(uint32_t cand, const uint16_t* __restrict__ seg, uint32_t ncand, float2 q, const HitTest& hit,
-                                                       uint16_t* col) {
-    uint32_t c = 0;
-#pragma unroll 4
-    for (uint32_t j = 0; j < ncand; ++j) {
-        const uint32_t s = seg[j];
-        const float2 d = lds_f2(cand + s * 8u) - q;
-        const float d2 = mag2(d);  // fl(fl(dx * dx) + fl(dy * dy)), neighborhood_search.rs:356
-        col[c * NB_THREADS] = (uint16_t)s;
-        c += hit(d2);
-    }
-    return c;
-}
 __global__ void __launch_bounds__(NB_THREADS) k_build_lists(ListArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ListSmem& S = *reinterpret_cast<ListSmem*>(smem_raw);
@@ -671,8 +641,6 @@ __global__ void __launch_bounds__(NB_THREADS) k_build_lists(ListArgs a) {
         cp_async_commit();
         const TileHeader h = tr.hdr;
         const bool fits = h.dyn_total <= a.cap_dyn && h.stat_total <= a.cap_stat;
-        int seg_overflow = 0;
-        uint16_t* const seg_base = &S.sl[LIST_SEG_MAX][0];  // rows LIST_SEG_MAX.. of the hit columns
         if (tid < 2 * TILE_CELLS) {
             const uint32_t which = tid / TILE_CELLS, lc = tid % TILE_CELLS;
             const uint32_t lx = morton_x(lc) + 1u, ly = morton_y(lc) + 1u;
@@ -709,48 +677,23 @@ __global__ void __launch_bounds__(NB_THREADS) k_build_lists(ListArgs a) {
             }
             if (cur != 0xFFFFFFFFu) S.crun[which][lc][nr++] = cur;
             S.ncand[which][lc] = tot;
-            if (which == 0) {
-                if (tot <= LIST_SEG_MAX) {  // expand the runs into the cell's flat slot array
-                    uint16_t* segw = seg_base + lc * LIST_SEG_STRIDE;
-                    uint32_t o = 0;
-                    for (uint32_t r = 0; r < nr; ++r) {
-                        const uint32_t run = S.crun[0][lc][r];
-                        const uint32_t s0 = run >> 16, len = run & 0xFFFFu;
-                        for (uint32_t e = 0; e < len; ++e) segw[o + e] = (uint16_t)(s0 + e);
-                        o += len;
-                    }
-                } else {
-                    seg_overflow = 1;
-                }
-            }
         }
         if (tid == 0) S.nk_max = 0u;
         if (tid < (NB_THREADS / 32) * LIST_WORDS) (&S.wk[0][0])[tid] = 0u;
-        const bool fast = !__syncthreads_or(seg_overflow) && fits && h.pcount <= NB_THREADS;
+        __syncthreads();
         uint32_t my_nk = 0, my_words = 0xFFu;
         uint16_t* const counts16 = reinterpret_cast<uint16_t*>(a.counts);
         if (fits) {
-            // fast tiles: one particle per thread, dynamic candidates from the expanded arrays; the barrier before the static scan
-            // (tiles near a boundary only) retires the arrays, whose rows the static hits may then use
-            uint32_t fast_hits = 0;
-            if (fast) {
-                if (tid < h.pcount) {
-                    const uint32_t lc = a.keys[h.pstart + tid] & (TILE_CELLS - 1);
-                    fast_hits = list_scan_expanded(cdyn_s, seg_base + lc * LIST_SEG_STRIDE, S.ncand[0][lc], cdyn[h.own_lo + tid], HitTest(a.g.radius_sq),
-                                                   &S.sl[0][tid]);
-                }
-                if (h.stat_total) __syncthreads();
-            }
             for (uint32_t tl = tid; tl < h.pcount; tl += NB_THREADS) {
                 const uint32_t i = h.pstart + tl;
                 const float2 q = cdyn[h.own_lo + tl];
                 const uint32_t lc = a.keys[i] & (TILE_CELLS - 1);
                 uint16_t* col = &S.sl[0][tid];
                 // dynamic candidates, ascending slot == ascending sorted index (neighborhood_search.rs:353-366)
-                const uint32_t hits_d = fast ? fast_hits : list_scan_candidates(cdyn_s, S.crun[0][lc], S.ncand[0][lc], q, a.g.radius_sq, col, 0u);
+                const uint32_t hits_d = list_scan_candidates(cdyn_s, S.crun[0][lc], S.ncand[0][lc], q, a.g.radius_sq, col, 0u);
                 const uint32_t cd = min(hits_d, (uint32_t)YASPH_MAXN);
                 // static candidates (neighborhood_search.rs:367-381)
-                const uint32_t c = h.stat_total ? list_scan_candidates(cstat_s, S.crun[1][lc], S.ncand[1][lc], q, a.g.radius_sq, col, cd) : cd;
+                const uint32_t c = list_scan_candidates(cstat_s, S.crun[1][lc], S.ncand[1][lc], q, a.g.radius_sq, col, cd);
                 const uint32_t ct = min(c, (uint32_t)YASPH_MAXN);
                 // the reference's bookkeeping: "too many neighbors" when the 64th entry is written (:360,375); a static hit
                 // with all 64 slots taken by dynamic neighbours indexes neighbor_set[64] and panics (:373) -- dropped here

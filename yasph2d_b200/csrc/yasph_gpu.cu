@@ -83,7 +83,15 @@ struct yasph_ctx {
     // density sweep) leave on a second stream while the rest of the step computes; only the velocities wait for the last pass
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_early[2] = {nullptr, nullptr};
-    float *early_pos_out = nullptr, *early_dens_out = nullptr;  // pinned host destinations of the current yasph_step_host call
+    float *early_pos_out = nullptr, *early_dens_out = nullptr, *early_vel_out = nullptr;  // pinned host destinations of the current yasph_step_host call
+    bool early_vel_stale = false;  // the velocities changed after their speculative download (the solve needed more iterations)
+    struct PendingDownload {
+        float* host = nullptr;
+        const void* dev = nullptr;
+        size_t bytes = 0;
+    } pending[2];  // positions, densities: event recorded, copy not submitted yet
+    cudaEvent_t ev_host[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // yasph_host_step_times (YASPH_FLAG_PROFILE_PASSES)
+    float host_us[6] = {0, 0, 0, 0, 0, 0};
     // particle ids (YASPH_FLAG_TRACK_IDS) and the slab decomposition (multi-GPU)
     uint32_t *ids = nullptr, *ids_alt = nullptr;
     struct Slab {
@@ -388,6 +396,8 @@ static void free_all(yasph_ctx* c) {
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     for (int i = 0; i < 2; ++i)
         if (c->ev_early[i]) cudaEventDestroy(c->ev_early[i]);
+    for (int i = 0; i < 6; ++i)
+        if (c->ev_host[i]) cudaEventDestroy(c->ev_host[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
 }
 
@@ -430,6 +440,7 @@ extern "C" int32_t yasph_create(const yasph_config* cfg, yasph_ctx** out) {
     CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) CUC(cudaEventCreateWithFlags(&c->ev_early[i], cudaEventDisableTiming));
+    for (int i = 0; i < 6; ++i) CUC(cudaEventCreate(&c->ev_host[i]));
 
     c->cap_n = cfg->max_particles;
     c->cap_m = cfg->max_boundary;
@@ -1045,7 +1056,47 @@ static int32_t slab_exchange_particles(yasph_ctx* c, const GatherPlan& gp, uint3
     return YASPH_OK;
 }
 
-static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp) {
+// yasph_step_host hands results to the caller's (pinned) arrays as soon as they are final instead of after the step:
+//   positions   once the gather has produced the sorted order -- enqueued right AFTER the neighbourhood update's read-back,
+//               because a read-back issued while a large download is in flight waits for that download to drain (measured:
+//               the zero-copy publish, like a small DMA copy, completes only after the bulk copy ahead of it on the link);
+//   densities   after the density sweep, behind the positions on the copy stream;
+//   velocities  on the main stream right after the last Jacobi kernel launched, BEFORE the solve's read-back, so the copy
+//               runs while the host waits for the control block; if the solve then turns out to need more iterations the
+//               copy is stale and yasph_step_host repeats it.
+// A download is marked where its array becomes final (event on the main stream) but SUBMITTED only after the step's remaining
+// kernels have been enqueued (submit_downloads): kernel launches issued while a bulk download occupies the link were
+// measured to start ~20 us late each.
+static int32_t early_download(yasph_ctx* c, float** host_dst, const void* dev, size_t bytes, int which) {
+    if (!*host_dst) return YASPH_OK;
+    CU(cudaEventRecord(c->ev_early[which], c->stream));
+    c->pending[which].host = *host_dst;
+    c->pending[which].dev = dev;
+    c->pending[which].bytes = bytes;
+    *host_dst = nullptr;  // done for this call
+    return YASPH_OK;
+}
+static int32_t submit_downloads(yasph_ctx* c) {
+    for (int which = 0; which < 2; ++which) {
+        auto& p = c->pending[which];
+        if (!p.host) continue;
+        CU(cudaStreamWaitEvent(c->copy_stream, c->ev_early[which], 0));
+        CU(cudaMemcpyAsync(p.host, p.dev, p.bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+        if (c->cfg.flags & YASPH_FLAG_PROFILE_PASSES) CU(cudaEventRecord(c->ev_host[2 + which], c->copy_stream));
+        p.host = nullptr;
+    }
+    return YASPH_OK;
+}
+static int32_t early_velocities(yasph_ctx* c, const float2* final_vel) {
+    if (!c->early_vel_out) return YASPH_OK;
+    if (c->cfg.flags & YASPH_FLAG_PROFILE_PASSES) CU(cudaEventRecord(c->ev_host[4], c->stream));
+    CU(cudaMemcpyAsync(c->early_vel_out, final_vel, (size_t)c->n * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+    if (c->cfg.flags & YASPH_FLAG_PROFILE_PASSES) CU(cudaEventRecord(c->ev_host[5], c->stream));
+    c->early_vel_stale = false;
+    return YASPH_OK;
+}
+
+static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp, bool positions_final = false) {
     uint32_t n = c->n;
     c->lists_valid = false;
     c->slab.own_idx_valid = false;
@@ -1114,6 +1165,7 @@ static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp
     // the largest tile (their shared-memory size).
     TRY(read_control(c));
     TRY(check_capacity_flags(c));
+    if (positions_final && !c->slab.active) TRY(early_download(c, &c->early_pos_out, c->pos, (size_t)n * sizeof(float2), 0));
     if (c->slab.active) {
         auto& sl = c->slab;
         const Control& h = *c->h_ctl;
@@ -1469,16 +1521,6 @@ static ViscParams visc_params(const yasph_ctx* c) {
     return v;
 }
 
-// yasph_step_host: start the download of an array that no later pass of this step writes, behind everything queued so far
-static int32_t early_download(yasph_ctx* c, float** host_dst, const void* dev, size_t bytes, int which) {
-    if (!*host_dst) return YASPH_OK;
-    CU(cudaEventRecord(c->ev_early[which], c->stream));
-    CU(cudaStreamWaitEvent(c->copy_stream, c->ev_early[which], 0));
-    CU(cudaMemcpyAsync(*host_dst, dev, bytes, cudaMemcpyDeviceToHost, c->copy_stream));
-    *host_dst = nullptr;  // done for this call
-    return YASPH_OK;
-}
-
 // Runs one Jacobi solve (density: SOLVER 0 / divergence: SOLVER 1): optional warm start, then A/B iterations launched in
 // chunks of `speculative_iterations`; kernels past the converged iteration exit immediately on the device-side stop_iter.
 // first_a_done: pass A of iteration 0 (with its reduction and decision) already ran fused into the density+alpha sweep.
@@ -1552,8 +1594,13 @@ static int32_t jacobi_solve(yasph_ctx* c, bool first_a_done = false) {
             }
         }
         pass_end(c);  // the pass times are device time of the launches; the read-back below is host latency
+        // v* becomes the velocity (dfsph.rs:524) unless the loop goes on: worth a download when this chunk reaches the previous
+        // solve's iteration count (a stale copy costs its transfer time ahead of the next chunk's kernels)
+        if (SOLVER == 1) TRY(submit_downloads(c));
+        if (SOLVER == 1 && it >= prev_iters) TRY(early_velocities(c, c->vstar));
         TRY(read_control(c));
         if (c->h_ctl->stop_iter[SOLVER] != 0xFFFFFFFFu) break;
+        if (SOLVER == 1) c->early_vel_stale = true;
         if (it > sp.max_iters + spec + 1) return fail(c, YASPH_ERR_STATE, "jacobi_solve: device loop control did not terminate");
         chunk = slab ? 1u : spec;
     }
@@ -1630,9 +1677,8 @@ static int32_t dfsph_step(yasph_ctx* c) {
             gp.a1[1] = &c->stiff;
             gp.alt1[1] = &c->f_alt1;
         }
-        TRY(neighborhood_update(c, true, gp));
+        TRY(neighborhood_update(c, true, gp, true));  // positions are final (dfsph.rs:502-512)
     }
-    TRY(early_download(c, &c->early_pos_out, c->pos, (size_t)c->n * sizeof(float2), 0));  // positions are final (dfsph.rs:502-512)
     pass_begin(c, YASPH_PASS_DENSITY_ALPHA);
     k_begin_divergence<<<1, 32, 0, c->stream>>>(c->ctl);
     CHECK_LAUNCH();
@@ -1682,9 +1728,8 @@ static int32_t wcsph_step(yasph_ctx* c) {
     gp.alt2[0] = &c->pos_alt;
     gp.a2[1] = &c->vel;
     gp.alt2[1] = &c->vel_alt;
-    TRY(neighborhood_update(c, true, gp));  // wscsph.rs:153
+    TRY(neighborhood_update(c, true, gp, true));  // wscsph.rs:153; positions are final (wscsph.rs:141-153)
     n = c->n;
-    TRY(early_download(c, &c->early_pos_out, c->pos, (size_t)n * sizeof(float2), 0));  // positions are final (wscsph.rs:141-153)
     pass_begin(c, YASPH_PASS_DENSITY_ALPHA);
     TRY((launch_density<1, true>(c)));  // Poly6, wscsph.rs:154; + Tait pressure per particle (wscsph.rs:91-92)
     pass_end(c);
@@ -1721,7 +1766,11 @@ extern "C" int32_t yasph_step(yasph_ctx* c, yasph_step_report* report) {
     else
         TRY(dfsph_step(c));
     // the divergence solve ends with a read-back and launches nothing after it: the DFSPH step's control block is current
-    if (c->cfg.solver == YASPH_SOLVER_WCSPH) TRY(read_control(c));
+    if (c->cfg.solver == YASPH_SOLVER_WCSPH) {
+        TRY(submit_downloads(c));
+        TRY(early_velocities(c, c->vel));
+        TRY(read_control(c));
+    }
     pass_resolve(c);
     TRY(check_capacity_flags(c));
     fill_report(c, report);
@@ -1744,27 +1793,60 @@ extern "C" int32_t yasph_step_host(yasph_ctx* c, float* pos_xy, float* vel_xy, f
     if (c->slab.active) return fail(c, YASPH_ERR_STATE, "yasph_step_host: the particle count of a slab changes with migration, use yasph_step_host_slab");
     CU(cudaSetDevice(c->device));
     if (n != c->n) TRY(reset_particle_set(c, n));
+    const bool prof = (c->cfg.flags & YASPH_FLAG_PROFILE_PASSES) != 0;
+    if (prof) CU(cudaEventRecord(c->ev_host[0], c->stream));
     CU(cudaMemcpyAsync(c->pos, pos_xy, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->vel, vel_xy, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+    if (prof) CU(cudaEventRecord(c->ev_host[1], c->stream));
     // Pinned (or registered) host arrays take their results as soon as they are final, on the copy stream, overlapped with the
     // remaining passes; pageable arrays would block the launching thread in mid-step, so they are copied at the end as before.
-    const bool pin_pos = is_pinned_host(pos_xy), pin_dens = densities && is_pinned_host(densities);
+    const bool pin_pos = is_pinned_host(pos_xy), pin_vel = is_pinned_host(vel_xy), pin_dens = densities && is_pinned_host(densities);
     c->early_pos_out = pin_pos ? pos_xy : nullptr;
     c->early_dens_out = pin_dens ? densities : nullptr;
+    c->early_vel_out = pin_vel ? vel_xy : nullptr;
+    c->early_vel_stale = true;  // until a download has been enqueued
     int32_t rc = yasph_step(c, report);
     // still armed: the step did not pass the hand-over point
     float* late_pos = (!pin_pos || c->early_pos_out) ? pos_xy : nullptr;
     float* late_dens = densities && (!pin_dens || c->early_dens_out) ? densities : nullptr;
-    c->early_pos_out = c->early_dens_out = nullptr;
+    const bool late_vel = !pin_vel || c->early_vel_stale;
+    c->early_pos_out = c->early_dens_out = c->early_vel_out = nullptr;
+    if (rc != YASPH_OK) c->pending[0].host = c->pending[1].host = nullptr;
     if (rc != YASPH_OK) {
+        cudaStreamSynchronize(c->stream);
         cudaStreamSynchronize(c->copy_stream);  // nothing of this call stays in flight towards the caller's arrays
         return rc;
     }
-    CU(cudaMemcpyAsync(vel_xy, c->vel, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
-    if (late_pos) CU(cudaMemcpyAsync(late_pos, c->pos, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
-    if (late_dens) CU(cudaMemcpyAsync(late_dens, c->dens, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (late_vel) {
+        if (prof) CU(cudaEventRecord(c->ev_host[4], c->stream));
+        CU(cudaMemcpyAsync(vel_xy, c->vel, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+        if (prof) CU(cudaEventRecord(c->ev_host[5], c->stream));
+    }
+    if (late_pos) {
+        CU(cudaMemcpyAsync(late_pos, c->pos, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+        if (prof) CU(cudaEventRecord(c->ev_host[2], c->stream));
+    }
+    if (late_dens) {
+        CU(cudaMemcpyAsync(late_dens, c->dens, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        if (prof) CU(cudaEventRecord(c->ev_host[3], c->stream));
+    }
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaStreamSynchronize(c->copy_stream));
+    if (prof) {
+        for (int i = 0; i < 6; ++i) c->host_us[i] = 0.f;
+        for (int i = 1; i < 6; ++i) {
+            if (i == 3 && !densities) continue;
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, c->ev_host[0], c->ev_host[i]) == cudaSuccess) c->host_us[i] = ms * 1000.f;
+        }
+        cudaGetLastError();
+    }
+    return YASPH_OK;
+}
+
+extern "C" int32_t yasph_host_step_times(yasph_ctx* c, float* out_us) {
+    if (!c || !out_us) return YASPH_ERR_INVALID_ARGUMENT;
+    memcpy(out_us, c->host_us, sizeof(c->host_us));
     return YASPH_OK;
 }
 

@@ -172,6 +172,12 @@ class GpuContext:
         self._ck(capi.lib().yasph_pass_times(self.h, _f32p(out)))
         return dict(zip(capi.PASS_NAMES, out.tolist()))
 
+    def host_step_times_us(self):
+        """Device timeline of the last step_host call (see yasph_host_step_times)."""
+        out = np.zeros(6, np.float32)
+        self._ck(capi.lib().yasph_host_step_times(self.h, _f32p(out)))
+        return dict(zip(("start", "uploaded", "positions_on_host", "densities_on_host", "kernels_done", "velocities_on_host"), out.tolist()))
+
     def launch_count(self):
         v = C.c_uint64(0)
         self._ck(capi.lib().yasph_launch_count(self.h, C.byref(v)))
