@@ -35,7 +35,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="tank", choices=["tank", "dam_break"])
+    ap.add_argument("--workload", default="tank", choices=["tank", "dam_break", "neighbors"])
+    ap.add_argument("--neighbors-n", default="100000,1000000,4000000,16000000,64000000", help="particle counts of the config-5 sweep")
+    ap.add_argument("--neighbors-radius", default="0.5,0.75,1.0,1.25", help="search radii of the config-5 sweep")
     ap.add_argument("--columns-per-gpu", type=int, default=2000)
     ap.add_argument("--rows", type=int, default=1000)
     ap.add_argument("--presteps", type=int, default=200)
@@ -131,8 +133,65 @@ def run_cpu(args, columns, steps, warmup):
             "ms_per_step": 1e3 * dt / steps, "n": w.n, "iters_density_mean": its[0] / steps, "iters_divergence_mean": its[1] / steps}
 
 
+def neighbor_sweep(args):
+    """BASELINE.json configs[4]: neighbour search only, uniform points at density 10 / unit^2, seed
+    123456789 (neighborhood_search.rs:531-538, benches/benchmarks/neighborhood_search.rs:9-29).  Warm = the points are already
+    in sorted order (what the reference's bench measures after its first update), cold = shuffled.  GB/s are algorithmic bytes
+    (B_ns = 140 + 4K per particle for the whole update, B_list = 16 + 4K for the list build) over device time."""
+    import torch
+    import yasph2d_b200 as y
+    from oracle import pyoracle as po  # input generator only (the reference's SmallRng stream restated): not on the timed path
+
+    capi = y.capi
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    rows = []
+    for n in [int(x) for x in args.neighbors_n.split(",")]:
+        r = np.zeros(2 * n, np.float32)
+        po.lib().yo_rng_fill(123456789, r.ctypes.data_as(po.C.POINTER(po.C.c_float)), 2 * n)
+        pos = (r.reshape(n, 2) * np.float32(np.sqrt(np.float32(n) / np.float32(10.0)))).astype(np.float32)
+        del r
+        for radius in [float(x) for x in args.neighbors_radius.split(",")]:
+            ns = y.NeighborhoodSearch(radius, max_particles=n, max_boundary=1)
+            ctx = ns.ctx
+            ctx.upload_particles(pos)
+            ctx.neighborhood_update()  # cold-start allocation effects out of the way
+            ctx.set_flags(capi.FLAG_PROFILE_PASSES)
+            res = {"n": n, "radius": radius}
+            for kind in ("cold", "warm"):
+                acc, reps = {}, 3
+                for _ in range(reps):
+                    if kind == "cold":
+                        ctx.upload_particles(pos)  # the generator's order: random in space
+                    rep = ctx.neighborhood_update()
+                    for k, v in ctx.pass_times_us().items():
+                        acc[k] = acc.get(k, 0.0) + v / reps
+                K = rep.total_neighbors / n
+                t_all = acc["sort"] + acc["gather"] + acc["cells_tiles"] + acc["lists"]
+                res.update({"mean_neighbors": round(K, 2), "capped": int(rep.neighbors_capped),
+                            kind + "_us": round(t_all, 1), kind + "_lists_us": round(acc["lists"], 1),
+                            kind + "_GBps": round((140 + 4 * K) * n / (t_all * 1e-6) / 1e9, 1),
+                            kind + "_lists_GBps": round((16 + 4 * K) * n / (acc["lists"] * 1e-6) / 1e9, 1),
+                            kind + "_Mparticles_per_s": round(n / t_all, 1)})
+            res["warm_frac_of_hbm_peak"] = round(res["warm_GBps"] / peak, 4)
+            rows.append(res)
+            print("# " + json.dumps(res), file=sys.stderr, flush=True)
+            ctx.close()
+            del ns, ctx
+            torch.cuda.empty_cache()
+    print(json.dumps({"metric": "neighbour search only (BASELINE configs[4]): algorithmic GB/s of update_dynamic", "unit": "GB/s", "n_gpus": 1,
+                      "peak": peak, "data": "synthetic uniform points, density 10, seed 123456789", "sweep": rows}))
+    return 0
+
+
 def main():
     args = parse()
+    if args.workload == "neighbors":
+        return neighbor_sweep(args)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
