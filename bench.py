@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--cpu-columns", type=int, default=250, help="fluid columns of the bounded CPU sample (rows as the workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-peer-transport", action="store_true", help="multi-GPU: keep halo exchanges and all-reduces on NCCL (A/B of the peer-memory transport)")
     return ap.parse_args()
 
 
@@ -241,6 +242,8 @@ def main():
 
     cfg = capi.default_config(2.0, 10000.0, 100.0, capi.SOLVER_DFSPH)
     cfg.device = local_rank
+    if args.no_peer_transport:
+        cfg.flags |= capi.FLAG_NO_PEER_TRANSPORT
     if world == 1:
         n = n_global
         cfg.max_particles, cfg.max_boundary = n, m

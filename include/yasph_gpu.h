@@ -113,6 +113,7 @@ typedef struct yasph_config {
 #define YASPH_FLAG_PERMUTE_WARMSTART 1u /* permute kappa/stiffness with the particles; default off = reference behaviour (quirk Q1: dfsph.rs:512 passes only v*) */
 #define YASPH_FLAG_PROFILE_PASSES 2u    /* record a CUDA event pair per pass (see yasph_pass_times) */
 #define YASPH_FLAG_TRACK_IDS 4u         /* carry a uint32 id with every particle through re-sorts and migration (YASPH_FIELD_ID) */
+#define YASPH_FLAG_NO_PEER_TRANSPORT 8u /* slab mode: keep every exchange on NCCL send/recv + all-reduce instead of stores into the peers' mapped mailboxes */
 
 /* Fills every field with the reference's defaults for the given world parameters
  * (FluidParticleWorld::new(smoothing_factor, particle_density, fluid_density), main.rs:85-89). */
@@ -215,9 +216,10 @@ typedef struct yasph_slab_info {
     uint32_t n_local;               /* owned + ghost particles */
     uint32_t n_ghost_left, n_ghost_right;
     uint32_t migrated_out_left, migrated_out_right, migrated_in;  /* of the last neighbourhood update */
+    uint32_t peer_transport;        /* 1: per-pass halo exchanges and all-reduces run as stores into the peers' mapped mailboxes (NVLink); 0: NCCL / loopback */
     uint64_t n_global;
-    uint64_t halo_exchanges;        /* halo exchanges (NCCL send/recv groups) since creation */
-    uint64_t allreduces;            /* NCCL all-reduces since creation */
+    uint64_t halo_exchanges;        /* halo exchanges since creation */
+    uint64_t allreduces;            /* all-reduces since creation */
 } yasph_slab_info;
 int32_t yasph_slab_get(yasph_ctx* ctx, yasph_slab_info* out);
 /* cell column of an x coordinate under the context's grid (neighborhood_search.rs:52-58), for host-side partitioning */

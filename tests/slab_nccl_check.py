@@ -35,6 +35,8 @@ def main():
     uid = slab.broadcast_unique_id(dist)
     cfg = base_config(len(pos), len(boundary))
     cfg.device = local
+    if os.environ.get("SLAB_TRANSPORT", "peer") == "nccl":
+        cfg.flags |= y.capi.FLAG_NO_PEER_TRANSPORT
     ctx, ranges, id_map = slab.make_slab_context(cfg, rank, world, uid, pos, vel, boundary)
     reps, snaps, infos = [], {}, []
     for s in range(steps):
@@ -56,6 +58,7 @@ def main():
             ok, msg = False, str(e)[:400]
         print(json.dumps({"check": "slab_nccl", "world": world, "steps": steps, "first_migration": fm, "ranges": ranges, "result": msg,
                           "n_own_final": [g["infos"][-1]["n_own"] for g in gathered],
+                          "peer_transport": min(g["infos"][-1]["peer_transport"] for g in gathered),
                           "halo_exchanges": gathered[0]["infos"][-1]["halo_exchanges"], "allreduces": gathered[0]["infos"][-1]["allreduces"]}))
     flag = [ok]
     dist.broadcast_object_list(flag, src=0)

@@ -103,8 +103,10 @@ def test_slab_world_one_equals_plain_context():
         assert np.array_equal(snaps1[29][k], merged[29][k])
 
 
-def test_nccl_transport_two_gpus():
-    """The same equivalence through the NCCL transport, one process per GPU (needs >= 2 GPUs on the box)."""
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
+def test_two_gpus_one_process_per_gpu(transport):
+    """The same equivalence with one process per GPU (needs >= 2 GPUs on the box): halo exchanges and all-reduces as stores
+    into the peers' mapped mailboxes over NVLink ("peer", the default), or everything through NCCL ("nccl")."""
     import os
     import subprocess
     import sys
@@ -116,6 +118,8 @@ def test_nccl_transport_two_gpus():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29517",
            os.path.join(root, "tests", "slab_nccl_check.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    env = dict(os.environ, SLAB_TRANSPORT=transport)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
     assert '"result": "ok"' in r.stdout, r.stdout[-2000:]
+    assert ('"peer_transport": %d' % (1 if transport == "peer" else 0)) in r.stdout, r.stdout[-2000:]

@@ -17,7 +17,7 @@ KERNEL_WENDLAND_C2, KERNEL_POLY6, KERNEL_SPIKY, KERNEL_CUBIC = 0, 1, 2, 3
 (FIELD_POSITION, FIELD_VELOCITY, FIELD_DENSITY, FIELD_ALPHA, FIELD_KAPPA, FIELD_STIFFNESS, FIELD_ACCELERATION, FIELD_CELL_KEY,
  FIELD_SORT_PERMUTATION, FIELD_BOUNDARY, FIELD_ID, FIELD_GHOST) = range(12)
 FIELD_LOCAL_BIT = 0x100
-FLAG_PERMUTE_WARMSTART, FLAG_PROFILE_PASSES, FLAG_TRACK_IDS = 1, 2, 4
+FLAG_PERMUTE_WARMSTART, FLAG_PROFILE_PASSES, FLAG_TRACK_IDS, FLAG_NO_PEER_TRANSPORT = 1, 2, 4, 8
 COMM_ID_BYTES = 128
 NUM_PASSES = 16
 PASS_NAMES = ["viscosity", "predict", "density_warm", "density_solve", "advect_keygen", "sort", "gather", "cells_tiles", "lists",
@@ -70,7 +70,7 @@ class SlabInfo(C.Structure):
     _fields_ = [
         ("rank", C.c_int32), ("world", C.c_int32), ("col_lo", C.c_uint32), ("col_hi", C.c_uint32), ("n_own", C.c_uint32), ("n_local", C.c_uint32),
         ("n_ghost_left", C.c_uint32), ("n_ghost_right", C.c_uint32), ("migrated_out_left", C.c_uint32),
-        ("migrated_out_right", C.c_uint32), ("migrated_in", C.c_uint32), ("n_global", C.c_uint64),
+        ("migrated_out_right", C.c_uint32), ("migrated_in", C.c_uint32), ("peer_transport", C.c_uint32), ("n_global", C.c_uint64),
         ("halo_exchanges", C.c_uint64), ("allreduces", C.c_uint64),
     ]
 

@@ -262,7 +262,7 @@ struct Control {
     unsigned long long slab_ghost;       // ghosts from the left | right rank, in sorted order
     unsigned long long slab_own;         // owned particles (low word)
     unsigned int err_slab;               // a particle arrived that this rank does not own (moved more than one slab in a step)
-    unsigned int pad_slab;
+    unsigned int err_comm;               // peer-memory transport: bit 0 a halo message, bit 1 an all-reduce contribution did not arrive in time
 };
 
 // slab decomposition parameters handed to the key-generating kernels (active == 0: single GPU)

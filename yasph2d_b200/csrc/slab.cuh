@@ -124,6 +124,126 @@ __global__ void k_halo_unpack(T* __restrict__ field, const uint32_t* __restrict_
         field[idx_r[k - nl]] = buf_r[k - nl];
 }
 
+// ---- peer-memory transport (NVLink / NVSwitch, one process per GPU) ---------------------------------------------------------
+// Every rank owns a MAILBOX in its device memory that its peers map (CUDA IPC) and write with plain stores over NVLink:
+//   halo exchange    k_halo_push gathers the send lists and stores the values straight into the neighbours' mailboxes, the last
+//                    CTA then publishes the sequence number (release, system scope); k_halo_pull on the receiving rank waits
+//                    for that number (acquire) and scatters the payload to the ghost slots -- two small kernels per exchange and
+//                    rank, no staging copy, no collective call;
+//   all-reduce       k_allreduce_peer stores the rank's scalar into every peer's mailbox, waits for every peer's scalar and
+//                    combines them in rank order (every rank computes the same bits).
+// Payload and all-reduce slots are double-buffered by the parity of the sequence number: the ranks run the same sequence of
+// exchanges, every exchange moves data in both directions of a link, so a rank can be at most one exchange ahead of a peer
+// that still reads the previous payload.  A wait that exceeds PEER_TIMEOUT_NS raises Control::err_comm instead of hanging.
+constexpr int PEER_MAX_RANKS = 16;
+constexpr unsigned long long PEER_TIMEOUT_NS = 4000000000ull;
+struct PeerBoxHeader {
+    unsigned long long halo_flag[2];            // [side]: sequence number of the last complete halo message from that side
+    unsigned long long ar_flag[PEER_MAX_RANKS]; // [source rank]: sequence number of its last all-reduce contribution
+    double ar_val[2][PEER_MAX_RANKS];           // [parity][source rank]
+};
+constexpr size_t PEER_HEADER_BYTES = (sizeof(PeerBoxHeader) + 255) & ~(size_t)255;
+__host__ __device__ inline size_t peer_box_bytes(uint32_t max_halo) { return PEER_HEADER_BYTES + 4 * (size_t)max_halo * 8; }
+__host__ __device__ inline unsigned char* peer_payload(void* box, uint32_t max_halo, unsigned parity, int side) {
+    return reinterpret_cast<unsigned char*>(box) + PEER_HEADER_BYTES + (size_t)(parity * 2 + side) * max_halo * 8;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// waits until *flag >= seq; false on timeout
+__device__ __forceinline__ bool peer_wait(const unsigned long long* flag, unsigned long long seq) {
+    const unsigned long long t0 = global_timer_ns();
+    while (ld_acquire_sys(flag) < seq) {
+        __nanosleep(200);
+        if (global_timer_ns() - t0 > PEER_TIMEOUT_NS) return false;
+    }
+    return true;
+}
+// dst_l / dst_r: payload of this exchange in the left / right neighbour's mailbox (null: no neighbour on that side)
+template <typename T>
+__global__ void k_halo_push(const T* __restrict__ field, const uint32_t* __restrict__ idx_l, uint32_t nl, const uint32_t* __restrict__ idx_r, uint32_t nr,
+                            T* dst_l, T* dst_r, unsigned long long* flag_l, unsigned long long* flag_r, unsigned long long seq, unsigned int* ticket) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nl)
+        dst_l[k] = field[idx_l[k]];
+    else if (k < nl + nr)
+        dst_r[k - nl] = field[idx_r[k - nl]];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(ticket, 1u);
+        if (t == gridDim.x - 1) {  // every CTA's stores are ordered before its ticket
+            *ticket = 0u;
+            __threadfence_system();
+            if (flag_l) st_release_sys(flag_l, seq);
+            if (flag_r) st_release_sys(flag_r, seq);
+        }
+    }
+}
+// src_l / src_r: payload of this exchange in the own mailbox; flag_l / flag_r: own halo flags (null: no neighbour on that side)
+template <typename T>
+__global__ void k_halo_pull(T* __restrict__ field, const uint32_t* __restrict__ idx_l, uint32_t nl, const uint32_t* __restrict__ idx_r, uint32_t nr,
+                            const T* src_l, const T* src_r, const unsigned long long* flag_l, const unsigned long long* flag_r, unsigned long long seq,
+                            Control* ctl) {
+    __shared__ int ok;
+    if (threadIdx.x == 0) {
+        ok = 1;
+        if (flag_l && !peer_wait(flag_l, seq)) ok = 0;
+        if (flag_r && !peer_wait(flag_r, seq)) ok = 0;
+        if (!ok) atomicOr(&ctl->err_comm, 1u);
+    }
+    __syncthreads();
+    if (!ok) return;
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nl)
+        field[idx_l[k]] = __ldcg(&src_l[k]);  // written by the peer: read at the L2, never from a stale L1 line
+    else if (k < nl + nr)
+        field[idx_r[k - nl]] = __ldcg(&src_r[k - nl]);
+}
+// one warp; boxes[r] = rank r's mailbox as mapped here (boxes[rank] = the own one); value in place at dev_ptr
+__global__ void k_allreduce_peer(void* dev_ptr, int is_double_sum, PeerBoxHeader* const* __restrict__ boxes, int rank, int world, unsigned long long seq,
+                                 Control* ctl) {
+    const int lane = threadIdx.x;
+    const unsigned parity = (unsigned)(seq & 1ull);
+    const double mine = is_double_sum ? *reinterpret_cast<const double*>(dev_ptr) : (double)*reinterpret_cast<const float*>(dev_ptr);
+    if (lane < world) {
+        PeerBoxHeader* b = boxes[lane];
+        reinterpret_cast<volatile double*>(b->ar_val[parity])[rank] = mine;
+        __threadfence_system();
+        st_release_sys(&b->ar_flag[rank], seq);
+    }
+    __syncwarp();
+    PeerBoxHeader* me = boxes[rank];
+    bool ok = true;
+    if (lane < world) ok = peer_wait(&me->ar_flag[lane], seq);
+    ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) {
+        if (!ok) {
+            atomicOr(&ctl->err_comm, 2u);
+        } else {
+            double acc = __ldcg(&me->ar_val[parity][0]);
+            for (int r = 1; r < world; ++r) {
+                const double v = __ldcg(&me->ar_val[parity][r]);
+                acc = is_double_sum ? acc + v : fmax(acc, v);
+            }
+            if (is_double_sum)
+                *reinterpret_cast<double*>(dev_ptr) = acc;
+            else
+                *reinterpret_cast<float*>(dev_ptr) = (float)acc;
+        }
+    }
+}
+
 // compaction / scatter of one field between the local sorted array (owned + ghosts) and an owned-only array
 template <typename T>
 __global__ void k_own_compact(const T* __restrict__ field, const uint32_t* __restrict__ own_idx, uint32_t n_own, T* __restrict__ out) {

@@ -116,6 +116,13 @@ struct yasph_ctx {
         uint32_t mig_out[2] = {0, 0}, mig_in = 0;
         bool own_idx_valid = false;
         uint64_t halo_exchanges = 0, allreduces = 0;
+        // peer-memory transport (slab.cuh): the own mailbox, the peers' mailboxes as mapped into this process, sequence numbers
+        bool peer = false, peer_tried = false;
+        void* box = nullptr;
+        void* peer_box[PEER_MAX_RANKS] = {};
+        PeerBoxHeader** d_boxes = nullptr;  // device copy of peer_box (all-reduce kernel)
+        unsigned int* d_ticket = nullptr;
+        uint64_t halo_seq = 0, ar_seq = 0;
     } slab;
     // state flags
     bool have_particles = false, lists_valid = false, dfsph_ready = false;
@@ -132,6 +139,7 @@ struct yasph_ctx {
 // error helpers
 // ---------------------------------------------------------------------------------------------------------------------
 static void fabric_mark_failed(yasph_ctx* c);
+static void peer_teardown(yasph_ctx* c);
 static int32_t fail(yasph_ctx* c, int32_t code, const char* fmt, ...) {
     char buf[512];
     va_list ap;
@@ -223,6 +231,7 @@ struct NcclApi {
     decltype(&ncclSend) Send = nullptr;
     decltype(&ncclRecv) Recv = nullptr;
     decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr;
     std::string error;
 };
 static NcclApi g_nccl;
@@ -254,6 +263,7 @@ static bool nccl_load() {
     NCCL_SYM(Send, "ncclSend")
     NCCL_SYM(Recv, "ncclRecv")
     NCCL_SYM(AllReduce, "ncclAllReduce")
+    NCCL_SYM(AllGather, "ncclAllGather")
 #undef NCCL_SYM
     g_nccl.handle = h;
     return true;
@@ -387,6 +397,7 @@ static void free_all(yasph_ctx* c) {
         if (c->slab.ev_ready[sd]) cudaEventDestroy(c->slab.ev_ready[sd]);
         if (c->slab.ev_done[sd]) cudaEventDestroy(c->slab.ev_done[sd]);
     }
+    peer_teardown(c);
     comm_destroy(c);
     for (auto e : c->event_pool) cudaEventDestroy(e);
     for (auto& e : c->events) {
@@ -738,6 +749,9 @@ static int32_t read_control(yasph_ctx* c) {
     return YASPH_OK;
 }
 static int32_t check_capacity_flags(yasph_ctx* c) {
+    if (c->h_ctl->err_comm)
+        return fail(c, YASPH_ERR_COMM, "peer-memory transport: rank %d waited more than %.0f s for a neighbour (mask %u)", c->slab.rank, PEER_TIMEOUT_NS * 1e-9,
+                    c->h_ctl->err_comm);
     if (c->h_ctl->err_tile_count)
         return fail(c, YASPH_ERR_CAPACITY, "%u non-empty tiles exceed max_tiles=%u (particles too sparse for the configured capacity)", c->h_ctl->err_tile_count, c->max_tiles);
     if (c->h_ctl->err_tile_capacity)
@@ -915,6 +929,29 @@ static int32_t halo_exchange(yasph_ctx* c, T* field) {
     pass_begin(c, YASPH_PASS_HALO);
     auto& sl = c->slab;
     const uint32_t ns = sl.n_send[0] + sl.n_send[1], ng = sl.n_ghost[0] + sl.n_ghost[1];
+    if (sl.peer) {
+        // stores into the neighbours' mailboxes, then the scatter of what the neighbours stored here (slab.cuh)
+        const uint64_t seq = ++sl.halo_seq;
+        const unsigned par = (unsigned)(seq & 1u);
+        const bool hl = has_left(c), hr = has_right(c);
+        void* bl = hl ? sl.peer_box[sl.rank - 1] : nullptr;
+        void* br = hr ? sl.peer_box[sl.rank + 1] : nullptr;
+        // my data arrives on the RIGHT side of my left neighbour and on the LEFT side of my right neighbour
+        k_halo_push<T><<<ns ? blocks_for(ns, 256) : 1, 256, 0, c->stream>>>(
+            field, sl.send_idx[0], hl ? sl.n_send[0] : 0u, sl.send_idx[1], hr ? sl.n_send[1] : 0u,
+            hl ? reinterpret_cast<T*>(peer_payload(bl, sl.max_halo, par, 1)) : nullptr, hr ? reinterpret_cast<T*>(peer_payload(br, sl.max_halo, par, 0)) : nullptr,
+            hl ? &reinterpret_cast<PeerBoxHeader*>(bl)->halo_flag[1] : nullptr, hr ? &reinterpret_cast<PeerBoxHeader*>(br)->halo_flag[0] : nullptr, seq, sl.d_ticket);
+        CHECK_LAUNCH();
+        PeerBoxHeader* me = reinterpret_cast<PeerBoxHeader*>(sl.box);
+        k_halo_pull<T><<<ng ? blocks_for(ng, 256) : 1, 256, 0, c->stream>>>(
+            field, sl.ghost_idx[0], hl ? sl.n_ghost[0] : 0u, sl.ghost_idx[1], hr ? sl.n_ghost[1] : 0u,
+            reinterpret_cast<const T*>(peer_payload(sl.box, sl.max_halo, par, 0)), reinterpret_cast<const T*>(peer_payload(sl.box, sl.max_halo, par, 1)),
+            hl ? &me->halo_flag[0] : nullptr, hr ? &me->halo_flag[1] : nullptr, seq, c->ctl);
+        CHECK_LAUNCH();
+        sl.halo_exchanges++;
+        pass_end(c);
+        return YASPH_OK;
+    }
     if (ns) {
         k_halo_pack<T><<<blocks_for(ns, 256), 256, 0, c->stream>>>(field, sl.send_idx[0], sl.n_send[0], sl.send_idx[1], sl.n_send[1],
                                                                    reinterpret_cast<T*>(sl.sbuf[0]), reinterpret_cast<T*>(sl.sbuf[1]));
@@ -938,6 +975,13 @@ static int32_t halo_exchange(yasph_ctx* c, T* field) {
 static int32_t allreduce_scalar(yasph_ctx* c, void* dev_ptr, ncclDataType_t type, ncclRedOp_t op) {
     if (!c->slab.active || c->slab.world < 2) return YASPH_OK;
     if (c->slab.fabric) return loopback_allreduce(c, dev_ptr, type == ncclDouble && op == ncclSum);
+    if (c->slab.peer) {
+        k_allreduce_peer<<<1, 32, 0, c->stream>>>(dev_ptr, type == ncclDouble && op == ncclSum ? 1 : 0, c->slab.d_boxes, c->slab.rank, c->slab.world,
+                                                  ++c->slab.ar_seq, c->ctl);
+        CHECK_LAUNCH();
+        c->slab.allreduces++;
+        return YASPH_OK;
+    }
     NC(g_nccl.AllReduce(dev_ptr, dev_ptr, 1, type, op, (ncclComm_t)c->slab.comm, c->stream));
     c->slab.allreduces++;
     return YASPH_OK;
@@ -1911,6 +1955,89 @@ extern "C" int32_t yasph_comm_init_loopback(yasph_ctx* c, void* fabric, int32_t 
     return YASPH_OK;
 }
 
+// Peer-memory transport: allocate the mailbox, hand its IPC handle to every rank (all-gather over the NCCL communicator that
+// exists anyway), map the peers' mailboxes.  Collective; falls back to NCCL send/recv + all-reduce on every rank if any rank
+// cannot map a peer (no NVLink / peer access) or YASPH_FLAG_NO_PEER_TRANSPORT is set.
+static int32_t peer_setup(yasph_ctx* c) {
+    auto& sl = c->slab;
+    if (sl.peer_tried || !sl.comm || sl.world < 2) return YASPH_OK;
+    sl.peer_tried = true;
+    if (sl.world > PEER_MAX_RANKS) return YASPH_OK;
+    ncclComm_t comm = (ncclComm_t)sl.comm;
+    int ok = (c->cfg.flags & YASPH_FLAG_NO_PEER_TRANSPORT) ? 0 : 1;
+    const size_t bytes = peer_box_bytes(sl.max_halo);
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    if (ok && cudaMalloc(&sl.box, bytes) != cudaSuccess) ok = 0;
+    if (ok && cudaMemset(sl.box, 0, bytes) != cudaSuccess) ok = 0;
+    if (ok && cudaIpcGetMemHandle(&mine, sl.box) != cudaSuccess) ok = 0;
+    cudaGetLastError();
+    // all-gather (ok flag, handle) records
+    struct Rec {
+        int ok;
+        int pad;
+        cudaIpcMemHandle_t h;
+    };
+    Rec rec;
+    rec.ok = ok;
+    rec.pad = 0;
+    rec.h = mine;
+    Rec* d_all = nullptr;
+    CU(cudaMalloc((void**)&d_all, sizeof(Rec) * (sl.world + 1)));
+    CU(cudaMemcpyAsync(d_all + sl.world, &rec, sizeof(Rec), cudaMemcpyHostToDevice, c->stream));
+    NC(g_nccl.AllGather(d_all + sl.world, d_all, sizeof(Rec), ncclChar, comm, c->stream));
+    std::vector<Rec> all(sl.world);
+    CU(cudaMemcpyAsync(all.data(), d_all, sizeof(Rec) * sl.world, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int r = 0; r < sl.world; ++r) ok = ok && all[r].ok;
+    if (ok) {
+        for (int r = 0; r < sl.world && ok; ++r) {
+            if (r == sl.rank) {
+                sl.peer_box[r] = sl.box;
+            } else if (cudaIpcOpenMemHandle(&sl.peer_box[r], all[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                sl.peer_box[r] = nullptr;
+                ok = 0;
+                cudaGetLastError();
+            }
+        }
+    }
+    // every rank must take the same path: all-reduce the verdict (the record buffer doubles as scratch)
+    int* d_ok = reinterpret_cast<int*>(d_all);
+    CU(cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    NC(g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, comm, c->stream));
+    CU(cudaMemcpyAsync(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaFree(d_all));
+    if (ok) {
+        CU(cudaMalloc((void**)&sl.d_boxes, sizeof(void*) * PEER_MAX_RANKS));
+        CU(cudaMemcpy(sl.d_boxes, sl.peer_box, sizeof(void*) * PEER_MAX_RANKS, cudaMemcpyHostToDevice));
+        CU(cudaMalloc((void**)&sl.d_ticket, sizeof(unsigned int)));
+        CU(cudaMemset(sl.d_ticket, 0, sizeof(unsigned int)));
+        sl.peer = true;
+    } else {
+        for (int r = 0; r < sl.world; ++r)
+            if (r != sl.rank && sl.peer_box[r]) cudaIpcCloseMemHandle(sl.peer_box[r]);
+        memset(sl.peer_box, 0, sizeof(sl.peer_box));
+        if (sl.box) cudaFree(sl.box);
+        sl.box = nullptr;
+        cudaGetLastError();
+    }
+    return YASPH_OK;
+}
+static void peer_teardown(yasph_ctx* c) {
+    auto& sl = c->slab;
+    for (int r = 0; r < PEER_MAX_RANKS; ++r)
+        if (r != sl.rank && sl.peer_box[r]) cudaIpcCloseMemHandle(sl.peer_box[r]);
+    memset(sl.peer_box, 0, sizeof(sl.peer_box));
+    if (sl.box) cudaFree(sl.box);
+    if (sl.d_boxes) cudaFree(sl.d_boxes);
+    if (sl.d_ticket) cudaFree(sl.d_ticket);
+    sl.box = nullptr;
+    sl.d_boxes = nullptr;
+    sl.d_ticket = nullptr;
+    sl.peer = false;
+}
+
 extern "C" int32_t yasph_slab_set(yasph_ctx* c, uint32_t col_lo, uint32_t col_hi, uint64_t n_global, uint32_t id_base) {
     if (!c) return YASPH_ERR_INVALID_ARGUMENT;
     auto& sl = c->slab;
@@ -1937,6 +2064,7 @@ extern "C" int32_t yasph_slab_set(yasph_ctx* c, uint32_t col_lo, uint32_t col_hi
         CU(dmalloc(&sl.d_cnt, 4));
         CU(cudaMallocHost((void**)&sl.h_cnt, 4 * sizeof(uint32_t)));
     }
+    TRY(peer_setup(c));
     sl.active = true;
     sl.n_own = 0;
     sl.n_ghost[0] = sl.n_ghost[1] = sl.n_send[0] = sl.n_send[1] = 0;
@@ -1963,6 +2091,7 @@ extern "C" int32_t yasph_slab_get(yasph_ctx* c, yasph_slab_info* out) {
     out->migrated_out_left = sl.mig_out[0];
     out->migrated_out_right = sl.mig_out[1];
     out->migrated_in = sl.mig_in;
+    out->peer_transport = sl.peer ? 1u : 0u;
     out->n_global = sl.active ? sl.n_global : c->n;
     out->halo_exchanges = sl.halo_exchanges;
     out->allreduces = sl.allreduces;
