@@ -143,9 +143,13 @@ struct PeerBoxHeader {
     double ar_val[2][PEER_MAX_RANKS];           // [parity][source rank]
 };
 constexpr size_t PEER_HEADER_BYTES = (sizeof(PeerBoxHeader) + 255) & ~(size_t)255;
-__host__ __device__ inline size_t peer_box_bytes(uint32_t max_halo) { return PEER_HEADER_BYTES + 4 * (size_t)max_halo * 8; }
+constexpr size_t PEER_RECORD_MAX_BYTES = 3 * 8 + 3 * 4;  // the widest particle record (three float2 + three float arrays)
+constexpr size_t PEER_MSG_HEADER_BYTES = 16;             // record messages: count of records, then the SoA block
+// one payload slot holds the largest message: a halo field (8 bytes per particle) or a block of particle records
+__host__ __device__ inline size_t peer_slot_bytes(uint32_t max_halo) { return (PEER_MSG_HEADER_BYTES + (size_t)max_halo * PEER_RECORD_MAX_BYTES + 255) & ~(size_t)255; }
+__host__ __device__ inline size_t peer_box_bytes(uint32_t max_halo) { return PEER_HEADER_BYTES + 4 * peer_slot_bytes(max_halo); }
 __host__ __device__ inline unsigned char* peer_payload(void* box, uint32_t max_halo, unsigned parity, int side) {
-    return reinterpret_cast<unsigned char*>(box) + PEER_HEADER_BYTES + (size_t)(parity * 2 + side) * max_halo * 8;
+    return reinterpret_cast<unsigned char*>(box) + PEER_HEADER_BYTES + (size_t)(parity * 2 + side) * peer_slot_bytes(max_halo);
 }
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -210,6 +214,93 @@ __global__ void k_halo_pull(T* __restrict__ field, const uint32_t* __restrict__ 
     else if (k < nl + nr)
         field[idx_r[k - nl]] = __ldcg(&src_r[k - nl]);
 }
+// ---- particle records (migrants, ghosts) through the mailboxes: the COUNTS stay on the device ------------------------------
+// k_records_push reads how many particles the ordered selection picked for each side (device memory), packs them straight
+// into the neighbours' mailboxes behind a 16-byte header carrying the count, and publishes the sequence number.
+// k_records_pull waits for both neighbours, appends their records at `first` (left arrivals, then right), and reports the
+// four counts (out left/right, in left/right) to the host through mapped memory -- the one thing the host has to learn
+// before it can size the next launches.  Replaces: count exchange (copy, NCCL group, copy, stream sync) + pack + NCCL group
+// + unpack.
+struct PeerCounts {  // mapped host memory
+    uint32_t out[2], in[2];
+    uint32_t seq;
+};
+__global__ void k_records_push(RecordArrays arr, const uint32_t* __restrict__ idx_l, const uint32_t* __restrict__ idx_r,
+                               const unsigned long long* __restrict__ counts, uint32_t cap, unsigned char* dst_l, unsigned char* dst_r,
+                               unsigned long long* flag_l, unsigned long long* flag_r, unsigned long long seq, unsigned int* ticket) {
+    const unsigned long long cc = *counts;
+    const uint32_t nl = dst_l ? min((uint32_t)(cc & 0xFFFFFFFFull), cap) : 0u, nr = dst_r ? min((uint32_t)(cc >> 32), cap) : 0u;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < nl + nr; k += gridDim.x * blockDim.x) {
+        const bool right = k >= nl;
+        const uint32_t kk = right ? k - nl : k, cnt = right ? nr : nl;
+        const uint32_t s = (right ? idx_r : idx_l)[kk];
+        unsigned char* buf = (right ? dst_r : dst_l) + PEER_MSG_HEADER_BYTES;
+        float2* b2 = reinterpret_cast<float2*>(buf);
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+            if (q < arr.n2) b2[(size_t)q * cnt + kk] = arr.a2[q][s];
+        float* b1 = reinterpret_cast<float*>(buf + (size_t)arr.n2 * 8 * cnt);
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+            if (q < arr.n1) b1[(size_t)q * cnt + kk] = arr.a1[q][s];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (dst_l) *reinterpret_cast<uint32_t*>(dst_l) = nl;
+        if (dst_r) *reinterpret_cast<uint32_t*>(dst_r) = nr;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(ticket, 1u);
+        if (t == gridDim.x - 1) {
+            *ticket = 0u;
+            __threadfence_system();
+            if (flag_l) st_release_sys(flag_l, seq);
+            if (flag_r) st_release_sys(flag_r, seq);
+        }
+    }
+}
+__global__ void k_records_pull(RecordArrays arr, uint32_t first, uint32_t cap_n, uint32_t cap_halo, const unsigned char* src_l, const unsigned char* src_r,
+                               const unsigned long long* flag_l, const unsigned long long* flag_r, unsigned long long seq, uint8_t* __restrict__ pflag,
+                               const unsigned long long* __restrict__ my_counts, PeerCounts* host_counts, uint32_t host_seq, Control* ctl) {
+    __shared__ int ok;
+    if (threadIdx.x == 0) {
+        ok = 1;
+        if (flag_l && !peer_wait(flag_l, seq)) ok = 0;
+        if (flag_r && !peer_wait(flag_r, seq)) ok = 0;
+        if (!ok) atomicOr(&ctl->err_comm, 4u);
+    }
+    __syncthreads();
+    const uint32_t nl = (ok && flag_l) ? __ldcg(reinterpret_cast<const uint32_t*>(src_l)) : 0u;
+    const uint32_t nr = (ok && flag_r) ? __ldcg(reinterpret_cast<const uint32_t*>(src_r)) : 0u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {  // the host only needs the counts; the kernels it launches next are stream-ordered behind this one
+        const unsigned long long cc = *my_counts;
+        volatile PeerCounts* h = host_counts;
+        h->out[0] = (uint32_t)(cc & 0xFFFFFFFFull);
+        h->out[1] = (uint32_t)(cc >> 32);
+        h->in[0] = nl;
+        h->in[1] = nr;
+        __threadfence_system();
+        h->seq = host_seq;
+        __threadfence_system();
+    }
+    if (nl > cap_halo || nr > cap_halo || (unsigned long long)first + nl + nr > cap_n) return;  // the host fails the step on these counts
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < nl + nr; k += gridDim.x * blockDim.x) {
+        const bool right = k >= nl;
+        const uint32_t kk = right ? k - nl : k, cnt = right ? nr : nl;
+        const unsigned char* buf = (right ? src_r : src_l) + PEER_MSG_HEADER_BYTES;
+        const float2* b2 = reinterpret_cast<const float2*>(buf);
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+            if (q < arr.n2) arr.a2[q][first + k] = __ldcg(&b2[(size_t)q * cnt + kk]);
+        const float* b1 = reinterpret_cast<const float*>(buf + (size_t)arr.n2 * 8 * cnt);
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+            if (q < arr.n1) arr.a1[q][first + k] = __ldcg(&b1[(size_t)q * cnt + kk]);
+        pflag[first + k] = 0;
+    }
+}
+
 // one warp; boxes[r] = rank r's mailbox as mapped here (boxes[rank] = the own one); value in place at dev_ptr
 __global__ void k_allreduce_peer(void* dev_ptr, int is_double_sum, PeerBoxHeader* const* __restrict__ boxes, int rank, int world, unsigned long long seq,
                                  Control* ctl) {

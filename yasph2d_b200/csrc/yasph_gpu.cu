@@ -123,6 +123,9 @@ struct yasph_ctx {
         PeerBoxHeader** d_boxes = nullptr;  // device copy of peer_box (all-reduce kernel)
         unsigned int* d_ticket = nullptr;
         uint64_t halo_seq = 0, ar_seq = 0;
+        PeerCounts* h_pcounts = nullptr;  // mapped pinned: counts of the last record exchange
+        PeerCounts* d_pcounts = nullptr;  // its device address
+        uint32_t pcounts_seq = 0;
     } slab;
     // state flags
     bool have_particles = false, lists_valid = false, dfsph_ready = false;
@@ -726,18 +729,14 @@ __global__ void k_publish_control(const Control* __restrict__ ctl, uint32_t* __r
         __threadfence_system();
     }
 }
-static int32_t read_control(yasph_ctx* c) {
-    static_assert(sizeof(Control) % 4 == 0, "Control is published word by word");
-    const unsigned int seq = ++c->pub_seq;
-    k_publish_control<<<1, 64, 0, c->stream>>>(c->ctl, reinterpret_cast<uint32_t*>(&c->d_pub->ctl), &c->d_pub->seq, seq);
-    CHECK_LAUNCH();
-    volatile unsigned int* vs = &c->h_pub->seq;
+// polls a sequence number a kernel writes into mapped host memory
+static int32_t wait_published(yasph_ctx* c, volatile unsigned int* vs, unsigned int seq) {
     for (uint32_t spins = 0; *vs != seq; ++spins) {
         if ((spins & 0xFFFu) == 0xFFFu) {  // now and then: has the stream died (or drained without publishing)?
             const cudaError_t q = cudaStreamQuery(c->stream);
             if (q != cudaErrorNotReady) {
-                if (q != cudaSuccess) return fail(c, YASPH_ERR_CUDA, "%s while waiting for the control block", cudaGetErrorString(q));
-                if (*vs != seq) return fail(c, YASPH_ERR_CUDA, "control block was not published");
+                if (q != cudaSuccess) return fail(c, YASPH_ERR_CUDA, "%s while waiting for a device-published value", cudaGetErrorString(q));
+                if (*vs != seq) return fail(c, YASPH_ERR_CUDA, "device-published value did not arrive");
             }
         }
 #if defined(__x86_64__)
@@ -745,6 +744,14 @@ static int32_t read_control(yasph_ctx* c) {
 #endif
     }
     std::atomic_thread_fence(std::memory_order_acquire);
+    return YASPH_OK;
+}
+static int32_t read_control(yasph_ctx* c) {
+    static_assert(sizeof(Control) % 4 == 0, "Control is published word by word");
+    const unsigned int seq = ++c->pub_seq;
+    k_publish_control<<<1, 64, 0, c->stream>>>(c->ctl, reinterpret_cast<uint32_t*>(&c->d_pub->ctl), &c->d_pub->seq, seq);
+    CHECK_LAUNCH();
+    TRY(wait_published(c, &c->h_pub->seq, seq));
     memcpy(c->h_ctl, const_cast<const Control*>(&c->h_pub->ctl), sizeof(Control));
     return YASPH_OK;
 }
@@ -1011,6 +1018,36 @@ static RecordArrays record_arrays(const GatherPlan& gp) {
 // Slab mode, between key generation and the sort: particles that left the slab migrate to the adjacent rank, the ghosts of
 // the previous structure are dropped, and the first / last owned columns are exchanged as the new ghosts.  On return
 // *n_sort particles (old local + arrivals) carry sort keys (dropped ones YASPH_KEY_DROPPED) and *n_keep of them survive.
+// Peer transport: the records picked by the last ordered selection (index lists sel[0] / sel[1], counts in *d_counts on the
+// device) go to the left / right neighbour's mailbox, the neighbours' records are appended at `first`; out / in = the counts.
+static int32_t peer_exchange_records(yasph_ctx* c, const RecordArrays& ra, const unsigned long long* d_counts, uint32_t first, uint32_t out[2], uint32_t in[2]) {
+    auto& sl = c->slab;
+    const uint64_t seq = ++sl.halo_seq;
+    const unsigned par = (unsigned)(seq & 1u);
+    const bool hl = has_left(c), hr = has_right(c);
+    void* bl = hl ? sl.peer_box[sl.rank - 1] : nullptr;
+    void* br = hr ? sl.peer_box[sl.rank + 1] : nullptr;
+    PeerBoxHeader* me = reinterpret_cast<PeerBoxHeader*>(sl.box);
+    const int grid = 64;  // grid-stride: the counts are known on the device only
+    k_records_push<<<grid, 256, 0, c->stream>>>(ra, sl.sel[0], sl.sel[1], d_counts, sl.max_halo, hl ? peer_payload(bl, sl.max_halo, par, 1) : nullptr,
+                                                hr ? peer_payload(br, sl.max_halo, par, 0) : nullptr,
+                                                hl ? &reinterpret_cast<PeerBoxHeader*>(bl)->halo_flag[1] : nullptr,
+                                                hr ? &reinterpret_cast<PeerBoxHeader*>(br)->halo_flag[0] : nullptr, seq, sl.d_ticket);
+    CHECK_LAUNCH();
+    const uint32_t hseq = ++sl.pcounts_seq;
+    k_records_pull<<<grid, 256, 0, c->stream>>>(ra, first, c->cap_n, sl.max_halo, peer_payload(sl.box, sl.max_halo, par, 0), peer_payload(sl.box, sl.max_halo, par, 1),
+                                                hl ? &me->halo_flag[0] : nullptr, hr ? &me->halo_flag[1] : nullptr, seq, sl.pflag, d_counts, sl.d_pcounts, hseq,
+                                                c->ctl);
+    CHECK_LAUNCH();
+    TRY(wait_published(c, &sl.h_pcounts->seq, hseq));
+    for (int sd = 0; sd < 2; ++sd) {
+        out[sd] = sl.h_pcounts->out[sd];
+        in[sd] = sl.h_pcounts->in[sd];
+    }
+    sl.halo_exchanges++;
+    return YASPH_OK;
+}
+
 static int32_t slab_exchange_particles(yasph_ctx* c, const GatherPlan& gp, uint32_t n_old, uint32_t* n_sort, uint32_t* n_keep) {
     auto& sl = c->slab;
     const RecordArrays ra = record_arrays(gp);
@@ -1019,8 +1056,13 @@ static int32_t slab_exchange_particles(yasph_ctx* c, const GatherPlan& gp, uint3
     const uint32_t ghosts_old = sl.n_ghost[0] + sl.n_ghost[1];
     // (1) migrants: ordered selection by classification flag, counts to both neighbours
     TRY(select_pair(c, FlagSelIn{sl.pflag, (uint8_t)SLAB_MIG_LEFT, (uint8_t)SLAB_MIG_RIGHT}, n_old, sl.sel[0], sl.sel[1], nullptr, sl.max_halo, &c->ctl->slab_migrants));
-    TRY(exchange_counts(c, &c->ctl->slab_migrants));
-    uint32_t out[2] = {sl.h_cnt[0], sl.h_cnt[1]}, in[2] = {sl.h_cnt[2], sl.h_cnt[3]};
+    uint32_t out[2], in[2];
+    if (sl.peer) {
+        TRY(peer_exchange_records(c, ra, &c->ctl->slab_migrants, n_old, out, in));
+    } else {
+        TRY(exchange_counts(c, &c->ctl->slab_migrants));
+        out[0] = sl.h_cnt[0], out[1] = sl.h_cnt[1], in[0] = sl.h_cnt[2], in[1] = sl.h_cnt[3];
+    }
     // a particle that leaves through an end of the domain has no rank to go to
     if ((out[0] && !has_left(c)) || (out[1] && !has_right(c)))
         return fail(c, YASPH_ERR_STATE, "rank %d: %u / %u particles left the domain's first / last slab [%u, %u)", sl.rank, out[0], out[1], sl.col_lo, sl.col_hi);
@@ -1032,7 +1074,7 @@ static int32_t slab_exchange_particles(yasph_ctx* c, const GatherPlan& gp, uint3
     uint32_t n1 = n_old + in[0] + in[1];
     if (n1 > c->cap_n) return fail(c, YASPH_ERR_CAPACITY, "rank %d: %u local particles after migration > max_particles=%u", sl.rank, n1, c->cap_n);
     if (out[0] + out[1] + in[0] + in[1]) {
-        for (int sd = 0; sd < 2; ++sd)
+        for (int sd = 0; sd < 2 && !sl.peer; ++sd)
             if (out[sd]) {
                 k_pack_records<<<blocks_for(out[sd], 256), 256, 0, c->stream>>>(ra, sl.sel[sd], out[sd], sl.sbuf[sd]);
                 CHECK_LAUNCH();
@@ -1040,9 +1082,9 @@ static int32_t slab_exchange_particles(yasph_ctx* c, const GatherPlan& gp, uint3
         const void* sb[2] = {sl.sbuf[0], sl.sbuf[1]};
         void* rb[2] = {sl.rbuf[0], sl.rbuf[1]};
         const size_t sby[2] = {out[0] * rec, out[1] * rec}, rby[2] = {in[0] * rec, in[1] * rec};
-        TRY(neighbor_sendrecv(c, sb, sby, rb, rby));
+        if (!sl.peer) TRY(neighbor_sendrecv(c, sb, sby, rb, rby));
         uint32_t first = n_old;
-        for (int sd = 0; sd < 2; ++sd)
+        for (int sd = 0; sd < 2 && !sl.peer; ++sd)
             if (in[sd]) {
                 k_unpack_records<<<blocks_for(in[sd], 256), 256, 0, c->stream>>>(ra, first, in[sd], sl.rbuf[sd], sl.pflag);
                 CHECK_LAUNCH();
@@ -1060,15 +1102,20 @@ static int32_t slab_exchange_particles(yasph_ctx* c, const GatherPlan& gp, uint3
     // (2) ghosts: the owned particles of the first / last owned column, in pre-sort order, to the left / right rank
     const uint32_t ca = has_left(c) ? sl.col_lo : 0xFFFFFFFFu, cb = has_right(c) ? sl.col_hi - 1u : 0xFFFFFFFFu;
     TRY(select_pair(c, ColumnSelIn{c->keys[0], sl.pflag, ca, cb}, n1, sl.sel[0], sl.sel[1], nullptr, sl.max_halo, &c->ctl->slab_ghost_send));
-    TRY(exchange_counts(c, &c->ctl->slab_ghost_send));
-    uint32_t gout[2] = {sl.h_cnt[0], sl.h_cnt[1]}, gin[2] = {sl.h_cnt[2], sl.h_cnt[3]};
+    uint32_t gout[2], gin[2];
+    if (sl.peer) {
+        TRY(peer_exchange_records(c, ra, &c->ctl->slab_ghost_send, n1, gout, gin));
+    } else {
+        TRY(exchange_counts(c, &c->ctl->slab_ghost_send));
+        gout[0] = sl.h_cnt[0], gout[1] = sl.h_cnt[1], gin[0] = sl.h_cnt[2], gin[1] = sl.h_cnt[3];
+    }
     for (int sd = 0; sd < 2; ++sd)
         if (gout[sd] > sl.max_halo || gin[sd] > sl.max_halo)
             return fail(c, YASPH_ERR_CAPACITY, "rank %d: %u ghosts out / %u in on side %d exceed max_halo=%u", sl.rank, gout[sd], gin[sd], sd, sl.max_halo);
     const uint32_t n2 = n1 + gin[0] + gin[1];
     if (n2 > c->cap_n) return fail(c, YASPH_ERR_CAPACITY, "rank %d: %u local particles with ghosts > max_particles=%u", sl.rank, n2, c->cap_n);
     if (gout[0] + gout[1] + gin[0] + gin[1]) {
-        for (int sd = 0; sd < 2; ++sd)
+        for (int sd = 0; sd < 2 && !sl.peer; ++sd)
             if (gout[sd]) {
                 k_pack_records<<<blocks_for(gout[sd], 256), 256, 0, c->stream>>>(ra, sl.sel[sd], gout[sd], sl.sbuf[sd]);
                 CHECK_LAUNCH();
@@ -1076,9 +1123,9 @@ static int32_t slab_exchange_particles(yasph_ctx* c, const GatherPlan& gp, uint3
         const void* sb[2] = {sl.sbuf[0], sl.sbuf[1]};
         void* rb[2] = {sl.rbuf[0], sl.rbuf[1]};
         const size_t sby[2] = {gout[0] * rec, gout[1] * rec}, rby[2] = {gin[0] * rec, gin[1] * rec};
-        TRY(neighbor_sendrecv(c, sb, sby, rb, rby));
+        if (!sl.peer) TRY(neighbor_sendrecv(c, sb, sby, rb, rby));
         uint32_t first = n1;
-        for (int sd = 0; sd < 2; ++sd)
+        for (int sd = 0; sd < 2 && !sl.peer; ++sd)
             if (gin[sd]) {
                 k_unpack_records<<<blocks_for(gin[sd], 256), 256, 0, c->stream>>>(ra, first, gin[sd], sl.rbuf[sd], sl.pflag);
                 CHECK_LAUNCH();
@@ -2013,6 +2060,9 @@ static int32_t peer_setup(yasph_ctx* c) {
         CU(cudaMemcpy(sl.d_boxes, sl.peer_box, sizeof(void*) * PEER_MAX_RANKS, cudaMemcpyHostToDevice));
         CU(cudaMalloc((void**)&sl.d_ticket, sizeof(unsigned int)));
         CU(cudaMemset(sl.d_ticket, 0, sizeof(unsigned int)));
+        CU(cudaHostAlloc((void**)&sl.h_pcounts, sizeof(PeerCounts), cudaHostAllocMapped));
+        memset(sl.h_pcounts, 0, sizeof(PeerCounts));
+        CU(cudaHostGetDevicePointer((void**)&sl.d_pcounts, sl.h_pcounts, 0));
         sl.peer = true;
     } else {
         for (int r = 0; r < sl.world; ++r)
@@ -2032,6 +2082,9 @@ static void peer_teardown(yasph_ctx* c) {
     if (sl.box) cudaFree(sl.box);
     if (sl.d_boxes) cudaFree(sl.d_boxes);
     if (sl.d_ticket) cudaFree(sl.d_ticket);
+    if (sl.h_pcounts) cudaFreeHost(sl.h_pcounts);
+    sl.h_pcounts = nullptr;
+    sl.d_pcounts = nullptr;
     sl.box = nullptr;
     sl.d_boxes = nullptr;
     sl.d_ticket = nullptr;
