@@ -67,19 +67,43 @@ def pass_bytes(K):
     }
 
 
-def clocks_sampler(stop, out, device_index):
-    """nvidia-smi clocks line of /opt/skills/guides/B200_PROFILING.md, sampled during the timed region."""
+def clocks_sampler(stop, out, device_index, errors=None):
+    """SM clock, power and throttle reasons sampled during the timed regions: NVML in-process (a sample per ~2 ms, so that even
+    a timed region of a few milliseconds is covered), else the nvidia-smi clocks line of /opt/skills/guides/B200_PROFILING.md."""
+    try:
+        import pynvml as nv
+
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(device_index)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = [getattr(nv, "nvmlClocksThrottleReason" + n) for n in ("HwSlowdown", "HwThermalSlowdown", "SwThermalSlowdown", "SwPowerCap")]
+        while True:
+            r = reasons(h)
+            try:
+                watts = "%.2f" % (nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+            except Exception:
+                watts = "0"
+            out.append([str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx), watts] + [("Active" if (r & b) else "Not Active") for b in bits]
+                       + [time.perf_counter()])
+            if stop.wait(0.002):
+                return
+    except Exception as e:  # no NVML binding on this box: fall back to the command-line tool
+        if errors is not None:
+            errors.append("nvml: %r" % (e,))
     q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-    while not stop.is_set():
+    while True:
         try:
             r = subprocess.run(["nvidia-smi", "-i", str(device_index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
                                capture_output=True, text=True, timeout=5)
             f = [x.strip() for x in r.stdout.strip().split(",")]
             if len(f) >= 7:
-                out.append(f)
-        except Exception:
-            pass
-        stop.wait(0.2)
+                out.append(f[:7] + [time.perf_counter()])
+        except Exception as e:
+            if errors is not None:
+                errors.append("nvidia-smi: %r" % (e,))
+        if stop.wait(0.2):
+            return
 
 
 def summarize_clocks(samples):
@@ -262,6 +286,11 @@ def main():
     del hw
     stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=torch.device("cuda", local_rank))
 
+    # clocks sampler: started before the pre-steps (NVML initialisation takes longer than a short timed region); only the
+    # samples stamped inside the timed region are reported
+    stop, samples, clock_errors, window = threading.Event(), [], [], {}
+    th = threading.Thread(target=clocks_sampler, args=(stop, samples, local_rank, clock_errors), daemon=True)
+    th.start()
     for _ in range(args.presteps):
         ctx.step()
     if world > 1:
@@ -275,11 +304,13 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = []
         l0 = ctx.launch_count()
+        window.setdefault("t0", time.perf_counter())  # the first timed region (device-resident steps) is the one the clocks belong to
         e0.record(stream)
         for _ in range(steps):
             reps.append(step_fn())
         e1.record(stream)
         torch.cuda.synchronize()
+        window.setdefault("t1", time.perf_counter())
         barrier()
         ms = e0.elapsed_time(e1)
         launches = ctx.launch_count() - l0
@@ -290,12 +321,14 @@ def main():
         return ms, reps, launches
 
     # ---- device-resident throughput (`value`) with clocks sampled during the timed region ----
-    stop, samples = threading.Event(), []
-    th = threading.Thread(target=clocks_sampler, args=(stop, samples, local_rank), daemon=True)
-    th.start()
     ms, reps, launches = timed(ctx.step, args.steps, args.warmup)
     stop.set()
     th.join(timeout=3)
+    in_window = [s_ for s_ in samples if window["t0"] <= s_[7] <= window["t1"]]
+    clocks = summarize_clocks(in_window if in_window else samples[-1:])
+    clocks["window"] = "timed region" if in_window else "nearest sample (the timed region is shorter than one sampling period)"
+    if clock_errors:
+        clocks["sampler_notes"] = clock_errors[:2]
     if world == 1:
         n_total = n
     else:
@@ -427,7 +460,7 @@ def main():
                 "mean_neighbors": round(K, 2), "iters_density": it_rho, "iters_divergence": it_div, "warm_density": w_rho, "warm_divergence": w_div,
                 "arithmetic": "strict f32, no FMA contraction, IEEE div/sqrt (bit-exact vs oracle)",
             },
-            "gpu_launches": int(launches), "clocks": summarize_clocks(samples), "roofline": roofline,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
         }
         if e2e:
             line["e2e"] = e2e

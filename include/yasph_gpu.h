@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define YASPH_ABI_VERSION 2u
+#define YASPH_ABI_VERSION 3u
 #define YASPH_MAX_NEIGHBORS 64u /* neighborhood_search.rs:322 */
 
 typedef struct yasph_ctx yasph_ctx;
@@ -159,6 +159,26 @@ int32_t yasph_upload_particles(yasph_ctx* ctx, const float* pos_xy, const float*
 /* Any pointer may be NULL.  Arrays are in the current sorted order, as the reference leaves its Vecs. */
 int32_t yasph_download_particles(yasph_ctx* ctx, float* pos_xy, float* vel_xy, float* densities);
 int32_t yasph_download_field(yasph_ctx* ctx, int32_t field, void* out, uint64_t out_bytes);
+
+/* ---- checkpoint / resume (the reference has no counterpart: its solver state dies with the process) ----
+ * What a solver carries from one simulation_step to the next besides positions and velocities: DFSPH the two warm-start
+ * arrays and the iteration counts that switch the warm starts on (dfsph.rs:36-41, 199, 354), WCSPH the accelerations of the
+ * previous step (wscsph.rs:22, 141-150); plus TimeManager's current step (timemanager.rs:136-138).  Densities, alpha factors
+ * and the neighbour lists are functions of the (sorted) positions and are rebuilt.
+ * Resume: yasph_set_boundary, yasph_upload_particles(sorted positions, velocities of the checkpoint), yasph_solver_state_set
+ * (runs the solver's first-call initialisation, dfsph.rs:419-428, right away), then yasph_upload_field for KAPPA / STIFFNESS
+ * (DFSPH) or ACCELERATION (WCSPH).  The following steps are bit-identical to the uninterrupted run. */
+typedef struct yasph_solver_state {
+    uint64_t step_ns;             /* TimeManager::simulation_step */
+    uint32_t iters_density;       /* num_density_correction_iterations of the last solve */
+    uint32_t iters_divergence;    /* num_divergence_correction_iterations of the last solve */
+    uint32_t initialized;         /* get: the solver has run its first-call initialisation; set: run it now */
+    uint32_t reserved;
+} yasph_solver_state;
+int32_t yasph_solver_state_get(yasph_ctx* ctx, yasph_solver_state* out);
+int32_t yasph_solver_state_set(yasph_ctx* ctx, const yasph_solver_state* in);
+/* overwrite a per-particle solver array (same order as yasph_download_field): YASPH_FIELD_KAPPA, _STIFFNESS, _ACCELERATION */
+int32_t yasph_upload_field(yasph_ctx* ctx, int32_t field, const void* data, uint64_t bytes);
 int32_t yasph_num_particles(const yasph_ctx* ctx, uint32_t* n, uint32_t* m);
 
 /* ---- solver --------------------------------------------------------------------------------------------------- */
@@ -230,13 +250,14 @@ int32_t yasph_step_host_slab(yasph_ctx* ctx, float* pos_xy, float* vel_xy, float
                              uint32_t* n_out, yasph_step_report* report);
 
 /* ---- measurement ----------------------------------------------------------------------------------------------- */
-#define YASPH_NUM_PASSES 16
+#define YASPH_NUM_PASSES 17
 /* Per-pass device time of the last step in microseconds (needs YASPH_FLAG_PROFILE_PASSES), index = yasph_pass. */
 typedef enum yasph_pass {
     YASPH_PASS_VISCOSITY = 0, YASPH_PASS_PREDICT = 1, YASPH_PASS_DENSITY_WARM = 2, YASPH_PASS_DENSITY_SOLVE = 3,
     YASPH_PASS_ADVECT_KEYGEN = 4, YASPH_PASS_SORT = 5, YASPH_PASS_GATHER = 6, YASPH_PASS_CELLS_TILES = 7,
     YASPH_PASS_LISTS = 8, YASPH_PASS_DENSITY_ALPHA = 9, YASPH_PASS_DIVERGENCE_WARM = 10, YASPH_PASS_DIVERGENCE_SOLVE = 11,
-    YASPH_PASS_WCSPH_ACCEL = 12, YASPH_PASS_WCSPH_KICK = 13, YASPH_PASS_HALO = 14, YASPH_PASS_TOTAL = 15
+    YASPH_PASS_WCSPH_ACCEL = 12, YASPH_PASS_WCSPH_KICK = 13, YASPH_PASS_HALO = 14 /* per-pass halo exchanges */,
+    YASPH_PASS_MIGRATE = 15 /* slab mode: migrant + ghost particle exchange of a neighbourhood update */, YASPH_PASS_TOTAL = 16
 } yasph_pass;
 int32_t yasph_pass_times(yasph_ctx* ctx, float* out_us /* [YASPH_NUM_PASSES] */);
 /* Device timeline of the last yasph_step_host call in microseconds from its first upload (needs YASPH_FLAG_PROFILE_PASSES):

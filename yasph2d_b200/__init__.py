@@ -4,6 +4,7 @@ The product is libyasph_gpu.so (CUDA, C ABI in include/yasph_gpu.h).  This packa
 binding (_capi) and the host-side mirror of the reference's Solver / FluidParticleWorld / NeighborhoodSearch surface (host).
 """
 from . import _capi as capi  # noqa: F401
+from . import stateio  # noqa: F401
 from .host import (  # noqa: F401
     ConstantFluidProperties,
     DFSPHSolver,

@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libyasph_gpu.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_NEIGHBORS = 64
 SOLVER_DFSPH, SOLVER_WCSPH = 0, 1
 VISCOSITY_XSPH, VISCOSITY_PHYSICAL = 0, 1
@@ -19,9 +19,9 @@ KERNEL_WENDLAND_C2, KERNEL_POLY6, KERNEL_SPIKY, KERNEL_CUBIC = 0, 1, 2, 3
 FIELD_LOCAL_BIT = 0x100
 FLAG_PERMUTE_WARMSTART, FLAG_PROFILE_PASSES, FLAG_TRACK_IDS, FLAG_NO_PEER_TRANSPORT = 1, 2, 4, 8
 COMM_ID_BYTES = 128
-NUM_PASSES = 16
+NUM_PASSES = 17
 PASS_NAMES = ["viscosity", "predict", "density_warm", "density_solve", "advect_keygen", "sort", "gather", "cells_tiles", "lists",
-              "density_alpha", "divergence_warm", "divergence_solve", "wcsph_accel", "wcsph_kick", "halo", "total"]
+              "density_alpha", "divergence_warm", "divergence_solve", "wcsph_accel", "wcsph_kick", "halo", "migrate", "total"]
 STATUS_NAMES = {0: "OK", 1: "INVALID_ARGUMENT", 2: "CUDA", 3: "CAPACITY", 4: "STATE", 5: "NONFINITE", 6: "NO_DEVICE", 7: "COMM"}
 
 # every symbol include/yasph_gpu.h declares (tests check that the library exports all of them)
@@ -30,6 +30,7 @@ EXPORTED_SYMBOLS = [
     "yasph_set_boundary", "yasph_upload_particles", "yasph_download_particles", "yasph_download_field", "yasph_num_particles",
     "yasph_clear_cached", "yasph_step", "yasph_step_host", "yasph_time_get_step_ns", "yasph_time_set_step_ns", "yasph_time_restart",
     "yasph_neighborhood_update", "yasph_neighbors_download", "yasph_update_densities", "yasph_compute_alpha", "yasph_pass_times", "yasph_host_step_times",
+    "yasph_solver_state_get", "yasph_solver_state_set", "yasph_upload_field",
     "yasph_launch_count", "yasph_stream", "yasph_scene_fluid_rect", "yasph_scene_boundary_line", "yasph_scene_boundary_thick_line",
     "yasph_duration_from_secs_f32", "yasph_duration_as_secs_f32",
     "yasph_comm_unique_id", "yasph_comm_init", "yasph_slab_set", "yasph_slab_get", "yasph_cell_column", "yasph_step_host_slab",
@@ -76,6 +77,11 @@ class SlabInfo(C.Structure):
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class SolverState(C.Structure):
+    _fields_ = [("step_ns", C.c_uint64), ("iters_density", C.c_uint32), ("iters_divergence", C.c_uint32), ("initialized", C.c_uint32),
+                ("reserved", C.c_uint32)]
 
 
 class YasphError(RuntimeError):
@@ -129,6 +135,9 @@ def lib():
     sig("yasph_compute_alpha", C.c_int32, vp)
     sig("yasph_pass_times", C.c_int32, vp, f32p)
     sig("yasph_host_step_times", C.c_int32, vp, f32p)
+    sig("yasph_solver_state_get", C.c_int32, vp, C.POINTER(SolverState))
+    sig("yasph_solver_state_set", C.c_int32, vp, C.POINTER(SolverState))
+    sig("yasph_upload_field", C.c_int32, vp, C.c_int32, C.c_void_p, C.c_uint64)
     sig("yasph_launch_count", C.c_int32, vp, u64p)
     sig("yasph_stream", C.c_int32, vp, C.POINTER(vp))
     sig("yasph_scene_fluid_rect", C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_uint64, f32p,

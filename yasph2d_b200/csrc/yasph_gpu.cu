@@ -1206,7 +1206,7 @@ static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp
     uint32_t n_sort = n;
     if (c->slab.active) {
         pass_end(c);
-        pass_begin(c, YASPH_PASS_HALO);
+        pass_begin(c, YASPH_PASS_MIGRATE);
         TRY(slab_exchange_particles(c, gp, n, &n_sort, &n));
         pass_end(c);
         pass_begin(c, YASPH_PASS_SORT);
@@ -1698,29 +1698,32 @@ static int32_t jacobi_solve(yasph_ctx* c, bool first_a_done = false) {
     return YASPH_OK;
 }
 
+// dfsph.rs:419-428: first call (or particle count changed): zero the warm-start arrays, sort, densities, alpha
+static int32_t dfsph_initialize(yasph_ctx* c) {
+    CU(cudaMemsetAsync(c->kappa, 0, (size_t)c->cap_n * sizeof(float), c->stream));
+    CU(cudaMemsetAsync(c->stiff, 0, (size_t)c->cap_n * sizeof(float), c->stream));
+    GatherPlan gp;
+    gp.n2 = 2;
+    gp.a2[0] = &c->pos;
+    gp.alt2[0] = &c->pos_alt;
+    gp.a2[1] = &c->vel;
+    gp.alt2[1] = &c->vel_alt;
+    TRY(neighborhood_update(c, false, gp));
+    pass_begin(c, YASPH_PASS_DENSITY_ALPHA);
+    OpDensityAlpha<0, true> da;
+    da.dens = c->dens;
+    da.alpha = c->alpha;
+    da.rho_p = nullptr;
+    da.stiffness = 0.f;
+    TRY(launch_sweep(c, da));
+    pass_end(c);
+    TRY(halo_exchange(c, c->dens));  // rho_j of the ghosts for the viscosity pass
+    c->dfsph_ready = true;
+    return YASPH_OK;
+}
+
 static int32_t dfsph_step(yasph_ctx* c) {
-    if (!c->dfsph_ready) {
-        // dfsph.rs:419-428: first call (or particle count changed): zero the warm-start arrays, sort, densities, alpha
-        CU(cudaMemsetAsync(c->kappa, 0, (size_t)c->cap_n * sizeof(float), c->stream));
-        CU(cudaMemsetAsync(c->stiff, 0, (size_t)c->cap_n * sizeof(float), c->stream));
-        GatherPlan gp;
-        gp.n2 = 2;
-        gp.a2[0] = &c->pos;
-        gp.alt2[0] = &c->pos_alt;
-        gp.a2[1] = &c->vel;
-        gp.alt2[1] = &c->vel_alt;
-        TRY(neighborhood_update(c, false, gp));
-        pass_begin(c, YASPH_PASS_DENSITY_ALPHA);
-        OpDensityAlpha<0, true> da;
-        da.dens = c->dens;
-        da.alpha = c->alpha;
-        da.rho_p = nullptr;
-        da.stiffness = 0.f;
-        TRY(launch_sweep(c, da));
-        pass_end(c);
-        TRY(halo_exchange(c, c->dens));  // rho_j of the ghosts for the viscosity pass
-        c->dfsph_ready = true;
-    }
+    if (!c->dfsph_ready) TRY(dfsph_initialize(c));
     const uint32_t n = c->n;  // local particles (slab mode: owned + ghosts); the neighbourhood update below changes it
     k_begin_step<<<1, 32, 0, c->stream>>>(c->ctl);
     CHECK_LAUNCH();
@@ -1845,6 +1848,58 @@ static int32_t wcsph_step(yasph_ctx* c) {
     k_timestep_apply<1><<<blocks_for(n, 256), 256, 0, c->stream>>>(c->ctl, c->tp, c->radius * 2.0f, c->vel, c->accel, c->vel, n);
     CHECK_LAUNCH();
     pass_end(c);
+    return YASPH_OK;
+}
+
+extern "C" int32_t yasph_solver_state_get(yasph_ctx* c, yasph_solver_state* out) {
+    if (!c || !out) return YASPH_ERR_INVALID_ARGUMENT;
+    CU(cudaSetDevice(c->device));
+    TRY(read_control(c));
+    memset(out, 0, sizeof(*out));
+    out->step_ns = c->h_ctl->step_ns;
+    out->iters_density = c->h_ctl->iters[0];
+    out->iters_divergence = c->h_ctl->iters[1];
+    out->initialized = (c->cfg.solver == YASPH_SOLVER_WCSPH || c->dfsph_ready) ? 1u : 0u;
+    return YASPH_OK;
+}
+extern "C" int32_t yasph_solver_state_set(yasph_ctx* c, const yasph_solver_state* in) {
+    if (!c || !in) return YASPH_ERR_INVALID_ARGUMENT;
+    if (c->slab.active) return fail(c, YASPH_ERR_STATE, "yasph_solver_state_set: not available in slab mode");
+    if (!c->have_particles || c->n == 0) return fail(c, YASPH_ERR_STATE, "yasph_solver_state_set: upload the particles first");
+    CU(cudaSetDevice(c->device));
+    if (in->initialized && c->cfg.solver == YASPH_SOLVER_DFSPH && !c->dfsph_ready) {
+        TRY(dfsph_initialize(c));
+        TRY(read_control(c));
+        TRY(check_capacity_flags(c));
+    }
+    const unsigned int it[2] = {in->iters_density, in->iters_divergence};
+    CU(cudaMemcpyAsync(&c->ctl->iters[0], it, sizeof(it), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(&c->ctl->step_ns, &in->step_ns, sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->h_ctl->iters[0] = it[0];
+    c->h_ctl->iters[1] = it[1];
+    c->h_ctl->step_ns = in->step_ns;
+    return YASPH_OK;
+}
+extern "C" int32_t yasph_upload_field(yasph_ctx* c, int32_t field, const void* data, uint64_t bytes) {
+    if (!c || !data) return YASPH_ERR_INVALID_ARGUMENT;
+    if (c->slab.active) return fail(c, YASPH_ERR_STATE, "yasph_upload_field: not available in slab mode");
+    CU(cudaSetDevice(c->device));
+    void* dst = nullptr;
+    size_t elem = sizeof(float);
+    switch (field) {
+        case YASPH_FIELD_KAPPA: dst = c->kappa; break;
+        case YASPH_FIELD_STIFFNESS: dst = c->stiff; break;
+        case YASPH_FIELD_ACCELERATION:
+            dst = c->accel;
+            elem = sizeof(float2);
+            break;
+        default: return fail(c, YASPH_ERR_INVALID_ARGUMENT, "yasph_upload_field: field %d cannot be uploaded", field);
+    }
+    if (bytes != (uint64_t)c->n * elem)
+        return fail(c, YASPH_ERR_INVALID_ARGUMENT, "yasph_upload_field: %llu bytes, expected %zu", (unsigned long long)bytes, (size_t)c->n * elem);
+    if (bytes) CU(cudaMemcpyAsync(dst, data, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
     return YASPH_OK;
 }
 

@@ -120,6 +120,19 @@ class GpuContext:
         self._ck(capi.lib().yasph_download_field(self.h, field, out.ctypes.data_as(C.c_void_p), out.nbytes))
         return out
 
+    def solver_state(self):
+        st = capi.SolverState()
+        self._ck(capi.lib().yasph_solver_state_get(self.h, C.byref(st)))
+        return st
+
+    def set_solver_state(self, step_ns, iters_density=0, iters_divergence=0, initialized=True):
+        st = capi.SolverState(int(step_ns), int(iters_density), int(iters_divergence), 1 if initialized else 0, 0)
+        self._ck(capi.lib().yasph_solver_state_set(self.h, C.byref(st)))
+
+    def upload_field(self, field, data):
+        data = np.ascontiguousarray(data, np.float32)
+        self._ck(capi.lib().yasph_upload_field(self.h, field, data.ctypes.data_as(C.c_void_p), data.nbytes))
+
     def clear_cached(self):
         self._ck(capi.lib().yasph_clear_cached(self.h))
 
