@@ -95,10 +95,11 @@ typedef struct yasph_config {
     float wcsph_stiffness;               /* B = rho0 * c^2 / 7, c = 1/sqrt(0.01) */
     float wcsph_boundary_force_factor;   /* 1.0 */
     /* TimeManager step policy, timemanager.rs:38-59 / main.rs:115-127 */
-    int32_t adaptive_timestep;           /* 0 = FixedTimeStep, 1 = AdaptiveTimeStep (no TargetFrameLength) */
+    int32_t adaptive_timestep;           /* 0 = FixedTimeStep, 1 = AdaptiveTimeStep */
     uint64_t timestep_fixed_ns;
     uint64_t timestep_min_ns;            /* from_secs_f32(1/60/400) = 41667 */
     uint64_t timestep_max_ns;            /* from_secs_f32(1/120/3)  = 2777778 */
+    uint64_t timestep_target_frame_ns;   /* AdaptiveTimeStepTarget: 0 = None, else TargetFrameLength (timemanager.rs:23-36, 268-274) */
     float cfl_factor;                    /* 1.5 (DFSPH) / 0.2 (WCSPH), main.rs:115-118 */
     /* implementation knobs (0 = default) */
     uint32_t max_tiles;                  /* capacity for 8x8-cell tiles; default max_particles/32 + 4096 */
@@ -192,7 +193,12 @@ int32_t yasph_step_host(yasph_ctx* ctx, float* pos_xy, float* vel_xy, float* den
 /* ---- TimeManager mirror ------------------------------------------------------------------------------------- */
 int32_t yasph_time_get_step_ns(const yasph_ctx* ctx, uint64_t* step_ns);
 int32_t yasph_time_set_step_ns(yasph_ctx* ctx, uint64_t step_ns);
-int32_t yasph_time_restart(yasph_ctx* ctx); /* TimeManager::restart (timemanager.rs:131-133) */
+int32_t yasph_time_restart(yasph_ctx* ctx);
+/* TimeManager::total_simulated_time as it stands when simulation_step is called, i.e. after the frame loop has added the
+ * current step (timemanager.rs:246); only the TargetFrameLength rule reads it (timemanager.rs:268-274).  Without this call the
+ * context keeps the sum itself (every yasph_step adds its entry step, as the frame loop does before each step). */
+int32_t yasph_time_set_total_simulated_ns(yasph_ctx* ctx, uint64_t total_ns);
+int32_t yasph_time_get_total_simulated_ns(const yasph_ctx* ctx, uint64_t* total_ns); /* TimeManager::restart (timemanager.rs:131-133) */
 
 /* ---- neighbourhood-only surface ------------------------------------------------------------------------------ */
 /* Re-sorts positions and velocities and rebuilds cells, tiles and the neighbour lists. */

@@ -99,6 +99,9 @@ def lib():
     sig("yo_time_simulation_step", C.c_uint64, vp)
     sig("yo_time_update", C.c_uint64, vp, C.c_float, C.c_float)
     sig("yo_time_set_step", None, vp, C.c_uint64)
+    sig("yo_time_set_target", None, vp, C.c_uint64)
+    sig("yo_time_perform_step", None, vp)
+    sig("yo_time_total", C.c_uint64, vp)
     sig("yo_dfsph_new", vp, vp, C.c_int, C.c_float)
     sig("yo_dfsph_free", None, vp)
     sig("yo_dfsph_clear", None, vp)
@@ -241,7 +244,7 @@ class World:
 class TimeManager:
     """Restated TimeManager step logic (timemanager.rs:104-138,252-279)."""
 
-    def __init__(self, adaptive=True, fixed_ns=0, min_ns=None, max_ns=None, cfl_factor=1.5):
+    def __init__(self, adaptive=True, fixed_ns=0, min_ns=None, max_ns=None, cfl_factor=1.5, target_frame_ns=0):
         L = lib()
         if min_ns is None:
             min_ns = L.yo_duration_from_secs_f32(np.float32(1.0) / np.float32(60.0) / np.float32(400.0))  # main.rs:124
@@ -249,6 +252,9 @@ class TimeManager:
             max_ns = L.yo_duration_from_secs_f32(np.float32(1.0) / np.float32(120.0) / np.float32(3.0))  # main.rs:123
         self.min_ns, self.max_ns, self.cfl_factor, self.adaptive, self.fixed_ns = min_ns, max_ns, cfl_factor, adaptive, fixed_ns
         self.h_ = L.yo_time_new(int(adaptive), fixed_ns, min_ns, max_ns, cfl_factor)
+        self.target_frame_ns = int(target_frame_ns)
+        if target_frame_ns:
+            L.yo_time_set_target(self.h_, int(target_frame_ns))
 
     def __del__(self):
         if getattr(self, "h_", None) and _lib is not None:
@@ -263,6 +269,13 @@ class TimeManager:
 
     def set_step_ns(self, ns):
         lib().yo_time_set_step(self.h_, ns)
+
+    def perform_step(self):
+        """The frame loop's bookkeeping ahead of a step (timemanager.rs:243-247): total_simulated_time += simulation_step."""
+        lib().yo_time_perform_step(self.h_)
+
+    def total_simulated_ns(self):
+        return lib().yo_time_total(self.h_)
 
 
 class DFSPHSolver:

@@ -295,14 +295,22 @@ static Real duration_as_secs_f32(uint64_t ns) {  // std Duration::as_secs_f32
     return (Real)secs + (Real)nanos / 1.0e9f;
 }
 struct TimeManager {
-    int adaptive;  // 0 = FixedTimeStep, 1 = AdaptiveTimeStep (timestep_target_frame = None)
+    int adaptive;  // 0 = FixedTimeStep, 1 = AdaptiveTimeStep
     uint64_t fixed_ns, min_ns, max_ns;
     Real cfl_factor;
     uint64_t simulation_step_ns;
-    // timemanager.rs:105-109
-    void reset() { simulation_step_ns = adaptive ? min_ns : fixed_ns; }
+    uint64_t target_ns = 0;             // AdaptiveTimeStepTarget: 0 = None, else TargetFrameLength (timemanager.rs:23-36)
+    uint64_t total_simulated_ns = 0;    // timemanager.rs:92
+    // timemanager.rs:105-109, 131-133
+    void reset() {
+        simulation_step_ns = adaptive ? min_ns : fixed_ns;
+        total_simulated_ns = 0;
+    }
     // timemanager.rs:136-138
     uint64_t simulation_step() const { return simulation_step_ns; }
+    // the bookkeeping of simulation_frame_loop when it decides to perform a step (timemanager.rs:243-247); the frame pacing
+    // around it (render-time comparison, step dropping) belongs to the application
+    void perform_step() { total_simulated_ns += simulation_step_ns; }
     // timemanager.rs:252-279
     uint64_t update_simulation_step(Real particle_diameter, Real max_velocity) {
         if (!adaptive) {
@@ -312,6 +320,10 @@ struct TimeManager {
             uint64_t time_cfl = duration_from_secs_f32(cfl_factor * 0.4f * particle_diameter / (max_velocity + VELOCITY_EPSILON));
             uint64_t upper = std::min(max_ns, simulation_step_ns * 2);
             uint64_t lower = min_ns;
+            if (target_ns) {  // timemanager.rs:268-272
+                uint64_t time_to_target = total_simulated_ns - target_ns * (uint64_t)(uint32_t)(total_simulated_ns / target_ns);
+                lower = std::min(min_ns, time_to_target);
+            }
             simulation_step_ns = std::max(lower, std::min(upper, time_cfl));
         }
         return simulation_step_ns;
@@ -1207,6 +1219,9 @@ void yo_time_free(void* t) { delete (TimeManager*)t; }
 uint64_t yo_time_simulation_step(void* t) { return ((TimeManager*)t)->simulation_step(); }
 uint64_t yo_time_update(void* t, float diameter, float max_velocity) { return ((TimeManager*)t)->update_simulation_step(diameter, max_velocity); }
 void yo_time_set_step(void* t, uint64_t ns) { ((TimeManager*)t)->simulation_step_ns = ns; }
+void yo_time_set_target(void* t, uint64_t ns) { ((TimeManager*)t)->target_ns = ns; }
+void yo_time_perform_step(void* t) { ((TimeManager*)t)->perform_step(); }
+uint64_t yo_time_total(void* t) { return ((TimeManager*)t)->total_simulated_ns; }
 
 // ---- solvers ----
 void* yo_dfsph_new(void* world, int visc_kind, float visc_param) {

@@ -225,6 +225,36 @@ def test_physical_viscosity_model():
     compare_state(ctx, ow, 79)
 
 
+def test_target_frame_length_stepping():
+    """AdaptiveTimeStepTarget::TargetFrameLength (timemanager.rs:268-274), evaluated on the device from the total the context
+    accumulates (device-resident stepping) or the host supplies (the drop-in call): dt and state identical to the oracle."""
+    target = 1_000_000
+    w, ow = make_worlds()
+    w2, _ = make_worlds()
+    # a few very fast particles: the CFL time drops below timestep_min, so the lower bound (the part the target rule changes) decides
+    for world in (w, w2):
+        world.particles.velocities[:10, 0] = 300.0
+    ow.set_particles(ow.positions(), w.particles.velocities)
+    ctx = gpu_ctx(w, timestep_target_frame_ns=target)
+    tm = y.TimeManager(y.SimulationStepConfig.AdaptiveTimeStep(cfl_factor=1.5, target_frame_ns=target))
+    solver = y.DFSPHSolver(y.XSPHViscosityModel(w2.properties.smoothing_length()), w2.properties.smoothing_length())
+    otm, osolver = po.TimeManager(cfl_factor=1.5, target_frame_ns=target), po.DFSPHSolver(ow)
+    dts = []
+    for s in range(60):
+        otm.perform_step()  # the application's frame loop (timemanager.rs:243-247)
+        tm.perform_step()
+        orep = osolver.simulation_step(ow, otm)
+        rep = ctx.step()
+        rep2 = solver.simulation_step(w2, tm)
+        assert rep.dt_ns == orep.dt_ns == rep2.dt_ns, (s, rep.dt_ns, orep.dt_ns, rep2.dt_ns)
+        dts.append(rep.dt_ns)
+    assert ctx.total_simulated_ns() == otm.total_simulated_ns() == tm.total_simulated_time_ns
+    assert min(dts) < otm.min_ns  # the rule did pull a step below timestep_min
+    pos, vel, _ = ctx.download_particles()
+    assert np.array_equal(pos, ow.positions()) and np.array_equal(vel, ow.velocities())
+    assert np.array_equal(w2.particles.positions, ow.positions())
+
+
 def test_clear_cached_and_reset():
     """reset_simulation (main.rs:292-298): clear_cached_data + TimeManager::restart + scene rebuild reproduces the run."""
     w, ow = make_worlds()

@@ -28,7 +28,7 @@ STATUS_NAMES = {0: "OK", 1: "INVALID_ARGUMENT", 2: "CUDA", 3: "CAPACITY", 4: "ST
 EXPORTED_SYMBOLS = [
     "yasph_config_default", "yasph_create", "yasph_destroy", "yasph_last_error", "yasph_get_config", "yasph_set_flags", "yasph_get_properties",
     "yasph_set_boundary", "yasph_upload_particles", "yasph_download_particles", "yasph_download_field", "yasph_num_particles",
-    "yasph_clear_cached", "yasph_step", "yasph_step_host", "yasph_time_get_step_ns", "yasph_time_set_step_ns", "yasph_time_restart",
+    "yasph_clear_cached", "yasph_step", "yasph_step_host", "yasph_time_get_step_ns", "yasph_time_set_step_ns", "yasph_time_restart", "yasph_time_set_total_simulated_ns", "yasph_time_get_total_simulated_ns",
     "yasph_neighborhood_update", "yasph_neighbors_download", "yasph_update_densities", "yasph_compute_alpha", "yasph_pass_times", "yasph_host_step_times",
     "yasph_solver_state_get", "yasph_solver_state_set", "yasph_upload_field",
     "yasph_launch_count", "yasph_stream", "yasph_scene_fluid_rect", "yasph_scene_boundary_line", "yasph_scene_boundary_thick_line",
@@ -48,7 +48,7 @@ class Config(C.Structure):
         ("dfsph_max_divergence_error", C.c_float), ("dfsph_max_divergence_iters", C.c_uint32),
         ("wcsph_stiffness", C.c_float), ("wcsph_boundary_force_factor", C.c_float),
         ("adaptive_timestep", C.c_int32), ("timestep_fixed_ns", C.c_uint64), ("timestep_min_ns", C.c_uint64),
-        ("timestep_max_ns", C.c_uint64), ("cfl_factor", C.c_float),
+        ("timestep_max_ns", C.c_uint64), ("timestep_target_frame_ns", C.c_uint64), ("cfl_factor", C.c_float),
         ("max_tiles", C.c_uint32), ("tile_dynamic_capacity", C.c_uint32), ("tile_static_capacity", C.c_uint32),
         ("speculative_iterations", C.c_uint32), ("flags", C.c_uint32), ("max_halo", C.c_uint32), ("reserved", C.c_uint32),
     ]
@@ -129,6 +129,8 @@ def lib():
     sig("yasph_time_get_step_ns", C.c_int32, vp, u64p)
     sig("yasph_time_set_step_ns", C.c_int32, vp, C.c_uint64)
     sig("yasph_time_restart", C.c_int32, vp)
+    sig("yasph_time_set_total_simulated_ns", C.c_int32, vp, C.c_uint64)
+    sig("yasph_time_get_total_simulated_ns", C.c_int32, vp, u64p)
     sig("yasph_neighborhood_update", C.c_int32, vp, rp)
     sig("yasph_neighbors_download", C.c_int32, vp, u16p, u16p, u32p)
     sig("yasph_update_densities", C.c_int32, vp, C.c_int32)

@@ -213,13 +213,20 @@ __host__ __device__ inline float duration_as_secs_f32(uint64_t ns) {
 struct TimeParams {
     int adaptive;
     uint64_t fixed_ns, min_ns, max_ns;
+    uint64_t target_ns;  // AdaptiveTimeStepTarget::TargetFrameLength, 0 = None
     float cfl_factor;
 };
-__host__ __device__ inline uint64_t update_simulation_step(const TimeParams& t, uint64_t prev_ns, float particle_diameter, float max_velocity) {
+// total_ns: TimeManager::total_simulated_time at the time of the call (it already includes the running step, timemanager.rs:246)
+__host__ __device__ inline uint64_t update_simulation_step(const TimeParams& t, uint64_t prev_ns, float particle_diameter, float max_velocity,
+                                                           uint64_t total_ns) {
     if (!t.adaptive) return t.fixed_ns;
     uint64_t time_cfl = duration_from_secs_f32(t.cfl_factor * 0.4f * particle_diameter / (max_velocity + 0.00001f));
     uint64_t upper = t.max_ns < prev_ns * 2 ? t.max_ns : prev_ns * 2;
     uint64_t lower = t.min_ns;
+    if (t.target_ns) {  // timemanager.rs:268-272: total - target * ((total / target) as u32), then min with timestep_min
+        const uint64_t time_to_target = total_ns - t.target_ns * (uint64_t)(uint32_t)(total_ns / t.target_ns);
+        lower = lower < time_to_target ? lower : time_to_target;
+    }
     uint64_t m = upper < time_cfl ? upper : time_cfl;
     return lower > m ? lower : m;
 }
@@ -262,6 +269,9 @@ struct Control {
     unsigned long long slab_ghost;       // ghosts from the left | right rank, in sorted order
     unsigned long long slab_own;         // owned particles (low word)
     unsigned int err_slab;               // a particle arrived that this rank does not own (moved more than one slab in a step)
+    unsigned long long total_simulated_ns;  // TimeManager::total_simulated_time before the frame loop's addition for the running step
+    unsigned int total_is_current;          // 1: the host supplied the total incl. the running step (k_begin_step must not add it again)
+    unsigned int pad_time;
     unsigned int err_comm;               // peer-memory transport: bit 0 a halo message, bit 1 an all-reduce contribution did not arrive in time
 };
 

@@ -833,6 +833,11 @@ __global__ void k_begin_step(Control* ctl) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         ctl->step_prev_ns = ctl->step_ns;
         ctl->dt_prev = duration_as_secs_f32(ctl->step_ns);
+        // the frame loop's `total_simulated_time += simulation_step` ahead of the step (timemanager.rs:246)
+        if (ctl->total_is_current)
+            ctl->total_is_current = 0u;
+        else
+            ctl->total_simulated_ns += ctl->step_ns;
         ctl->max_v2_bits = 0u;
         ctl->not_converged = 0u;
         ctl->nonfinite = 0u;
@@ -844,7 +849,7 @@ template <int MODE>
 __global__ void k_timestep_apply(Control* ctl, TimeParams tp, float particle_diameter, const float2* vel_in,
                                  const float2* __restrict__ accel, float2* vel_out, uint32_t n) {
     const float max_velocity = sqrtf(__uint_as_float(ctl->max_v2_bits));
-    const unsigned long long step = update_simulation_step(tp, ctl->step_prev_ns, particle_diameter, max_velocity);
+    const unsigned long long step = update_simulation_step(tp, ctl->step_prev_ns, particle_diameter, max_velocity, ctl->total_simulated_ns);
     const float dt = duration_as_secs_f32(step);
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {

@@ -483,6 +483,7 @@ extern "C" int32_t yasph_create(const yasph_config* cfg, yasph_ctx** out) {
     c->tp.fixed_ns = cfg->timestep_fixed_ns;
     c->tp.min_ns = cfg->timestep_min_ns;
     c->tp.max_ns = cfg->timestep_max_ns;
+    c->tp.target_ns = cfg->timestep_target_frame_ns;
     c->tp.cfl_factor = cfg->cfl_factor;
 
     const size_t N = c->cap_n, M = c->cap_m, NM = N > M ? N : M;
@@ -1501,8 +1502,30 @@ extern "C" int32_t yasph_time_set_step_ns(yasph_ctx* c, uint64_t step_ns) {
     CU(cudaStreamSynchronize(c->stream));
     return YASPH_OK;
 }
+extern "C" int32_t yasph_time_set_total_simulated_ns(yasph_ctx* c, uint64_t total_ns) {
+    if (!c) return YASPH_ERR_INVALID_ARGUMENT;
+    CU(cudaSetDevice(c->device));
+    struct {
+        unsigned long long total;
+        unsigned int is_current, pad;
+    } v = {total_ns, 1u, 0u};
+    static_assert(offsetof(Control, total_is_current) == offsetof(Control, total_simulated_ns) + 8, "the pair is written with one copy");
+    CU(cudaMemcpyAsync(&c->ctl->total_simulated_ns, &v, 12, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return YASPH_OK;
+}
+extern "C" int32_t yasph_time_get_total_simulated_ns(const yasph_ctx* cc, uint64_t* total_ns) {
+    yasph_ctx* c = const_cast<yasph_ctx*>(cc);
+    if (!c || !total_ns) return YASPH_ERR_INVALID_ARGUMENT;
+    CU(cudaSetDevice(c->device));
+    TRY(read_control(c));
+    *total_ns = c->h_ctl->total_simulated_ns;
+    return YASPH_OK;
+}
 extern "C" int32_t yasph_time_restart(yasph_ctx* c) {
     if (!c) return YASPH_ERR_INVALID_ARGUMENT;
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemsetAsync(&c->ctl->total_simulated_ns, 0, 12, c->stream));  // timemanager.rs:131-133: total_simulated_time = 0
     return yasph_time_set_step_ns(c, c->cfg.adaptive_timestep ? c->cfg.timestep_min_ns : c->cfg.timestep_fixed_ns);
 }
 

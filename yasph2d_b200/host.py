@@ -156,6 +156,14 @@ class GpuContext:
         self._ck(capi.lib().yasph_time_get_step_ns(self.h, C.byref(v)))
         return v.value
 
+    def set_total_simulated_ns(self, ns):
+        self._ck(capi.lib().yasph_time_set_total_simulated_ns(self.h, int(ns)))
+
+    def total_simulated_ns(self):
+        v = C.c_uint64(0)
+        self._ck(capi.lib().yasph_time_get_total_simulated_ns(self.h, C.byref(v)))
+        return v.value
+
     def set_time_step_ns(self, ns):
         self._ck(capi.lib().yasph_time_set_step_ns(self.h, int(ns)))
 
@@ -340,22 +348,23 @@ def tank_scene(world, columns, rows, x0=1.0, y0=0.2, wall_thickness=4, jitter=0.
 class SimulationStepConfig:
     """timemanager.rs:38-59.  Durations are integer nanoseconds."""
 
-    def __init__(self, adaptive, fixed_ns=0, timestep_min_ns=0, timestep_max_ns=0, cfl_factor=1.0):
+    def __init__(self, adaptive, fixed_ns=0, timestep_min_ns=0, timestep_max_ns=0, cfl_factor=1.0, target_frame_ns=0):
         self.adaptive, self.fixed_ns = bool(adaptive), int(fixed_ns)
         self.timestep_min_ns, self.timestep_max_ns, self.cfl_factor = int(timestep_min_ns), int(timestep_max_ns), float(cfl_factor)
+        self.target_frame_ns = int(target_frame_ns)  # AdaptiveTimeStepTarget: 0 = None, else TargetFrameLength (timemanager.rs:23-36)
 
     @classmethod
     def FixedTimeStep(cls, step_ns):
         return cls(False, fixed_ns=step_ns)
 
     @classmethod
-    def AdaptiveTimeStep(cls, timestep_max_ns=None, timestep_min_ns=None, cfl_factor=1.5):
+    def AdaptiveTimeStep(cls, timestep_max_ns=None, timestep_min_ns=None, cfl_factor=1.5, target_frame_ns=0):
         L = capi.lib()
         if timestep_max_ns is None:
             timestep_max_ns = L.yasph_duration_from_secs_f32(f32(1.0) / f32(120.0) / f32(3.0))  # main.rs:123
         if timestep_min_ns is None:
             timestep_min_ns = L.yasph_duration_from_secs_f32(f32(1.0) / f32(60.0) / f32(400.0))  # main.rs:124
-        return cls(True, timestep_min_ns=timestep_min_ns, timestep_max_ns=timestep_max_ns, cfl_factor=cfl_factor)
+        return cls(True, timestep_min_ns=timestep_min_ns, timestep_max_ns=timestep_max_ns, cfl_factor=cfl_factor, target_frame_ns=target_frame_ns)
 
 
 class TimeManager:
@@ -373,6 +382,11 @@ class TimeManager:
 
     def simulation_step(self):  # :136-138, nanoseconds
         return self._simulation_step_ns
+
+    def perform_step(self):
+        """The bookkeeping simulation_frame_loop does when it lets a step happen (timemanager.rs:243-247); the application
+        calls it before Solver.simulation_step.  Only the TargetFrameLength rule reads the total (:268-274)."""
+        self.total_simulated_time_ns += self._simulation_step_ns
 
     def simulation_step_secs(self):
         return capi.lib().yasph_duration_as_secs_f32(self._simulation_step_ns)
@@ -442,6 +456,7 @@ class Solver:
         sc = time_manager.step_config
         cfg.adaptive_timestep = int(sc.adaptive)
         cfg.timestep_fixed_ns, cfg.timestep_min_ns, cfg.timestep_max_ns, cfg.cfl_factor = sc.fixed_ns, sc.timestep_min_ns, sc.timestep_max_ns, sc.cfl_factor
+        cfg.timestep_target_frame_ns = sc.target_frame_ns
         for k, v in self.knobs.items():
             setattr(cfg, k, v)
         self._configure(cfg)
@@ -460,6 +475,8 @@ class Solver:
         if time_manager.simulation_step() != self._ctx_step_ns:
             self.ctx.set_time_step_ns(time_manager.simulation_step())
             self._ctx_step_ns = time_manager.simulation_step()
+        if time_manager.step_config.target_frame_ns:  # the rule reads TimeManager's total, which the application advances
+            self.ctx.set_total_simulated_ns(time_manager.total_simulated_time_ns)
 
     def _after(self, rep, time_manager):
         self._ctx_step_ns = rep.dt_ns
