@@ -544,7 +544,11 @@ struct RunsPrefetch {
 // branch-free: the candidate's slot is stored to the thread's column of a shared-memory list at row min(count, 64) and the
 // count advances by the hit predicate, so the first 64 hits survive exactly as the reference's early exit leaves them.
 // The column is then packed into 8-byte words of four u16 slots.
-constexpr int NB_THREADS = TILE_THREADS;
+#ifndef YASPH_NB_THREADS
+#define YASPH_NB_THREADS 256
+#endif
+constexpr int NB_THREADS = YASPH_NB_THREADS;  // CTA size of the list build (a multiple of 32, >= 2 * TILE_CELLS)
+static_assert(NB_THREADS % 32 == 0 && NB_THREADS >= 2 * TILE_CELLS && sizeof(TileRuns) / 16 <= NB_THREADS, "list-build CTA size");
 constexpr int NB_ROWS = YASPH_MAXN + 1;  // row 64 absorbs everything past the cap
 struct ListSmem {
     TileRuns runs[3];

@@ -1283,7 +1283,7 @@ static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp
     if (c->num_tiles) {
         const size_t bytes = list_smem_bytes(c->cap_dyn, c->cap_stat);
         ListArgs la{tile_tables(c), c->pos, c->bpos, c->keys[0], c->grid, c->ctl, c->lists, c->counts, c->tile_nk, c->cap_dyn, c->cap_stat};
-        k_build_lists<<<persistent_grid(c, k_build_lists, bytes), NB_THREADS, bytes, c->stream>>>(la);
+        k_build_lists<<<persistent_grid(c, k_build_lists, bytes, NB_THREADS), NB_THREADS, bytes, c->stream>>>(la);
         CHECK_LAUNCH();
     }
     pass_end(c);
