@@ -126,10 +126,10 @@ __global__ void k_halo_unpack(T* __restrict__ field, const uint32_t* __restrict_
 
 // ---- peer-memory transport (NVLink / NVSwitch, one process per GPU) ---------------------------------------------------------
 // Every rank owns a MAILBOX in its device memory that its peers map (CUDA IPC) and write with plain stores over NVLink:
-//   halo exchange    k_halo_push gathers the send lists and stores the values straight into the neighbours' mailboxes, the last
-//                    CTA then publishes the sequence number (release, system scope); k_halo_pull on the receiving rank waits
-//                    for that number (acquire) and scatters the payload to the ghost slots -- two small kernels per exchange and
-//                    rank, no staging copy, no collective call;
+//   halo exchange    k_halo_exchange gathers the send lists and stores the values straight into the neighbours' mailboxes, the
+//                    last CTA to finish publishes the sequence number (release, system scope); the same kernel then waits for
+//                    the neighbours' numbers (acquire) and scatters what they stored here to the ghost slots -- one small kernel
+//                    per exchange and rank, no staging copy, no collective call;
 //   all-reduce       k_allreduce_peer stores the rank's scalar into every peer's mailbox, waits for every peer's scalar and
 //                    combines them in rank order (every rank computes the same bits).
 // Payload and all-reduce slots are double-buffered by the parity of the sequence number: the ranks run the same sequence of
@@ -173,34 +173,34 @@ __device__ __forceinline__ bool peer_wait(const unsigned long long* flag, unsign
     }
     return true;
 }
-// dst_l / dst_r: payload of this exchange in the left / right neighbour's mailbox (null: no neighbour on that side)
+// push and pull of one exchange in ONE launch: every CTA first stores its share of the send lists into the neighbours'
+// mailboxes (the last one to finish publishes the sequence number), then waits for the neighbours' numbers and scatters its
+// share of what they stored here.  Grid-stride loops over a grid of at most one CTA per SM: all CTAs are resident at once, so
+// a CTA that already waits for the other rank can never keep a CTA that still has to push from running.
 template <typename T>
-__global__ void k_halo_push(const T* __restrict__ field, const uint32_t* __restrict__ idx_l, uint32_t nl, const uint32_t* __restrict__ idx_r, uint32_t nr,
-                            T* dst_l, T* dst_r, unsigned long long* flag_l, unsigned long long* flag_r, unsigned long long seq, unsigned int* ticket) {
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < nl)
-        dst_l[k] = field[idx_l[k]];
-    else if (k < nl + nr)
-        dst_r[k - nl] = field[idx_r[k - nl]];
+__global__ void k_halo_exchange(T* __restrict__ field, const uint32_t* __restrict__ send_l, uint32_t nsl, const uint32_t* __restrict__ send_r, uint32_t nsr,
+                                T* dst_l, T* dst_r, unsigned long long* pflag_l, unsigned long long* pflag_r, const uint32_t* __restrict__ ghost_l,
+                                uint32_t ngl, const uint32_t* __restrict__ ghost_r, uint32_t ngr, const T* src_l, const T* src_r,
+                                const unsigned long long* flag_l, const unsigned long long* flag_r, unsigned long long seq, unsigned int* ticket,
+                                Control* ctl) {
+    const uint32_t k0 = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    for (uint32_t k = k0; k < nsl + nsr; k += stride) {
+        if (k < nsl)
+            dst_l[k] = field[send_l[k]];
+        else
+            dst_r[k - nsl] = field[send_r[k - nsl]];
+    }
     __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int t = atomicAdd(ticket, 1u);
-        if (t == gridDim.x - 1) {  // every CTA's stores are ordered before its ticket
-            *ticket = 0u;
-            __threadfence_system();
-            if (flag_l) st_release_sys(flag_l, seq);
-            if (flag_r) st_release_sys(flag_r, seq);
-        }
-    }
-}
-// src_l / src_r: payload of this exchange in the own mailbox; flag_l / flag_r: own halo flags (null: no neighbour on that side)
-template <typename T>
-__global__ void k_halo_pull(T* __restrict__ field, const uint32_t* __restrict__ idx_l, uint32_t nl, const uint32_t* __restrict__ idx_r, uint32_t nr,
-                            const T* src_l, const T* src_r, const unsigned long long* flag_l, const unsigned long long* flag_r, unsigned long long seq,
-                            Control* ctl) {
     __shared__ int ok;
     if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(ticket, 1u);
+        if (t == gridDim.x - 1) {
+            *ticket = 0u;
+            __threadfence_system();
+            if (pflag_l) st_release_sys(pflag_l, seq);
+            if (pflag_r) st_release_sys(pflag_r, seq);
+        }
         ok = 1;
         if (flag_l && !peer_wait(flag_l, seq)) ok = 0;
         if (flag_r && !peer_wait(flag_r, seq)) ok = 0;
@@ -208,12 +208,14 @@ __global__ void k_halo_pull(T* __restrict__ field, const uint32_t* __restrict__ 
     }
     __syncthreads();
     if (!ok) return;
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < nl)
-        field[idx_l[k]] = __ldcg(&src_l[k]);  // written by the peer: read at the L2, never from a stale L1 line
-    else if (k < nl + nr)
-        field[idx_r[k - nl]] = __ldcg(&src_r[k - nl]);
+    for (uint32_t k = k0; k < ngl + ngr; k += stride) {
+        if (k < ngl)
+            field[ghost_l[k]] = __ldcg(&src_l[k]);
+        else
+            field[ghost_r[k - ngl]] = __ldcg(&src_r[k - ngl]);
+    }
 }
+
 // ---- particle records (migrants, ghosts) through the mailboxes: the COUNTS stay on the device ------------------------------
 // k_records_push reads how many particles the ordered selection picked for each side (device memory), packs them straight
 // into the neighbours' mailboxes behind a 16-byte header carrying the count, and publishes the sequence number.
@@ -301,9 +303,14 @@ __global__ void k_records_pull(RecordArrays arr, uint32_t first, uint32_t cap_n,
     }
 }
 
-// one warp; boxes[r] = rank r's mailbox as mapped here (boxes[rank] = the own one); value in place at dev_ptr
+// one warp; boxes[r] = rank r's mailbox as mapped here (boxes[rank] = the own one); value in place at dev_ptr.
+// After: a functor the reduced value is handed to on the spot (the Jacobi loop decision, sweeps.cuh), saving its own launch.
+struct NoAfter {
+    __device__ __forceinline__ void operator()(Control*) const {}
+};
+template <class After>
 __global__ void k_allreduce_peer(void* dev_ptr, int is_double_sum, PeerBoxHeader* const* __restrict__ boxes, int rank, int world, unsigned long long seq,
-                                 Control* ctl) {
+                                 Control* ctl, After after) {
     const int lane = threadIdx.x;
     const unsigned parity = (unsigned)(seq & 1ull);
     const double mine = is_double_sum ? *reinterpret_cast<const double*>(dev_ptr) : (double)*reinterpret_cast<const float*>(dev_ptr);
@@ -331,6 +338,7 @@ __global__ void k_allreduce_peer(void* dev_ptr, int is_double_sum, PeerBoxHeader
                 *reinterpret_cast<double*>(dev_ptr) = acc;
             else
                 *reinterpret_cast<float*>(dev_ptr) = (float)acc;
+            after(ctl);
         }
     }
 }

@@ -638,6 +638,16 @@ struct OpJacobiA {
         if (c.ghost == nullptr) jacobi_decide<SOLVER>(c.ctl, sp, iter_index, c.n_avg, c.rho0);  // slab mode: after the all-reduce
     }
 };
+// the same decision as the tail of the residual all-reduce kernel (slab.cuh: k_allreduce_peer)
+template <int SOLVER>
+struct JacobiDecideAfter {
+    SolverParams sp;
+    uint32_t iter_index;
+    float n_avg, rho0;
+    __device__ __forceinline__ void operator()(Control* ctl) const {
+        if (iter_index < ctl->stop_iter[SOLVER]) jacobi_decide<SOLVER>(ctl, sp, iter_index, n_avg, rho0);
+    }
+};
 template <int SOLVER>
 __global__ void k_jacobi_decide(Control* ctl, SolverParams sp, uint32_t iter_index, float n_avg, float rho0) {
     if (threadIdx.x == 0 && blockIdx.x == 0 && iter_index < ctl->stop_iter[SOLVER]) jacobi_decide<SOLVER>(ctl, sp, iter_index, n_avg, rho0);

@@ -945,16 +945,16 @@ static int32_t halo_exchange(yasph_ctx* c, T* field) {
         void* bl = hl ? sl.peer_box[sl.rank - 1] : nullptr;
         void* br = hr ? sl.peer_box[sl.rank + 1] : nullptr;
         // my data arrives on the RIGHT side of my left neighbour and on the LEFT side of my right neighbour
-        k_halo_push<T><<<ns ? blocks_for(ns, 256) : 1, 256, 0, c->stream>>>(
-            field, sl.send_idx[0], hl ? sl.n_send[0] : 0u, sl.send_idx[1], hr ? sl.n_send[1] : 0u,
-            hl ? reinterpret_cast<T*>(peer_payload(bl, sl.max_halo, par, 1)) : nullptr, hr ? reinterpret_cast<T*>(peer_payload(br, sl.max_halo, par, 0)) : nullptr,
-            hl ? &reinterpret_cast<PeerBoxHeader*>(bl)->halo_flag[1] : nullptr, hr ? &reinterpret_cast<PeerBoxHeader*>(br)->halo_flag[0] : nullptr, seq, sl.d_ticket);
-        CHECK_LAUNCH();
         PeerBoxHeader* me = reinterpret_cast<PeerBoxHeader*>(sl.box);
-        k_halo_pull<T><<<ng ? blocks_for(ng, 256) : 1, 256, 0, c->stream>>>(
-            field, sl.ghost_idx[0], hl ? sl.n_ghost[0] : 0u, sl.ghost_idx[1], hr ? sl.n_ghost[1] : 0u,
+        const uint32_t nsl = hl ? sl.n_send[0] : 0u, nsr = hr ? sl.n_send[1] : 0u, ngl = hl ? sl.n_ghost[0] : 0u, ngr = hr ? sl.n_ghost[1] : 0u;
+        const uint32_t work = std::max(nsl + nsr, ngl + ngr);
+        const uint32_t grid = std::max(1u, std::min(blocks_for(work, 256), (uint32_t)c->num_sms));  // all CTAs resident (k_halo_exchange)
+        k_halo_exchange<T><<<grid, 256, 0, c->stream>>>(
+            field, sl.send_idx[0], nsl, sl.send_idx[1], nsr, hl ? reinterpret_cast<T*>(peer_payload(bl, sl.max_halo, par, 1)) : nullptr,
+            hr ? reinterpret_cast<T*>(peer_payload(br, sl.max_halo, par, 0)) : nullptr, hl ? &reinterpret_cast<PeerBoxHeader*>(bl)->halo_flag[1] : nullptr,
+            hr ? &reinterpret_cast<PeerBoxHeader*>(br)->halo_flag[0] : nullptr, sl.ghost_idx[0], ngl, sl.ghost_idx[1], ngr,
             reinterpret_cast<const T*>(peer_payload(sl.box, sl.max_halo, par, 0)), reinterpret_cast<const T*>(peer_payload(sl.box, sl.max_halo, par, 1)),
-            hl ? &me->halo_flag[0] : nullptr, hr ? &me->halo_flag[1] : nullptr, seq, c->ctl);
+            hl ? &me->halo_flag[0] : nullptr, hr ? &me->halo_flag[1] : nullptr, seq, sl.d_ticket, c->ctl);
         CHECK_LAUNCH();
         sl.halo_exchanges++;
         pass_end(c);
@@ -984,8 +984,8 @@ static int32_t allreduce_scalar(yasph_ctx* c, void* dev_ptr, ncclDataType_t type
     if (!c->slab.active || c->slab.world < 2) return YASPH_OK;
     if (c->slab.fabric) return loopback_allreduce(c, dev_ptr, type == ncclDouble && op == ncclSum);
     if (c->slab.peer) {
-        k_allreduce_peer<<<1, 32, 0, c->stream>>>(dev_ptr, type == ncclDouble && op == ncclSum ? 1 : 0, c->slab.d_boxes, c->slab.rank, c->slab.world,
-                                                  ++c->slab.ar_seq, c->ctl);
+        k_allreduce_peer<NoAfter><<<1, 32, 0, c->stream>>>(dev_ptr, type == ncclDouble && op == ncclSum ? 1 : 0, c->slab.d_boxes, c->slab.rank, c->slab.world,
+                                                           ++c->slab.ar_seq, c->ctl, NoAfter());
         CHECK_LAUNCH();
         c->slab.allreduces++;
         return YASPH_OK;
@@ -1685,9 +1685,17 @@ static int32_t jacobi_solve(yasph_ctx* c, bool first_a_done = false) {
             }
             if (c->slab.active) {
                 // global residual: sum over the ranks, then the loop decision every rank takes identically
-                TRY(allreduce_scalar(c, &c->ctl->resid_sum, ncclDouble, ncclSum));
-                k_jacobi_decide<SOLVER><<<1, 32, 0, c->stream>>>(c->ctl, sp, it, (float)c->slab.n_global, c->cfg.fluid_density);
-                CHECK_LAUNCH();
+                if (c->slab.peer && c->slab.world > 1) {  // residual all-reduce and the loop decision in one launch
+                    JacobiDecideAfter<SOLVER> after{sp, it, (float)c->slab.n_global, c->cfg.fluid_density};
+                    k_allreduce_peer<JacobiDecideAfter<SOLVER>><<<1, 32, 0, c->stream>>>(&c->ctl->resid_sum, 1, c->slab.d_boxes, c->slab.rank, c->slab.world,
+                                                                                        ++c->slab.ar_seq, c->ctl, after);
+                    CHECK_LAUNCH();
+                    c->slab.allreduces++;
+                } else {
+                    TRY(allreduce_scalar(c, &c->ctl->resid_sum, ncclDouble, ncclSum));
+                    k_jacobi_decide<SOLVER><<<1, 32, 0, c->stream>>>(c->ctl, sp, it, (float)c->slab.n_global, c->cfg.fluid_density);
+                    CHECK_LAUNCH();
+                }
                 if (slab) {
                     pass_end(c);
                     TRY(halo_exchange(c, c->err_buf));  // k_j of the ghosts for pass B
