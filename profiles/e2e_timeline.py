@@ -1,3 +1,5 @@
+"""Wall time and device timeline of yasph_step_host on the bench workload (2 M-particle tank, pinned host arrays), plus the per-pass
+times inside the call next to those of a device-resident step.  Run on a GPU box: python profiles/e2e_timeline.py"""
 import sys, os, json, numpy as np, torch
 sys.path.insert(0, os.getcwd())
 import yasph2d_b200 as y
@@ -20,7 +22,7 @@ ctx.set_flags(capi.FLAG_PROFILE_PASSES)
 tl = []
 for _ in range(5):
     ctx.step_host(pos, vel, den); tl.append(ctx.host_step_times_us())
-print("mode", os.environ.get("YASPH_E2E_MODE", "0"), "ms/call %.3f" % ms, {k: round(float(np.mean([t[k] for t in tl[2:]]))) for k in tl[0]})
+print("ms/call %.3f" % ms, {k: round(float(np.mean([t[k] for t in tl[2:]]))) for k in tl[0]})
 pt = ctx.pass_times_us()
 print("e2e passes", {k: round(v) for k, v in pt.items() if v > 0.5})
 ctx.step(); print("resident passes", {k: round(v) for k, v in ctx.pass_times_us().items() if v > 0.5})
