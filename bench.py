@@ -401,7 +401,7 @@ def main():
     roofline = {
         "bound": "hbm", "kernel": "%s (%s)" % (dominant, " + ".join(k.replace("void ", "").split("(")[0] for k in pass_kernels[dominant])),
         "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-        "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
+        "frac": round(achieved / peak, 4), "frac_of_nominal_8000_GBps": round(achieved / 8000.0, 4), "traffic": traffic, "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
         "traffic_source": traffic_src, "alg_bytes_per_launch": round(d_bpp * n, 0), "peak_source": peak_kind,
         "whole_step": {"alg_bytes_per_particle_step": round(step_bytes, 1), "GBps": round(step_bytes * n_total * args.steps / (ms * 1e-3) / 1e9, 1),
                        "frac_per_gpu": round(step_bytes * n_total / world * args.steps / (ms * 1e-3) / 1e9 / peak, 4)},
