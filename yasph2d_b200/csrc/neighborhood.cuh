@@ -491,6 +491,33 @@ __device__ __forceinline__ uint32_t run_slot_to_global(const uint2* runs, uint32
     }
     return runs[lo].x + (s - runs[lo].y);
 }
+// the same for U slots at once: branch-free searches of fixed depth, advanced in lockstep, so that the shared-memory loads of
+// the U searches are in flight together (a producer warp's staging time is this dependent chain, not its instruction count)
+template <int U>
+__device__ __forceinline__ void run_slots_to_global(const uint2* runs, const uint32_t (&s)[U], uint32_t (&g)[U]) {
+    static_assert(MAX_RUNS <= 64, "six halvings cover the table");
+    uint32_t lo[U], hi[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        lo[u] = 0;
+        hi[u] = MAX_RUNS - 1;
+    }
+#pragma unroll
+    for (int it = 0; it < 6; ++it) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t mid = (lo[u] + hi[u] + 1) >> 1;
+            const bool le = runs[mid].y <= s[u];
+            lo[u] = le ? mid : lo[u];
+            hi[u] = le ? hi[u] : mid - 1;
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const uint2 r = runs[lo[u]];
+        g[u] = r.x + (s[u] - r.y);
+    }
+}
 __device__ __forceinline__ uint32_t dyn_slot_to_global(const TileRuns& tr, uint32_t s) {
     uint32_t o = s - tr.hdr.own_lo;  // own particles are one contiguous copy
     if (o < tr.hdr.pcount) return tr.hdr.pstart + o;
@@ -563,6 +590,10 @@ struct ListSmem {
 };
 inline size_t list_smem_bytes(uint32_t cap_dyn, uint32_t cap_stat) { return sizeof(ListSmem) + 2 * ((size_t)cap_dyn + cap_stat) * sizeof(float2); }
 
+// Apron index table: the list build, which resolves every apron slot of a tile to its global particle index anyway, records
+// the first APRON_TABLE of them per tile; the sweeps' producer warps (five sweeps per step) then stage the apron without
+// walking the copy-run table again.  Slots beyond the table (very full aprons) fall back to the run look-up.
+constexpr uint32_t APRON_TABLE = 192;
 struct ListArgs {
     TileTables tt;
     const float2* pos;
@@ -574,6 +605,7 @@ struct ListArgs {
     uint32_t* counts;   // low half: count_dynamic | count_total << 8 of particle i; high half: work order of i's tile (see k_build_lists)
     uint32_t* tile_nk;  // [tile] most list words of any particle of the tile
     uint32_t cap_dyn, cap_stat;
+    uint32_t* apron_idx;  // [tile][APRON_TABLE]
 };
 __device__ __forceinline__ void list_issue_stage(const ListArgs& a, uint32_t t, const TileRuns& tr, float2* sdyn, float2* sstat, uint32_t (*cs)[REGION_CELLS]) {
     const TileHeader& h = tr.hdr;
@@ -583,7 +615,9 @@ __device__ __forceinline__ void list_issue_stage(const ListArgs& a, uint32_t t, 
     for (uint32_t s = threadIdx.x; s < h.pcount; s += NB_THREADS) cp_async<8>(&sdyn[h.own_lo + s], &a.pos[h.pstart + s]);
     for (uint32_t q = threadIdx.x, na = tile_apron_count(h); q < na; q += NB_THREADS) {
         const uint32_t s = tile_apron_slot(h, q);
-        cp_async<8>(&sdyn[s], &a.pos[run_slot_to_global(tr.rd, s)]);
+        const uint32_t g = run_slot_to_global(tr.rd, s);
+        cp_async<8>(&sdyn[s], &a.pos[g]);
+        if (q < APRON_TABLE) a.apron_idx[(size_t)t * APRON_TABLE + q] = g;
     }
     for (uint32_t s = threadIdx.x; s < h.stat_total; s += NB_THREADS) cp_async<8>(&sstat[s], &a.bpos[run_slot_to_global(tr.rs, s)]);
 }

@@ -47,12 +47,17 @@ constexpr int SW_THREADS = 32 * (SW_PRODUCER_WARPS + SW_CONSUMER_WARPS);
 #ifndef YASPH_SWEEP_STAGES
 #define YASPH_SWEEP_STAGES 3
 #endif
+#ifndef YASPH_SWEEP_APRON_UNROLL
+#define YASPH_SWEEP_APRON_UNROLL 2  // apron elements a producer lane stages at a time (their copy-run look-ups interleave)
+#endif
+constexpr int SW_APRON_PER_LANE = (APRON_TABLE + 32 * SW_PRODUCER_WARPS - 1) / (32 * SW_PRODUCER_WARPS);  // table entries a producer lane prefetches
 constexpr int SW_STAGES = YASPH_SWEEP_STAGES;  // stages of the shared-memory ring (fewer at run time when tiles are very large)
 constexpr uint32_t SW_MAX_STAGED_WORDS = 8;  // list words per particle staged in shared memory (the rest, if any, is read from global memory)
 
 struct SweepCommon {
     TileTables tt;
     const uint32_t* tile_nk;  // [tile] most list words of any particle of the tile
+    const uint32_t* apron_idx;  // [tile][APRON_TABLE] global index of the tile's first apron slots (written by the list build)
     const unsigned long long* lists;
     const uint32_t* counts;   // per particle: count_dynamic | count_total << 8
     const float2* pos;
@@ -69,6 +74,9 @@ struct SweepCommon {
     // slab mode (multi-GPU): ghosts are excluded from the reductions, the residual average runs over the global particle count
     // and the convergence decision is taken after the all-reduce (k_jacobi_decide)
     const uint8_t* ghost;  // null on a single GPU
+#ifdef YASPH_SWEEP_TIMING
+    unsigned long long* dbg;  // [8] cycle counters (profiling builds only)
+#endif
     float n_avg;           // particle count of dfsph.rs:221,376 as f32
 };
 
@@ -192,7 +200,14 @@ __device__ __forceinline__ uint32_t word_slot(unsigned long long w, uint32_t q) 
 // ~36 short runs) and the boundary candidates are copied element-wise with cp.async, spread over the producer warps.
 template <class Op>
 __device__ __forceinline__ void sweep_stage_tile(const SweepCommon& c, const Op& op, const TileRuns& tr, uint32_t nk_tile, const SweepStage<Op>& st, void* full_bar,
-                                                 uint32_t pw) {
+                                                 uint32_t pw, const uint32_t (&pre_ap)[SW_APRON_PER_LANE]
+#ifdef YASPH_SWEEP_TIMING
+                                                 , long long* tsplit
+#endif
+                                                 ) {
+#ifdef YASPH_SWEEP_TIMING
+    long long z0 = clock64();
+#endif
     typedef SweepLayout<Op> L;
     const uint32_t lane = lane_id();
     const uint32_t first = pw * 32u + lane, stride = 32u * SW_PRODUCER_WARPS;  // the producer warps interleave
@@ -206,34 +221,62 @@ __device__ __forceinline__ void sweep_stage_tile(const SweepCommon& c, const Op&
         *st.nk = fits ? nk : 0xFFFFFFFFu;
     }
     if (fits) {
-        for (uint32_t a = first, na = tile_apron_count(h); a < na; a += stride) {
+        // apron: the first APRON_TABLE slots come with their global index from the list build's table (prefetched into
+        // registers one tile ahead), the rest -- very full aprons only -- through the copy-run table
+        const uint32_t na = tile_apron_count(h);
+#pragma unroll
+        for (int u = 0; u < SW_APRON_PER_LANE; ++u) {
+            const uint32_t a = first + (uint32_t)u * stride;
+            if (a < na && a < APRON_TABLE) {
+                const uint32_t s = tile_apron_slot(h, a), g = pre_ap[u];
+                cp_async<8>(&st.pos[s], &c.pos[g]);
+                if constexpr (Op::NPAY >= 1) cp_async<sizeof(typename Op::P0)>(&st.p0[s], &op.pay0()[g]);
+                if constexpr (Op::NPAY >= 2) cp_async<sizeof(typename Op::P1)>(&st.p1[s], &op.pay1()[g]);
+            }
+        }
+        for (uint32_t a = (uint32_t)SW_APRON_PER_LANE * stride + first; a < na; a += stride) {
             const uint32_t s = tile_apron_slot(h, a);
             const uint32_t g = run_slot_to_global(tr.rd, s);
             cp_async<8>(&st.pos[s], &c.pos[g]);
             if constexpr (Op::NPAY >= 1) cp_async<sizeof(typename Op::P0)>(&st.p0[s], &op.pay0()[g]);
             if constexpr (Op::NPAY >= 2) cp_async<sizeof(typename Op::P1)>(&st.p1[s], &op.pay1()[g]);
         }
+#ifdef YASPH_SWEEP_TIMING
+        tsplit[0] += clock64() - z0;
+        z0 = clock64();
+#endif
         if (Op::USES_STATIC)
             for (uint32_t s = first; s < h.stat_total; s += stride) cp_async<8>(&st.stat[s], &c.bpos[run_slot_to_global(tr.rs, s)]);
     }
+#ifdef YASPH_SWEEP_TIMING
+    tsplit[1] += clock64() - z0;
+    z0 = clock64();
+#endif
     cp_async_mbar_arrive_noinc(full_bar);  // 32 arrivals per producer warp: this lane's copies have landed
     __syncwarp();                          // lane 0's header stores are ordered before its arrival below
-    if (lane == 0 && pw == 0) {
-        if (fits) {
-            const uint32_t lbytes = (nk * h.pcount * 8u + 15u) & ~15u;  // the first nk list words of every particle: one contiguous block
-            mbar_arrive_expect_tx(full_bar, nel * (uint32_t)(sizeof(float2) + L::P0 + L::P1 + 4 + L::O0 + L::O1) + lbytes);
-            const size_t g0 = h.pstart - d;
-            const uint32_t s0 = h.own_lo - d;
-            bulk_copy_g2s(st.pos + s0, c.pos + g0, nel * (uint32_t)sizeof(float2), full_bar);
-            if constexpr (Op::NPAY >= 1) bulk_copy_g2s(st.p0 + s0, op.pay0() + g0, nel * (uint32_t)L::P0, full_bar);
-            if constexpr (Op::NPAY >= 2) bulk_copy_g2s(st.p1 + s0, op.pay1() + g0, nel * (uint32_t)L::P1, full_bar);
-            bulk_copy_g2s(st.cnt, c.counts + g0, nel * 4u, full_bar);
-            if constexpr (Op::NOWN >= 1) bulk_copy_g2s(st.o0, op.own0() + g0, nel * (uint32_t)L::O0, full_bar);
-            if constexpr (Op::NOWN >= 2) bulk_copy_g2s(st.o1, op.own1() + g0, nel * (uint32_t)L::O1, full_bar);
-            if (lbytes) bulk_copy_g2s(st.lists, c.lists + (size_t)h.pstart * LIST_WORDS, lbytes, full_bar);
-        } else {
-            mbar_arrive(full_bar);
-        }
+    // The bulk copies: lane 0 of producer warp 0 announces the byte count with its arrival; the copies themselves are dealt to
+    // the first lanes of ALL producer warps (each is a separately issued instruction, so only different warps overlap them).
+    // The phase cannot complete before lane 0's arrival, hence a copy that lands before the byte count is announced is fine.
+    if (fits) {
+        const uint32_t lbytes = (nk * h.pcount * 8u + 15u) & ~15u;  // the first nk list words of every particle: one contiguous block
+        const size_t g0 = h.pstart - d;
+        const uint32_t s0 = h.own_lo - d;
+        if (pw == 0 && lane == 0) mbar_arrive_expect_tx(full_bar, nel * (uint32_t)(sizeof(float2) + L::P0 + L::P1 + 4 + L::O0 + L::O1) + lbytes);
+        // copy j goes to warp j % SW_PRODUCER_WARPS, lane j / SW_PRODUCER_WARPS
+        auto mine = [&](uint32_t j) { return pw == j % SW_PRODUCER_WARPS && lane == j / SW_PRODUCER_WARPS; };
+        if (mine(0)) bulk_copy_g2s(st.pos + s0, c.pos + g0, nel * (uint32_t)sizeof(float2), full_bar);
+        if (mine(1) && lbytes) bulk_copy_g2s(st.lists, c.lists + (size_t)h.pstart * LIST_WORDS, lbytes, full_bar);
+        if (mine(2)) bulk_copy_g2s(st.cnt, c.counts + g0, nel * 4u, full_bar);
+        if constexpr (Op::NPAY >= 1)
+            if (mine(3)) bulk_copy_g2s(st.p0 + s0, op.pay0() + g0, nel * (uint32_t)L::P0, full_bar);
+        if constexpr (Op::NOWN >= 1)
+            if (mine(4)) bulk_copy_g2s(st.o0, op.own0() + g0, nel * (uint32_t)L::O0, full_bar);
+        if constexpr (Op::NPAY >= 2)
+            if (mine(5)) bulk_copy_g2s(st.p1 + s0, op.pay1() + g0, nel * (uint32_t)L::P1, full_bar);
+        if constexpr (Op::NOWN >= 2)
+            if (mine(6)) bulk_copy_g2s(st.o1, op.own1() + g0, nel * (uint32_t)L::O1, full_bar);
+    } else if (pw == 0 && lane == 0) {
+        mbar_arrive(full_bar);
     }
 }
 
@@ -269,40 +312,84 @@ __global__ void __launch_bounds__(SW_THREADS, YASPH_SWEEP_MIN_CTAS) k_sweep(Swee
         uint32_t pre_nk = 0;
         const uint32_t NV = sizeof(TileRuns) / 16;
         static_assert(sizeof(TileRuns) / 16 <= 64, "two uint4 per lane");
+        uint32_t pre_ap[SW_APRON_PER_LANE], cur_ap[SW_APRON_PER_LANE];
         auto prefetch = [&](uint32_t t) {
             if (t < ntiles) {
                 const uint4* src = reinterpret_cast<const uint4*>(c.tt.runs + t);
                 if (lane < NV) pre[0] = src[lane];
                 if (lane + 32 < NV) pre[1] = src[lane + 32];
                 pre_nk = c.tile_nk[t];
+#pragma unroll
+                for (int u = 0; u < SW_APRON_PER_LANE; ++u) {
+                    const uint32_t a = warp * 32u + lane + (uint32_t)u * (32u * SW_PRODUCER_WARPS);
+                    pre_ap[u] = a < APRON_TABLE ? c.apron_idx[(size_t)t * APRON_TABLE + a] : 0u;
+                }
             }
         };
         prefetch(blockIdx.x);
         uint32_t k = 0, stage = 0, round = 0;  // round: completed passes over the ring
+#ifdef YASPH_SWEEP_TIMING
+        long long t_wait = 0, t_issue = 0, t_total = clock64(), n_tiles = 0, tsplit[2] = {0, 0};
+#endif
         for (uint32_t t = blockIdx.x; t < ntiles; t += G, ++k) {
             TileRuns& tr = runs[k & 1u];
             uint4* dst = reinterpret_cast<uint4*>(&tr);
             if (lane < NV) dst[lane] = pre[0];
             if (lane + 32 < NV) dst[lane + 32] = pre[1];
             const uint32_t nk_tile = pre_nk;
+#pragma unroll
+            for (int u = 0; u < SW_APRON_PER_LANE; ++u) cur_ap[u] = pre_ap[u];
             __syncwarp();
             prefetch(t + G);  // in flight while this tile is staged
+#ifdef YASPH_SWEEP_TIMING
+            long long q0 = clock64();
+#endif
             if (round) mbar_wait<YASPH_SWEEP_PSLEEP>(&empty_bar[stage], (round - 1u) & 1u);  // every consumer warp has released the stage
             const SweepStage<Op> st(stage0 + stage * sbytes, c.cap_dyn, c.cap_stat, c.cap_pc);
-            sweep_stage_tile(c, op, tr, nk_tile, st, &full_bar[stage], warp);
+#ifdef YASPH_SWEEP_TIMING
+            long long q1 = clock64();
+#endif
+#ifdef YASPH_SWEEP_TIMING
+            sweep_stage_tile(c, op, tr, nk_tile, st, &full_bar[stage], warp, cur_ap, tsplit);
+#else
+            sweep_stage_tile(c, op, tr, nk_tile, st, &full_bar[stage], warp, cur_ap);
+#endif
+#ifdef YASPH_SWEEP_TIMING
+            t_wait += q1 - q0;
+            t_issue += clock64() - q1;
+            ++n_tiles;
+#endif
             if (++stage == NS) {
                 stage = 0;
                 ++round;
             }
         }
+#ifdef YASPH_SWEEP_TIMING
+        if (lane == 0 && c.dbg) {
+            atomicAdd(&c.dbg[2], (unsigned long long)(clock64() - t_total));
+            atomicAdd(&c.dbg[3], (unsigned long long)t_wait);
+            atomicAdd(&c.dbg[4], (unsigned long long)t_issue);
+            atomicAdd(&c.dbg[5], (unsigned long long)n_tiles);
+            atomicAdd(&c.dbg[7], (unsigned long long)tsplit[0]);
+        }
+#endif
     } else {
         // ---------------- consumers ----------------
         const uint32_t cw = warp - SW_PRODUCER_WARPS;
         uint32_t chunk_base = 0;  // chunks (32 particles) of all earlier tiles of this CTA: chunks are dealt round-robin to the warps
         uint32_t stage = 0, round = 0;
+#ifdef YASPH_SWEEP_TIMING
+        long long t_wait = 0, t_total = clock64(), n_chunks = 0;
+#endif
         for (uint32_t t = blockIdx.x; t < ntiles; t += G) {
             const SweepStage<Op> st(stage0 + stage * sbytes, c.cap_dyn, c.cap_stat, c.cap_pc);
+#ifdef YASPH_SWEEP_TIMING
+            long long q0 = clock64();
+#endif
             mbar_wait<YASPH_SWEEP_CSLEEP>(&full_bar[stage], round & 1u);
+#ifdef YASPH_SWEEP_TIMING
+            t_wait += clock64() - q0;
+#endif
             const TileHeader h = *st.hdr;
             const uint32_t nk_st = *st.nk;
             const uint32_t nchunks = (h.pcount + 31u) >> 5;
@@ -368,12 +455,27 @@ __global__ void __launch_bounds__(SW_THREADS, YASPH_SWEEP_MIN_CTAS) k_sweep(Swee
             chunk_base += nchunks;
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[stage]);  // this warp is done with the stage
+#ifdef YASPH_SWEEP_TIMING
+            n_chunks += (nchunks + SW_CONSUMER_WARPS - 1 - ((cw + SW_CONSUMER_WARPS - (chunk_base - nchunks) % SW_CONSUMER_WARPS) % SW_CONSUMER_WARPS)) / SW_CONSUMER_WARPS;
+#endif
             if (++stage == NS) {
                 stage = 0;
                 ++round;
             }
         }
+#ifdef YASPH_SWEEP_TIMING
+        if (lane == 0 && c.dbg) {
+            atomicAdd(&c.dbg[0], (unsigned long long)(clock64() - t_total));
+            atomicAdd(&c.dbg[1], (unsigned long long)t_wait);
+            atomicAdd(&c.dbg[6], (unsigned long long)n_chunks);
+        }
+#endif
     }
+#ifdef YASPH_SWEEP_TIMING
+    if (warp >= SW_PRODUCER_WARPS && lane == 0 && c.dbg) {
+        // consumer counters live in the consumer branch's scope: re-derive is not possible here, so they are flushed there
+    }
+#endif
     if (Op::REDUCE != REDUCE_NONE) {
         __shared__ double wred[SW_THREADS / 32];
         __shared__ bool is_last;

@@ -59,10 +59,14 @@ struct yasph_ctx {
     unsigned long long* lists = nullptr;
     uint32_t* counts = nullptr;   // per particle: count_dynamic | count_total << 8
     uint32_t* tile_nk = nullptr;  // per tile: most list words of any of its particles
+    uint32_t* apron_idx = nullptr;  // per tile: global index of its first APRON_TABLE apron slots (list build -> sweeps)
     // scratch
     uint32_t* radix_scratch = nullptr;
     unsigned long long *scan_chunks = nullptr, *scan_total = nullptr;
     double* partials = nullptr;
+#ifdef YASPH_SWEEP_TIMING
+    unsigned long long* sweep_dbg = nullptr;
+#endif
     Control* ctl = nullptr;
     Control* h_ctl = nullptr;  // pinned mirror
     // read-back channel: a one-warp kernel copies the control block into mapped host memory and bumps `seq`; the host polls it
@@ -385,7 +389,7 @@ static void free_all(yasph_ctx* c) {
     void* ptrs[] = {c->pos, c->pos_alt, c->vel, c->vel_alt, c->vstar, c->vstar_alt, c->accel, c->dens, c->alpha, c->kappa, c->stiff, c->err_buf,
                     c->f_alt0, c->f_alt1, c->keys[0], c->keys[1], c->idx[0], c->idx[1], c->cell_key, c->cell_start, c->tile_key, c->tile_pstart,
                     c->tile_cstart, c->bpos, c->bpos_alt, c->scell_key, c->scell_start, c->stile_key, c->stile_cstart, c->tile_runs, c->cslot_d,
-                    c->cslot_s, c->lists, c->counts, c->tile_nk,
+                    c->cslot_s, c->lists, c->counts, c->tile_nk, c->apron_idx,
                     c->radix_scratch, c->scan_chunks, c->scan_total, c->partials, c->ctl, c->exp_cd, c->exp_ct, c->exp_lists,
                     c->ids, c->ids_alt, c->slab.pflag, c->slab.sel[0], c->slab.sel[1], c->slab.send_idx[0], c->slab.send_idx[1],
                     c->slab.ghost_idx[0], c->slab.ghost_idx[1], c->slab.own_idx, c->slab.sbuf[0], c->slab.sbuf[1], c->slab.rbuf[0],
@@ -522,6 +526,7 @@ extern "C" int32_t yasph_create(const yasph_config* cfg, yasph_ctx** out) {
     CUC(dmalloc(&c->lists, N * LIST_WORDS));
     CUC(dmalloc(&c->counts, N));
     CUC(dmalloc(&c->tile_nk, (size_t)c->max_tiles + 1));
+    CUC(dmalloc(&c->apron_idx, ((size_t)c->max_tiles + 1) * APRON_TABLE));
     CUC(dmalloc(&c->radix_scratch, radix_scratch_words((uint32_t)NM)));
     CUC(dmalloc(&c->scan_chunks, (size_t)scan_num_chunks((uint32_t)NM) + 1));
     CUC(dmalloc(&c->scan_total, 1));
@@ -556,6 +561,10 @@ extern "C" int32_t yasph_create(const yasph_config* cfg, yasph_ctx** out) {
     CUC(allow_max_smem(c, k_build_lists));
     CUC(allow_max_smem(c, k_radix_pass));
     CUC(dmalloc(&c->partials, (size_t)c->max_tiles + 1));
+#ifdef YASPH_SWEEP_TIMING
+    CUC(dmalloc(&c->sweep_dbg, 8));
+    CUC(cudaMemset(c->sweep_dbg, 0, 64));
+#endif
 
     // TimeManager::new: initial step = timestep_min / fixed (timemanager.rs:106-109); DFSPHSolver::new iteration counts (dfsph.rs:51,55)
     memset(c->h_ctl, 0, sizeof(Control));
@@ -671,6 +680,7 @@ static SweepCommon sweep_common(const yasph_ctx* c) {
     s.lists = c->lists;
     s.counts = c->counts;
     s.tile_nk = c->tile_nk;
+    s.apron_idx = c->apron_idx;
     s.cap_pc = c->cap_pc;
     s.nk_stage = 0;  // launch_sweep
     s.pos = c->pos;
@@ -684,6 +694,9 @@ static SweepCommon sweep_common(const yasph_ctx* c) {
     s.rho0 = c->cfg.fluid_density;
     s.partials = c->partials;
     s.ghost = c->slab.active ? c->slab.pflag : nullptr;
+#ifdef YASPH_SWEEP_TIMING
+    s.dbg = c->sweep_dbg;
+#endif
     s.n_avg = c->slab.active ? (float)c->slab.n_global : (float)c->n;
     return s;
 }
@@ -1282,7 +1295,7 @@ static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp
     pass_begin(c, YASPH_PASS_LISTS);
     if (c->num_tiles) {
         const size_t bytes = list_smem_bytes(c->cap_dyn, c->cap_stat);
-        ListArgs la{tile_tables(c), c->pos, c->bpos, c->keys[0], c->grid, c->ctl, c->lists, c->counts, c->tile_nk, c->cap_dyn, c->cap_stat};
+        ListArgs la{tile_tables(c), c->pos, c->bpos, c->keys[0], c->grid, c->ctl, c->lists, c->counts, c->tile_nk, c->cap_dyn, c->cap_stat, c->apron_idx};
         k_build_lists<<<persistent_grid(c, k_build_lists, bytes, NB_THREADS), NB_THREADS, bytes, c->stream>>>(la);
         CHECK_LAUNCH();
     }
@@ -1933,6 +1946,16 @@ extern "C" int32_t yasph_upload_field(yasph_ctx* c, int32_t field, const void* d
     CU(cudaStreamSynchronize(c->stream));
     return YASPH_OK;
 }
+
+#ifdef YASPH_SWEEP_TIMING
+// profiling builds only: cycle counters of the sweep pipeline since the last call (then reset)
+extern "C" int32_t yasph_debug_sweep_counters(yasph_ctx* c, unsigned long long* out8) {
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpy(out8, c->sweep_dbg, 64, cudaMemcpyDeviceToHost));
+    CU(cudaMemset(c->sweep_dbg, 0, 64));
+    return YASPH_OK;
+}
+#endif
 
 extern "C" int32_t yasph_step(yasph_ctx* c, yasph_step_report* report) {
     if (!c) return YASPH_ERR_INVALID_ARGUMENT;
