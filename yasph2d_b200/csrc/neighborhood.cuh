@@ -491,33 +491,6 @@ __device__ __forceinline__ uint32_t run_slot_to_global(const uint2* runs, uint32
     }
     return runs[lo].x + (s - runs[lo].y);
 }
-// the same for U slots at once: branch-free searches of fixed depth, advanced in lockstep, so that the shared-memory loads of
-// the U searches are in flight together (a producer warp's staging time is this dependent chain, not its instruction count)
-template <int U>
-__device__ __forceinline__ void run_slots_to_global(const uint2* runs, const uint32_t (&s)[U], uint32_t (&g)[U]) {
-    static_assert(MAX_RUNS <= 64, "six halvings cover the table");
-    uint32_t lo[U], hi[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        lo[u] = 0;
-        hi[u] = MAX_RUNS - 1;
-    }
-#pragma unroll
-    for (int it = 0; it < 6; ++it) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint32_t mid = (lo[u] + hi[u] + 1) >> 1;
-            const bool le = runs[mid].y <= s[u];
-            lo[u] = le ? mid : lo[u];
-            hi[u] = le ? hi[u] : mid - 1;
-        }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const uint2 r = runs[lo[u]];
-        g[u] = r.x + (s[u] - r.y);
-    }
-}
 __device__ __forceinline__ uint32_t dyn_slot_to_global(const TileRuns& tr, uint32_t s) {
     uint32_t o = s - tr.hdr.own_lo;  // own particles are one contiguous copy
     if (o < tr.hdr.pcount) return tr.hdr.pstart + o;
@@ -606,6 +579,9 @@ struct ListArgs {
     uint32_t* tile_nk;  // [tile] most list words of any particle of the tile
     uint32_t cap_dyn, cap_stat;
     uint32_t* apron_idx;  // [tile][APRON_TABLE]
+#ifdef YASPH_LIST_TIMING
+    unsigned long long* dbg;  // [8] cycle counters per phase (profiling builds only)
+#endif
 };
 __device__ __forceinline__ void list_issue_stage(const ListArgs& a, uint32_t t, const TileRuns& tr, float2* sdyn, float2* sstat, uint32_t (*cs)[REGION_CELLS]) {
     const TileHeader& h = tr.hdr;
@@ -665,6 +641,12 @@ __global__ void __launch_bounds__(NB_THREADS) k_build_lists(ListArgs a) {
         cp_async_commit();
     }
     uint32_t k = 0;
+#ifdef YASPH_LIST_TIMING
+    long long tph[6] = {0, 0, 0, 0, 0, 0}, tz = clock64(), t_begin = tz;
+#define LT_MARK(i) { long long now_ = clock64(); tph[i] += now_ - tz; tz = now_; }
+#else
+#define LT_MARK(i)
+#endif
     for (uint32_t t = blockIdx.x; t < ntiles; t += G, ++k) {
         const uint32_t b = k & 1u;
         const float2* cdyn = sdyn[b];
@@ -675,8 +657,10 @@ __global__ void __launch_bounds__(NB_THREADS) k_build_lists(ListArgs a) {
         pre.load(a.tt.runs + t + 2 * G, have2);
         cp_async_wait_all();
         __syncthreads();  // this tile's copies have landed; everybody is done with the previous tile
+        LT_MARK(0)  // waiting for the staged tile
         if (t + G < ntiles) list_issue_stage(a, t + G, S.runs[(k + 1) % 3u], sdyn[b ^ 1u], sdyn[b ^ 1u] + a.cap_dyn, S.cs[b ^ 1u]);
         cp_async_commit();
+        LT_MARK(1)  // issuing the next tile's copies
         const TileHeader h = tr.hdr;
         const bool fits = h.dyn_total <= a.cap_dyn && h.stat_total <= a.cap_stat;
         if (tid < 2 * TILE_CELLS) {
@@ -719,6 +703,7 @@ __global__ void __launch_bounds__(NB_THREADS) k_build_lists(ListArgs a) {
         if (tid == 0) S.nk_max = 0u;
         if (tid < (NB_THREADS / 32) * LIST_WORDS) (&S.wk[0][0])[tid] = 0u;
         __syncthreads();
+        LT_MARK(2)  // cell phase (incl. its barrier)
         uint32_t my_nk = 0, my_words = 0xFFu;
         uint16_t* const counts16 = reinterpret_cast<uint16_t*>(a.counts);
         if (fits) {
@@ -762,6 +747,7 @@ __global__ void __launch_bounds__(NB_THREADS) k_build_lists(ListArgs a) {
                 my_total += ct;
             }
         }
+        LT_MARK(3)  // candidate scan + packing + stores
         my_nk = __reduce_max_sync(0xffffffffu, my_nk);
         if (lane_id() == 0 && my_nk) atomicMax(&S.nk_max, my_nk);
         // Work order of the tile: its particles sorted (stably) by their number of list words.  The sweeps hand 32 consecutive
@@ -803,7 +789,15 @@ __global__ void __launch_bounds__(NB_THREADS) k_build_lists(ListArgs a) {
             cta_nk = max(cta_nk, S.nk_max);
         }
         pre.store(S.runs[(k + 2) % 3u], have2);
+        LT_MARK(4)  // work order (two barriers)
     }
+#ifdef YASPH_LIST_TIMING
+    if (lane_id() == 0 && a.dbg) {
+        for (int i = 0; i < 5; ++i) atomicAdd(&a.dbg[i], (unsigned long long)tph[i]);
+        atomicAdd(&a.dbg[5], (unsigned long long)(clock64() - t_begin));
+        atomicAdd(&a.dbg[6], (unsigned long long)k);
+    }
+#endif
     cp_async_wait_all();
     // statistics: warp reduce, one global atomic per CTA
 #pragma unroll

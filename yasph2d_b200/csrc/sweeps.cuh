@@ -47,9 +47,6 @@ constexpr int SW_THREADS = 32 * (SW_PRODUCER_WARPS + SW_CONSUMER_WARPS);
 #ifndef YASPH_SWEEP_STAGES
 #define YASPH_SWEEP_STAGES 3
 #endif
-#ifndef YASPH_SWEEP_APRON_UNROLL
-#define YASPH_SWEEP_APRON_UNROLL 2  // apron elements a producer lane stages at a time (their copy-run look-ups interleave)
-#endif
 constexpr int SW_APRON_PER_LANE = (APRON_TABLE + 32 * SW_PRODUCER_WARPS - 1) / (32 * SW_PRODUCER_WARPS);  // table entries a producer lane prefetches
 constexpr int SW_STAGES = YASPH_SWEEP_STAGES;  // stages of the shared-memory ring (fewer at run time when tiles are very large)
 constexpr uint32_t SW_MAX_STAGED_WORDS = 8;  // list words per particle staged in shared memory (the rest, if any, is read from global memory)

@@ -64,7 +64,7 @@ struct yasph_ctx {
     uint32_t* radix_scratch = nullptr;
     unsigned long long *scan_chunks = nullptr, *scan_total = nullptr;
     double* partials = nullptr;
-#ifdef YASPH_SWEEP_TIMING
+#if defined(YASPH_SWEEP_TIMING) || defined(YASPH_LIST_TIMING)
     unsigned long long* sweep_dbg = nullptr;
 #endif
     Control* ctl = nullptr;
@@ -561,7 +561,7 @@ extern "C" int32_t yasph_create(const yasph_config* cfg, yasph_ctx** out) {
     CUC(allow_max_smem(c, k_build_lists));
     CUC(allow_max_smem(c, k_radix_pass));
     CUC(dmalloc(&c->partials, (size_t)c->max_tiles + 1));
-#ifdef YASPH_SWEEP_TIMING
+#if defined(YASPH_SWEEP_TIMING) || defined(YASPH_LIST_TIMING)
     CUC(dmalloc(&c->sweep_dbg, 8));
     CUC(cudaMemset(c->sweep_dbg, 0, 64));
 #endif
@@ -1296,6 +1296,9 @@ static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp
     if (c->num_tiles) {
         const size_t bytes = list_smem_bytes(c->cap_dyn, c->cap_stat);
         ListArgs la{tile_tables(c), c->pos, c->bpos, c->keys[0], c->grid, c->ctl, c->lists, c->counts, c->tile_nk, c->cap_dyn, c->cap_stat, c->apron_idx};
+#ifdef YASPH_LIST_TIMING
+        la.dbg = c->sweep_dbg;
+#endif
         k_build_lists<<<persistent_grid(c, k_build_lists, bytes, NB_THREADS), NB_THREADS, bytes, c->stream>>>(la);
         CHECK_LAUNCH();
     }
@@ -1947,8 +1950,8 @@ extern "C" int32_t yasph_upload_field(yasph_ctx* c, int32_t field, const void* d
     return YASPH_OK;
 }
 
-#ifdef YASPH_SWEEP_TIMING
-// profiling builds only: cycle counters of the sweep pipeline since the last call (then reset)
+#if defined(YASPH_SWEEP_TIMING) || defined(YASPH_LIST_TIMING)
+// profiling builds only: cycle counters of the sweep pipeline / the list build since the last call (then reset)
 extern "C" int32_t yasph_debug_sweep_counters(yasph_ctx* c, unsigned long long* out8) {
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaMemcpy(out8, c->sweep_dbg, 64, cudaMemcpyDeviceToHost));
