@@ -262,6 +262,8 @@ struct Control {
     unsigned int err_tile_count;      // more tiles than max_tiles
     // last-block tickets
     unsigned int ticket[4];
+    // tile queue of the persistent sweeps (sweeps.cuh): tiles handed out beyond the first one per CTA, CTAs that have finished
+    unsigned int tile_next, cta_done;
     // slab mode (multi-GPU): counts of the ordered selections of a neighbourhood update
     unsigned long long slab_migrants;    // low word: migrants to the left rank, high word: to the right rank
     unsigned long long slab_ghost_send;  // own particles in the first / last owned column (sent as ghosts)

@@ -1,6 +1,7 @@
 // sweeps.cuh -- every neighbour-dependent per-particle pass of the WCSPH / DFSPH solvers as one tile-staged kernel.
 //
-// Skeleton (k_sweep): persistent CTAs, each walking tiles blockIdx.x, blockIdx.x + gridDim.x, ...  A tile's own particles
+// Skeleton (k_sweep): persistent CTAs; a CTA starts with tile blockIdx.x and takes every further tile from a device-wide queue
+// (one atomic per tile, fetched a tile ahead), so CTAs on slower SMs or with heavier tiles simply take fewer.  A tile's own particles
 // plus the 1-cell apron are staged into shared memory (positions, up to two per-pass payload arrays, boundary positions)
 // with cp.async, DOUBLE-BUFFERED: while the CTA computes tile k from buffer k&1 the copies for tile k+1 are in flight into
 // the other buffer and the copy-run table of tile k+2 is on its way through registers, so the global-memory latency of the
@@ -49,6 +50,8 @@ constexpr int SW_THREADS = 32 * (SW_PRODUCER_WARPS + SW_CONSUMER_WARPS);
 #endif
 constexpr int SW_APRON_PER_LANE = (APRON_TABLE + 32 * SW_PRODUCER_WARPS - 1) / (32 * SW_PRODUCER_WARPS);  // table entries a producer lane prefetches
 constexpr int SW_STAGES = YASPH_SWEEP_STAGES;  // stages of the shared-memory ring (fewer at run time when tiles are very large)
+static_assert(2 * YASPH_SWEEP_STAGES * 8 <= 96, "barriers and the tile hand-over words share the 128-byte head");
+constexpr uint32_t SW_NK_DONE = 0xFFFFFFFEu;  // stage marker: no more tiles
 constexpr uint32_t SW_MAX_STAGED_WORDS = 8;  // list words per particle staged in shared memory (the rest, if any, is read from global memory)
 
 struct SweepCommon {
@@ -131,7 +134,7 @@ struct SweepLayout {
     static constexpr size_t P1 = Op::NPAY >= 2 ? sizeof(typename Op::P1) : 0;
     static constexpr size_t O0 = Op::NOWN >= 1 ? sizeof(typename Op::O0) : 0;
     static constexpr size_t O1 = Op::NOWN >= 2 ? sizeof(typename Op::O1) : 0;
-    static constexpr size_t HEAD = 128;                                   // barriers
+    static constexpr size_t HEAD = 128;                                   // barriers, then (offset 96) the producers' tile hand-over words
     static constexpr size_t RUNS = 2 * SW_PRODUCER_WARPS * sizeof(TileRuns);  // every producer warp's copy-run tables
     static constexpr size_t STAGE_HDR = 48;                               // TileHeader + nk, padded to 16
     __host__ __device__ static size_t stage_bytes(uint32_t cap_dyn, uint32_t cap_stat, uint32_t cap_pc, uint32_t nk_stage) {
@@ -323,12 +326,32 @@ __global__ void __launch_bounds__(SW_THREADS, YASPH_SWEEP_MIN_CTAS) k_sweep(Swee
                 }
             }
         };
-        prefetch(blockIdx.x);
+        // tile queue: this CTA's first tile is blockIdx.x, the others come from ctl->tile_next.  The leader lane fetches the ticket
+        // for the tile after next while the current one is staged (the atomic's round trip hides behind the staging) and hands
+        // it to the other producer lanes through shared memory at the producers' own barrier.
+        volatile uint32_t* next_tile = reinterpret_cast<volatile uint32_t*>(smem_raw + 96);
+        const bool leader = threadIdx.x == 0;
+        auto producers_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(32 * SW_PRODUCER_WARPS) : "memory"); };
+        uint32_t t_cur = blockIdx.x, ticket = 0;
+        if (leader) next_tile[0] = G + atomicAdd(&c.ctl->tile_next, 1u);
+        producers_sync();
+        uint32_t t_nxt = next_tile[0];
+        prefetch(t_cur);
         uint32_t k = 0, stage = 0, round = 0;  // round: completed passes over the ring
 #ifdef YASPH_SWEEP_TIMING
         long long t_wait = 0, t_issue = 0, t_total = clock64(), n_tiles = 0, tsplit[2] = {0, 0};
 #endif
-        for (uint32_t t = blockIdx.x; t < ntiles; t += G, ++k) {
+        for (;; ++k) {
+            if (t_cur >= ntiles) {  // the queue is empty: tell the consumers through one more stage
+                if (round) mbar_wait<YASPH_SWEEP_PSLEEP>(&empty_bar[stage], (round - 1u) & 1u);
+                const SweepStage<Op> st(stage0 + stage * sbytes, c.cap_dyn, c.cap_stat, c.cap_pc);
+                if (leader) *st.nk = SW_NK_DONE;
+                cp_async_mbar_arrive_noinc(&full_bar[stage]);
+                __syncwarp();
+                if (leader) mbar_arrive(&full_bar[stage]);
+                break;
+            }
+            if (leader) ticket = G + atomicAdd(&c.ctl->tile_next, 1u);  // the tile after next; consumed at the end of this iteration
             TileRuns& tr = runs[k & 1u];
             uint4* dst = reinterpret_cast<uint4*>(&tr);
             if (lane < NV) dst[lane] = pre[0];
@@ -337,7 +360,7 @@ __global__ void __launch_bounds__(SW_THREADS, YASPH_SWEEP_MIN_CTAS) k_sweep(Swee
 #pragma unroll
             for (int u = 0; u < SW_APRON_PER_LANE; ++u) cur_ap[u] = pre_ap[u];
             __syncwarp();
-            prefetch(t + G);  // in flight while this tile is staged
+            prefetch(t_nxt);  // in flight while this tile is staged
 #ifdef YASPH_SWEEP_TIMING
             long long q0 = clock64();
 #endif
@@ -360,6 +383,10 @@ __global__ void __launch_bounds__(SW_THREADS, YASPH_SWEEP_MIN_CTAS) k_sweep(Swee
                 stage = 0;
                 ++round;
             }
+            if (leader) next_tile[(k + 1u) & 1u] = ticket;
+            producers_sync();
+            t_cur = t_nxt;
+            t_nxt = next_tile[(k + 1u) & 1u];
         }
 #ifdef YASPH_SWEEP_TIMING
         if (lane == 0 && c.dbg) {
@@ -367,7 +394,6 @@ __global__ void __launch_bounds__(SW_THREADS, YASPH_SWEEP_MIN_CTAS) k_sweep(Swee
             atomicAdd(&c.dbg[3], (unsigned long long)t_wait);
             atomicAdd(&c.dbg[4], (unsigned long long)t_issue);
             atomicAdd(&c.dbg[5], (unsigned long long)n_tiles);
-            atomicAdd(&c.dbg[7], (unsigned long long)tsplit[0]);
         }
 #endif
     } else {
@@ -378,7 +404,7 @@ __global__ void __launch_bounds__(SW_THREADS, YASPH_SWEEP_MIN_CTAS) k_sweep(Swee
 #ifdef YASPH_SWEEP_TIMING
         long long t_wait = 0, t_total = clock64(), n_chunks = 0;
 #endif
-        for (uint32_t t = blockIdx.x; t < ntiles; t += G) {
+        for (;;) {
             const SweepStage<Op> st(stage0 + stage * sbytes, c.cap_dyn, c.cap_stat, c.cap_pc);
 #ifdef YASPH_SWEEP_TIMING
             long long q0 = clock64();
@@ -387,8 +413,9 @@ __global__ void __launch_bounds__(SW_THREADS, YASPH_SWEEP_MIN_CTAS) k_sweep(Swee
 #ifdef YASPH_SWEEP_TIMING
             t_wait += clock64() - q0;
 #endif
-            const TileHeader h = *st.hdr;
             const uint32_t nk_st = *st.nk;
+            if (nk_st == SW_NK_DONE) break;  // the producers found the tile queue empty
+            const TileHeader h = *st.hdr;
             const uint32_t nchunks = (h.pcount + 31u) >> 5;
             const uint32_t od = h.pstart & 3u;  // the per-particle operand arrays are staged from the 4-element-aligned index below pstart
             if (nk_st != 0xFFFFFFFFu) {
@@ -465,14 +492,20 @@ __global__ void __launch_bounds__(SW_THREADS, YASPH_SWEEP_MIN_CTAS) k_sweep(Swee
             atomicAdd(&c.dbg[0], (unsigned long long)(clock64() - t_total));
             atomicAdd(&c.dbg[1], (unsigned long long)t_wait);
             atomicAdd(&c.dbg[6], (unsigned long long)n_chunks);
+            atomicMax(&c.dbg[7], (unsigned long long)(clock64() - t_total));  // longest-lived consumer warp of any launch since the reset
         }
 #endif
     }
-#ifdef YASPH_SWEEP_TIMING
-    if (warp >= SW_PRODUCER_WARPS && lane == 0 && c.dbg) {
-        // consumer counters live in the consumer branch's scope: re-derive is not possible here, so they are flushed there
+    // the last CTA to get here re-arms the tile queue for the next sweep (nobody fetches a ticket any more: every CTA's
+    // producers have seen the queue empty before their CTA counts itself done)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&c.ctl->cta_done, 1u) == gridDim.x - 1) {
+            c.ctl->tile_next = 0u;
+            c.ctl->cta_done = 0u;
+        }
     }
-#endif
     if (Op::REDUCE != REDUCE_NONE) {
         __shared__ double wred[SW_THREADS / 32];
         __shared__ bool is_last;
