@@ -280,12 +280,22 @@ __device__ __forceinline__ void sweep_stage_tile(const SweepCommon& c, const Op&
     }
 }
 
+#ifdef YASPH_SWEEP_TIMING
+__device__ __forceinline__ unsigned long long global_timer_ns_sweep() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
 template <class Op>
 __global__ void __launch_bounds__(SW_THREADS, YASPH_SWEEP_MIN_CTAS) k_sweep(SweepCommon c, Op op) {
     typedef typename Op::P0 P0;
     typedef typename Op::P1 P1;
     typedef SweepLayout<Op> L;
     if (op.skip(c.ctl)) return;
+#ifdef YASPH_SWEEP_TIMING
+    if (threadIdx.x == 0 && c.dbg) atomicMin(&c.dbg[8], global_timer_ns_sweep());
+#endif
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* full_bar = reinterpret_cast<unsigned long long*>(smem_raw);
     unsigned long long* empty_bar = full_bar + SW_STAGES;
@@ -504,6 +514,13 @@ __global__ void __launch_bounds__(SW_THREADS, YASPH_SWEEP_MIN_CTAS) k_sweep(Swee
         if (atomicAdd(&c.ctl->cta_done, 1u) == gridDim.x - 1) {
             c.ctl->tile_next = 0u;
             c.ctl->cta_done = 0u;
+#ifdef YASPH_SWEEP_TIMING
+            if (c.dbg) {  // span of this launch as seen from inside: first CTA's first instruction to the last CTA's last
+                atomicAdd(&c.dbg[9], global_timer_ns_sweep() - c.dbg[8]);
+                atomicAdd(&c.dbg[10], 1ull);
+                c.dbg[8] = ~0ull;
+            }
+#endif
         }
     }
     if (Op::REDUCE != REDUCE_NONE) {

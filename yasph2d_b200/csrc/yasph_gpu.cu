@@ -562,8 +562,9 @@ extern "C" int32_t yasph_create(const yasph_config* cfg, yasph_ctx** out) {
     CUC(allow_max_smem(c, k_radix_pass));
     CUC(dmalloc(&c->partials, (size_t)c->max_tiles + 1));
 #if defined(YASPH_SWEEP_TIMING) || defined(YASPH_LIST_TIMING)
-    CUC(dmalloc(&c->sweep_dbg, 8));
-    CUC(cudaMemset(c->sweep_dbg, 0, 64));
+    CUC(dmalloc(&c->sweep_dbg, 16));
+    CUC(cudaMemset(c->sweep_dbg, 0, 128));
+    CUC(cudaMemset(c->sweep_dbg + 8, 0xFF, 8));
 #endif
 
     // TimeManager::new: initial step = timestep_min / fixed (timemanager.rs:106-109); DFSPHSolver::new iteration counts (dfsph.rs:51,55)
@@ -1954,8 +1955,9 @@ extern "C" int32_t yasph_upload_field(yasph_ctx* c, int32_t field, const void* d
 // profiling builds only: cycle counters of the sweep pipeline / the list build since the last call (then reset)
 extern "C" int32_t yasph_debug_sweep_counters(yasph_ctx* c, unsigned long long* out8) {
     CU(cudaStreamSynchronize(c->stream));
-    CU(cudaMemcpy(out8, c->sweep_dbg, 64, cudaMemcpyDeviceToHost));
-    CU(cudaMemset(c->sweep_dbg, 0, 64));
+    CU(cudaMemcpy(out8, c->sweep_dbg, 128, cudaMemcpyDeviceToHost));
+    CU(cudaMemset(c->sweep_dbg, 0, 128));
+    CU(cudaMemset(c->sweep_dbg + 8, 0xFF, 8));
     return YASPH_OK;
 }
 #endif
