@@ -28,19 +28,31 @@ __device__ __forceinline__ T warp_sum(T v) {
     return v;
 }
 
+// Every input functor of this library returns a PAIR OF FLAGS: bit 0 and bit 32 of the 64-bit value, each 0 or 1 (cell head /
+// tile head, selected for list A / list B).  The two data passes exploit that: a warp's exclusive prefix and total come
+// from two ballots and population counts instead of a five-step shuffle scan of 64-bit values.
+__device__ __forceinline__ void warp_flag_scan(unsigned long long v, unsigned lt, unsigned long long& excl, unsigned long long& total) {
+    const unsigned ba = __ballot_sync(0xffffffffu, (uint32_t)v != 0u), bb = __ballot_sync(0xffffffffu, (uint32_t)(v >> 32) != 0u);
+    excl = (unsigned long long)__popc(ba & lt) | ((unsigned long long)__popc(bb & lt) << 32);
+    total = (unsigned long long)__popc(ba) | ((unsigned long long)__popc(bb) << 32);
+}
+
 // chunk_sums[b] = sum of in(i) over chunk b
 template <typename T, typename In>
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(In in, uint32_t n, T* __restrict__ chunk_sums) {
+    static_assert(sizeof(T) == 8, "pair of flags");
     __shared__ T wsum[SCAN_WARPS];
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    const unsigned lt = lanemask_lt();
     const uint32_t base = blockIdx.x * SCAN_CHUNK + warp * (32 * SCAN_ITEMS);
-    T s = 0;
+    T s = 0;  // warp-uniform
 #pragma unroll
     for (int r = 0; r < SCAN_ITEMS; ++r) {
         uint32_t i = base + r * 32 + lane;
-        if (i < n) s += in(i);
+        T ex, tot;
+        warp_flag_scan(i < n ? in(i) : (T)0, lt, ex, tot);
+        s += tot;
     }
-    s = warp_sum(s);
     if (lane == 0) wsum[warp] = s;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -82,15 +94,18 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(In in, uint32_t n, 
     __shared__ T wsum[SCAN_WARPS];
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
     const uint32_t base = blockIdx.x * SCAN_CHUNK + warp * (32 * SCAN_ITEMS);
+    static_assert(sizeof(T) == 8, "pair of flags");
+    const unsigned lt = lanemask_lt();
     T v[SCAN_ITEMS], ex[SCAN_ITEMS];
-    T carry = 0;
+    T carry = 0;  // warp-uniform
 #pragma unroll
     for (int r = 0; r < SCAN_ITEMS; ++r) {
         uint32_t i = base + r * 32 + lane;
         v[r] = i < n ? in(i) : (T)0;
-        T inc = warp_inclusive_scan(v[r]);
-        ex[r] = carry + inc - v[r];
-        carry += __shfl_sync(0xffffffffu, inc, 31);
+        T e, tot;
+        warp_flag_scan(v[r], lt, e, tot);
+        ex[r] = carry + e;
+        carry += tot;
     }
     if (lane == 0) wsum[warp] = carry;
     __syncthreads();
