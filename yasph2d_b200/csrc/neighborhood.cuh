@@ -333,9 +333,12 @@ __global__ void __launch_bounds__(TT_WARPS * 32) k_tile_tables(TileTableArgs a, 
             if (lane < 9) S.blk_seq[lane] = seq0;
         }
         __syncwarp();
+        // most tiles have no boundary cell anywhere in their 3x3 blocks: the static half of steps 2 and 4 is skipped for them
+        const bool any_static = __any_sync(0xffffffffu, lane < 9 && S.blk_lo[1][lane] < S.blk_hi[1][lane]);
         // 2. cell lookups.  Own block (both grids): walk the block's cells and scatter them; apron: search the block's range.
 #pragma unroll
         for (int which = 0; which < 2; ++which) {
+            if (which == 1 && !any_static) break;
             const uint32_t* ckey = which ? a.scell_key : a.cell_key;
             const uint32_t* cstart = which ? a.scell_start : a.cell_start;
             const uint32_t olo = S.blk_lo[which][4], ohi = S.blk_hi[which][4];
@@ -396,6 +399,13 @@ __global__ void __launch_bounds__(TT_WARPS * 32) k_tile_tables(TileTableArgs a, 
 #pragma unroll
         for (int which = 0; which < 2; ++which) {
             uint2* runs = which ? out->rs : out->rd;
+            if (which == 1 && !any_static) {  // no boundary candidates: empty slot table, no runs
+                for (uint32_t r = lane; r < REGION_CELLS; r += 32) S.slot[1][r] = 0u;
+                totals[1] = 0u;
+                nruns[1] = 0u;
+                for (uint32_t q = lane; q < (uint32_t)MAX_RUNS; q += 32) runs[q] = make_uint2(0u, 0xFFFFFFFFu);
+                break;
+            }
             uint32_t carry = 0, carry_runs = 0, carry_end = 0, carry_q = 0;
             bool carry_valid = false;
             for (uint32_t q0 = 0; q0 < REGION_CELLS; q0 += 32) {
