@@ -84,6 +84,12 @@ __device__ __forceinline__ void radix_hist_flush(RadixHistSmem& sh, uint32_t* __
     }
 }
 
+#ifdef YASPH_RADIX_TIMING
+__device__ unsigned long long g_radix_dbg[8];
+#define RT_MARK(i) { long long now_ = clock64(); if (threadIdx.x == 0) atomicAdd(&g_radix_dbg[i], (unsigned long long)(now_ - rz)); rz = now_; }
+#else
+#define RT_MARK(i)
+#endif
 // ---- one pass -------------------------------------------------------------------------------------------------------------
 struct RadixPassSmem {
     uint32_t cnt[RS_WARPS][RS_BINS];  // per-warp digit counts, then exclusive prefix over the warps
@@ -106,6 +112,9 @@ __global__ void __launch_bounds__(RS_THREADS)
     const uint32_t* ghist = scratch + RS_PASSES + pass * RS_BINS;
     volatile uint32_t* status = scratch + RS_PASSES + RS_PASSES * RS_BINS + (size_t)pass * ntiles * RS_BINS;
     static_assert(RS_THREADS >= RS_BINS && RS_BINS == 256, "thread d < RS_BINS owns digit d");
+#ifdef YASPH_RADIX_TIMING
+    long long rz = clock64();
+#endif
     if (tid == 0) {
         S.tile = atomicAdd(&scratch[pass], 1u);
         S.trivial = 0u;
@@ -126,6 +135,7 @@ __global__ void __launch_bounds__(RS_THREADS)
         val[r] = valid ? vals_in[i] : 0u;
     }
     __syncthreads();
+    RT_MARK(0)  // ticket + load
     if (S.trivial) {
 #pragma unroll
         for (int r = 0; r < RS_ITEMS; ++r) {
@@ -151,6 +161,7 @@ __global__ void __launch_bounds__(RS_THREADS)
         rank[r] = b + (uint32_t)__popc(mask & lt);
     }
     __syncthreads();
+    RT_MARK(1)  // rank
     // 2. per digit (thread == digit): prefix over the warps, tile count, publish, look back
     uint32_t tcount = 0;
     if (owner) {
@@ -213,6 +224,7 @@ __global__ void __launch_bounds__(RS_THREADS)
         S.gbin[tid] = gex + excl - lex;
     }
     __syncthreads();
+    RT_MARK(2)  // digit prefix, publish, look back
     // 3. reorder the tile by digit in shared memory
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; ++r) {
@@ -225,6 +237,7 @@ __global__ void __launch_bounds__(RS_THREADS)
         }
     }
     __syncthreads();
+    RT_MARK(3)  // reorder in shared memory
     // 4. write every digit's run contiguously
     const uint32_t tile_n = min((uint32_t)RS_TILE, n - tile * RS_TILE);
 #pragma unroll
@@ -237,6 +250,10 @@ __global__ void __launch_bounds__(RS_THREADS)
             vals_out[gp] = S.sval[lp];
         }
     }
+    RT_MARK(4)  // write out
+#ifdef YASPH_RADIX_TIMING
+    if (tid == 0) atomicAdd(&g_radix_dbg[5], 1ull);
+#endif
 }
 
 }  // namespace yasph

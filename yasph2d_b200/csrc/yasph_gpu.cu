@@ -1962,6 +1962,16 @@ extern "C" int32_t yasph_debug_sweep_counters(yasph_ctx* c, unsigned long long* 
 }
 #endif
 
+#ifdef YASPH_RADIX_TIMING
+extern "C" int32_t yasph_debug_radix_counters(yasph_ctx* c, unsigned long long* out8) {
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpyFromSymbol(out8, g_radix_dbg, 64));
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    CU(cudaMemcpyToSymbol(g_radix_dbg, z, 64));
+    return YASPH_OK;
+}
+#endif
+
 extern "C" int32_t yasph_step(yasph_ctx* c, yasph_step_report* report) {
     if (!c) return YASPH_ERR_INVALID_ARGUMENT;
     if (!c->have_particles || (c->n == 0 && !c->slab.active)) return fail(c, YASPH_ERR_STATE, "yasph_step: no particles uploaded");
