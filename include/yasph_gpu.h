@@ -136,7 +136,7 @@ typedef struct yasph_step_report {
     uint32_t not_converged;       /* bit 0: density solver hit its cap (dfsph.rs:236), bit 1: divergence solver (dfsph.rs:391) */
     uint32_t num_cells;           /* non-empty cells of the dynamic grid */
     uint32_t num_tiles;           /* non-empty 8x8-cell tiles */
-    uint32_t reserved;
+    uint32_t list_rebuilds;       /* list builds launched ahead of the tile-size read-back that had to be repeated, since creation */
     uint64_t total_neighbors;     /* sum over particles of count_total after the step's list build */
 } yasph_step_report;
 

@@ -255,6 +255,28 @@ def test_target_frame_length_stepping():
     assert np.array_equal(w2.particles.positions, ow.positions())
 
 
+def test_early_list_build_is_repeated_when_its_size_guess_is_too_small(monkeypatch):
+    """The list build is launched before the tile sizes of the new structure are known, with the previous sizes plus a margin
+    (neighborhood_update); with the margin forced to -60 % the guess is too small every step, the lists must be built again, and
+    the run must still be the oracle's."""
+    monkeypatch.setenv("YASPH_DEBUG_LIST_MARGIN_PCT", "-60")
+    w, ow = make_worlds()
+    ctx = gpu_ctx(w)
+    monkeypatch.delenv("YASPH_DEBUG_LIST_MARGIN_PCT")
+    otm, osolver = po.TimeManager(cfl_factor=1.5), po.DFSPHSolver(ow)
+    for s in range(30):
+        rep, orep = ctx.step(), osolver.simulation_step(ow, otm)
+        assert rep.dt_ns == orep.dt_ns and (rep.iters_density, rep.iters_divergence) == (orep.iters_density, orep.iters_divergence), s
+        assert rep.total_neighbors == ow.neighbor_stats()["total"], s
+    assert rep.list_rebuilds >= 25, rep.list_rebuilds
+    compare_state(ctx, ow, 29)
+    # the default margin never needs a rebuild on this scene
+    ctx2 = gpu_ctx(w)
+    for s in range(30):
+        rep2 = ctx2.step()
+    assert rep2.list_rebuilds == 0
+
+
 def test_clear_cached_and_reset():
     """reset_simulation (main.rs:292-298): clear_cached_data + TimeManager::restart + scene rebuild reproduces the run."""
     w, ow = make_worlds()

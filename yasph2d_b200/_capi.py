@@ -60,7 +60,7 @@ class StepReport(C.Structure):
         ("iters_density", C.c_uint32), ("iters_divergence", C.c_uint32), ("avg_density_error", C.c_float),
         ("avg_divergence", C.c_float), ("warm_density", C.c_uint32), ("warm_divergence", C.c_uint32),
         ("neighbors_capped", C.c_uint32), ("neighbors_dropped", C.c_uint32), ("not_converged", C.c_uint32),
-        ("num_cells", C.c_uint32), ("num_tiles", C.c_uint32), ("reserved", C.c_uint32), ("total_neighbors", C.c_uint64),
+        ("num_cells", C.c_uint32), ("num_tiles", C.c_uint32), ("list_rebuilds", C.c_uint32), ("total_neighbors", C.c_uint64),
     ]
 
     def as_dict(self):

@@ -133,6 +133,10 @@ struct yasph_ctx {
     } slab;
     // state flags
     bool have_particles = false, lists_valid = false, dfsph_ready = false;
+    int list_margin_pct = 12;
+    uint64_t list_rebuilds = 0;     // early list builds that had to be repeated
+    bool lists_valid_once = false;  // cap_dyn / cap_stat / num_tiles describe an earlier structure of this particle set
+    cudaEvent_t ev_tables = nullptr;
     uint64_t launches = 0;
     // profiling
     std::vector<PassEvent> events;
@@ -416,6 +420,7 @@ static void free_all(yasph_ctx* c) {
         if (c->ev_early[i]) cudaEventDestroy(c->ev_early[i]);
     for (int i = 0; i < 6; ++i)
         if (c->ev_host[i]) cudaEventDestroy(c->ev_host[i]);
+    if (c->ev_tables) cudaEventDestroy(c->ev_tables);
     if (c->stream) cudaStreamDestroy(c->stream);
 }
 
@@ -459,6 +464,8 @@ extern "C" int32_t yasph_create(const yasph_config* cfg, yasph_ctx** out) {
     CUC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) CUC(cudaEventCreateWithFlags(&c->ev_early[i], cudaEventDisableTiming));
     for (int i = 0; i < 6; ++i) CUC(cudaEventCreate(&c->ev_host[i]));
+    CUC(cudaEventCreateWithFlags(&c->ev_tables, cudaEventDisableTiming));
+    if (const char* e = getenv("YASPH_DEBUG_LIST_MARGIN_PCT")) c->list_margin_pct = atoi(e);
 
     c->cap_n = cfg->max_particles;
     c->cap_m = cfg->max_boundary;
@@ -761,10 +768,10 @@ static int32_t wait_published(yasph_ctx* c, volatile unsigned int* vs, unsigned 
     std::atomic_thread_fence(std::memory_order_acquire);
     return YASPH_OK;
 }
-static int32_t read_control(yasph_ctx* c) {
+static int32_t read_control(yasph_ctx* c, cudaStream_t stream = nullptr) {
     static_assert(sizeof(Control) % 4 == 0, "Control is published word by word");
     const unsigned int seq = ++c->pub_seq;
-    k_publish_control<<<1, 64, 0, c->stream>>>(c->ctl, reinterpret_cast<uint32_t*>(&c->d_pub->ctl), &c->d_pub->seq, seq);
+    k_publish_control<<<1, 64, 0, stream ? stream : c->stream>>>(c->ctl, reinterpret_cast<uint32_t*>(&c->d_pub->ctl), &c->d_pub->seq, seq);
     CHECK_LAUNCH();
     TRY(wait_published(c, &c->h_pub->seq, seq));
     memcpy(c->h_ctl, const_cast<const Control*>(&c->h_pub->ctl), sizeof(Control));
@@ -1268,8 +1275,31 @@ static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp
     }
     pass_end(c);
     // The one host round trip of the neighbourhood update: tile count (grid of every tile kernel until the next update) and
-    // the largest tile (their shared-memory size).
-    TRY(read_control(c));
+    // the largest tile (their shared-memory size).  The list build does not wait for it when the previous structure's sizes are
+    // known: it is launched right away with those sizes plus a margin (its result does not depend on the capacities, only its
+    // shared-memory layout does), the control block is published from the second stream while it runs, and the sizes are
+    // checked afterwards -- a structure that outgrew the margin gets its lists built again.
+    bool lists_launched = false;
+    uint32_t spec_dyn = 0, spec_stat = 0;
+    if (c->lists_valid_once && c->num_tiles && n) {
+        // margin: 12.5 % + 16 slots; YASPH_DEBUG_LIST_MARGIN_PCT (read at yasph_create) overrides the percentage so that a test
+        // can force the rebuild path with an undersized guess
+        const int pct = c->list_margin_pct;
+        spec_dyn = (uint32_t)std::max<long long>(16, ((long long)c->cap_dyn * (100 + pct) / 100 + 31) & ~15ll);
+        spec_stat = (uint32_t)std::max<long long>(16, ((long long)c->cap_stat * (100 + pct) / 100 + 31) & ~15ll);
+        const size_t bytes = list_smem_bytes(spec_dyn, spec_stat);
+        if (bytes <= c->smem_optin) {
+            CU(cudaEventRecord(c->ev_tables, c->stream));
+            pass_begin(c, YASPH_PASS_LISTS);
+            ListArgs la{tile_tables(c), c->pos, c->bpos, c->keys[0], c->grid, c->ctl, c->lists, c->counts, c->tile_nk, spec_dyn, spec_stat, c->apron_idx};
+            k_build_lists<<<persistent_grid(c, k_build_lists, bytes, NB_THREADS), NB_THREADS, bytes, c->stream>>>(la);
+            CHECK_LAUNCH();
+            pass_end(c);
+            lists_launched = true;
+            CU(cudaStreamWaitEvent(c->copy_stream, c->ev_tables, 0));
+        }
+    }
+    TRY(read_control(c, lists_launched ? c->copy_stream : nullptr));
     TRY(check_capacity_flags(c));
     if (positions_final && !c->slab.active) TRY(early_download(c, &c->early_pos_out, c->pos, (size_t)n * sizeof(float2), 0));
     if (c->slab.active) {
@@ -1293,8 +1323,14 @@ static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp
     if (worst_smem_bytes(c->cap_dyn, c->cap_stat, c->cap_pc) > c->smem_optin)
         return fail(c, YASPH_ERR_CAPACITY, "a tile stages %u dynamic / %u static candidates: %zu bytes of shared memory per CTA, the device allows %zu",
                     c->h_ctl->max_dyn_total, c->h_ctl->max_stat_total, worst_smem_bytes(c->cap_dyn, c->cap_stat, c->cap_pc), c->smem_optin);
+    if (lists_launched && (c->h_ctl->max_dyn_total > spec_dyn || c->h_ctl->max_stat_total > spec_stat)) {
+        // the structure outgrew the margin: the early launch skipped the tiles that did not fit -- build the lists again
+        CU(cudaMemsetAsync(&c->ctl->total_neighbors, 0, sizeof(unsigned long long) + 2 * sizeof(unsigned int), c->stream));
+        lists_launched = false;
+        c->list_rebuilds++;
+    }
     pass_begin(c, YASPH_PASS_LISTS);
-    if (c->num_tiles) {
+    if (c->num_tiles && !lists_launched) {
         const size_t bytes = list_smem_bytes(c->cap_dyn, c->cap_stat);
         ListArgs la{tile_tables(c), c->pos, c->bpos, c->keys[0], c->grid, c->ctl, c->lists, c->counts, c->tile_nk, c->cap_dyn, c->cap_stat, c->apron_idx};
 #ifdef YASPH_LIST_TIMING
@@ -1305,6 +1341,7 @@ static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp
     }
     pass_end(c);
     c->lists_valid = true;
+    c->lists_valid_once = true;
     return YASPH_OK;
 }
 
@@ -1324,6 +1361,7 @@ static void fill_report(const yasph_ctx* c, yasph_step_report* r) {
     r->warm_divergence = h.warm[1];
     r->neighbors_capped = h.capped;
     r->neighbors_dropped = h.dropped;
+    r->list_rebuilds = (uint32_t)c->list_rebuilds;  // early list builds repeated since creation (the guess of the tile capacities was too small)
     r->not_converged = h.not_converged;
     r->num_cells = h.num_cells;
     r->num_tiles = h.num_tiles;
