@@ -86,6 +86,7 @@ struct yasph_ctx {
     // yasph_step_host: results that are final before the step ends (sorted positions after the gather, densities after the
     // density sweep) leave on a second stream while the rest of the step computes; only the velocities wait for the last pass
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t ctl_stream = nullptr;  // publishes the control block while the early list build runs (never carries copies)
     cudaEvent_t ev_early[2] = {nullptr, nullptr};
     float *early_pos_out = nullptr, *early_dens_out = nullptr, *early_vel_out = nullptr;  // pinned host destinations of the current yasph_step_host call
     bool early_vel_stale = false;  // the velocities changed after their speculative download (the solve needed more iterations)
@@ -416,6 +417,7 @@ static void free_all(yasph_ctx* c) {
         cudaEventDestroy(e.b);
     }
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->ctl_stream) cudaStreamDestroy(c->ctl_stream);
     for (int i = 0; i < 2; ++i)
         if (c->ev_early[i]) cudaEventDestroy(c->ev_early[i]);
     for (int i = 0; i < 6; ++i)
@@ -462,6 +464,7 @@ extern "C" int32_t yasph_create(const yasph_config* cfg, yasph_ctx** out) {
     CUC(cudaSetDevice(c->device));
     CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&c->ctl_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) CUC(cudaEventCreateWithFlags(&c->ev_early[i], cudaEventDisableTiming));
     for (int i = 0; i < 6; ++i) CUC(cudaEventCreate(&c->ev_host[i]));
     CUC(cudaEventCreateWithFlags(&c->ev_tables, cudaEventDisableTiming));
@@ -1279,9 +1282,14 @@ static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp
     // known: it is launched right away with those sizes plus a margin (its result does not depend on the capacities, only its
     // shared-memory layout does), the control block is published from the second stream while it runs, and the sizes are
     // checked afterwards -- a structure that outgrew the margin gets its lists built again.
+    // yasph_step_host: the sorted positions are final here; mark the point (the copy itself is submitted later, see early_download).
+    // With downloads overlapping the rest of the step the early list build below does not pay: measured 1.79 ms per call with it,
+    // 1.70 ms without (the list kernel runs 30 us longer under the download), so such calls read the sizes back first.
+    const bool downloads_armed = positions_final && !c->slab.active && c->early_pos_out != nullptr;
+    if (positions_final && !c->slab.active) TRY(early_download(c, &c->early_pos_out, c->pos, (size_t)n * sizeof(float2), 0));
     bool lists_launched = false;
     uint32_t spec_dyn = 0, spec_stat = 0;
-    if (c->lists_valid_once && c->num_tiles && n) {
+    if (c->lists_valid_once && c->num_tiles && n && c->list_margin_pct > -100 && !downloads_armed) {  // margin <= -100: no early launch (A/B)
         // margin: 12.5 % + 16 slots; YASPH_DEBUG_LIST_MARGIN_PCT (read at yasph_create) overrides the percentage so that a test
         // can force the rebuild path with an undersized guess
         const int pct = c->list_margin_pct;
@@ -1296,12 +1304,11 @@ static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp
             CHECK_LAUNCH();
             pass_end(c);
             lists_launched = true;
-            CU(cudaStreamWaitEvent(c->copy_stream, c->ev_tables, 0));
+            CU(cudaStreamWaitEvent(c->ctl_stream, c->ev_tables, 0));
         }
     }
-    TRY(read_control(c, lists_launched ? c->copy_stream : nullptr));
+    TRY(read_control(c, lists_launched ? c->ctl_stream : nullptr));
     TRY(check_capacity_flags(c));
-    if (positions_final && !c->slab.active) TRY(early_download(c, &c->early_pos_out, c->pos, (size_t)n * sizeof(float2), 0));
     if (c->slab.active) {
         auto& sl = c->slab;
         const Control& h = *c->h_ctl;
