@@ -100,7 +100,9 @@ __global__ void __launch_bounds__(KG_THREADS)
 // dfsph.rs:502-509 (advect) fused with the key generation of the following re-sort
 __global__ void __launch_bounds__(KG_THREADS)
     k_advect_keygen(float2* __restrict__ pos, const float2* __restrict__ vstar, uint32_t n, const Control* __restrict__ ctl, GridParams g,
-                    uint32_t* __restrict__ keys, uint32_t* __restrict__ idx, uint32_t* __restrict__ sort_scratch, SlabParams sp) {
+                    uint32_t* __restrict__ keys, uint32_t* __restrict__ idx, uint32_t* __restrict__ sort_scratch, SlabParams sp, uint32_t only_if_converged) {
+    // launched ahead of the density solver's read-back (dfsph_step): nothing may move unless that solve has finished
+    if (only_if_converged && ctl->stop_iter[0] == 0xFFFFFFFFu) return;
     __shared__ RadixHistSmem sh;
     radix_hist_init(sh);
     const float dt = ctl->dt;

@@ -135,6 +135,7 @@ struct yasph_ctx {
     // state flags
     bool have_particles = false, lists_valid = false, dfsph_ready = false;
     int list_margin_pct = 12;
+    bool spec_advect = false, spec_advect_done = false;  // advect + sort enqueued ahead of the density solver's read-back (dfsph_step)
     uint64_t list_rebuilds = 0;     // early list builds that had to be repeated
     bool lists_valid_once = false;  // cap_dyn / cap_stat / num_tiles describe an earlier structure of this particle set
     cudaEvent_t ev_tables = nullptr;
@@ -1212,7 +1213,7 @@ static int32_t early_velocities(yasph_ctx* c, const float2* final_vel) {
     return YASPH_OK;
 }
 
-static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp, bool positions_final = false) {
+static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp, bool positions_final = false, bool sorted_ready = false) {
     uint32_t n = c->n;
     c->lists_valid = false;
     c->slab.own_idx_valid = false;
@@ -1237,7 +1238,7 @@ static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp
         pass_begin(c, YASPH_PASS_SORT);
         c->n = n;
     }
-    TRY(radix_sort(c, n_sort));
+    if (!sorted_ready) TRY(radix_sort(c, n_sort));
     pass_end(c);
     pass_begin(c, YASPH_PASS_GATHER);
     if (n) {
@@ -1700,6 +1701,23 @@ static ViscParams visc_params(const yasph_ctx* c) {
 // Runs one Jacobi solve (density: SOLVER 0 / divergence: SOLVER 1): optional warm start, then A/B iterations launched in
 // chunks of `speculative_iterations`; kernels past the converged iteration exit immediately on the device-side stop_iter.
 // first_a_done: pass A of iteration 0 (with its reduction and decision) already ran fused into the density+alpha sweep.
+// advect (dfsph.rs:502-509) fused with the key generation, then the radix sort of the re-sort (dfsph.rs:512)
+static int32_t enqueue_advect_sort(yasph_ctx* c, bool only_if_converged) {
+    const uint32_t n = c->n;
+    pass_begin(c, YASPH_PASS_ADVECT_KEYGEN);
+    TRY(radix_prepare(c, n));
+    k_advect_keygen<<<keygen_grid(n, c->num_sms), KG_THREADS, 0, c->stream>>>(c->pos, c->vstar, n, c->ctl, c->grid, c->keys[0], c->idx[0], c->radix_scratch,
+                                                                            slab_params(c), only_if_converged ? 1u : 0u);
+    CHECK_LAUNCH();
+    pass_end(c);
+    if (only_if_converged) {  // the sort too (neighborhood_update skips it then)
+        pass_begin(c, YASPH_PASS_SORT);
+        TRY(radix_sort(c, n));
+        pass_end(c);
+    }
+    return YASPH_OK;
+}
+
 template <int SOLVER>
 static int32_t jacobi_solve(yasph_ctx* c, bool first_a_done = false) {
     const float rho0 = c->cfg.fluid_density;
@@ -1782,8 +1800,23 @@ static int32_t jacobi_solve(yasph_ctx* c, bool first_a_done = false) {
         // solve's iteration count (a stale copy costs its transfer time ahead of the next chunk's kernels)
         if (SOLVER == 1) TRY(submit_downloads(c));
         if (SOLVER == 1 && it >= prev_iters) TRY(early_velocities(c, c->vstar));
-        TRY(read_control(c));
-        if (c->h_ctl->stop_iter[SOLVER] != 0xFFFFFFFFu) break;
+        // Density solve, device-resident stepping: when this chunk reaches the previous solve's iteration count, what follows
+        // the solve -- advect + key generation + sort -- is enqueued now, guarded on the device by the solver's own verdict, and
+        // the control block is published from the side stream while it runs: the GPU does not idle through the read-back.  If
+        // the solve needs more iterations the guarded advect did nothing and the (then meaningless) sort is simply repeated.
+        bool spec_now = false;
+        if (SOLVER == 0 && c->spec_advect && it >= prev_iters) {
+            CU(cudaEventRecord(c->ev_tables, c->stream));
+            CU(cudaStreamWaitEvent(c->ctl_stream, c->ev_tables, 0));
+            TRY(enqueue_advect_sort(c, true));
+            spec_now = true;
+            c->spec_advect = false;  // once per solve
+        }
+        TRY(read_control(c, spec_now ? c->ctl_stream : nullptr));
+        if (c->h_ctl->stop_iter[SOLVER] != 0xFFFFFFFFu) {
+            if (spec_now) c->spec_advect_done = true;
+            break;
+        }
         if (SOLVER == 1) c->early_vel_stale = true;
         if (it > sp.max_iters + spec + 1) return fail(c, YASPH_ERR_STATE, "jacobi_solve: device loop control did not terminate");
         chunk = slab ? 1u : spec;
@@ -1841,14 +1874,13 @@ static int32_t dfsph_step(yasph_ctx* c) {
     CHECK_LAUNCH();
     pass_end(c);
     TRY(halo_exchange(c, c->vstar));  // ghosts: v* of their owners (their own accelerations are incomplete)
+    c->spec_advect = !c->slab.active && c->early_pos_out == nullptr && c->early_vel_out == nullptr;  // device-resident stepping on one GPU
+    c->spec_advect_done = false;
     TRY(jacobi_solve<0>(c));  // dfsph.rs:496
-    // advect (dfsph.rs:502-509) fused with the key generation of the re-sort (dfsph.rs:512)
-    pass_begin(c, YASPH_PASS_ADVECT_KEYGEN);
-    TRY(radix_prepare(c, n));
-    k_advect_keygen<<<keygen_grid(n, c->num_sms), KG_THREADS, 0, c->stream>>>(c->pos, c->vstar, n, c->ctl, c->grid, c->keys[0], c->idx[0], c->radix_scratch,
-                                                                            slab_params(c));
-    CHECK_LAUNCH();
-    pass_end(c);
+    c->spec_advect = false;
+    // advect (dfsph.rs:502-509) fused with the key generation of the re-sort (dfsph.rs:512) -- unless it already ran ahead of the read-back
+    const bool sorted_ready = c->spec_advect_done;
+    if (!sorted_ready) TRY(enqueue_advect_sort(c, false));
     {
         // the reference also permutes the old velocities, which are discarded at the final swap (quirk Q7): skipped.
         GatherPlan gp;
@@ -1864,7 +1896,7 @@ static int32_t dfsph_step(yasph_ctx* c) {
             gp.a1[1] = &c->stiff;
             gp.alt1[1] = &c->f_alt1;
         }
-        TRY(neighborhood_update(c, true, gp, true));  // positions are final (dfsph.rs:502-512)
+        TRY(neighborhood_update(c, true, gp, true, sorted_ready));  // positions are final (dfsph.rs:502-512)
     }
     pass_begin(c, YASPH_PASS_DENSITY_ALPHA);
     k_begin_divergence<<<1, 32, 0, c->stream>>>(c->ctl);
