@@ -28,6 +28,8 @@ class StepReport(C.Structure):
         ("avg_divergence", C.c_float),
         ("warm_density", C.c_uint32),
         ("warm_divergence", C.c_uint32),
+        ("not_converged", C.c_uint32),
+        ("pad", C.c_uint32),
     ]
 
 
@@ -106,6 +108,7 @@ def lib():
     sig("yo_dfsph_free", None, vp)
     sig("yo_dfsph_clear", None, vp)
     sig("yo_dfsph_step", None, vp, vp, vp, C.POINTER(StepReport))
+    sig("yo_dfsph_set_params", None, vp, C.c_float, C.c_uint32, C.c_float, C.c_uint32)
     sig("yo_dfsph_get", None, vp, f32p, f32p, f32p)
     sig("yo_dfsph_alpha", None, vp, vp, f32p)
     sig("yo_wcsph_new", vp, vp, C.c_int, C.c_float)
@@ -289,6 +292,10 @@ class DFSPHSolver:
 
     def clear_cached_data(self):
         lib().yo_dfsph_clear(self.h_)
+
+    def set_params(self, max_avg_density_error=0.0, max_density_iters=0, max_divergence_error=0.0, max_divergence_iters=0):
+        """dfsph.rs:49-50,53-54 (plain fields of DFSPHSolver); 0 keeps the current value."""
+        lib().yo_dfsph_set_params(self.h_, max_avg_density_error, int(max_density_iters), max_divergence_error, int(max_divergence_iters))
 
     def simulation_step(self, world, time):
         rep = StepReport()

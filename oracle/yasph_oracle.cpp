@@ -734,6 +734,8 @@ struct StepReport {
     uint32_t iters_density, iters_divergence;
     Real avg_density_error, avg_divergence;
     uint32_t warm_density, warm_divergence;
+    uint32_t not_converged;  // bit 0: the density solver, bit 1: the divergence solver left its loop through the iteration cap (dfsph.rs:236-245, 391-400)
+    uint32_t pad;
 };
 
 struct DFSPH {
@@ -832,6 +834,7 @@ struct DFSPH {
     }
     void correct_density_error(Real dt, World& w, std::vector<V2>& vel) {  // :195-247
         rep.warm_density = 0;
+        rep.not_converged = 0;
         if (iters_density > 1) {
             for (auto& k : kappa) k = 0.5f * rmax(k, -0.5f * w.fluid_density * w.fluid_density);  // :201-203
             correct_velocity_density(dt, w, vel, nullptr);
@@ -848,7 +851,10 @@ struct DFSPH {
             Real rel = avg / w.fluid_density;
             rep.avg_density_error = avg;
             if (rel * dt < max_avg_density_error) break;
-            if (iters_density > max_iters_density) break;
+            if (iters_density > max_iters_density) {  // :236-245 (the reference prints a warning and carries on)
+                rep.not_converged |= 1u;
+                break;
+            }
         }
     }
     void compute_density_change(const World& w, const std::vector<V2>& vel, std::vector<Real>& chg) {  // :249-280
@@ -915,7 +921,10 @@ struct DFSPH {
             Real avg = sum_f64(scratch) / (Real)scratch.size() / w.fluid_density;
             rep.avg_divergence = avg;
             if (avg * dt < max_divergence_error) break;
-            if (iters_divergence > max_iters_divergence) break;
+            if (iters_divergence > max_iters_divergence) {  // :391-400
+                rep.not_converged |= 2u;
+                break;
+            }
         }
     }
     void simulation_step(World& w, TimeManager& tm) {  // :414-525
@@ -1234,6 +1243,14 @@ void yo_dfsph_step(void* s, void* w, void* t, StepReport* rep) {
     DFSPH* d = (DFSPH*)s;
     d->simulation_step(*(World*)w, *(TimeManager*)t);
     if (rep) *rep = d->rep;
+}
+// tolerances and iteration caps (dfsph.rs:49-50,53-54 are plain fields of DFSPHSolver); a value <= 0 / 0 keeps the current one
+void yo_dfsph_set_params(void* s, float max_avg_density_error, uint32_t max_density_iters, float max_divergence_error, uint32_t max_divergence_iters) {
+    DFSPH* d = (DFSPH*)s;
+    if (max_avg_density_error > 0.0f) d->max_avg_density_error = max_avg_density_error;
+    if (max_density_iters) d->max_iters_density = max_density_iters;
+    if (max_divergence_error > 0.0f) d->max_divergence_error = max_divergence_error;
+    if (max_divergence_iters) d->max_iters_divergence = max_divergence_iters;
 }
 void yo_dfsph_get(void* s, float* alpha, float* kappa, float* stiffness) {
     DFSPH* d = (DFSPH*)s;
