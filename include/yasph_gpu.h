@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define YASPH_ABI_VERSION 3u
+#define YASPH_ABI_VERSION 4u
 #define YASPH_MAX_NEIGHBORS 64u /* neighborhood_search.rs:322 */
 
 typedef struct yasph_ctx yasph_ctx;
@@ -175,6 +175,8 @@ typedef struct yasph_solver_state {
     uint32_t iters_divergence;    /* num_divergence_correction_iterations of the last solve */
     uint32_t initialized;         /* get: the solver has run its first-call initialisation; set: run it now */
     uint32_t reserved;
+    uint64_t total_simulated_ns;  /* TimeManager::total_simulated_time between steps (timemanager.rs:246): the lower bound of the
+                                   * TargetFrameLength rule depends on it (timemanager.rs:268-272) */
 } yasph_solver_state;
 int32_t yasph_solver_state_get(yasph_ctx* ctx, yasph_solver_state* out);
 int32_t yasph_solver_state_set(yasph_ctx* ctx, const yasph_solver_state* in);

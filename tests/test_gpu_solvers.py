@@ -202,6 +202,46 @@ def test_dfsph_iteration_caps_vs_oracle():
     assert ncv == 3 and warm[0] > 0 and warm[1] > 0, (ncv, warm)
 
 
+@pytest.mark.parametrize("solver_kind", ["dfsph", "wcsph"])
+def test_add_fluid_mid_run_grows_context_like_vec_resize(solver_kind):
+    """add_fluid_rect between steps (fluidparticleworld.rs:140-166): the reference's solvers resize their per-particle arrays
+    (dfsph.rs:419-423 keeps the warm-start values and zero-fills the tail; wscsph.rs:128) and carry on.  The context created for the
+    first scene is too small for the second, so the host mirror replaces it and moves the solver state over; the run equals the
+    oracle's, in which tight tolerances keep the warm starts active across the resize."""
+    w, ow = make_worlds()
+    if solver_kind == "dfsph":
+        tm, otm = y.TimeManager(y.SimulationStepConfig.AdaptiveTimeStep(cfl_factor=1.5)), po.TimeManager(cfl_factor=1.5)
+        solver = y.DFSPHSolver(y.XSPHViscosityModel(w.properties.smoothing_length()), w.properties.smoothing_length(), **TIGHT_GPU)
+        osolver = po.DFSPHSolver(ow)
+        osolver.set_params(**TIGHT_ORACLE)
+    else:
+        tm, otm = y.TimeManager(y.SimulationStepConfig.AdaptiveTimeStep(cfl_factor=0.2)), po.TimeManager(cfl_factor=0.2)
+        solver = y.WCSPHSolver(y.XSPHViscosityModel(w.properties.smoothing_length()), w.properties)
+        osolver = po.WCSPHSolver(ow)
+    warm_after = 0
+    for s in range(100):
+        if s == 60:
+            cap_before = solver.ctx.cfg.max_particles
+            w.add_fluid_rect(y.Rect(1.0, 1.2, 0.3, 0.3), 0.05)
+            ow.add_fluid_rect(1.0, 1.2, 0.3, 0.3, 0.05)
+            assert len(w.particles.positions) == ow.n > cap_before
+        rep, orep = solver.simulation_step(w, tm), osolver.simulation_step(ow, otm)
+        assert rep.dt_ns == orep.dt_ns, (s, rep.dt_ns, orep.dt_ns)
+        if solver_kind == "dfsph":
+            assert (rep.iters_density, rep.iters_divergence, rep.warm_density, rep.warm_divergence) == (
+                orep.iters_density, orep.iters_divergence, orep.warm_density, orep.warm_divergence), s
+            if s >= 60:
+                warm_after += rep.warm_density + rep.warm_divergence
+        if s in (59, 60, 61, 99):
+            assert np.array_equal(w.particles.positions, ow.positions()), s
+            assert np.array_equal(w.particles.velocities, ow.velocities()), s
+    assert solver.ctx.cfg.max_particles >= ow.n
+    if solver_kind == "dfsph":
+        assert warm_after > 0
+        _, ok, os_ = osolver.state(ow.n)
+        assert np.array_equal(solver.ctx.field(capi.FIELD_KAPPA), ok) and np.array_equal(solver.ctx.field(capi.FIELD_STIFFNESS), os_)
+
+
 def test_dfsph_step_host_equals_resident():
     """yasph_step_host (host arrays in/out every step, the drop-in call) == device-resident stepping."""
     w, ow = make_worlds()

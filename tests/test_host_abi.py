@@ -28,7 +28,7 @@ def test_struct_sizes_match_header():
     # the C structs are plain PODs with natural alignment; sizes are part of the ABI
     assert C.sizeof(capi.StepReport) == 80
     assert C.sizeof(capi.Config) == 152
-    assert C.sizeof(capi.SolverState) == 24
+    assert C.sizeof(capi.SolverState) == 32
     assert C.sizeof(capi.SlabInfo) == 72
 
 

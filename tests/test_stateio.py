@@ -101,3 +101,39 @@ def test_checkpoint_resume_is_bit_exact(tmp_path, solver, knobs):
     pa, va, da = a.download_particles()
     pc, vc, dc = c.download_particles()
     assert np.array_equal(pa, pc) and np.array_equal(va, vc) and np.array_equal(da, dc)
+
+
+@pytest.mark.gpu
+def test_checkpoint_resume_with_target_frame_length(tmp_path):
+    """TargetFrameLength stepping (timemanager.rs:268-274): the lower bound of dt depends on TimeManager::total_simulated_time, so
+    the checkpoint carries it (yasph_solver_state.total_simulated_ns); the resumed run repeats the uninterrupted one's dt."""
+    target = 1_000_000
+    w = y.dam_break_scene(y.FluidParticleWorld(2.0, 10000.0, 100.0))
+    w.particles.velocities[:10, 0] = 300.0  # the CFL time drops below timestep_min: the lower bound (the target rule) decides dt
+
+    def fresh():
+        c = _ctx(w, capi.SOLVER_DFSPH, timestep_target_frame_ns=target)
+        c.set_boundary(w.particles.boundary_particles)
+        c.upload_particles(w.particles.positions, w.particles.velocities)
+        return c
+
+    a, b = fresh(), fresh()
+    total, cut = 40, 17
+    reps_a = [a.step() for _ in range(total)]
+    assert min(r.dt_ns for r in reps_a[cut:]) < capi.default_config(2.0, 10000.0, 100.0, capi.SOLVER_DFSPH).timestep_min_ns  # the rule is active after the cut
+    for _ in range(cut):
+        b.step()
+    assert b.solver_state().total_simulated_ns == sum(r.dt_prev_ns for r in reps_a[:cut])
+    path = tmp_path / "ck_target.ysph"
+    stateio.checkpoint(b, path)
+    b.close()
+    c = _ctx(w, capi.SOLVER_DFSPH, timestep_target_frame_ns=target)
+    _, _, sol = stateio.resume(c, path)
+    assert sol["total_simulated_ns"] > 0
+    for s in range(cut, total):
+        r = c.step()
+        assert (r.dt_ns, r.iters_density, r.iters_divergence) == (reps_a[s].dt_ns, reps_a[s].iters_density, reps_a[s].iters_divergence), s
+    assert c.total_simulated_ns() == a.total_simulated_ns()
+    pa, va, _ = a.download_particles()
+    pc, vc, _ = c.download_particles()
+    assert np.array_equal(pa, pc) and np.array_equal(va, vc)

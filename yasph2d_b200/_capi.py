@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libyasph_gpu.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_NEIGHBORS = 64
 SOLVER_DFSPH, SOLVER_WCSPH = 0, 1
 VISCOSITY_XSPH, VISCOSITY_PHYSICAL = 0, 1
@@ -81,7 +81,7 @@ class SlabInfo(C.Structure):
 
 class SolverState(C.Structure):
     _fields_ = [("step_ns", C.c_uint64), ("iters_density", C.c_uint32), ("iters_divergence", C.c_uint32), ("initialized", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("reserved", C.c_uint32), ("total_simulated_ns", C.c_uint64)]
 
 
 class YasphError(RuntimeError):

@@ -134,6 +134,7 @@ struct yasph_ctx {
     } slab;
     // state flags
     bool have_particles = false, lists_valid = false, dfsph_ready = false;
+    uint32_t dfsph_n = 0;  // length of the DFSPH solver arrays (alpha / kappa / stiffness) as of their last resize (dfsph.rs:419-423)
     int list_margin_pct = 12;
     bool spec_advect = false, spec_advect_done = false;  // advect + sort enqueued ahead of the density solver's read-back (dfsph_step)
     uint64_t list_rebuilds = 0;     // early list builds that had to be repeated
@@ -465,7 +466,11 @@ extern "C" int32_t yasph_create(const yasph_config* cfg, yasph_ctx** out) {
     CUC(cudaSetDevice(c->device));
     CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    CUC(cudaStreamCreateWithFlags(&c->ctl_stream, cudaStreamNonBlocking));
+    {  // the control block is published from this stream while persistent kernels fill the SMs: highest priority
+        int prio_lo = 0, prio_hi = 0;
+        CUC(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CUC(cudaStreamCreateWithPriority(&c->ctl_stream, cudaStreamNonBlocking, prio_hi));
+    }
     for (int i = 0; i < 2; ++i) CUC(cudaEventCreateWithFlags(&c->ev_early[i], cudaEventDisableTiming));
     for (int i = 0; i < 6; ++i) CUC(cudaEventCreate(&c->ev_host[i]));
     CUC(cudaEventCreateWithFlags(&c->ev_tables, cudaEventDisableTiming));
@@ -646,6 +651,10 @@ static inline uint32_t blocks_for(uint32_t n, uint32_t threads) { return (n + th
 // Stable LSD radix sort of (keys[0], idx[0]) over n elements; result back in buffer 0 (4 passes).  radix_prepare must be
 // enqueued BEFORE the kernel that generates the keys, because that kernel accumulates the digit histograms.
 static int32_t radix_prepare(yasph_ctx* c, uint32_t n) {
+    // Slab mode: migrants and ghosts are appended between key generation and the sort (slab_exchange_particles), so the sort runs
+    // over up to n + 4 * max_halo pairs and its status area [pass][tiles(n_sort)][bins] is larger than tiles(n) suggests: zero
+    // the area of the largest count the exchange can produce (the layout is addressed with the tile count of the sort's launch).
+    if (c->slab.active) n = (uint32_t)std::min<uint64_t>(c->cap_n, (uint64_t)n + 4ull * c->slab.max_halo);
     if (n) CU(cudaMemsetAsync(c->radix_scratch, 0, radix_scratch_words(n) * sizeof(uint32_t), c->stream));
     return YASPH_OK;
 }
@@ -756,12 +765,14 @@ __global__ void k_publish_control(const Control* __restrict__ ctl, uint32_t* __r
     }
 }
 // polls a sequence number a kernel writes into mapped host memory
-static int32_t wait_published(yasph_ctx* c, volatile unsigned int* vs, unsigned int seq) {
+// `pub_stream`: the stream the publishing kernel was launched on (the main stream, or ctl_stream while the main stream is busy)
+static int32_t wait_published(yasph_ctx* c, volatile unsigned int* vs, unsigned int seq, cudaStream_t pub_stream) {
     for (uint32_t spins = 0; *vs != seq; ++spins) {
-        if ((spins & 0xFFFu) == 0xFFFu) {  // now and then: has the stream died (or drained without publishing)?
-            const cudaError_t q = cudaStreamQuery(c->stream);
+        if ((spins & 0xFFFu) == 0xFFFu) {  // now and then: has the publishing stream died (or drained without publishing)?
+            const cudaError_t q = cudaStreamQuery(pub_stream);
             if (q != cudaErrorNotReady) {
                 if (q != cudaSuccess) return fail(c, YASPH_ERR_CUDA, "%s while waiting for a device-published value", cudaGetErrorString(q));
+                std::atomic_thread_fence(std::memory_order_acquire);
                 if (*vs != seq) return fail(c, YASPH_ERR_CUDA, "device-published value did not arrive");
             }
         }
@@ -777,7 +788,7 @@ static int32_t read_control(yasph_ctx* c, cudaStream_t stream = nullptr) {
     const unsigned int seq = ++c->pub_seq;
     k_publish_control<<<1, 64, 0, stream ? stream : c->stream>>>(c->ctl, reinterpret_cast<uint32_t*>(&c->d_pub->ctl), &c->d_pub->seq, seq);
     CHECK_LAUNCH();
-    TRY(wait_published(c, &c->h_pub->seq, seq));
+    TRY(wait_published(c, &c->h_pub->seq, seq, stream ? stream : c->stream));
     memcpy(c->h_ctl, const_cast<const Control*>(&c->h_pub->ctl), sizeof(Control));
     return YASPH_OK;
 }
@@ -1065,7 +1076,7 @@ static int32_t peer_exchange_records(yasph_ctx* c, const RecordArrays& ra, const
                                                 hl ? &me->halo_flag[0] : nullptr, hr ? &me->halo_flag[1] : nullptr, seq, sl.pflag, d_counts, sl.d_pcounts, hseq,
                                                 c->ctl);
     CHECK_LAUNCH();
-    TRY(wait_published(c, &sl.h_pcounts->seq, hseq));
+    TRY(wait_published(c, &sl.h_pcounts->seq, hseq, c->stream));
     for (int sd = 0; sd < 2; ++sd) {
         out[sd] = sl.h_pcounts->out[sd];
         in[sd] = sl.h_pcounts->in[sd];
@@ -1683,6 +1694,7 @@ extern "C" int32_t yasph_clear_cached(yasph_ctx* c) {
     CU(cudaSetDevice(c->device));
     // DFSPH: dfsph.rs:406-412 (alpha / warm-start arrays dropped, iteration counts 0); WCSPH: wscsph.rs:122-124
     c->dfsph_ready = false;
+    c->dfsph_n = 0;
     unsigned int zero2[2] = {0u, 0u};
     CU(cudaMemcpyAsync(&c->ctl->iters[0], zero2, sizeof(zero2), cudaMemcpyHostToDevice, c->stream));
     c->h_ctl->iters[0] = c->h_ctl->iters[1] = 0u;
@@ -1826,8 +1838,14 @@ static int32_t jacobi_solve(yasph_ctx* c, bool first_a_done = false) {
 
 // dfsph.rs:419-428: first call (or particle count changed): zero the warm-start arrays, sort, densities, alpha
 static int32_t dfsph_initialize(yasph_ctx* c) {
-    CU(cudaMemsetAsync(c->kappa, 0, (size_t)c->cap_n * sizeof(float), c->stream));
-    CU(cudaMemsetAsync(c->stiff, 0, (size_t)c->cap_n * sizeof(float), c->stream));
+    // Vec::resize(n, 0.0) (dfsph.rs:420-423): existing warm-start values stay where they are, only a new tail is zero-filled
+    // (clear_cached_data empties the arrays: everything is zero-filled then).  Slab mode: the local set was rebuilt, start clean.
+    const uint32_t keep = c->slab.active ? 0u : std::min(c->dfsph_n, c->n);
+    if (keep < c->cap_n) {
+        CU(cudaMemsetAsync(c->kappa + keep, 0, (size_t)(c->cap_n - keep) * sizeof(float), c->stream));
+        CU(cudaMemsetAsync(c->stiff + keep, 0, (size_t)(c->cap_n - keep) * sizeof(float), c->stream));
+    }
+    c->dfsph_n = c->n;
     GatherPlan gp;
     gp.n2 = 2;
     gp.a2[0] = &c->pos;
@@ -1985,6 +2003,9 @@ extern "C" int32_t yasph_solver_state_get(yasph_ctx* c, yasph_solver_state* out)
     out->iters_density = c->h_ctl->iters[0];
     out->iters_divergence = c->h_ctl->iters[1];
     out->initialized = (c->cfg.solver == YASPH_SOLVER_WCSPH || c->dfsph_ready) ? 1u : 0u;
+    // between steps the device holds the total up to and including the last step (k_begin_step adds the next one); a total the host
+    // supplied for the coming step (total_is_current) already contains that step
+    out->total_simulated_ns = c->h_ctl->total_simulated_ns - (c->h_ctl->total_is_current ? c->h_ctl->step_ns : 0ull);
     return YASPH_OK;
 }
 extern "C" int32_t yasph_solver_state_set(yasph_ctx* c, const yasph_solver_state* in) {
@@ -2000,6 +2021,11 @@ extern "C" int32_t yasph_solver_state_set(yasph_ctx* c, const yasph_solver_state
     const unsigned int it[2] = {in->iters_density, in->iters_divergence};
     CU(cudaMemcpyAsync(&c->ctl->iters[0], it, sizeof(it), cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(&c->ctl->step_ns, &in->step_ns, sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    struct {
+        unsigned long long total;
+        unsigned int is_current, pad;
+    } tv = {in->total_simulated_ns, 0u, 0u};  // k_begin_step adds the next step itself
+    CU(cudaMemcpyAsync(&c->ctl->total_simulated_ns, &tv, 12, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     c->h_ctl->iters[0] = it[0];
     c->h_ctl->iters[1] = it[1];

@@ -125,8 +125,8 @@ class GpuContext:
         self._ck(capi.lib().yasph_solver_state_get(self.h, C.byref(st)))
         return st
 
-    def set_solver_state(self, step_ns, iters_density=0, iters_divergence=0, initialized=True):
-        st = capi.SolverState(int(step_ns), int(iters_density), int(iters_divergence), 1 if initialized else 0, 0)
+    def set_solver_state(self, step_ns, iters_density=0, iters_divergence=0, initialized=True, total_simulated_ns=0):
+        st = capi.SolverState(int(step_ns), int(iters_density), int(iters_divergence), 1 if initialized else 0, 0, int(total_simulated_ns))
         self._ck(capi.lib().yasph_solver_state_set(self.h, C.byref(st)))
 
     def upload_field(self, field, data):
@@ -441,7 +441,44 @@ class Solver:
 
     def _ensure_ctx(self, world, time_manager):
         if self.ctx is not None:
+            n, m = world.particles.num_dynamic_particles(), world.particles.num_boundary_particles()
+            if n <= self.ctx.cfg.max_particles and m <= self.ctx.cfg.max_boundary:
+                return
+            self._grow_ctx(world, time_manager, n, m)
             return
+        self._create_ctx(world, time_manager)
+
+    def _grow_ctx(self, world, time_manager, n, m):
+        """The reference accepts add_fluid_rect / add_boundary_* at any time (fluidparticleworld.rs:140-195); a context has fixed
+        capacities, so a world that outgrew them gets a new context with headroom.  The solver's carried state moves over: the
+        time step and iteration counts, and the per-particle arrays in their current order (DFSPH warm starts: Vec::resize keeps
+        them, dfsph.rs:420-423; WCSPH accelerations, wscsph.rs:128)."""
+        old = self.ctx
+        st = old.solver_state()
+        n_old = old.counts()[0]
+        carried = {}
+        if n_old:
+            if self.solver_kind == capi.SOLVER_DFSPH:
+                if st.initialized:
+                    carried = {capi.FIELD_KAPPA: old.field(capi.FIELD_KAPPA), capi.FIELD_STIFFNESS: old.field(capi.FIELD_STIFFNESS)}
+            else:
+                carried = {capi.FIELD_ACCELERATION: old.field(capi.FIELD_ACCELERATION)}
+        old.close()
+        self.ctx = None
+        self.max_particles = max(int(self.max_particles or 0), n + n // 2 + 1024)
+        self.max_boundary = max(int(self.max_boundary or 0), m + m // 2 + 1024)
+        self._create_ctx(world, time_manager)
+        world.boundary_changed = True  # _sync_inputs uploads the boundary into the new context
+        if n_old and n_old <= n:
+            # the first n_old host particles are the old set in the order of the last step (new fluid is appended, fluidparticleworld.rs:150)
+            self.ctx.set_boundary(world.particles.boundary_particles)
+            self.ctx.upload_particles(world.particles.positions[:n_old], world.particles.velocities[:n_old])
+            self.ctx.set_solver_state(st.step_ns, st.iters_density, st.iters_divergence, bool(st.initialized), st.total_simulated_ns)
+            for f, a in carried.items():
+                self.ctx.upload_field(f, a)
+            self._ctx_step_ns = st.step_ns
+
+    def _create_ctx(self, world, time_manager):
         p = world.properties
         cfg = capi.default_config(world.smoothing_factor, float(p.particle_density), float(p.fluid_density()), self.solver_kind)
         assert f32(cfg.smoothing_length) == p.smoothing_length()

@@ -66,7 +66,8 @@ def load_state(path):
 
 def checkpoint(ctx, path, boundary=None, params=None):
     """Everything a GpuContext needs to continue bit-exactly: sorted positions, velocities, the solver's carried arrays
-    (DFSPH warm starts / WCSPH accelerations), iteration counts and the current time step."""
+    (DFSPH warm starts / WCSPH accelerations), iteration counts, the current time step and the total simulated time (the
+    TargetFrameLength rule of timemanager.rs:268-272 depends on it)."""
     pos, vel, dens = ctx.download_particles()
     st = ctx.solver_state()
     arrays = {"positions": pos, "velocities": vel, "densities": dens}
@@ -78,7 +79,7 @@ def checkpoint(ctx, path, boundary=None, params=None):
         arrays["accelerations"] = ctx.field(capi.FIELD_ACCELERATION)
     arrays["boundary"] = ctx.field(capi.FIELD_BOUNDARY) if boundary is None else np.asarray(boundary, np.float32)
     solver = {"kind": int(ctx.cfg.solver), "step_ns": int(st.step_ns), "iters_density": int(st.iters_density),
-              "iters_divergence": int(st.iters_divergence), "initialized": int(st.initialized)}
+              "iters_divergence": int(st.iters_divergence), "initialized": int(st.initialized), "total_simulated_ns": int(st.total_simulated_ns)}
     save_state(path, arrays, params, solver)
 
 
@@ -89,7 +90,8 @@ def resume(ctx, path):
         raise ValueError("checkpoint of solver kind %s loaded into a context of kind %s" % (solver.get("kind"), ctx.cfg.solver))
     ctx.set_boundary(arrays["boundary"])
     ctx.upload_particles(arrays["positions"], arrays["velocities"])
-    ctx.set_solver_state(solver["step_ns"], solver["iters_density"], solver["iters_divergence"], bool(solver["initialized"]))
+    ctx.set_solver_state(solver["step_ns"], solver["iters_density"], solver["iters_divergence"], bool(solver["initialized"]),
+                         solver.get("total_simulated_ns", 0))
     if "kappa" in arrays:
         ctx.upload_field(capi.FIELD_KAPPA, arrays["kappa"])
         ctx.upload_field(capi.FIELD_STIFFNESS, arrays["stiffness"])
