@@ -41,6 +41,10 @@ def parse():
     ap.add_argument("--columns-per-gpu", type=int, default=2000)
     ap.add_argument("--rows", type=int, default=1000)
     ap.add_argument("--presteps", type=int, default=200)
+    ap.add_argument("--solver", default="dfsph", choices=["dfsph", "wcsph"], help="wcsph: BASELINE configs[0] (cfl 0.2, main.rs:115-118)")
+    ap.add_argument("--total-columns", type=int, default=0, help="strong scaling: ONE tank of this many fluid columns split over the ranks")
+    ap.add_argument("--collapse-presteps", type=int, default=1000, help="second timed regime: this many steps into the run (0 = skip)")
+    ap.add_argument("--cpu-collapse-presteps", type=int, default=2000, help="presteps of the CPU sample of the second regime (0 = skip)")
     ap.add_argument("--cpu-columns", type=int, default=250, help="fluid columns of the bounded CPU sample (rows as the workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -121,41 +125,49 @@ def summarize_clocks(samples):
 # ----------------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle (C++/OpenMP restatement of the reference) on a bounded sample of the workload
 # ----------------------------------------------------------------------------------------------------------------------
-def build_oracle_tank(po, columns, rows):
-    import yasph2d_b200 as y
-
-    hw = y.tank_scene(y.FluidParticleWorld(2.0, 10000.0, 100.0), columns, rows)
-    w = po.World()
-    w.set_particles(hw.particles.positions)
-    w.set_boundary(hw.particles.boundary_particles)
-    return w
-
-
-def run_cpu(args, columns, steps, warmup):
+def run_cpu(args, columns, steps, warmup, presteps=None):
+    """The reference's CPU path (its C++/OpenMP restatement, oracle/) on all host cores.  The scene comes from the oracle's own
+    restated builders (pyoracle.tank_scene / dam_break_scene): nothing of the product library is loaded by this arm."""
     from oracle import pyoracle as po
 
     cores = po.num_threads(os.cpu_count() or 1)
+    presteps = args.presteps if presteps is None else presteps
     if args.workload == "tank":
-        w = build_oracle_tank(po, columns, args.rows)
-        sample = "tank %d x %d = %d fluid particles (+%d boundary), %d presteps, %d timed steps" % (columns, args.rows, w.n, w.m, args.presteps, steps)
-        presteps = args.presteps
+        w = po.tank_scene(po.World(), columns, args.rows)
+        sample = "tank %d x %d = %d fluid particles (+%d boundary), %s, %d presteps, %d timed steps" % (columns, args.rows, w.n, w.m, args.solver.upper(), presteps, steps)
     else:
         w = po.dam_break_scene(po.World())
-        sample = "application dam-break scene, %d fluid + %d boundary particles, %d presteps, %d timed steps" % (w.n, w.m, args.presteps, steps)
-        presteps = args.presteps
-    tm = po.TimeManager(cfl_factor=1.5)
-    s = po.DFSPHSolver(w)
+        sample = "application dam-break scene (main.rs:177-196), %d fluid + %d boundary particles, %s, %d presteps, %d timed steps" % (w.n, w.m, args.solver.upper(), presteps, steps)
+    if args.solver == "wcsph":
+        tm, s = po.TimeManager(cfl_factor=0.2), po.WCSPHSolver(w)  # main.rs:115-118
+    else:
+        tm, s = po.TimeManager(cfl_factor=1.5), po.DFSPHSolver(w)
     for _ in range(presteps + warmup):
         s.simulation_step(w, tm)
-    its = [0, 0]
+    its, warm = [0, 0], [0, 0]
     t0 = time.perf_counter()
     for _ in range(steps):
         r = s.simulation_step(w, tm)
         its[0] += r.iters_density
         its[1] += r.iters_divergence
+        warm[0] += r.warm_density
+        warm[1] += r.warm_divergence
     dt = time.perf_counter() - t0
     return {"value": w.n * steps / dt, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-            "ms_per_step": 1e3 * dt / steps, "n": w.n, "iters_density_mean": its[0] / steps, "iters_divergence_mean": its[1] / steps}
+            "ms_per_step": 1e3 * dt / steps, "n": w.n, "iters_density_mean": its[0] / steps, "iters_divergence_mean": its[1] / steps,
+            "warm_density_mean": warm[0] / steps, "warm_divergence_mean": warm[1] / steps}
+
+
+def kernel_source_hash():
+    """sha256 over the CUDA sources: ties a committed ncu capture (profiles/r02/traffic.json) to the kernels it was taken from."""
+    import hashlib
+
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "yasph2d_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        h.update(f.encode())
+        h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
 
 
 def neighbor_sweep(args):
@@ -213,6 +225,45 @@ def neighbor_sweep(args):
     return 0
 
 
+def pass_groups(solver, pt, B, K, it_rho, it_div, w_rho, w_div):
+    """(us per step, algorithmic bytes per particle and step) of every timed pass group.  The density / alpha sweep also carries
+    iteration 0's density-change pass of the divergence solver whenever that solver's warm start does not run (OpDensityAlphaDiv):
+    its bytes (B_A,div = 20 + L) are credited to the group that spends the time."""
+    L = 8.0 + 4.0 * K
+    if solver == "wcsph":
+        return {
+            "kickdrift_keygen": (pt["advect_keygen"], 40.0),
+            "density": (pt["density_alpha"], 12 + L),
+            "wcsph_accel": (pt["wcsph_accel"], 28 + L),
+            "cfl_kick": (pt["wcsph_kick"], 40.0),
+            "lists": (pt["lists"], B["lists"]),
+            "neighborhood(sort+gather+cells+lists)": (pt["sort"] + pt["gather"] + pt["cells_tiles"] + pt["lists"], B["neighborhood"]),
+        }
+    fused = 1.0 - w_div  # fraction of steps whose iteration-0 pass A ran inside the density / alpha sweep
+    return {
+        "viscosity": (pt["viscosity"], B["viscosity"]),
+        "density_solve": (pt["density_solve"], B["density_iter"] * it_rho),
+        "density_warm": (pt["density_warm"], B["density_warm"] * w_rho),
+        "divergence_solve": (pt["divergence_solve"], B["divergence_iter"] * it_div - fused * (20 + L)),
+        "divergence_warm": (pt["divergence_warm"], B["divergence_warm"] * w_div),
+        "density_alpha": (pt["density_alpha"], B["density_alpha"] + fused * (20 + L)),
+        "density_alpha+divergence_solve": (pt["density_alpha"] + pt["divergence_solve"], B["density_alpha"] + B["divergence_iter"] * it_div),
+        "lists": (pt["lists"], B["lists"]),
+        "neighborhood(sort+gather+cells+lists)": (pt["sort"] + pt["gather"] + pt["cells_tiles"] + pt["lists"], B["neighborhood"]),
+    }
+
+
+PASS_KERNELS = {  # the kernel(s) behind each sweep group, as ncu names them
+    "viscosity": ["k_sweep<OpViscosity>"],
+    "density_solve": ["k_sweep<OpJacobiA<0>>", "k_sweep<OpJacobiB<0, 0>>"],
+    "divergence_solve": ["k_sweep<OpJacobiB<1, 0>>"],
+    "density_alpha": ["k_sweep<OpDensityAlphaDiv>"],
+    "lists": ["k_build_lists"],
+    "density": ["k_sweep<OpDensityAlpha<1, 0, 1>>"],
+    "wcsph_accel": ["k_sweep<OpWcsphAccel>"],
+}
+
+
 def main():
     args = parse()
     if args.workload == "neighbors":
@@ -220,16 +271,26 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    metric = METRIC if args.solver == "dfsph" else "particle-steps/sec (WCSPH, 2D dam-break)"
+    total_columns = args.total_columns if args.total_columns else args.columns_per_gpu * world
+    scaling = "strong" if args.total_columns else "weak"
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        cb = run_cpu(args, args.cpu_columns * 2, args.steps, args.warmup)
+        # N = 1: exactly the GPU arm's workload (tank, presteps, warm-up and step count).  N > 1: one GPU's share of the tank -- the
+        # CPU's particle-steps/s barely depend on the tank's width, and the full 16 M tank would take ~1.5 s per step here.
+        columns = args.columns_per_gpu if not args.total_columns else max(1, args.total_columns // world)
+        cb = run_cpu(args, columns, args.steps, args.warmup)
+        same = world == 1
         line = {
-            "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "impl": "reference", "metric": metric, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "DFSPH dam-break tank, CPU restatement of the reference (C++/OpenMP) -- not the Rust binary", "sample": cb["sample"]},
+            "config": {"workload": "%s, CPU restatement of the reference (C++/OpenMP, oracle/) -- not the Rust binary (no cargo in this image)" % workload_name(args, columns, 1),
+                       "sample": cb["sample"], "same_config_as_gpu_arm": same, "presteps": args.presteps,
+                       "iters_density": cb["iters_density_mean"], "iters_divergence": cb["iters_divergence_mean"],
+                       "warm_density": cb["warm_density_mean"], "warm_divergence": cb["warm_divergence_mean"]},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
@@ -256,15 +317,14 @@ def main():
     # ---- scene (host): every rank builds the whole scene (the jitter stream is sequential), then keeps its slab ----
     hw = y.FluidParticleWorld(2.0, 10000.0, 100.0)
     if args.workload == "tank":
-        y.tank_scene(hw, args.columns_per_gpu * world, args.rows)
-        workload = "DFSPH dam-break tank (BASELINE configs[3]): %d x %d fluid particles per GPU, %d in total" % (
-            args.columns_per_gpu, args.rows, args.columns_per_gpu * world * args.rows)
+        y.tank_scene(hw, total_columns, args.rows)
     else:
         y.dam_break_scene(hw)
-        workload = "DFSPH application dam-break scene (BASELINE configs[1], main.rs:177-196)"
+    workload = workload_name(args, total_columns // world if args.workload == "tank" else 0, world)
     n_global, m = hw.particles.num_dynamic_particles(), hw.particles.num_boundary_particles()
 
-    cfg = capi.default_config(2.0, 10000.0, 100.0, capi.SOLVER_DFSPH)
+    solver_kind = capi.SOLVER_DFSPH if args.solver == "dfsph" else capi.SOLVER_WCSPH
+    cfg = capi.default_config(2.0, 10000.0, 100.0, solver_kind)
     cfg.device = local_rank
     if args.no_peer_transport:
         cfg.flags |= capi.FLAG_NO_PEER_TRANSPORT
@@ -278,7 +338,7 @@ def main():
     else:
         from yasph2d_b200 import slab
 
-        # 1-D slab decomposition over cell columns: migration + ghost columns + per-pass halo exchange over NCCL
+        # 1-D slab decomposition over cell columns: migration + ghost columns + per-pass halo exchange, all-reduced residual
         cfg.max_particles, cfg.max_boundary = int(n_global / world * 1.3) + 65536, m
         uid = slab.broadcast_unique_id(dist)
         ctx, ranges, _ = slab.make_slab_context(cfg, rank, world, uid, hw.particles.positions, hw.particles.velocities, hw.particles.boundary_particles)
@@ -291,10 +351,14 @@ def main():
     stop, samples, clock_errors, window = threading.Event(), [], [], {}
     th = threading.Thread(target=clocks_sampler, args=(stop, samples, local_rank, clock_errors), daemon=True)
     th.start()
+    steps_done = [0]
+
+    def dev_step():
+        steps_done[0] += 1
+        return ctx.step()
+
     for _ in range(args.presteps):
-        ctx.step()
-    if world > 1:
-        n = ctx.counts()[0]
+        dev_step()
 
     def timed(step_fn, steps, warmup):
         for _ in range(warmup):
@@ -320,42 +384,6 @@ def main():
             ms = float(t.item())
         return ms, reps, launches
 
-    # ---- device-resident throughput (`value`) with clocks sampled during the timed region ----
-    ms, reps, launches = timed(ctx.step, args.steps, args.warmup)
-    stop.set()
-    th.join(timeout=3)
-    in_window = [s_ for s_ in samples if window["t0"] <= s_[7] <= window["t1"]]
-    clocks = summarize_clocks(in_window if in_window else samples[-1:])
-    clocks["window"] = "timed region" if in_window else "nearest sample (the timed region is shorter than one sampling period)"
-    if clock_errors:
-        clocks["sampler_notes"] = clock_errors[:2]
-    if world == 1:
-        n_total = n
-    else:
-        t = torch.tensor([ctx.counts()[0]], device="cuda", dtype=torch.int64)
-        dist.all_reduce(t)
-        n_total = int(t.item())
-        assert n_total == n_global, (n_total, n_global)
-    value = n_total * args.steps / (ms * 1e-3)
-    it_rho = float(np.mean([r.iters_density for r in reps]))
-    it_div = float(np.mean([r.iters_divergence for r in reps]))
-    w_rho = float(np.mean([r.warm_density for r in reps]))
-    w_div = float(np.mean([r.warm_divergence for r in reps]))
-    K = float(np.mean([r.total_neighbors for r in reps])) / n
-
-    # ---- per-pass device times (CUDA event pairs around every pass, on the launching stream) -> roofline ----
-    ctx.set_flags(capi.FLAG_PROFILE_PASSES)
-    acc = {}
-    psteps = max(3, min(args.steps, 10))
-    piters = [0.0, 0.0]
-    for _ in range(psteps):
-        r = ctx.step()
-        piters[0] += r.iters_density
-        piters[1] += r.iters_divergence
-        for k, v in ctx.pass_times_us().items():
-            acc[k] = acc.get(k, 0.0) + v
-    ctx.set_flags(0)
-    pt = {k: v / psteps for k, v in acc.items()}  # us per step
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -363,50 +391,93 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    B = pass_bytes(K)
-    # bytes per step for each timed pass group
-    groups = {
-        "viscosity": (pt["viscosity"], B["viscosity"]),
-        "density_solve": (pt["density_solve"], B["density_iter"] * piters[0] / psteps),
-        "divergence_solve": (pt["divergence_solve"], B["divergence_iter"] * piters[1] / psteps),
-        "density_alpha": (pt["density_alpha"], B["density_alpha"]),
-        "lists": (pt["lists"], B["lists"]),
-        "neighborhood(sort+gather+cells+lists)": (pt["sort"] + pt["gather"] + pt["cells_tiles"] + pt["lists"], B["neighborhood"]),
-    }
-    passes = {}
-    for k, (us, bpp) in groups.items():
-        gbs = (bpp * n) / (us * 1e-6) / 1e9 if us > 0 else 0.0
-        passes[k] = {"us_per_step": round(us, 2), "alg_bytes_per_particle": round(bpp, 1), "GBps": round(gbs, 1), "frac": round(gbs / peak, 4)}
-    dominant = max(("viscosity", "density_solve", "divergence_solve", "density_alpha", "lists"), key=lambda k: groups[k][0])
-    d_us, d_bpp = groups[dominant]
-    achieved = (d_bpp * n) / (d_us * 1e-6) / 1e9
-    step_bytes = (B["viscosity"] + B["predict"] + it_rho * B["density_iter"] + w_rho * B["density_warm"] + 4 + B["advect_keygen"] + B["neighborhood"]
-                  + B["density_alpha"] + it_div * B["divergence_iter"] + w_div * B["divergence_warm"] + 4)
-    # the kernel(s) behind each pass group, and the DRAM traffic ncu counted for one launch of them (committed capture)
-    pass_kernels = {
-        "viscosity": ["void k_sweep<OpViscosity>(SweepCommon, T1)"],
-        "density_solve": ["void k_sweep<OpJacobiA<0>>(SweepCommon, T1)", "void k_sweep<OpJacobiB<0, 0>>(SweepCommon, T1)"],
-        "divergence_solve": ["void k_sweep<OpJacobiB<1, 0>>(SweepCommon, T1)"],
-        "density_alpha": ["void k_sweep<OpDensityAlphaDiv>(SweepCommon, T1)"],
-        "lists": ["k_build_lists(ListArgs)"],
-    }
-    traffic, traffic_src = None, None
+    traffic_file = None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01", "traffic_v5.json")))
-        if n == 2000000 and world == 1:  # the capture is of this workload
-            traffic = sum(tj["kernels"][k]["dram_bytes_read"] + tj["kernels"][k]["dram_bytes_write"] for k in pass_kernels[dominant])
-            traffic_src = tj["source"]
+        traffic_file = json.load(open(os.path.join(ROOT, "profiles", "r02", "traffic.json")))
     except Exception:
         pass
-    roofline = {
-        "bound": "hbm", "kernel": "%s (%s)" % (dominant, " + ".join(k.replace("void ", "").split("(")[0] for k in pass_kernels[dominant])),
-        "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-        "frac": round(achieved / peak, 4), "frac_of_nominal_8000_GBps": round(achieved / 8000.0, 4), "traffic": traffic, "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
-        "traffic_source": traffic_src, "alg_bytes_per_launch": round(d_bpp * n, 0), "peak_source": peak_kind,
-        "whole_step": {"alg_bytes_per_particle_step": round(step_bytes, 1), "GBps": round(step_bytes * n_total * args.steps / (ms * 1e-3) / 1e9, 1),
-                       "frac_per_gpu": round(step_bytes * n_total / world * args.steps / (ms * 1e-3) / 1e9 / peak, 4)},
-        "passes": passes, "pass_us_per_step": {k: round(v, 2) for k, v in pt.items()},
-    }
+
+    def total_particles():
+        if world == 1:
+            return ctx.counts()[0]
+        t = torch.tensor([ctx.counts()[0]], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t)
+        return int(t.item())
+
+    def measure(label):
+        """Device-resident throughput of `--steps` steps, then per-pass device times (CUDA event pairs around every pass, recorded
+        on the library's launching stream) of a few more steps -> the roofline of every pass group."""
+        ms, reps, launches = timed(dev_step, args.steps, args.warmup)
+        n_total = total_particles()
+        assert n_total == n_global, (n_total, n_global)
+        n_loc = ctx.counts()[0]
+        res = {"regime": label, "first_timed_step": steps_done[0] - args.steps, "value": n_total * args.steps / (ms * 1e-3), "ms_per_step": ms / args.steps,
+               "gpu_launches": int(launches)}
+        it_rho = float(np.mean([r.iters_density for r in reps]))
+        it_div = float(np.mean([r.iters_divergence for r in reps]))
+        w_rho = float(np.mean([r.warm_density for r in reps]))
+        w_div = float(np.mean([r.warm_divergence for r in reps]))
+        K = float(np.mean([r.total_neighbors for r in reps])) / max(n_loc, 1)
+        ctx.set_flags(cfg.flags | capi.FLAG_PROFILE_PASSES)
+        acc, psteps, pit = {}, max(3, min(args.steps, 10)), [0.0, 0.0, 0.0, 0.0]
+        for _ in range(psteps):
+            r = dev_step()
+            for q, v in enumerate((r.iters_density, r.iters_divergence, r.warm_density, r.warm_divergence)):
+                pit[q] += v / psteps
+            for k, v in ctx.pass_times_us().items():
+                acc[k] = acc.get(k, 0.0) + v
+        ctx.set_flags(cfg.flags)
+        pt = {k: v / psteps for k, v in acc.items()}  # us per step
+        B = pass_bytes(K)
+        groups = pass_groups(args.solver, pt, B, K, *pit)
+        passes = {}
+        for k, (us, bpp) in groups.items():
+            gbs = (bpp * n_loc) / (us * 1e-6) / 1e9 if us > 0 else 0.0
+            passes[k] = {"us_per_step": round(us, 2), "alg_bytes_per_particle": round(bpp, 1), "GBps": round(gbs, 1), "frac": round(gbs / peak, 4)}
+        cands = [k for k in groups if k in PASS_KERNELS]
+        dominant = max(cands, key=lambda k: groups[k][0])
+        d_us, d_bpp = groups[dominant]
+        achieved = (d_bpp * n_loc) / (d_us * 1e-6) / 1e9
+        if args.solver == "wcsph":
+            step_bytes = 276 + 12 * K
+        else:
+            step_bytes = (B["viscosity"] + B["predict"] + it_rho * B["density_iter"] + w_rho * B["density_warm"] + 4 + B["advect_keygen"] + B["neighborhood"]
+                          + B["density_alpha"] + it_div * B["divergence_iter"] + w_div * B["divergence_warm"] + 4)
+        # DRAM traffic ncu counted per launch of the dominant group's kernels: from the committed capture of THESE kernel sources
+        traffic, traffic_src = None, None
+        if traffic_file and world == 1 and n_loc == traffic_file.get("particles") and args.solver == traffic_file.get("solver", "dfsph"):
+            if traffic_file.get("kernel_source_hash") == kernel_source_hash():
+                try:
+                    traffic = sum(traffic_file["kernels"][k]["dram_bytes_read"] + traffic_file["kernels"][k]["dram_bytes_write"] for k in PASS_KERNELS[dominant])
+                    traffic_src = traffic_file.get("source")
+                except KeyError:
+                    traffic_src = "profiles/r02/traffic.json has no entry for %s" % PASS_KERNELS[dominant]
+            else:
+                traffic_src = "profiles/r02/traffic.json was captured from other kernel sources (hash %s, now %s): not used" % (
+                    traffic_file.get("kernel_source_hash"), kernel_source_hash())
+        res.update({"mean_neighbors": round(K, 2), "iters_density": it_rho, "iters_divergence": it_div, "warm_density": w_rho, "warm_divergence": w_div})
+        res["roofline"] = {
+            "bound": "hbm", "kernel": "%s (%s)" % (dominant, " + ".join(PASS_KERNELS[dominant])),
+            "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+            "frac": round(achieved / peak, 4), "frac_of_nominal_8000_GBps": round(achieved / 8000.0, 4), "traffic": traffic,
+            "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)", "traffic_source": traffic_src,
+            "alg_bytes_per_launch": round(d_bpp * n_loc, 0), "peak_source": peak_kind,
+            "whole_step": {"alg_bytes_per_particle_step": round(step_bytes, 1), "GBps": round(step_bytes * n_total * args.steps / (ms * 1e-3) / 1e9, 1),
+                           "frac_per_gpu": round(step_bytes * n_total / world * args.steps / (ms * 1e-3) / 1e9 / peak, 4)},
+            "passes": passes, "pass_us_per_step": {k: round(v, 2) for k, v in pt.items()},
+        }
+        return res
+
+    # ---- regime "early": `--presteps` steps into the run (the headline: both arms run exactly this) ----
+    early = measure("early")
+    stop.set()
+    th.join(timeout=3)
+    in_window = [s_ for s_ in samples if window["t0"] <= s_[7] <= window["t1"]]
+    clocks = summarize_clocks(in_window if in_window else samples[-1:])
+    clocks["window"] = "timed region" if in_window else "nearest sample (the timed region is shorter than one sampling period)"
+    if clock_errors:
+        clocks["sampler_notes"] = clock_errors[:2]
+    n_total = n_global
 
     # ---- end to end through the reference-facing call with pinned HOST buffers ----
     e2e = None
@@ -422,6 +493,7 @@ def main():
         moved = [0, 0]
 
         def host_step():
+            steps_done[0] += 1
             if world == 1:
                 return ctx.step_host(pos[: n_cur[0]], vel[: n_cur[0]], den[: n_cur[0]])
             moved[0] += n_cur[0] * 16
@@ -434,34 +506,52 @@ def main():
         timeline = None
         if world == 1:  # where the call's time goes: device timeline of a few more calls (events on the library's streams; the event
             # records themselves queue behind the link traffic, so this run is slower than the timed one -- read it as an order)
-            ctx.set_flags(capi.FLAG_PROFILE_PASSES)
+            ctx.set_flags(cfg.flags | capi.FLAG_PROFILE_PASSES)
             tl = [dict(host_step() and ctx.host_step_times_us()) for _ in range(5)][2:]
-            ctx.set_flags(0)
+            ctx.set_flags(cfg.flags)
             timeline = {k: round(float(np.mean([t[k] for t in tl])), 1) for k in tl[0]}
         e2e = {"value": n_total * args.steps / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(n_total * 16), "d2h_bytes_per_step": int(n_total * 20),
                "ms_per_step": ems / args.steps, "device_timeline_us": timeline,
                "api": "yasph_step_host%s (upload pos+vel, simulation_step, download pos+vel+densities; bytes summed over ranks)" % ("" if world == 1 else "_slab")}
 
-    # ---- CPU baseline (rank 0, single-GPU run only) ----
+    # ---- regime "collapse": further into the run, where the divergence solver iterates and warm-starts ----
+    collapse = None
+    if args.collapse_presteps and args.solver == "dfsph" and args.workload == "tank":
+        while steps_done[0] < args.collapse_presteps:
+            dev_step()
+        collapse = measure("collapse")
+
+    # ---- CPU baseline (rank 0, single-GPU run only): bounded samples of the same tank, one per regime ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = run_cpu(args, args.cpu_columns, max(3, min(args.steps, 10)), 1)
-        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "ms_per_step", "iters_density_mean", "iters_divergence_mean")}
+        keys = ("value", "unit", "cores", "kind", "sample", "ms_per_step", "iters_density_mean", "iters_divergence_mean", "warm_divergence_mean")
+        c1 = run_cpu(args, args.cpu_columns, max(3, min(args.steps, 10)), 1)
+        cpu = {k: c1[k] for k in keys}
+        if collapse is not None and args.cpu_collapse_presteps:
+            # the narrow sample tank reaches the iterating regime later than the wide one (its waves reflect sooner): the sample is
+            # matched by solver work (iterations, warm start), not by step number
+            c2 = run_cpu(args, args.cpu_columns, max(3, min(args.steps, 10)), 1, presteps=args.cpu_collapse_presteps)
+            cpu["collapse"] = {k: c2[k] for k in keys}
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "metric": metric, "value": early["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": early["ms_per_step"], "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": workload, "particles_per_gpu": n, "boundary_particles": m, "presteps": args.presteps,
-                "parallelism": "1 GPU" if world == 1 else "1-D slab decomposition over cell columns, %d ranks, NCCL migration / ghost / halo exchange + all-reduced residual" % world,
+                "workload": workload, "solver": args.solver, "regime": "early", "particles_per_gpu": n, "particles_total": n_global, "boundary_particles": m,
+                "presteps": args.presteps,
+                "parallelism": "1 GPU" if world == 1 else "1-D slab decomposition over cell columns, %d ranks, peer-memory (NVLink) migration / ghost / halo exchange + all-reduced residual" % world,
                 "slab_ranges": ranges, "slab_info_rank0": (ctx.info().as_dict() if world > 1 else None),
                 "l2": "working set %.0f MB per GPU > 126 MB L2 (no explicit flush)" % (n * 240 / 1e6) if n * 240 > 126e6 else "working set fits L2 (small scene)",
-                "mean_neighbors": round(K, 2), "iters_density": it_rho, "iters_divergence": it_div, "warm_density": w_rho, "warm_divergence": w_div,
+                "mean_neighbors": early["mean_neighbors"], "iters_density": early["iters_density"], "iters_divergence": early["iters_divergence"],
+                "warm_density": early["warm_density"], "warm_divergence": early["warm_divergence"],
                 "arithmetic": "strict f32, no FMA contraction, IEEE div/sqrt (bit-exact vs oracle)",
             },
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "gpu_launches": early["gpu_launches"], "clocks": clocks, "roofline": early["roofline"],
         }
+        if collapse is not None:
+            line["regimes"] = {"early": {k: early[k] for k in ("first_timed_step", "value", "ms_per_step", "iters_density", "iters_divergence", "warm_density", "warm_divergence", "mean_neighbors")},
+                               "collapse": collapse}
         if e2e:
             line["e2e"] = e2e
         if cpu:
@@ -470,6 +560,13 @@ def main():
     if dist is not None:
         dist.destroy_process_group()
     return 0
+
+
+def workload_name(args, columns_per_gpu, world):
+    if args.workload != "tank":
+        return "%s application dam-break scene (BASELINE configs[0]/[1], main.rs:177-196)" % args.solver.upper()
+    return "%s dam-break tank (BASELINE configs[3]): %d x %d fluid particles per GPU, %d in total" % (
+        args.solver.upper(), columns_per_gpu, args.rows, columns_per_gpu * world * args.rows)
 
 
 if __name__ == "__main__":

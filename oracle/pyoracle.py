@@ -354,3 +354,23 @@ def dam_break_scene(world):
     world.add_boundary_thick_line((0.0, 2.5), (2.0, 2.5), 2)
     world.add_boundary_thick_line((-2.0, -0.5), (4.0, -0.5), 4)
     return world
+
+
+def tank_scene(world, columns, rows, x0=1.0, y0=0.2, wall_thickness=4, jitter=0.05, tank_height=None, obstacle=True):
+    """The dam-break tank of BASELINE.json configs 3 / 4, built with the oracle's own restated scene builders
+    (fluidparticleworld.rs:140-195) -- the same geometry as yasph2d_b200.tank_scene, so that bench.py's reference arm needs nothing
+    from the product library.  `world` must be empty."""
+    nppm = 100.0 * 0.9  # num_particles_per_meter = sqrt(particle_density) of the application's world (main.rs:85-89), 0.9x packing
+    w = (columns + 0.2) / nppm
+    h = (rows + 0.2) / nppm
+    world.add_fluid_rect(x0, y0, w, h, jitter)
+    assert world.n == columns * rows, (world.n, columns, rows)
+    x1 = x0 + w * 1.34 + 1.0
+    top = tank_height if tank_height is not None else y0 + h * 1.45
+    world.add_boundary_thick_line((0.0, 0.0), (x1, 0.0), wall_thickness)
+    world.add_boundary_thick_line((0.0, top), (x1, top), wall_thickness)
+    world.add_boundary_thick_line((0.0, 0.0), (0.0, top), wall_thickness)
+    world.add_boundary_thick_line((x1, 0.0), (x1, top), wall_thickness)
+    if obstacle:
+        world.add_boundary_thick_line((x0 + w + 0.3, 0.0), (x0 + w + 0.3 + 0.25 * h, 0.2 * h), 2)
+    return world

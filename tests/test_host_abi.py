@@ -80,6 +80,9 @@ def test_tank_scene_counts():
     w = y.tank_scene(y.FluidParticleWorld(2.0, 10000.0, 100.0), 300, 100)
     assert w.particles.num_dynamic_particles() == 30000
     assert w.particles.num_boundary_particles() > 1000
+    # the oracle's own builder of the same tank (bench.py's reference arm builds its scene with it, without the product library)
+    ow = po.tank_scene(po.World(), 300, 100)
+    assert np.array_equal(w.particles.positions, ow.positions()) and np.array_equal(w.particles.boundary_particles, ow.boundary())
 
 
 def test_duration_helpers_equal_oracle():
