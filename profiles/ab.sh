@@ -1,7 +1,7 @@
 #!/bin/bash
 # A/B timing of library variants: ./scratch_ab.sh variants/a.so variants/b.so ...
 for so in "$@"; do
-  YASPH_GPU_LIB=$PWD/$so python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ab.json 2> gpurun_out/ab.err || tail -5 gpurun_out/ab.err
+  YASPH_GPU_LIB=$PWD/$so python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-e2e --collapse-presteps 0 > gpurun_out/ab.json 2> gpurun_out/ab.err || tail -5 gpurun_out/ab.err
   python - "$so" <<'PY'
 import json,sys
 d=json.load(open('gpurun_out/ab.json'))
