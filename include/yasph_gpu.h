@@ -103,8 +103,9 @@ typedef struct yasph_config {
     float cfl_factor;                    /* 1.5 (DFSPH) / 0.2 (WCSPH), main.rs:115-118 */
     /* implementation knobs (0 = default) */
     uint32_t max_tiles;                  /* capacity for 8x8-cell tiles; default max_particles/32 + 4096 */
-    uint32_t tile_dynamic_capacity;      /* staged dynamic candidates per tile (default 2048) */
-    uint32_t tile_static_capacity;       /* staged boundary candidates per tile (default 1024) */
+    uint32_t tile_dynamic_capacity;      /* most dynamic candidates (tile + apron) a tile may STAGE in shared memory; 0 = whatever the SM holds.  Larger
+                                          * tiles (dense clusters) are processed unstaged from global memory: slow, same results */
+    uint32_t tile_static_capacity;       /* the same for boundary candidates */
     uint32_t speculative_iterations;     /* Jacobi iterations launched between two convergence read-backs (default 2) */
     uint32_t flags;                      /* YASPH_FLAG_* */
     uint32_t max_halo;                   /* slab mode: capacity (particles per side) of the ghost / migrant buffers; default max(65536, max_particles / 8) */

@@ -86,10 +86,27 @@ def test_oversized_tile_capacity_is_rejected():
     assert e.value.status == 3
 
 
-def test_capacity_error_is_loud():
+def test_tiles_too_large_to_stage_fall_back_to_global_memory():
+    """1250 particles per cell: far more candidates per tile than the configured staging capacity (and, without that knob, than
+    the shared memory of an SM holds).  The reference accepts any density up to its 64-neighbour cap
+    (neighborhood_search.rs:353-381); such tiles are processed unstaged, from global memory -- the lists equal the oracle's."""
     rng = np.random.default_rng(3)
-    pos = (rng.random((5000, 2)) * 2.0).astype(np.float32)  # 1250 particles per cell
+    pos = (rng.random((5000, 2)) * 2.0).astype(np.float32)
     ns = y.NeighborhoodSearch(1.0, max_particles=5000, tile_dynamic_capacity=256)
+    spos, _ = ns.update_dynamic(pos)
+    w = po.World(h=1.0)
+    w.set_particles(pos)
+    w.update_neighborhood()
+    assert np.array_equal(spos, w.positions())
+    assert_lists_equal(ns.ctx.neighbors(True), w.neighbors())
+    assert ns.last_report.neighbors_capped == w.neighbor_stats()["capped"] > 0  # every list is cut at 64 here
+
+
+def test_capacity_error_is_loud():
+    """What stays an error: more than 65535 staged candidates in one tile (neighbour slots are 16 bit)."""
+    rng = np.random.default_rng(3)
+    pos = (rng.random((70000, 2)) * 2.0).astype(np.float32)
+    ns = y.NeighborhoodSearch(1.0, max_particles=70000)
     with pytest.raises(capi.YasphError) as e:
         ns.update_dynamic(pos)
     assert e.value.status == 3  # YASPH_ERR_CAPACITY

@@ -192,6 +192,31 @@ def test_dfsph_tight_tolerance_tank_twin_vs_oracle():
     assert it_max[0] == 201 and (ncv & 1) == 1, (it_max, ncv)
 
 
+@pytest.mark.parametrize("solver_kind,cap", [("dfsph", 64), ("dfsph", 320), ("wcsph", 320)])
+def test_unstaged_tiles_step_like_the_oracle(solver_kind, cap):
+    """Staging capacity clipped below the dam break's tiles (cap 64: every tile; cap 320: the fuller ones, so staged and unstaged
+    tiles mix and their partial residual sums / CFL maxima are combined): the step runs the same passes from global memory for those
+    tiles and stays identical to the oracle."""
+    w, ow = make_worlds()
+    if solver_kind == "dfsph":
+        ctx = gpu_ctx(w, tile_dynamic_capacity=cap, tile_static_capacity=cap, **TIGHT_GPU)
+        otm, osolver = po.TimeManager(cfl_factor=1.5), po.DFSPHSolver(ow)
+        osolver.set_params(**TIGHT_ORACLE)
+    else:
+        ctx = gpu_ctx(w, capi.SOLVER_WCSPH, tile_dynamic_capacity=cap, tile_static_capacity=cap, cfl_factor=0.2)
+        otm, osolver = po.TimeManager(cfl_factor=0.2), po.WCSPHSolver(ow)
+    for s in range(90):
+        rep, orep = ctx.step(), osolver.simulation_step(ow, otm)
+        assert rep.dt_ns == orep.dt_ns, (s, rep.dt_ns, orep.dt_ns)
+        if solver_kind == "dfsph":
+            assert (rep.iters_density, rep.iters_divergence, rep.warm_density, rep.warm_divergence) == (
+                orep.iters_density, orep.iters_divergence, orep.warm_density, orep.warm_divergence), s
+            assert rep.avg_density_error == orep.avg_density_error and rep.avg_divergence == orep.avg_divergence, s
+        if s % 30 == 0 or s == 89:
+            compare_state(ctx, ow, s)
+    assert_lists_equal(ctx.neighbors(), ow.neighbors())
+
+
 def test_dfsph_iteration_caps_vs_oracle():
     """max_*_iters = 3 with tight tolerances: both loops leave through the cap after 4 iterations (the test is `> max` after the
     increment, dfsph.rs:236,391 -- quirk Q4) and report not_converged, exactly as the oracle."""

@@ -591,6 +591,7 @@ struct ListArgs {
     uint32_t* tile_nk;  // [tile] most list words of any particle of the tile
     uint32_t cap_dyn, cap_stat;
     uint32_t* apron_idx;  // [tile][APRON_TABLE]
+    uint32_t unstaged;    // 1: the launch of k_build_lists<true>
 #ifdef YASPH_LIST_TIMING
     unsigned long long* dbg;  // [8] cycle counters per phase (profiling builds only)
 #endif
@@ -599,15 +600,19 @@ __device__ __forceinline__ void list_issue_stage(const ListArgs& a, uint32_t t, 
     const TileHeader& h = tr.hdr;
     for (uint32_t q = threadIdx.x; q < 2 * REGION_CELLS; q += NB_THREADS)
         cp_async<4>(&cs[q / REGION_CELLS][q % REGION_CELLS], (q < REGION_CELLS ? a.tt.cslot_d : a.tt.cslot_s) + (size_t)t * REGION_CELLS + q % REGION_CELLS);
-    if (h.dyn_total > a.cap_dyn || h.stat_total > a.cap_stat) return;  // cannot happen: capacities are the maxima over all tiles
-    for (uint32_t s = threadIdx.x; s < h.pcount; s += NB_THREADS) cp_async<8>(&sdyn[h.own_lo + s], &a.pos[h.pstart + s]);
-    for (uint32_t q = threadIdx.x, na = tile_apron_count(h); q < na; q += NB_THREADS) {
+    // a tile that outgrows the staging capacity is not staged: its candidates are read from global memory (k_build_lists)
+    const bool fits = !a.unstaged && h.dyn_total <= a.cap_dyn && h.stat_total <= a.cap_stat;
+    if (a.unstaged) return;  // the second launch (tiles too large to stage) needs the cell tables only
+    if (fits)
+        for (uint32_t s = threadIdx.x; s < h.pcount; s += NB_THREADS) cp_async<8>(&sdyn[h.own_lo + s], &a.pos[h.pstart + s]);
+    for (uint32_t q = threadIdx.x, na = tile_apron_count(h); q < na && (fits || q < APRON_TABLE); q += NB_THREADS) {
         const uint32_t s = tile_apron_slot(h, q);
         const uint32_t g = run_slot_to_global(tr.rd, s);
-        cp_async<8>(&sdyn[s], &a.pos[g]);
-        if (q < APRON_TABLE) a.apron_idx[(size_t)t * APRON_TABLE + q] = g;
+        if (fits) cp_async<8>(&sdyn[s], &a.pos[g]);
+        if (q < APRON_TABLE) a.apron_idx[(size_t)t * APRON_TABLE + q] = g;  // the sweeps may stage this tile even when this launch does not
     }
-    for (uint32_t s = threadIdx.x; s < h.stat_total; s += NB_THREADS) cp_async<8>(&sstat[s], &a.bpos[run_slot_to_global(tr.rs, s)]);
+    if (fits)
+        for (uint32_t s = threadIdx.x; s < h.stat_total; s += NB_THREADS) cp_async<8>(&sstat[s], &a.bpos[run_slot_to_global(tr.rs, s)]);
 }
 // float2 at byte offset `off` of the CTA's dynamic shared memory (every `extern __shared__` array starts at its base): spelled
 // this way the compiler knows the address space and emits LDS instead of a generic load
@@ -635,6 +640,30 @@ __device__ __forceinline__ uint32_t list_scan_candidates(uint32_t cand, const ui
     }
     return c;
 }
+// The same for a tile that is too large to stage: every candidate's position comes from global memory through the tile's copy runs
+// (slot -> global index).  Slow and correct: the reference accepts any particle density (neighborhood_search.rs:353-381).
+template <bool STATIC>
+__device__ __forceinline__ uint32_t list_scan_candidates_global(const float2* __restrict__ gpos, const TileRuns* tr, const uint32_t* __restrict__ cruns, uint32_t ncand,
+                                                             float2 q, float radius_sq, uint16_t* col, uint32_t c) {
+    uint32_t r = 0, rem = 0, s = 0;
+    for (uint32_t j = 0; j < ncand; ++j) {
+        if (rem == 0) {
+            const uint32_t run = cruns[r++];
+            s = run >> 16;
+            rem = run & 0xFFFFu;
+        }
+        const float2 d = gpos[STATIC ? run_slot_to_global(tr->rs, s) : dyn_slot_to_global(*tr, s)] - q;
+        const float d2 = mag2(d);
+        col[min(c, (uint32_t)YASPH_MAXN) * NB_THREADS] = (uint16_t)s;
+        c += (d2 <= radius_sq && d2 > YASPH_MIN_DISTANCE) ? 1u : 0u;
+        ++s;
+        --rem;
+    }
+    return c;
+}
+// UNSTAGED == false: the tiles that fit the staging capacity (all of them, normally).  UNSTAGED == true: launched after it when
+// some tiles do not fit -- the same kernel working on exactly those tiles, from global memory.
+template <bool UNSTAGED>
 __global__ void __launch_bounds__(NB_THREADS) k_build_lists(ListArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ListSmem& S = *reinterpret_cast<ListSmem*>(smem_raw);
@@ -675,6 +704,7 @@ __global__ void __launch_bounds__(NB_THREADS) k_build_lists(ListArgs a) {
         LT_MARK(1)  // issuing the next tile's copies
         const TileHeader h = tr.hdr;
         const bool fits = h.dyn_total <= a.cap_dyn && h.stat_total <= a.cap_stat;
+        const bool mine = fits != UNSTAGED;  // the tiles of this launch
         if (tid < 2 * TILE_CELLS) {
             const uint32_t which = tid / TILE_CELLS, lc = tid % TILE_CELLS;
             const uint32_t lx = morton_x(lc) + 1u, ly = morton_y(lc) + 1u;
@@ -718,17 +748,19 @@ __global__ void __launch_bounds__(NB_THREADS) k_build_lists(ListArgs a) {
         LT_MARK(2)  // cell phase (incl. its barrier)
         uint32_t my_nk = 0, my_words = 0xFFu;
         uint16_t* const counts16 = reinterpret_cast<uint16_t*>(a.counts);
-        if (fits) {
+        if (mine) {
             for (uint32_t tl = tid; tl < h.pcount; tl += NB_THREADS) {
                 const uint32_t i = h.pstart + tl;
-                const float2 q = cdyn[h.own_lo + tl];
+                const float2 q = !UNSTAGED ? cdyn[h.own_lo + tl] : a.pos[i];
                 const uint32_t lc = a.keys[i] & (TILE_CELLS - 1);
                 uint16_t* col = &S.sl[0][tid];
                 // dynamic candidates, ascending slot == ascending sorted index (neighborhood_search.rs:353-366)
-                const uint32_t hits_d = list_scan_candidates(cdyn_s, S.crun[0][lc], S.ncand[0][lc], q, a.g.radius_sq, col, 0u);
+                const uint32_t hits_d = !UNSTAGED ? list_scan_candidates(cdyn_s, S.crun[0][lc], S.ncand[0][lc], q, a.g.radius_sq, col, 0u)
+                                                  : list_scan_candidates_global<false>(a.pos, &tr, S.crun[0][lc], S.ncand[0][lc], q, a.g.radius_sq, col, 0u);
                 const uint32_t cd = min(hits_d, (uint32_t)YASPH_MAXN);
                 // static candidates (neighborhood_search.rs:367-381)
-                const uint32_t c = list_scan_candidates(cstat_s, S.crun[1][lc], S.ncand[1][lc], q, a.g.radius_sq, col, cd);
+                const uint32_t c = !UNSTAGED ? list_scan_candidates(cstat_s, S.crun[1][lc], S.ncand[1][lc], q, a.g.radius_sq, col, cd)
+                                             : list_scan_candidates_global<true>(a.bpos, &tr, S.crun[1][lc], S.ncand[1][lc], q, a.g.radius_sq, col, cd);
                 const uint32_t ct = min(c, (uint32_t)YASPH_MAXN);
                 // the reference's bookkeeping: "too many neighbors" when the 64th entry is written (:360,375); a static hit
                 // with all 64 slots taken by dynamic neighbours indexes neighbor_set[64] and panics (:373) -- dropped here
@@ -765,7 +797,7 @@ __global__ void __launch_bounds__(NB_THREADS) k_build_lists(ListArgs a) {
         // Work order of the tile: its particles sorted (stably) by their number of list words.  The sweeps hand 32 consecutive
         // entries of this order to one warp, so the lanes of a warp walk lists of (nearly) equal length.  Stored in the high
         // half of counts[pstart + position].  Tiles of more than NB_THREADS particles keep the identity order.
-        const bool sortable = fits && h.pcount <= NB_THREADS;
+        const bool sortable = mine && h.pcount <= NB_THREADS;
         const unsigned same = __match_any_sync(0xffffffffu, my_words);
         if (sortable && my_words != 0xFFu && lane_id() == (unsigned)(__ffs(same) - 1)) S.wk[tid >> 5][my_words] = (uint32_t)__popc(same);
         __syncthreads();  // also orders this tile's reads of S.crun / S.ncand before the next tile's writes
@@ -793,10 +825,10 @@ __global__ void __launch_bounds__(NB_THREADS) k_build_lists(ListArgs a) {
                 const uint32_t position = S.wk_bin[my_words] + S.wk[tid >> 5][my_words] + (uint32_t)__popc(same & lanemask_lt());
                 counts16[2 * (size_t)(h.pstart + position) + 1] = (uint16_t)tid;
             }
-        } else if (fits) {
+        } else if (mine) {
             for (uint32_t tl = tid; tl < h.pcount; tl += NB_THREADS) counts16[2 * (size_t)(h.pstart + tl) + 1] = (uint16_t)tl;
         }
-        if (tid == 0) {
+        if (tid == 0 && mine) {
             a.tile_nk[t] = S.nk_max;
             cta_nk = max(cta_nk, S.nk_max);
         }

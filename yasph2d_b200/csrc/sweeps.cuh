@@ -71,6 +71,8 @@ struct SweepCommon {
     uint32_t n;
     float mass, rho0;
     double* partials;  // [gridDim.x]
+    double* partials_unstaged;      // [n_partials_unstaged] partial sums / maxima of k_sweep_unstaged (tiles too large to stage)
+    uint32_t n_partials_unstaged;   // 0 unless that kernel ran ahead of this pass's k_sweep
     // slab mode (multi-GPU): ghosts are excluded from the reductions, the residual average runs over the global particle count
     // and the convergence decision is taken after the all-reduce (k_jacobi_decide)
     const uint8_t* ghost;  // null on a single GPU
@@ -218,7 +220,7 @@ __device__ __forceinline__ void sweep_stage_tile(const SweepCommon& c, const Op&
     const uint32_t nk = nk_tile < c.nk_stage ? nk_tile : c.nk_stage;
     if (lane == 0 && pw == 0) {
         *st.hdr = h;
-        *st.nk = fits ? nk : 0xFFFFFFFFu;
+        *st.nk = fits ? nk : 0xFFFFFFFFu;  // a tile too large to stage is left to k_sweep_unstaged
     }
     if (fits) {
         // apron: the first APRON_TABLE slots come with their global index from the list build's table (prefetched into
@@ -277,6 +279,91 @@ __device__ __forceinline__ void sweep_stage_tile(const SweepCommon& c, const Op&
             if (mine(6)) bulk_copy_g2s(st.o1, op.own1() + g0, nel * (uint32_t)L::O1, full_bar);
     } else if (pw == 0 && lane == 0) {
         mbar_arrive(full_bar);
+    }
+}
+
+// One particle of a tile that is too large to stage (more candidates than the shared memory of an SM holds -- a dense cluster, as
+// a diverging run produces): everything comes from global memory, neighbour slots are translated to global indices through the
+// tile's copy runs.  Slow and correct, in the same order as the staged path, so the results are the same bits.
+template <class Op>
+__device__ __forceinline__ double sweep_particle_unstaged(const SweepCommon& c, const Op& op, uint32_t t, const TileHeader& h, uint32_t tl) {
+    typedef typename Op::P0 P0;
+    typedef typename Op::P1 P1;
+    const TileRuns* tr = c.tt.runs + t;
+    const uint32_t i = h.pstart + tl;
+    const float2 pi = c.pos[i];
+    P0 s0;
+    P1 s1;
+    if constexpr (Op::NPAY >= 1) s0 = op.pay0()[i];
+    if constexpr (Op::NPAY >= 2) s1 = op.pay1()[i];
+    const uint32_t cnt = c.counts[i] & 0xFFFFu;
+    const uint32_t cd = cnt & 0xFFu, ct = (cnt >> 8) & 0xFFu;
+    typename Op::O0 w0;
+    typename Op::O1 w1;
+    if constexpr (Op::NOWN >= 1) w0 = op.own0()[i];
+    if constexpr (Op::NOWN >= 2) w1 = op.own1()[i];
+    typename Op::Acc acc;
+    const bool active = op.init(c, acc, i, pi, s0, s1, ct);
+    const uint32_t nkd = (cd + 3u) >> 2;
+    if (active) {
+        for (uint32_t e = 0; e < cd; ++e) {  // the padding entries of the last dynamic word are simply not visited
+            const unsigned long long w = c.lists[list_word_index(h.pstart, h.pcount, e >> 2, tl)];
+            const uint32_t g = dyn_slot_to_global(*tr, unpack_slot(w, e));
+            P0 n0;
+            P1 n1;
+            if constexpr (Op::NPAY >= 1) n0 = op.pay0()[g];
+            if constexpr (Op::NPAY >= 2) n1 = op.pay1()[g];
+            op.dyn(c, acc, pi, s0, s1, c.pos[g], n0, n1);
+        }
+        if (Op::USES_STATIC) {
+            for (uint32_t e = 0; e < ct - cd; ++e) {
+                const unsigned long long w = c.lists[list_word_index(h.pstart, h.pcount, nkd + (e >> 2), tl)];
+                op.stat(c, acc, pi, s0, s1, c.bpos[run_slot_to_global(tr->rs, unpack_slot(w, e))]);
+            }
+        }
+    }
+    double r = op.finish(c, acc, i, pi, s0, s1, active, w0, w1);
+    if (Op::REDUCE != REDUCE_NONE && c.ghost != nullptr && c.ghost[i]) r = 0.0;
+    return r;
+}
+
+// the staging capacity test of the tile kernels (sweep_stage_tile applies the same one)
+__device__ __forceinline__ bool sweep_tile_fits(const SweepCommon& c, const TileHeader& h) {
+    const uint32_t nel = ((h.pstart & 3u) + h.pcount + 3u) & ~3u;
+    return h.dyn_total <= c.cap_dyn && h.stat_total <= c.cap_stat && nel <= c.cap_pc;
+}
+// The tiles k_sweep leaves out.  Launched BEFORE k_sweep<Op> of the same pass (only when such tiles exist): its per-CTA partial
+// sums / maxima are combined with k_sweep's own by k_sweep's last CTA.
+constexpr int SWU_THREADS = 256;
+template <class Op>
+__global__ void __launch_bounds__(SWU_THREADS) k_sweep_unstaged(SweepCommon c, Op op) {
+    if (op.skip(c.ctl)) return;
+    op.prepare(c);
+    const uint32_t ntiles = c.ctl->num_tiles;
+    double racc = 0.0;
+    for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const TileHeader h = c.tt.runs[t].hdr;
+        if (sweep_tile_fits(c, h)) continue;
+        for (uint32_t tl = threadIdx.x; tl < h.pcount; tl += SWU_THREADS) {
+            const double r = sweep_particle_unstaged<Op>(c, op, t, h, tl);
+            if (Op::REDUCE == REDUCE_SUM) racc += r;
+            if (Op::REDUCE == REDUCE_MAX) racc = fmax(racc, r);
+        }
+    }
+    if (Op::REDUCE != REDUCE_NONE) {
+        __shared__ double wred[SWU_THREADS / 32];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double u = __shfl_xor_sync(0xffffffffu, racc, o);
+            racc = Op::REDUCE == REDUCE_SUM ? racc + u : fmax(racc, u);
+        }
+        if (lane_id() == 0) wred[threadIdx.x >> 5] = racc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double tsum = wred[0];
+            for (int w = 1; w < SWU_THREADS / 32; ++w) tsum = Op::REDUCE == REDUCE_SUM ? tsum + wred[w] : fmax(tsum, wred[w]);
+            c.partials_unstaged[blockIdx.x] = tsum;
+        }
     }
 }
 
@@ -545,8 +632,8 @@ __global__ void __launch_bounds__(SW_THREADS, YASPH_SWEEP_MIN_CTAS) k_sweep(Swee
         if (is_last) {
             __threadfence();
             double v = 0.0;
-            for (uint32_t b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
-                double pb = reinterpret_cast<volatile double*>(c.partials)[b];
+            for (uint32_t b = threadIdx.x; b < gridDim.x + c.n_partials_unstaged; b += blockDim.x) {
+                double pb = b < gridDim.x ? reinterpret_cast<volatile double*>(c.partials)[b] : c.partials_unstaged[b - gridDim.x];
                 v = Op::REDUCE == REDUCE_SUM ? v + pb : fmax(v, pb);
             }
 #pragma unroll

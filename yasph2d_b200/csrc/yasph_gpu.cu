@@ -24,6 +24,8 @@ using namespace yasph;
 
 static thread_local std::string g_create_error;
 
+constexpr uint32_t UNSTAGED_GRID_MAX = 1024;  // CTAs of k_sweep_unstaged (their partial reductions follow k_sweep's in yasph_ctx::partials)
+
 struct PassEvent {
     int pass;
     cudaEvent_t a, b;
@@ -138,6 +140,7 @@ struct yasph_ctx {
     int list_margin_pct = 12;
     bool spec_advect = false, spec_advect_done = false;  // advect + sort enqueued ahead of the density solver's read-back (dfsph_step)
     uint64_t list_rebuilds = 0;     // early list builds that had to be repeated
+    bool unstaged_tiles = false;    // the current structure has tiles beyond the (clipped) staging capacities: every tile kernel is followed / preceded by its unstaged twin
     bool lists_valid_once = false;  // cap_dyn / cap_stat / num_tiles describe an earlier structure of this particle set
     cudaEvent_t ev_tables = nullptr;
     uint64_t launches = 0;
@@ -574,9 +577,10 @@ extern "C" int32_t yasph_create(const yasph_config* cfg, yasph_ctx** out) {
     CUC((prepare_sweep<OpJacobiB<1, false>>(c)));
     CUC((prepare_sweep<OpJacobiB<1, true>>(c)));
     CUC((prepare_sweep<OpWcsphAccel>(c)));
-    CUC(allow_max_smem(c, k_build_lists));
+    CUC(allow_max_smem(c, k_build_lists<false>));
+    CUC(allow_max_smem(c, k_build_lists<true>));
     CUC(allow_max_smem(c, k_radix_pass));
-    CUC(dmalloc(&c->partials, (size_t)c->max_tiles + 1));
+    CUC(dmalloc(&c->partials, (size_t)c->max_tiles + 1 + UNSTAGED_GRID_MAX));  // per-CTA partials of k_sweep, then of k_sweep_unstaged
 #if defined(YASPH_SWEEP_TIMING) || defined(YASPH_LIST_TIMING)
     CUC(dmalloc(&c->sweep_dbg, 16));
     CUC(cudaMemset(c->sweep_dbg, 0, 128));
@@ -714,6 +718,8 @@ static SweepCommon sweep_common(const yasph_ctx* c) {
     s.mass = c->mass;
     s.rho0 = c->cfg.fluid_density;
     s.partials = c->partials;
+    s.partials_unstaged = c->partials + c->max_tiles + 1;
+    s.n_partials_unstaged = 0;
     s.ghost = c->slab.active ? c->slab.pflag : nullptr;
 #ifdef YASPH_SWEEP_TIMING
     s.dbg = c->sweep_dbg;
@@ -733,6 +739,13 @@ template <class Op>
 static int32_t launch_sweep(yasph_ctx* c, Op op) {
     if (c->num_tiles == 0) return YASPH_OK;
     SweepCommon sc = sweep_common(c);
+    if (c->unstaged_tiles) {
+        // tiles too large to stage go first, from global memory; their partial reductions are picked up by k_sweep's last CTA
+        const uint32_t gu = std::min<uint32_t>(std::min<uint32_t>(c->num_tiles, (uint32_t)c->num_sms * 4u), UNSTAGED_GRID_MAX);
+        k_sweep_unstaged<Op><<<gu, SWU_THREADS, 0, c->stream>>>(sc, op);
+        CHECK_LAUNCH();
+        sc.n_partials_unstaged = gu;
+    }
     // List words staged per particle: what the lists needed at the last read-back (+1: they change slowly), bounded by what
     // lets three CTAs share an SM.  Any value is correct -- words beyond it are read from global memory.
     const uint32_t hint = c->h_ctl->max_nk ? c->h_ctl->max_nk + 1u : 4u;
@@ -1301,7 +1314,7 @@ static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp
     if (positions_final && !c->slab.active) TRY(early_download(c, &c->early_pos_out, c->pos, (size_t)n * sizeof(float2), 0));
     bool lists_launched = false;
     uint32_t spec_dyn = 0, spec_stat = 0;
-    if (c->lists_valid_once && c->num_tiles && n && c->list_margin_pct > -100 && !downloads_armed) {  // margin <= -100: no early launch (A/B)
+    if (c->lists_valid_once && c->num_tiles && n && c->list_margin_pct > -100 && !downloads_armed && !c->unstaged_tiles) {  // margin <= -100: no early launch (A/B)
         // margin: 12.5 % + 16 slots; YASPH_DEBUG_LIST_MARGIN_PCT (read at yasph_create) overrides the percentage so that a test
         // can force the rebuild path with an undersized guess
         const int pct = c->list_margin_pct;
@@ -1312,7 +1325,7 @@ static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp
             CU(cudaEventRecord(c->ev_tables, c->stream));
             pass_begin(c, YASPH_PASS_LISTS);
             ListArgs la{tile_tables(c), c->pos, c->bpos, c->keys[0], c->grid, c->ctl, c->lists, c->counts, c->tile_nk, spec_dyn, spec_stat, c->apron_idx};
-            k_build_lists<<<persistent_grid(c, k_build_lists, bytes, NB_THREADS), NB_THREADS, bytes, c->stream>>>(la);
+            k_build_lists<false><<<persistent_grid(c, k_build_lists<false>, bytes, NB_THREADS), NB_THREADS, bytes, c->stream>>>(la);
             CHECK_LAUNCH();
             pass_end(c);
             lists_launched = true;
@@ -1333,15 +1346,22 @@ static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp
         sl.n_own = n - g0 - g1;
     }
     c->num_tiles = n ? c->h_ctl->num_tiles : 0u;
+    // Staging capacities of the tile kernels: the largest tile, unless that exceeds the configured limits or the shared memory of
+    // an SM -- then the capacities are clipped and the tiles beyond them are processed unstaged, from global memory (slow and
+    // correct: the reference accepts any particle density up to its 64-neighbour cap, neighborhood_search.rs:353-381).
     c->cap_dyn = (c->h_ctl->max_dyn_total + 15u) & ~15u;
     c->cap_pc = (c->h_ctl->max_pcount + 6u + 15u) & ~15u;  // + the alignment surplus of the bulk copies
     c->cap_stat = (c->h_ctl->max_stat_total + 15u) & ~15u;
-    if ((c->lim_dyn && c->h_ctl->max_dyn_total > c->lim_dyn) || (c->lim_stat && c->h_ctl->max_stat_total > c->lim_stat))
-        return fail(c, YASPH_ERR_CAPACITY, "a tile stages %u dynamic / %u static candidates, above tile_dynamic_capacity=%u / tile_static_capacity=%u",
-                    c->h_ctl->max_dyn_total, c->h_ctl->max_stat_total, c->lim_dyn, c->lim_stat);
-    if (worst_smem_bytes(c->cap_dyn, c->cap_stat, c->cap_pc) > c->smem_optin)
-        return fail(c, YASPH_ERR_CAPACITY, "a tile stages %u dynamic / %u static candidates: %zu bytes of shared memory per CTA, the device allows %zu",
-                    c->h_ctl->max_dyn_total, c->h_ctl->max_stat_total, worst_smem_bytes(c->cap_dyn, c->cap_stat, c->cap_pc), c->smem_optin);
+    if (c->lim_dyn && c->cap_dyn > c->lim_dyn) c->cap_dyn = std::max(16u, c->lim_dyn & ~15u);
+    if (c->lim_stat && c->cap_stat > c->lim_stat) c->cap_stat = std::max(16u, c->lim_stat & ~15u);
+    if (c->lim_dyn && c->cap_pc > c->cap_dyn) c->cap_pc = c->cap_dyn;  // a tile's own particles are part of its dynamic candidates
+    while (worst_smem_bytes(c->cap_dyn, c->cap_stat, c->cap_pc) > c->smem_optin) {
+        // shrink the largest consumer by a quarter (bytes per slot: dynamic 24, static 8, own particle ~20 + staged list words)
+        const size_t bd = (size_t)c->cap_dyn * 24, bs = (size_t)c->cap_stat * 8, bp = (size_t)c->cap_pc * 20;
+        uint32_t* victim = bd >= bs && bd >= bp ? &c->cap_dyn : (bs >= bp ? &c->cap_stat : &c->cap_pc);
+        if (*victim <= 16u) return fail(c, YASPH_ERR_CAPACITY, "the tile kernels do not fit the device's shared memory (%zu bytes) at any capacity", c->smem_optin);
+        *victim = std::max(16u, (*victim - *victim / 4u) & ~15u);
+    }
     if (lists_launched && (c->h_ctl->max_dyn_total > spec_dyn || c->h_ctl->max_stat_total > spec_stat)) {
         // the structure outgrew the margin: the early launch skipped the tiles that did not fit -- build the lists again
         CU(cudaMemsetAsync(&c->ctl->total_neighbors, 0, sizeof(unsigned long long) + 2 * sizeof(unsigned int), c->stream));
@@ -1355,9 +1375,19 @@ static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp
 #ifdef YASPH_LIST_TIMING
         la.dbg = c->sweep_dbg;
 #endif
-        k_build_lists<<<persistent_grid(c, k_build_lists, bytes, NB_THREADS), NB_THREADS, bytes, c->stream>>>(la);
+        k_build_lists<false><<<persistent_grid(c, k_build_lists<false>, bytes, NB_THREADS), NB_THREADS, bytes, c->stream>>>(la);
+        CHECK_LAUNCH();
+        spec_dyn = c->cap_dyn;
+        spec_stat = c->cap_stat;
+    }
+    if (c->num_tiles && (c->h_ctl->max_dyn_total > spec_dyn || c->h_ctl->max_stat_total > spec_stat)) {
+        // tiles too large to stage (clipped capacities): the same kernel on exactly those tiles, candidates from global memory
+        const size_t bytes = list_smem_bytes(spec_dyn, spec_stat);
+        ListArgs la{tile_tables(c), c->pos, c->bpos, c->keys[0], c->grid, c->ctl, c->lists, c->counts, c->tile_nk, spec_dyn, spec_stat, c->apron_idx, 1u};
+        k_build_lists<true><<<persistent_grid(c, k_build_lists<true>, bytes, NB_THREADS), NB_THREADS, bytes, c->stream>>>(la);
         CHECK_LAUNCH();
     }
+    c->unstaged_tiles = c->h_ctl->max_dyn_total > c->cap_dyn || c->h_ctl->max_stat_total > c->cap_stat || ((c->h_ctl->max_pcount + 6u + 15u) & ~15u) > c->cap_pc;
     pass_end(c);
     c->lists_valid = true;
     c->lists_valid_once = true;
