@@ -192,6 +192,11 @@ int32_t yasph_step(yasph_ctx* ctx, yasph_step_report* report);
 /* The reference-facing call with HOST buffers: upload pos/vel (N particles), one step, download pos/vel/densities
  * into the same arrays (new sorted order) -- what `solver.simulation_step(&mut world, &mut time)` does to the Vecs. */
 int32_t yasph_step_host(yasph_ctx* ctx, float* pos_xy, float* vel_xy, float* densities, uint32_t n, yasph_step_report* report);
+/* The same with options.  YASPH_HOST_INPUT_UNCHANGED: the caller has not written to pos_xy / vel_xy since the previous
+ * yasph_step_host* call on this context handed them back (the reference's application only READS the particle arrays between steps,
+ * main.rs:242-258), so the device still holds their content and the upload is skipped; the arrays are outputs only. */
+#define YASPH_HOST_INPUT_UNCHANGED 1u
+int32_t yasph_step_host_ex(yasph_ctx* ctx, float* pos_xy, float* vel_xy, float* densities, uint32_t n, uint32_t options, yasph_step_report* report);
 
 /* ---- TimeManager mirror ------------------------------------------------------------------------------------- */
 int32_t yasph_time_get_step_ns(const yasph_ctx* ctx, uint64_t* step_ns);

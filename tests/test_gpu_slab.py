@@ -10,6 +10,7 @@ import numpy as np
 import pytest
 
 import yasph2d_b200 as y
+from yasph2d_b200 import slab
 from slab_common import neighbor_sets_global, run_single, run_slabs_loopback, scene_arrays
 from util import assert_close
 
@@ -68,6 +69,35 @@ def test_dfsph_slabs_match_single_context(world):
         info = r["infos"][-1]
         assert info["n_ghost_left"] + info["n_ghost_right"] > 0 and info["halo_exchanges"] > 0 and info["allreduces"] > 0
     assert sum(r["infos"][-1]["n_own"] for r in results) == len(pos)
+
+
+def test_slabs_of_many_sort_tiles_match_single_context():
+    """A tank twin of 160 x 192 particles in two slabs of ~15 000 particles: the re-sort of a slab runs over several radix tiles
+    (6144 pairs each), and migrants + ghosts appended between key generation and the sort push the count across a tile boundary for
+    at least one of the tried cuts -- the status area of the sort must be zeroed for the count that is actually sorted."""
+    w = y.tank_scene(y.FluidParticleWorld(2.0, 10000.0, 100.0), 160, 192)
+    pos, vel, boundary = w.particles.positions.copy(), w.particles.velocities.copy(), w.particles.boundary_particles.copy()
+    steps = 12
+    reps1, snaps1, _ = run_single(pos, vel, boundary, steps, range(steps))
+    cols = slab.cell_columns(pos[:, 0], 0.02)
+    mid = int(np.median(cols))
+    tiles = lambda n: (n + 6143) // 6144  # noqa: E731  (RS_TILE of sort.cuh)
+    # cuts at which the first update already crosses: rank 0 sorts its own particles plus the ghost column `cut`
+    cuts = [c for c in range(mid - 25, mid + 25) if tiles(int((cols < c).sum()) + int((cols == c).sum())) > tiles(int((cols < c).sum()))][:2]
+    assert cuts, "no cut crosses a radix tile boundary"
+    crossed = 0
+    for cut in cuts:
+        results, merged = run_slabs_loopback(2, pos, vel, boundary, steps, range(steps), ranges=[(0, cut), (cut, 65536)])
+        first_mig = first_migration(results, steps)
+        compare_runs(snaps1, merged, reps1, results, steps, first_mig)
+        for r in results:
+            n_prev = int((slab.owned_mask(cols, *r["ranges"][results.index(r)])).sum())
+            for info in r["infos"]:
+                n_sort = n_prev + info["migrated_in"] + info["n_ghost_left"] + info["n_ghost_right"]
+                crossed += (n_sort + 6143) // 6144 > (n_prev + 6143) // 6144
+                n_prev = info["n_local"]
+        assert sum(r["infos"][-1]["n_own"] for r in results) == len(pos)
+    assert crossed > 0, "no re-sort crossed a radix tile boundary: choose other cuts"
 
 
 def test_neighbor_sets_identical_as_global_ids():

@@ -283,6 +283,27 @@ def test_dfsph_step_host_equals_resident():
     assert np.array_equal(dens, w2.particles.densities)
 
 
+def test_step_host_input_unchanged_skips_the_upload():
+    """yasph_step_host_ex(YASPH_HOST_INPUT_UNCHANGED): the arrays are outputs only; same run as with the upload.  Poisoning the
+    host arrays before such a call shows that they are not read; a first call with the option (nothing on the device) is an error."""
+    w, _ = make_worlds()
+    a, b = gpu_ctx(w), gpu_ctx(w)
+    pa, va, da = w.particles.positions.copy(), w.particles.velocities.copy(), np.zeros(len(w.particles.positions), np.float32)
+    pb, vb, db = pa.copy(), va.copy(), da.copy()
+    for s in range(20):
+        ra = a.step_host(pa, va, da)
+        if s:
+            pb[:], vb[:] = np.nan, np.nan
+        rb = b.step_host(pb, vb, db, input_unchanged=s > 0)
+        assert ra.dt_ns == rb.dt_ns and np.array_equal(pa, pb) and np.array_equal(va, vb) and np.array_equal(da, db), s
+    cfg = capi.default_config(2.0, 10000.0, 100.0, capi.SOLVER_DFSPH)
+    cfg.max_particles, cfg.max_boundary = len(pa), 16
+    fresh = y.GpuContext(cfg)
+    with pytest.raises(capi.YasphError) as e:
+        fresh.step_host(pa, va, da, input_unchanged=True)
+    assert e.value.status == 4  # YASPH_ERR_STATE
+
+
 @pytest.mark.parametrize("solver,tight", [(capi.SOLVER_DFSPH, False), (capi.SOLVER_DFSPH, True), (capi.SOLVER_WCSPH, False)])
 def test_step_host_pinned_arrays_overlapped_download(solver, tight):
     """Pinned host arrays: positions and densities leave on the copy stream while the step still computes and the velocities

@@ -2136,15 +2136,23 @@ static bool is_pinned_host(const void* p) {
 }
 
 extern "C" int32_t yasph_step_host(yasph_ctx* c, float* pos_xy, float* vel_xy, float* densities, uint32_t n, yasph_step_report* report) {
+    return yasph_step_host_ex(c, pos_xy, vel_xy, densities, n, 0u, report);
+}
+extern "C" int32_t yasph_step_host_ex(yasph_ctx* c, float* pos_xy, float* vel_xy, float* densities, uint32_t n, uint32_t options, yasph_step_report* report) {
     if (!c || !pos_xy || !vel_xy) return YASPH_ERR_INVALID_ARGUMENT;
     if (n == 0 || n > c->cap_n) return fail(c, YASPH_ERR_CAPACITY, "yasph_step_host: n=%u out of range (max_particles=%u)", n, c->cap_n);
     if (c->slab.active) return fail(c, YASPH_ERR_STATE, "yasph_step_host: the particle count of a slab changes with migration, use yasph_step_host_slab");
     CU(cudaSetDevice(c->device));
+    const bool unchanged = (options & YASPH_HOST_INPUT_UNCHANGED) != 0;
+    if (unchanged && (!c->have_particles || n != c->n))
+        return fail(c, YASPH_ERR_STATE, "yasph_step_host_ex: YASPH_HOST_INPUT_UNCHANGED, but the device holds %u particles and the call passes %u", c->have_particles ? c->n : 0u, n);
     if (n != c->n) TRY(reset_particle_set(c, n));
     const bool prof = (c->cfg.flags & YASPH_FLAG_PROFILE_PASSES) != 0;
     if (prof) CU(cudaEventRecord(c->ev_host[0], c->stream));
-    CU(cudaMemcpyAsync(c->pos, pos_xy, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(c->vel, vel_xy, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+    if (!unchanged) {
+        CU(cudaMemcpyAsync(c->pos, pos_xy, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->vel, vel_xy, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+    }
     if (prof) CU(cudaEventRecord(c->ev_host[1], c->stream));
     // Pinned (or registered) host arrays take their results as soon as they are final, on the copy stream, overlapped with the
     // remaining passes; pageable arrays would block the launching thread in mid-step, so they are copied at the end as before.

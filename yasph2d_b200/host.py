@@ -144,11 +144,13 @@ class GpuContext:
         self._ck(capi.lib().yasph_step(self.h, C.byref(rep)))
         return rep
 
-    def step_host(self, pos, vel, dens=None):
-        """The reference-facing call: HOST arrays in, one simulation_step, HOST arrays out (in place)."""
+    def step_host(self, pos, vel, dens=None, input_unchanged=False):
+        """The reference-facing call: HOST arrays in, one simulation_step, HOST arrays out (in place).  input_unchanged: the arrays
+        still hold what the previous call handed back (the application only read them), so their upload is skipped."""
         assert pos.dtype == np.float32 and vel.dtype == np.float32 and pos.flags.c_contiguous and vel.flags.c_contiguous
         rep = capi.StepReport()
-        self._ck(capi.lib().yasph_step_host(self.h, _f32p(pos), _f32p(vel), _f32p(dens), len(pos), C.byref(rep)))
+        self._ck(capi.lib().yasph_step_host_ex(self.h, _f32p(pos), _f32p(vel), _f32p(dens), len(pos), capi.HOST_INPUT_UNCHANGED if input_unchanged else 0,
+                                               C.byref(rep)))
         return rep
 
     def time_step_ns(self):
