@@ -109,7 +109,10 @@ typedef struct yasph_config {
     uint32_t speculative_iterations;     /* Jacobi iterations launched between two convergence read-backs (default 2) */
     uint32_t flags;                      /* YASPH_FLAG_* */
     uint32_t max_halo;                   /* slab mode: capacity (particles per side) of the ghost / migrant buffers; default max(65536, max_particles / 8) */
-    uint32_t reserved;
+    uint32_t ghost_columns;              /* slab mode: width W (cell columns) of the ghost layer a rank keeps of each neighbour's slab; 0 = 1.  With W > 1 a rank
+                                          * recomputes its ghosts' per-pass values itself (same arithmetic, same order: same bits) and a pass needs a halo
+                                          * exchange only once the values it gathers are stale in the innermost ghost column -- none at all in a step of
+                                          * 2 + 2 Jacobi iterations with W = 8.  Must not exceed the width of the narrowest slab; the same on all ranks. */
 } yasph_config;
 
 #define YASPH_FLAG_PERMUTE_WARMSTART 1u /* permute kappa/stiffness with the particles; default off = reference behaviour (quirk Q1: dfsph.rs:512 passes only v*) */

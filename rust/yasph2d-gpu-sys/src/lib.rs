@@ -83,7 +83,7 @@ pub struct yasph_config {
     pub speculative_iterations: u32,
     pub flags: u32,
     pub max_halo: u32,
-    pub reserved: u32,
+    pub ghost_columns: u32,
 }
 
 #[repr(C)]

@@ -82,7 +82,7 @@ def neighbor_sets_global(ctx, id_map=None):
 def run_slabs_loopback(world, pos, vel, boundary, steps, checkpoints, solver=capi.SOLVER_DFSPH, neighbor_step=None, ranges=None, **kw):
     """`world` slabs of one scene on cuda:0, one thread per rank, loopback transport."""
     fabric = slab.LoopbackFabric(world)
-    cfg = base_config(len(pos), len(boundary), solver, **kw)
+    cfg = base_config(2 * len(pos), len(boundary), solver, **kw)  # room for the ghost layers
     results = [None] * world
     errors = []
 

@@ -33,7 +33,7 @@ def main():
     steps = int(os.environ.get("SLAB_STEPS", "120"))
     pos, vel, boundary = scene_arrays("dam")
     uid = slab.broadcast_unique_id(dist)
-    cfg = base_config(len(pos), len(boundary))
+    cfg = base_config(2 * len(pos), len(boundary))  # room for the ghost layers
     cfg.device = local
     if os.environ.get("SLAB_TRANSPORT", "peer") == "nccl":
         cfg.flags |= y.capi.FLAG_NO_PEER_TRANSPORT

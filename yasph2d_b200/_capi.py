@@ -51,7 +51,7 @@ class Config(C.Structure):
         ("adaptive_timestep", C.c_int32), ("timestep_fixed_ns", C.c_uint64), ("timestep_min_ns", C.c_uint64),
         ("timestep_max_ns", C.c_uint64), ("timestep_target_frame_ns", C.c_uint64), ("cfl_factor", C.c_float),
         ("max_tiles", C.c_uint32), ("tile_dynamic_capacity", C.c_uint32), ("tile_static_capacity", C.c_uint32),
-        ("speculative_iterations", C.c_uint32), ("flags", C.c_uint32), ("max_halo", C.c_uint32), ("reserved", C.c_uint32),
+        ("speculative_iterations", C.c_uint32), ("flags", C.c_uint32), ("max_halo", C.c_uint32), ("ghost_columns", C.c_uint32),
     ]
 
 

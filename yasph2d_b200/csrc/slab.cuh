@@ -22,18 +22,18 @@ struct FlagSelIn {
         return (f == va ? 1ull : 0ull) | ((f == vb ? 1ull : 0ull) << 32);
     }
 };
-// by cell column of the key among the particles that stay (pflag == 0): A: column == ca, B: column == cb
-// (0xFFFFFFFF disables a list: rank 0 has no left neighbour, the last rank no right one)
+// by cell column of the key among the particles that stay (pflag == 0): A: column in [a_lo, a_hi), B: column in [b_lo, b_hi)
+// (an empty range disables a list: rank 0 has no left neighbour, the last rank no right one)
 struct ColumnSelIn {
     const uint32_t* keys;
     const uint8_t* pflag;  // may be null: every particle counts
-    uint32_t ca, cb;
+    uint32_t a_lo, a_hi, b_lo, b_hi;
     __device__ __forceinline__ unsigned long long operator()(uint32_t i) const {
         if (pflag && pflag[i]) return 0ull;
         const uint32_t k = keys[i];
         if (k == YASPH_KEY_DROPPED) return 0ull;
         const uint32_t col = compact_1by1(k);
-        return (col == ca ? 1ull : 0ull) | ((col == cb ? 1ull : 0ull) << 32);
+        return ((col >= a_lo && col < a_hi) ? 1ull : 0ull) | (((col >= b_lo && col < b_hi) ? 1ull : 0ull) << 32);
     }
 };
 // ghosts of the sorted structure: A: column < col_lo (from the left rank), B: column >= col_hi (from the right rank)

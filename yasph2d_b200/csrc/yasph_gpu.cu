@@ -24,7 +24,8 @@ using namespace yasph;
 
 static thread_local std::string g_create_error;
 
-constexpr uint32_t UNSTAGED_GRID_MAX = 1024;  // CTAs of k_sweep_unstaged (their partial reductions follow k_sweep's in yasph_ctx::partials)
+constexpr uint32_t UNSTAGED_GRID_MAX = 1024;
+enum SlabField { SF_POS = 0, SF_VEL, SF_VSTAR, SF_DENS, SF_ALPHA, SF_KFAC, SF_KAPPA, SF_STIFF, SF_ACCEL, SLAB_NUM_FIELDS };  // CTAs of k_sweep_unstaged (their partial reductions follow k_sweep's in yasph_ctx::partials)
 
 struct PassEvent {
     int pass;
@@ -119,6 +120,13 @@ struct yasph_ctx {
         unsigned char* rbuf[2] = {nullptr, nullptr};  // receive buffers
         uint32_t *d_cnt = nullptr, *h_cnt = nullptr;  // [4]: send left/right, recv left/right
         uint32_t max_halo = 0;
+        uint32_t ghost_cols = 1;         // width W of the ghost layer in cell columns (yasph_config.ghost_columns)
+        // Validity of the ghosts' copy of every per-particle field: the number of ghost columns, counted from the slab's edge, whose
+        // values are the bits their owner holds.  A refresh (ghost records, halo exchange) sets W; a pass that gathers a field from
+        // the neighbours produces results that are right one column less far out than its inputs (the ghosts recompute what their
+        // owners compute: same arithmetic, same neighbour order).  A pass runs a halo exchange for an input only when that input is
+        // stale already in the first ghost column.
+        int valid[SLAB_NUM_FIELDS] = {};
         uint32_t n_own = 0, n_ghost[2] = {0, 0}, n_send[2] = {0, 0};
         uint32_t mig_out[2] = {0, 0}, mig_in = 0;
         bool own_idx_valid = false;
@@ -1028,6 +1036,30 @@ static int32_t halo_exchange(yasph_ctx* c, T* field) {
     return YASPH_OK;
 }
 
+// Slab mode bookkeeping around a pass (see yasph_ctx::Slab::valid).  `gathered`: fields the pass reads from NEIGHBOURS (they must be valid in
+// the first ghost column: refreshed by a halo exchange if not); `own`: fields it reads of the particle itself; returns the validity of
+// what the pass writes.  Elementwise passes have no gathered inputs.
+template <typename T>
+static int32_t slab_refresh(yasph_ctx* c, SlabField f, T* array) {
+    if (!c->slab.active || c->slab.world < 2) return YASPH_OK;
+    if (c->slab.valid[f] >= 1) return YASPH_OK;
+    TRY(halo_exchange(c, array));
+    c->slab.valid[f] = (int)c->slab.ghost_cols;
+    return YASPH_OK;
+}
+static int slab_out_valid(const yasph_ctx* c, std::initializer_list<SlabField> gathered, std::initializer_list<SlabField> own) {
+    int v = std::min((int)c->slab.ghost_cols, c->slab.valid[SF_POS]);  // positions are gathered by every neighbour pass (and bound the lists themselves)
+    for (SlabField f : gathered) v = std::min(v, c->slab.valid[f]);
+    v -= 1;
+    for (SlabField f : own) v = std::min(v, c->slab.valid[f]);
+    return std::max(v, 0);
+}
+static int slab_own_valid(const yasph_ctx* c, std::initializer_list<SlabField> own) {
+    int v = (int)c->slab.ghost_cols;
+    for (SlabField f : own) v = std::min(v, c->slab.valid[f]);
+    return v;
+}
+
 // in-place all-reduce of one scalar of the control block over the ranks
 static int32_t allreduce_scalar(yasph_ctx* c, void* dev_ptr, ncclDataType_t type, ncclRedOp_t op) {
     if (!c->slab.active || c->slab.world < 2) return YASPH_OK;
@@ -1150,8 +1182,11 @@ static int32_t slab_exchange_particles(yasph_ctx* c, const GatherPlan& gp, uint3
     }
     sl.mig_in = in[0] + in[1];
     // (2) ghosts: the owned particles of the first / last owned column, in pre-sort order, to the left / right rank
-    const uint32_t ca = has_left(c) ? sl.col_lo : 0xFFFFFFFFu, cb = has_right(c) ? sl.col_hi - 1u : 0xFFFFFFFFu;
-    TRY(select_pair(c, ColumnSelIn{c->keys[0], sl.pflag, ca, cb}, n1, sl.sel[0], sl.sel[1], nullptr, sl.max_halo, &c->ctl->slab_ghost_send));
+    // the first / last W owned columns (W = ghost_cols) go to the left / right rank; an empty range disables a side
+    const uint32_t W = sl.ghost_cols;
+    const uint32_t a_lo = sl.col_lo, a_hi = has_left(c) ? std::min(sl.col_lo + W, sl.col_hi) : sl.col_lo;
+    const uint32_t b_hi = sl.col_hi, b_lo = has_right(c) ? (sl.col_hi - sl.col_lo > W ? sl.col_hi - W : sl.col_lo) : sl.col_hi;
+    TRY(select_pair(c, ColumnSelIn{c->keys[0], sl.pflag, a_lo, a_hi, b_lo, b_hi}, n1, sl.sel[0], sl.sel[1], nullptr, sl.max_halo, &c->ctl->slab_ghost_send));
     uint32_t gout[2], gin[2];
     if (sl.peer) {
         TRY(peer_exchange_records(c, ra, &c->ctl->slab_ghost_send, n1, gout, gin));
@@ -1257,6 +1292,14 @@ static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp
     if (c->slab.active) {
         pass_end(c);
         pass_begin(c, YASPH_PASS_MIGRATE);
+        // the ghost records carry exactly the permuted arrays: those are fresh on all W ghost columns afterwards, everything else is stale
+        for (int f = 0; f < SLAB_NUM_FIELDS; ++f) c->slab.valid[f] = 0;
+        auto mark = [&](const void* arr) {
+            const SlabField f = arr == c->pos ? SF_POS : arr == c->vel ? SF_VEL : arr == c->vstar ? SF_VSTAR : arr == c->kappa ? SF_KAPPA : arr == c->stiff ? SF_STIFF : SLAB_NUM_FIELDS;
+            if (f != SLAB_NUM_FIELDS) c->slab.valid[f] = (int)c->slab.ghost_cols;
+        };
+        for (int q = 0; q < gp.n2; ++q) mark(*gp.a2[q]);
+        for (int q = 0; q < gp.n1; ++q) mark(*gp.a1[q]);
         TRY(slab_exchange_particles(c, gp, n, &n_sort, &n));
         pass_end(c);
         pass_begin(c, YASPH_PASS_SORT);
@@ -1297,8 +1340,10 @@ static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp
         // per-pass halo lists of the new structure, in sorted order: what this rank sends (its first / last owned column) and
         // where its ghosts sit; the ghost flags; counts come back with the control block below
         auto& sl = c->slab;
-        const uint32_t ca = has_left(c) ? sl.col_lo : 0xFFFFFFFFu, cb = has_right(c) ? sl.col_hi - 1u : 0xFFFFFFFFu;
-        TRY(select_pair(c, ColumnSelIn{c->keys[0], nullptr, ca, cb}, n, sl.send_idx[0], sl.send_idx[1], nullptr, sl.max_halo, &c->ctl->slab_send));
+        const uint32_t W = sl.ghost_cols;
+        const uint32_t a_lo = sl.col_lo, a_hi = has_left(c) ? std::min(sl.col_lo + W, sl.col_hi) : sl.col_lo;
+        const uint32_t b_hi = sl.col_hi, b_lo = has_right(c) ? (sl.col_hi - sl.col_lo > W ? sl.col_hi - W : sl.col_lo) : sl.col_hi;
+        TRY(select_pair(c, ColumnSelIn{c->keys[0], nullptr, a_lo, a_hi, b_lo, b_hi}, n, sl.send_idx[0], sl.send_idx[1], nullptr, sl.max_halo, &c->ctl->slab_send));
         TRY(select_pair(c, GhostSelIn{c->keys[0], sl.col_lo, sl.col_hi}, n, sl.ghost_idx[0], sl.ghost_idx[1], sl.pflag, sl.max_halo, &c->ctl->slab_ghost));
     }
     pass_end(c);
@@ -1429,6 +1474,7 @@ static int32_t reset_particle_set(yasph_ctx* c, uint32_t n) {
         sl.n_own = n;
         sl.n_ghost[0] = sl.n_ghost[1] = sl.n_send[0] = sl.n_send[1] = 0;
         sl.own_idx_valid = false;
+        for (int f = 0; f < SLAB_NUM_FIELDS; ++f) sl.valid[f] = 0;
         c->dfsph_ready = false;  // the ghosts are gone: the structure must be rebuilt
         if (n) CU(cudaMemsetAsync(sl.pflag, 0, n, c->stream));
     }
@@ -1764,6 +1810,7 @@ template <int SOLVER>
 static int32_t jacobi_solve(yasph_ctx* c, bool first_a_done = false) {
     const float rho0 = c->cfg.fluid_density;
     float* warm_arr = SOLVER == 0 ? c->kappa : c->stiff;
+    const SlabField warm_field = SOLVER == 0 ? SF_KAPPA : SF_STIFF;
     pass_begin(c, SOLVER == 0 ? YASPH_PASS_DENSITY_WARM : YASPH_PASS_DIVERGENCE_WARM);
     // The warm start runs iff the previous solve took more than one iteration (dfsph.rs:199,354).  The host mirror of the
     // control block still holds that count (it is refreshed at every read-back and this solve has not started), so the
@@ -1776,9 +1823,11 @@ static int32_t jacobi_solve(yasph_ctx* c, bool first_a_done = false) {
         w.warm = warm_arr;
         w.clamp_min = -0.5f * rho0 * rho0;
         w.iter_index = 0;
-        TRY(launch_sweep(c, w));
         pass_end(c);
-        TRY(halo_exchange(c, c->vstar));  // slab mode: the warm start moved the owners' v*
+        TRY(slab_refresh(c, warm_field, warm_arr));  // slab mode: the ghosts' warm-start values, if stale
+        pass_begin(c, SOLVER == 0 ? YASPH_PASS_DENSITY_WARM : YASPH_PASS_DIVERGENCE_WARM);
+        TRY(launch_sweep(c, w));
+        c->slab.valid[SF_VSTAR] = slab_out_valid(c, {warm_field}, {SF_VSTAR});
     }
     pass_end(c);
     SolverParams sp;
@@ -1796,6 +1845,12 @@ static int32_t jacobi_solve(yasph_ctx* c, bool first_a_done = false) {
         pass_begin(c, solve_pass);
         for (uint32_t q = 0; q < chunk; ++q, ++it) {
             if (!(first_a_done && it == 0)) {
+                if (slab) {
+                    pass_end(c);
+                    TRY(slab_refresh(c, SF_VSTAR, c->vstar));  // v* of the ghosts, if stale in the first ghost column
+                    pass_begin(c, solve_pass);
+                }
+                c->slab.valid[SF_KFAC] = slab_out_valid(c, {SF_VSTAR}, {SF_DENS, SF_ALPHA});
                 OpJacobiA<SOLVER> a;
                 a.vstar = c->vstar;
                 a.dens = c->dens;
@@ -1820,10 +1875,12 @@ static int32_t jacobi_solve(yasph_ctx* c, bool first_a_done = false) {
                 }
                 if (slab) {
                     pass_end(c);
-                    TRY(halo_exchange(c, c->err_buf));  // k_j of the ghosts for pass B
+                    TRY(slab_refresh(c, SF_KFAC, c->err_buf));  // k_j of the ghosts for pass B, if stale
                     pass_begin(c, solve_pass);
                 }
             }
+            c->slab.valid[SF_VSTAR] = slab_out_valid(c, {SF_KFAC}, {SF_VSTAR});
+            c->slab.valid[warm_field] = it == 0 ? c->slab.valid[SF_KFAC] : slab_own_valid(c, {warm_field, SF_KFAC});
             OpJacobiB<SOLVER, false> b;
             b.vstar = c->vstar;
             b.kfac = c->err_buf;
@@ -1831,11 +1888,6 @@ static int32_t jacobi_solve(yasph_ctx* c, bool first_a_done = false) {
             b.clamp_min = 0.f;
             b.iter_index = it;
             TRY(launch_sweep(c, b));
-            if (slab) {
-                pass_end(c);
-                TRY(halo_exchange(c, c->vstar));  // v* of the ghosts for the next pass A / the advection
-                pass_begin(c, solve_pass);
-            }
         }
         pass_end(c);  // the pass times are device time of the launches; the read-back below is host latency
         // v* becomes the velocity (dfsph.rs:524) unless the loop goes on: worth a download when this chunk reaches the previous
@@ -1883,6 +1935,7 @@ static int32_t dfsph_initialize(yasph_ctx* c) {
     gp.a2[1] = &c->vel;
     gp.alt2[1] = &c->vel_alt;
     TRY(neighborhood_update(c, false, gp));
+    if (c->slab.active) c->slab.valid[SF_KAPPA] = c->slab.valid[SF_STIFF] = (int)c->slab.ghost_cols;  // all zero, on every rank
     pass_begin(c, YASPH_PASS_DENSITY_ALPHA);
     OpDensityAlpha<0, true> da;
     da.dens = c->dens;
@@ -1891,7 +1944,7 @@ static int32_t dfsph_initialize(yasph_ctx* c) {
     da.stiffness = 0.f;
     TRY(launch_sweep(c, da));
     pass_end(c);
-    TRY(halo_exchange(c, c->dens));  // rho_j of the ghosts for the viscosity pass
+    c->slab.valid[SF_DENS] = c->slab.valid[SF_ALPHA] = slab_out_valid(c, {SF_POS}, {});
     c->dfsph_ready = true;
     return YASPH_OK;
 }
@@ -1901,7 +1954,10 @@ static int32_t dfsph_step(yasph_ctx* c) {
     const uint32_t n = c->n;  // local particles (slab mode: owned + ghosts); the neighbourhood update below changes it
     k_begin_step<<<1, 32, 0, c->stream>>>(c->ctl);
     CHECK_LAUNCH();
-    // non-pressure forces + CFL maximum (dfsph.rs:436-477)
+    // non-pressure forces + CFL maximum (dfsph.rs:436-477); slab mode: v_j and rho_j of the ghosts, if stale
+    TRY(slab_refresh(c, SF_VEL, c->vel));
+    TRY(slab_refresh(c, SF_DENS, c->dens));
+    c->slab.valid[SF_ACCEL] = slab_out_valid(c, {SF_POS, SF_VEL, SF_DENS}, {});
     pass_begin(c, YASPH_PASS_VISCOSITY);
     {
         OpViscosity v;
@@ -1921,7 +1977,7 @@ static int32_t dfsph_step(yasph_ctx* c) {
     k_timestep_apply<0><<<blocks_for(n, 256), 256, 0, c->stream>>>(c->ctl, c->tp, c->radius * 2.0f, c->vel, c->accel, c->vstar, n);
     CHECK_LAUNCH();
     pass_end(c);
-    TRY(halo_exchange(c, c->vstar));  // ghosts: v* of their owners (their own accelerations are incomplete)
+    c->slab.valid[SF_VSTAR] = slab_own_valid(c, {SF_VEL, SF_ACCEL});  // the ghosts predict with their own (recomputed) accelerations
     c->spec_advect = !c->slab.active && c->early_pos_out == nullptr && c->early_vel_out == nullptr;  // device-resident stepping on one GPU
     c->spec_advect_done = false;
     TRY(jacobi_solve<0>(c));  // dfsph.rs:496
@@ -1929,6 +1985,7 @@ static int32_t dfsph_step(yasph_ctx* c) {
     // advect (dfsph.rs:502-509) fused with the key generation of the re-sort (dfsph.rs:512) -- unless it already ran ahead of the read-back
     const bool sorted_ready = c->spec_advect_done;
     if (!sorted_ready) TRY(enqueue_advect_sort(c, false));
+    c->slab.valid[SF_POS] = slab_own_valid(c, {SF_POS, SF_VSTAR});
     {
         // the reference also permutes the old velocities, which are discarded at the final swap (quirk Q7): skipped.
         GatherPlan gp;
@@ -1962,6 +2019,7 @@ static int32_t dfsph_step(yasph_ctx* c) {
         f.sp.max_error = c->cfg.dfsph_max_divergence_error;
         f.sp.max_iters = c->cfg.dfsph_max_divergence_iters;
         TRY(launch_sweep(c, f));
+        c->slab.valid[SF_KFAC] = slab_out_valid(c, {SF_POS, SF_VSTAR}, {});
     } else {
         OpDensityAlpha<0, true> da;  // dfsph.rs:516-518
         da.dens = c->dens;
@@ -1972,9 +2030,10 @@ static int32_t dfsph_step(yasph_ctx* c) {
     }
     pass_end(c);
     TRY(early_download(c, &c->early_dens_out, c->dens, (size_t)c->n * sizeof(float), 1));  // densities are final (dfsph.rs:516)
-    TRY(halo_exchange(c, c->dens));  // rho_j of the ghosts for the next step's viscosity pass
+    c->slab.valid[SF_DENS] = c->slab.valid[SF_ALPHA] = slab_out_valid(c, {SF_POS}, {});
     TRY(jacobi_solve<1>(c, fuse_div_a0));  // dfsph.rs:521
     std::swap(c->vel, c->vstar);    // dfsph.rs:524
+    std::swap(c->slab.valid[SF_VEL], c->slab.valid[SF_VSTAR]);
     return YASPH_OK;
 }
 
@@ -1983,6 +2042,8 @@ static int32_t wcsph_step(yasph_ctx* c) {
     k_begin_step<<<1, 32, 0, c->stream>>>(c->ctl);
     CHECK_LAUNCH();
     // leap frog 1 (wscsph.rs:141-150) fused with key generation
+    c->slab.valid[SF_VEL] = slab_own_valid(c, {SF_VEL, SF_ACCEL});
+    c->slab.valid[SF_POS] = slab_own_valid(c, {SF_POS, SF_VEL});
     pass_begin(c, YASPH_PASS_ADVECT_KEYGEN);
     TRY(radix_prepare(c, n));
     k_kickdrift_keygen<<<keygen_grid(n, c->num_sms), KG_THREADS, 0, c->stream>>>(c->pos, c->vel, c->accel, n, c->ctl, c->grid, c->keys[0], c->idx[0],
@@ -2001,7 +2062,10 @@ static int32_t wcsph_step(yasph_ctx* c) {
     TRY((launch_density<1, true>(c)));  // Poly6, wscsph.rs:154; + Tait pressure per particle (wscsph.rs:91-92)
     pass_end(c);
     TRY(early_download(c, &c->early_dens_out, c->dens, (size_t)n * sizeof(float), 1));  // densities are final (wscsph.rs:154)
-    TRY(halo_exchange(c, c->vstar));  // (rho, p) of the ghosts
+    c->slab.valid[SF_DENS] = c->slab.valid[SF_VSTAR] = slab_out_valid(c, {SF_POS}, {});  // (rho, p) lives in the v* buffer
+    TRY(slab_refresh(c, SF_VSTAR, c->vstar));  // (rho, p) and v of the ghosts, if stale in the first ghost column
+    TRY(slab_refresh(c, SF_VEL, c->vel));
+    c->slab.valid[SF_ACCEL] = slab_out_valid(c, {SF_POS, SF_VEL, SF_VSTAR}, {});
     pass_begin(c, YASPH_PASS_WCSPH_ACCEL);
     {
         OpWcsphAccel a;  // wscsph.rs:155
@@ -2021,6 +2085,7 @@ static int32_t wcsph_step(yasph_ctx* c) {
     k_timestep_apply<1><<<blocks_for(n, 256), 256, 0, c->stream>>>(c->ctl, c->tp, c->radius * 2.0f, c->vel, c->accel, c->vel, n);
     CHECK_LAUNCH();
     pass_end(c);
+    c->slab.valid[SF_VEL] = slab_own_valid(c, {SF_VEL, SF_ACCEL});
     return YASPH_OK;
 }
 
@@ -2369,6 +2434,9 @@ extern "C" int32_t yasph_slab_set(yasph_ctx* c, uint32_t col_lo, uint32_t col_hi
     sl.n_global = n_global;
     sl.id_base = id_base;
     sl.max_halo = c->cfg.max_halo;
+    sl.ghost_cols = c->cfg.ghost_columns ? c->cfg.ghost_columns : 1u;
+    if (sl.world > 1 && sl.rank > 0 && sl.rank + 1 < sl.world && col_hi - col_lo < sl.ghost_cols)
+        return fail(c, YASPH_ERR_INVALID_ARGUMENT, "yasph_slab_set: slab [%u, %u) is narrower than the ghost layer (ghost_columns = %u)", col_lo, col_hi, sl.ghost_cols);
     if (!sl.pflag) {
         CU(dmalloc(&sl.pflag, (size_t)c->cap_n));
         CU(cudaMemsetAsync(sl.pflag, 0, c->cap_n, c->stream));
@@ -2440,6 +2508,7 @@ extern "C" int32_t yasph_step_host_slab(yasph_ctx* c, float* pos_xy, float* vel_
             CHECK_LAUNCH();
             k_own_scatter<float2><<<blocks_for(n_in, 256), 256, 0, c->stream>>>(c->vel, sl.own_idx, n_in, c->vel_alt);
             CHECK_LAUNCH();
+            sl.valid[SF_VEL] = 0;  // the caller may have changed the velocities it owns: the neighbours' ghosts of them are refreshed
         }
     } else {
         TRY(reset_particle_set(c, n_in));
