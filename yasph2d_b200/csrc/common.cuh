@@ -275,6 +275,8 @@ struct Control {
     unsigned int total_is_current;          // 1: the host supplied the total incl. the running step (k_begin_step must not add it again)
     unsigned int pad_time;
     unsigned int err_comm;               // peer-memory transport: bit 0 a halo message, bit 1 an all-reduce contribution did not arrive in time
+    unsigned int slab_sel4[4];           // slab mode: counts of the four-way selection of an update (migrants left | right, ghost layer left | right)
+    unsigned int slab_cnt[10];           // SlabCounts (slab.cuh) of the running particle exchange
 };
 
 // slab decomposition parameters handed to the key-generating kernels (active == 0: single GPU)

@@ -151,9 +151,16 @@ struct GatherArgs {
     const float* in1[3];
     float* out1[3];
     int n2, n1;
+    // slab mode (null otherwise): ghost flags of the NEW structure from the sorted keys (a particle whose cell column lies outside
+    // [col_lo, col_hi) is a ghost copy of a particle the left / right rank owns) and their counts (left | right << 32)
+    const uint32_t* keys;
+    uint8_t* ghost;
+    unsigned long long* ghost_count;
+    uint32_t col_lo, col_hi;
 };
 __global__ void k_gather(const uint32_t* __restrict__ perm, uint32_t n, GatherArgs a) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    bool gl = false, gr = false;
     if (k < n) {
         uint32_t s = perm[k];
 #pragma unroll
@@ -162,6 +169,16 @@ __global__ void k_gather(const uint32_t* __restrict__ perm, uint32_t n, GatherAr
 #pragma unroll
         for (int q = 0; q < 3; ++q)
             if (q < a.n1) a.out1[q][k] = a.in1[q][s];
+        if (a.ghost) {
+            const uint32_t col = compact_1by1(a.keys[k]);
+            gl = col < a.col_lo;
+            gr = col >= a.col_hi;
+            a.ghost[k] = (gl || gr) ? 1 : 0;
+        }
+    }
+    if (a.ghost) {
+        const unsigned ml = __ballot_sync(0xffffffffu, gl), mr = __ballot_sync(0xffffffffu, gr);
+        if ((ml | mr) && lane_id() == 0) atomicAdd(a.ghost_count, (unsigned long long)__popc(ml) | ((unsigned long long)__popc(mr) << 32));
     }
 }
 

@@ -63,6 +63,118 @@ struct IndexPairOut {
     }
 };
 
+// ---- the four lists of a neighbourhood update in ONE ordered selection ------------------------------------------------------
+// After key generation has classified every local particle (slab_classify: stays / migrates left / right / dropped ghost), the
+// update needs, each in ascending index order: the migrants to the left and to the right rank, and the stayers in the first /
+// last W owned columns (the ghost layers the left / right rank keeps of this slab).  One reduce / scan / apply over four flags.
+struct Select4In {
+    const uint32_t* keys;
+    const uint8_t* pflag;
+    uint32_t a_lo, a_hi, b_lo, b_hi;  // ghost-send column ranges (left | right); empty = side disabled
+    __device__ __forceinline__ uint32_t operator()(uint32_t i) const {
+        const uint8_t f = pflag[i];
+        if (f == SLAB_MIG_LEFT) return 1u;
+        if (f == SLAB_MIG_RIGHT) return 2u;
+        if (f != SLAB_STAY) return 0u;
+        const uint32_t col = compact_1by1(keys[i]);
+        return ((col >= a_lo && col < a_hi) ? 4u : 0u) | ((col >= b_lo && col < b_hi) ? 8u : 0u);
+    }
+};
+__device__ __forceinline__ uint4 operator+(uint4 a, uint4 b) { return make_uint4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+// per-warp exclusive prefix and total of four flags over 32 lanes
+__device__ __forceinline__ void warp_flag_scan4(uint32_t m, unsigned lt, uint4& excl, uint4& total) {
+    const unsigned b0 = __ballot_sync(0xffffffffu, m & 1u), b1 = __ballot_sync(0xffffffffu, m & 2u), b2 = __ballot_sync(0xffffffffu, m & 4u),
+                   b3 = __ballot_sync(0xffffffffu, m & 8u);
+    excl = make_uint4(__popc(b0 & lt), __popc(b1 & lt), __popc(b2 & lt), __popc(b3 & lt));
+    total = make_uint4(__popc(b0), __popc(b1), __popc(b2), __popc(b3));
+}
+__global__ void __launch_bounds__(SCAN_THREADS) k_select4_reduce(Select4In in, uint32_t n, uint4* __restrict__ chunk_sums) {
+    __shared__ uint4 wsum[SCAN_WARPS];
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    const unsigned lt = lanemask_lt();
+    const uint32_t base = blockIdx.x * SCAN_CHUNK + warp * (32 * SCAN_ITEMS);
+    uint4 s = make_uint4(0, 0, 0, 0);
+#pragma unroll 4
+    for (int r = 0; r < SCAN_ITEMS; ++r) {
+        const uint32_t i = base + r * 32 + lane;
+        uint4 ex, tot;
+        warp_flag_scan4(i < n ? in(i) : 0u, lt, ex, tot);
+        s = s + tot;
+    }
+    if (lane == 0) wsum[warp] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint4 t = wsum[0];
+        for (int w = 1; w < SCAN_WARPS; ++w) t = t + wsum[w];
+        chunk_sums[blockIdx.x] = t;
+    }
+}
+// in-place exclusive scan of chunk_sums[0..nchunks) by ONE block; totals -> totals_out[4]
+__global__ void __launch_bounds__(SCAN_THREADS) k_select4_chunks(uint4* __restrict__ chunk_sums, uint32_t nchunks, uint32_t* __restrict__ totals_out) {
+    __shared__ uint4 wsum[SCAN_WARPS];
+    __shared__ uint4 carry_s;
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    if (threadIdx.x == 0) carry_s = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    for (uint32_t base = 0; base < nchunks; base += SCAN_THREADS) {
+        const uint32_t i = base + threadIdx.x;
+        const uint4 v = i < nchunks ? chunk_sums[i] : make_uint4(0, 0, 0, 0);
+        uint4 inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint4 u = make_uint4(__shfl_up_sync(0xffffffffu, inc.x, o), __shfl_up_sync(0xffffffffu, inc.y, o), __shfl_up_sync(0xffffffffu, inc.z, o),
+                                       __shfl_up_sync(0xffffffffu, inc.w, o));
+            if (lane >= (uint32_t)o) inc = inc + u;
+        }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        uint4 off = carry_s;
+        for (uint32_t w = 0; w < warp; ++w) off = off + wsum[w];
+        if (i < nchunks) chunk_sums[i] = make_uint4(off.x + inc.x - v.x, off.y + inc.y - v.y, off.z + inc.z - v.z, off.w + inc.w - v.w);
+        __syncthreads();
+        if (threadIdx.x == SCAN_THREADS - 1) carry_s = off + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        totals_out[0] = carry_s.x;
+        totals_out[1] = carry_s.y;
+        totals_out[2] = carry_s.z;
+        totals_out[3] = carry_s.w;
+    }
+}
+// out[q][prefix_q(i)] = i for every i with flag q set (q = 0..3), up to `cap` entries per list
+__global__ void __launch_bounds__(SCAN_THREADS) k_select4_apply(Select4In in, uint32_t n, const uint4* __restrict__ chunk_offsets, uint32_t* __restrict__ out0,
+                                                                uint32_t* __restrict__ out1, uint32_t* __restrict__ out2, uint32_t* __restrict__ out3, uint32_t cap) {
+    __shared__ uint4 wsum[SCAN_WARPS];
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    const uint32_t base = blockIdx.x * SCAN_CHUNK + warp * (32 * SCAN_ITEMS);
+    const unsigned lt = lanemask_lt();
+    uint32_t m[SCAN_ITEMS];
+    uint4 ex[SCAN_ITEMS];
+    uint4 carry = make_uint4(0, 0, 0, 0);  // warp-uniform
+#pragma unroll
+    for (int r = 0; r < SCAN_ITEMS; ++r) {
+        const uint32_t i = base + r * 32 + lane;
+        m[r] = i < n ? in(i) : 0u;
+        uint4 e, tot;
+        warp_flag_scan4(m[r], lt, e, tot);
+        ex[r] = carry + e;
+        carry = carry + tot;
+    }
+    if (lane == 0) wsum[warp] = carry;
+    __syncthreads();
+    uint4 off = chunk_offsets[blockIdx.x];
+    for (uint32_t w = 0; w < warp; ++w) off = off + wsum[w];
+#pragma unroll
+    for (int r = 0; r < SCAN_ITEMS; ++r) {
+        const uint32_t i = base + r * 32 + lane;
+        if (m[r] & 1u) { const uint32_t e = off.x + ex[r].x; if (e < cap) out0[e] = i; }
+        if (m[r] & 2u) { const uint32_t e = off.y + ex[r].y; if (e < cap) out1[e] = i; }
+        if (m[r] & 4u) { const uint32_t e = off.z + ex[r].z; if (e < cap) out2[e] = i; }
+        if (m[r] & 8u) { const uint32_t e = off.w + ex[r].w; if (e < cap) out3[e] = i; }
+    }
+}
+
 // ---- particle records (migrants, ghosts): SoA block of `count` records, 8-byte arrays first ---------------------------
 struct RecordArrays {
     float2* a2[3];
@@ -70,11 +182,12 @@ struct RecordArrays {
     int n2, n1;
 };
 __host__ __device__ inline size_t record_bytes(int n2, int n1) { return (size_t)n2 * 8 + (size_t)n1 * 4; }
-// buf <- arrays[idx[k]], k < count
-__global__ void k_pack_records(RecordArrays arr, const uint32_t* __restrict__ idx, uint32_t count, unsigned char* __restrict__ buf) {
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+// buf <- arrays[idx(k)], k < na + nb, idx(k) = k < na ? idx_a[k] : idx_b[k - na]: one message = the migrants, then the ghost layer
+__global__ void k_pack_records(RecordArrays arr, const uint32_t* __restrict__ idx_a, uint32_t na, const uint32_t* __restrict__ idx_b, uint32_t nb,
+                               unsigned char* __restrict__ buf) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x, count = na + nb;
     if (k >= count) return;
-    const uint32_t s = idx[k];
+    const uint32_t s = k < na ? idx_a[k] : idx_b[k - na];
     float2* b2 = reinterpret_cast<float2*>(buf);
 #pragma unroll
     for (int q = 0; q < 3; ++q)
@@ -84,18 +197,20 @@ __global__ void k_pack_records(RecordArrays arr, const uint32_t* __restrict__ id
     for (int q = 0; q < 3; ++q)
         if (q < arr.n1) b1[(size_t)q * count + k] = arr.a1[q][s];
 }
-// arrays[first + k] <- buf, k < count; the new particles are not ghosts of the current structure (pflag = 0)
-__global__ void k_unpack_records(RecordArrays arr, uint32_t first, uint32_t count, const unsigned char* __restrict__ buf, uint8_t* __restrict__ pflag) {
+// arrays[first + k] <- record src_off + k of a message of `stride` records, k < count; the new particles are not ghosts of the
+// current structure (pflag = 0)
+__global__ void k_unpack_records(RecordArrays arr, uint32_t first, uint32_t count, const unsigned char* __restrict__ buf, uint32_t stride, uint32_t src_off,
+                                 uint8_t* __restrict__ pflag) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= count) return;
     const float2* b2 = reinterpret_cast<const float2*>(buf);
 #pragma unroll
     for (int q = 0; q < 3; ++q)
-        if (q < arr.n2) arr.a2[q][first + k] = b2[(size_t)q * count + k];
-    const float* b1 = reinterpret_cast<const float*>(buf + (size_t)arr.n2 * 8 * count);
+        if (q < arr.n2) arr.a2[q][first + k] = b2[(size_t)q * stride + src_off + k];
+    const float* b1 = reinterpret_cast<const float*>(buf + (size_t)arr.n2 * 8 * stride);
 #pragma unroll
     for (int q = 0; q < 3; ++q)
-        if (q < arr.n1) arr.a1[q][first + k] = b1[(size_t)q * count + k];
+        if (q < arr.n1) arr.a1[q][first + k] = b1[(size_t)q * stride + src_off + k];
     pflag[first + k] = 0;
 }
 // a migrant that arrived must lie inside the slab (particles move less than a cell per step; a slab is many cells wide)
@@ -216,26 +331,34 @@ __global__ void k_halo_exchange(T* __restrict__ field, const uint32_t* __restric
     }
 }
 
-// ---- particle records (migrants, ghosts) through the mailboxes: the COUNTS stay on the device ------------------------------
-// k_records_push reads how many particles the ordered selection picked for each side (device memory), packs them straight
-// into the neighbours' mailboxes behind a 16-byte header carrying the count, and publishes the sequence number.
-// k_records_pull waits for both neighbours, appends their records at `first` (left arrivals, then right), and reports the
-// four counts (out left/right, in left/right) to the host through mapped memory -- the one thing the host has to learn
-// before it can size the next launches.  Replaces: count exchange (copy, NCCL group, copy, stream sync) + pack + NCCL group
-// + unpack.
+// ---- particle records (migrants + ghost layers) through the mailboxes: the COUNTS stay on the device ------------------------
+// One message per neighbour and update: [count of migrants, count of ghost-layer particles | SoA block of both, migrants first].
+// k_records_push reads how many particles the ordered selection picked (device memory), packs them straight into the neighbours'
+// mailboxes and publishes the sequence number.  k_records_pull waits for both neighbours and appends their records behind the old
+// local set: [migrants from the left | migrants from the right | ghosts from the left | ghosts from the right].  k_slab_retain then
+// appends copies of this rank's own OUT-migrants that landed in a neighbour's first W columns: the neighbour owns them now, and they
+// are part of the ghost layer this rank keeps of that neighbour (behind the received ghosts: the same order the neighbour's own sort
+// gives them, after its stayers of the same cell).  It hands all counts to the host through mapped memory -- the ONE thing the host
+// waits for in the exchange, to size the sort.
+struct SlabCounts {  // device memory (Control::slab_cnt)
+    uint32_t out_m[2], out_g[2];  // sent: migrants / ghost-layer particles to the left | right rank
+    uint32_t in_m[2], in_g[2];    // received
+    uint32_t retained[2];         // own out-migrants kept as ghosts of the left | right rank
+};
 struct PeerCounts {  // mapped host memory
-    uint32_t out[2], in[2];
+    SlabCounts cnt;
     uint32_t seq;
 };
-__global__ void k_records_push(RecordArrays arr, const uint32_t* __restrict__ idx_l, const uint32_t* __restrict__ idx_r,
-                               const unsigned long long* __restrict__ counts, uint32_t cap, unsigned char* dst_l, unsigned char* dst_r,
+__global__ void k_records_push(RecordArrays arr, const uint32_t* __restrict__ idx_ml, const uint32_t* __restrict__ idx_mr, const uint32_t* __restrict__ idx_gl,
+                               const uint32_t* __restrict__ idx_gr, const uint32_t* __restrict__ counts4, uint32_t cap, unsigned char* dst_l, unsigned char* dst_r,
                                unsigned long long* flag_l, unsigned long long* flag_r, unsigned long long seq, unsigned int* ticket) {
-    const unsigned long long cc = *counts;
-    const uint32_t nl = dst_l ? min((uint32_t)(cc & 0xFFFFFFFFull), cap) : 0u, nr = dst_r ? min((uint32_t)(cc >> 32), cap) : 0u;
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < nl + nr; k += gridDim.x * blockDim.x) {
-        const bool right = k >= nl;
-        const uint32_t kk = right ? k - nl : k, cnt = right ? nr : nl;
-        const uint32_t s = (right ? idx_r : idx_l)[kk];
+    const uint32_t nml = dst_l ? min(counts4[0], cap) : 0u, ngl = dst_l ? min(counts4[2], cap - nml) : 0u;
+    const uint32_t nmr = dst_r ? min(counts4[1], cap) : 0u, ngr = dst_r ? min(counts4[3], cap - nmr) : 0u;
+    const uint32_t tl = nml + ngl, tr = nmr + ngr;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < tl + tr; k += gridDim.x * blockDim.x) {
+        const bool right = k >= tl;
+        const uint32_t kk = right ? k - tl : k, cnt = right ? tr : tl, nm = right ? nmr : nml;
+        const uint32_t s = kk < nm ? (right ? idx_mr : idx_ml)[kk] : (right ? idx_gr : idx_gl)[kk - nm];
         unsigned char* buf = (right ? dst_r : dst_l) + PEER_MSG_HEADER_BYTES;
         float2* b2 = reinterpret_cast<float2*>(buf);
 #pragma unroll
@@ -247,8 +370,14 @@ __global__ void k_records_push(RecordArrays arr, const uint32_t* __restrict__ id
             if (q < arr.n1) b1[(size_t)q * cnt + kk] = arr.a1[q][s];
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        if (dst_l) *reinterpret_cast<uint32_t*>(dst_l) = nl;
-        if (dst_r) *reinterpret_cast<uint32_t*>(dst_r) = nr;
+        if (dst_l) {
+            reinterpret_cast<uint32_t*>(dst_l)[0] = nml;
+            reinterpret_cast<uint32_t*>(dst_l)[1] = ngl;
+        }
+        if (dst_r) {
+            reinterpret_cast<uint32_t*>(dst_r)[0] = nmr;
+            reinterpret_cast<uint32_t*>(dst_r)[1] = ngr;
+        }
     }
     __threadfence_system();
     __syncthreads();
@@ -264,7 +393,7 @@ __global__ void k_records_push(RecordArrays arr, const uint32_t* __restrict__ id
 }
 __global__ void k_records_pull(RecordArrays arr, uint32_t first, uint32_t cap_n, uint32_t cap_halo, const unsigned char* src_l, const unsigned char* src_r,
                                const unsigned long long* flag_l, const unsigned long long* flag_r, unsigned long long seq, uint8_t* __restrict__ pflag,
-                               const unsigned long long* __restrict__ my_counts, PeerCounts* host_counts, uint32_t host_seq, Control* ctl) {
+                               const uint32_t* __restrict__ counts4, SlabCounts* dc, Control* ctl) {
     __shared__ int ok;
     if (threadIdx.x == 0) {
         ok = 1;
@@ -273,33 +402,89 @@ __global__ void k_records_pull(RecordArrays arr, uint32_t first, uint32_t cap_n,
         if (!ok) atomicOr(&ctl->err_comm, 4u);
     }
     __syncthreads();
-    const uint32_t nl = (ok && flag_l) ? __ldcg(reinterpret_cast<const uint32_t*>(src_l)) : 0u;
-    const uint32_t nr = (ok && flag_r) ? __ldcg(reinterpret_cast<const uint32_t*>(src_r)) : 0u;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {  // the host only needs the counts; the kernels it launches next are stream-ordered behind this one
-        const unsigned long long cc = *my_counts;
-        volatile PeerCounts* h = host_counts;
-        h->out[0] = (uint32_t)(cc & 0xFFFFFFFFull);
-        h->out[1] = (uint32_t)(cc >> 32);
-        h->in[0] = nl;
-        h->in[1] = nr;
-        __threadfence_system();
-        h->seq = host_seq;
-        __threadfence_system();
+    const uint32_t nml = (ok && flag_l) ? __ldcg(reinterpret_cast<const uint32_t*>(src_l)) : 0u, ngl = (ok && flag_l) ? __ldcg(reinterpret_cast<const uint32_t*>(src_l) + 1) : 0u;
+    const uint32_t nmr = (ok && flag_r) ? __ldcg(reinterpret_cast<const uint32_t*>(src_r)) : 0u, ngr = (ok && flag_r) ? __ldcg(reinterpret_cast<const uint32_t*>(src_r) + 1) : 0u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        dc->out_m[0] = counts4[0];
+        dc->out_m[1] = counts4[1];
+        dc->out_g[0] = counts4[2];
+        dc->out_g[1] = counts4[3];
+        dc->in_m[0] = nml;
+        dc->in_m[1] = nmr;
+        dc->in_g[0] = ngl;
+        dc->in_g[1] = ngr;
     }
-    if (nl > cap_halo || nr > cap_halo || (unsigned long long)first + nl + nr > cap_n) return;  // the host fails the step on these counts
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < nl + nr; k += gridDim.x * blockDim.x) {
-        const bool right = k >= nl;
-        const uint32_t kk = right ? k - nl : k, cnt = right ? nr : nl;
+    const uint32_t tl = nml + ngl, tr = nmr + ngr;
+    if (tl > cap_halo || tr > cap_halo || (unsigned long long)first + tl + tr > cap_n) return;  // the host fails the step on these counts
+    const uint32_t base_g = first + nml + nmr;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < tl + tr; k += gridDim.x * blockDim.x) {
+        const bool right = k >= tl;
+        const uint32_t kk = right ? k - tl : k, cnt = right ? tr : tl, nm = right ? nmr : nml;
+        const uint32_t dst = kk < nm ? first + (right ? nml : 0u) + kk : base_g + (right ? ngl : 0u) + (kk - nm);
         const unsigned char* buf = (right ? src_r : src_l) + PEER_MSG_HEADER_BYTES;
         const float2* b2 = reinterpret_cast<const float2*>(buf);
 #pragma unroll
         for (int q = 0; q < 3; ++q)
-            if (q < arr.n2) arr.a2[q][first + k] = __ldcg(&b2[(size_t)q * cnt + kk]);
+            if (q < arr.n2) arr.a2[q][dst] = __ldcg(&b2[(size_t)q * cnt + kk]);
         const float* b1 = reinterpret_cast<const float*>(buf + (size_t)arr.n2 * 8 * cnt);
 #pragma unroll
         for (int q = 0; q < 3; ++q)
-            if (q < arr.n1) arr.a1[q][first + k] = __ldcg(&b1[(size_t)q * cnt + kk]);
-        pflag[first + k] = 0;
+            if (q < arr.n1) arr.a1[q][dst] = __ldcg(&b1[(size_t)q * cnt + kk]);
+        pflag[dst] = 0;
+    }
+}
+// one warp: ordered copies of the out-migrants that stay visible as ghosts, then the counts for the host (see above).
+// arr.a2[0] are the positions (already advanced): the migrant's new cell column decides.
+__global__ void k_slab_retain(RecordArrays arr, GridParams g, const uint32_t* __restrict__ idx_ml, const uint32_t* __restrict__ idx_mr, SlabCounts* dc, uint32_t n_old,
+                              uint32_t cap_n, uint32_t cap_halo, uint32_t col_lo, uint32_t col_hi, uint32_t W, uint8_t* __restrict__ pflag, PeerCounts* host_counts,
+                              uint32_t host_seq) {
+    const uint32_t lane = threadIdx.x;
+    const unsigned lt = lanemask_lt();
+    uint32_t dst = n_old + dc->in_m[0] + dc->in_m[1] + dc->in_g[0] + dc->in_g[1];
+    uint32_t kept[2] = {0u, 0u};
+    const bool sane = dc->in_m[0] + dc->in_g[0] <= cap_halo && dc->in_m[1] + dc->in_g[1] <= cap_halo && dst <= cap_n;
+    for (int side = 0; side < 2 && sane; ++side) {
+        const uint32_t* idx = side ? idx_mr : idx_ml;
+        const uint32_t count = min(dc->out_m[side], cap_halo);
+        for (uint32_t base = 0; base < count; base += 32u) {
+            const uint32_t k = base + lane;
+            uint32_t s = 0;
+            bool keep = false;
+            if (k < count) {
+                s = idx[k];
+                const uint32_t col = compact_1by1(position_to_cidx(g, arr.a2[0][s]));
+                keep = side ? (col >= col_hi && col - col_hi < W) : (col < col_lo && col_lo - col <= W);
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, keep);
+            const uint32_t d = dst + (uint32_t)__popc(mask & lt);
+            if (keep && d < cap_n) {
+#pragma unroll
+                for (int q = 0; q < 3; ++q)
+                    if (q < arr.n2) arr.a2[q][d] = arr.a2[q][s];
+#pragma unroll
+                for (int q = 0; q < 3; ++q)
+                    if (q < arr.n1) arr.a1[q][d] = arr.a1[q][s];
+                pflag[d] = 0;
+            }
+            dst += (uint32_t)__popc(mask);
+            kept[side] += (uint32_t)__popc(mask);
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        dc->retained[0] = kept[0];
+        dc->retained[1] = kept[1];
+        volatile PeerCounts* h = host_counts;
+        for (int q = 0; q < 2; ++q) {
+            h->cnt.out_m[q] = dc->out_m[q];
+            h->cnt.out_g[q] = dc->out_g[q];
+            h->cnt.in_m[q] = dc->in_m[q];
+            h->cnt.in_g[q] = dc->in_g[q];
+            h->cnt.retained[q] = kept[q];
+        }
+        __threadfence_system();
+        h->seq = host_seq;
+        __threadfence_system();
     }
 }
 

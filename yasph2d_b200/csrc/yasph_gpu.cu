@@ -112,7 +112,10 @@ struct yasph_ctx {
         cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
         uint64_t link_seq[2] = {0, 0};
         uint8_t* pflag = nullptr;        // [cap_n] ghost flag of the current structure / classification during an update
-        uint32_t* sel[2] = {nullptr, nullptr};    // scratch index lists of the ordered selections (migrants, ghost sends) [max_halo]
+        uint32_t* sel[2] = {nullptr, nullptr};    // index lists of an update's four-way selection: migrants to the left | right rank [max_halo]
+        uint32_t* sel_g[2] = {nullptr, nullptr};  // ... and the stayers in the first | last W owned columns (ghost layer of the left | right rank)
+        uint4* sel4_chunks = nullptr;             // per-chunk counts of that selection
+        bool halo_lists_valid = false;            // send_idx / ghost_idx describe the current structure (built on demand: ensure_halo_lists)
         uint32_t* send_idx[2] = {nullptr, nullptr};   // per-pass halo send lists (left, right), sorted order [max_halo]
         uint32_t* ghost_idx[2] = {nullptr, nullptr};  // ghosts from the left / right rank, sorted order [max_halo]
         uint32_t* own_idx = nullptr;     // owned particles, sorted order [cap_n] (built on demand)
@@ -409,7 +412,7 @@ static void free_all(yasph_ctx* c) {
                     c->tile_cstart, c->bpos, c->bpos_alt, c->scell_key, c->scell_start, c->stile_key, c->stile_cstart, c->tile_runs, c->cslot_d,
                     c->cslot_s, c->lists, c->counts, c->tile_nk, c->apron_idx,
                     c->radix_scratch, c->scan_chunks, c->scan_total, c->partials, c->ctl, c->exp_cd, c->exp_ct, c->exp_lists,
-                    c->ids, c->ids_alt, c->slab.pflag, c->slab.sel[0], c->slab.sel[1], c->slab.send_idx[0], c->slab.send_idx[1],
+                    c->ids, c->ids_alt, c->slab.pflag, c->slab.sel[0], c->slab.sel[1], c->slab.sel_g[0], c->slab.sel_g[1], c->slab.sel4_chunks, c->slab.send_idx[0], c->slab.send_idx[1],
                     c->slab.ghost_idx[0], c->slab.ghost_idx[1], c->slab.own_idx, c->slab.sbuf[0], c->slab.sbuf[1], c->slab.rbuf[0],
                     c->slab.rbuf[1], c->slab.d_cnt};
     for (void* p : ptrs)
@@ -418,6 +421,7 @@ static void free_all(yasph_ctx* c) {
     if (c->h_pub) cudaFreeHost(c->h_pub);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->slab.h_cnt) cudaFreeHost(c->slab.h_cnt);
+    if (c->slab.h_pcounts) cudaFreeHost(c->slab.h_pcounts);
     for (int sd = 0; sd < 2; ++sd) {
         if (c->slab.ev_ready[sd]) cudaEventDestroy(c->slab.ev_ready[sd]);
         if (c->slab.ev_done[sd]) cudaEventDestroy(c->slab.ev_done[sd]);
@@ -972,18 +976,30 @@ static int32_t neighbor_sendrecv(yasph_ctx* c, const void* const sbuf[2], const 
     return YASPH_OK;
 }
 
-// exchanges the pair of counts in `packed` (device: left | right << 32) with the neighbours; afterwards h_cnt[0..1] = sent
-// left / right, h_cnt[2..3] = received from left / right (synchronises the stream)
-static int32_t exchange_counts(yasph_ctx* c, const unsigned long long* packed) {
-    uint32_t* d = c->slab.d_cnt;
-    CU(cudaMemcpyAsync(d, packed, 2 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
-    CU(cudaMemsetAsync(d + 2, 0, 2 * sizeof(uint32_t), c->stream));
-    const void* sb[2] = {d, d + 1};
-    void* rb[2] = {d + 2, d + 3};
-    const size_t by[2] = {sizeof(uint32_t), sizeof(uint32_t)};
-    TRY(neighbor_sendrecv(c, sb, by, rb, by));
-    CU(cudaMemcpyAsync(c->slab.h_cnt, d, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+// Per-pass halo lists of the current structure, in sorted order: what this rank sends (its first / last W owned columns) and where
+// its ghosts sit.  Entry k of a send list is entry k of the neighbour's ghost list (slab.cuh "ordering contract").  Built on demand:
+// with ghost layers a pass rarely needs an exchange (yasph_ctx::Slab::valid).
+static int32_t ensure_halo_lists(yasph_ctx* c) {
+    auto& sl = c->slab;
+    if (sl.halo_lists_valid) return YASPH_OK;
+    const uint32_t W = sl.ghost_cols, n = c->n;
+    const uint32_t a_lo = sl.col_lo, a_hi = has_left(c) ? std::min(sl.col_lo + W, sl.col_hi) : sl.col_lo;
+    const uint32_t b_hi = sl.col_hi, b_lo = has_right(c) ? (sl.col_hi - sl.col_lo > W ? sl.col_hi - W : sl.col_lo) : sl.col_hi;
+    TRY(select_pair(c, ColumnSelIn{c->keys[0], nullptr, a_lo, a_hi, b_lo, b_hi}, n, sl.send_idx[0], sl.send_idx[1], nullptr, sl.max_halo, &c->ctl->slab_send));
+    TRY(select_pair(c, GhostSelIn{c->keys[0], sl.col_lo, sl.col_hi}, n, sl.ghost_idx[0], sl.ghost_idx[1], nullptr, sl.max_halo, &c->ctl->slab_own));
+    unsigned long long cnt[2] = {0, 0};
+    CU(cudaMemcpyAsync(&cnt[0], &c->ctl->slab_send, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(&cnt[1], &c->ctl->slab_own, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    sl.n_send[0] = (uint32_t)(cnt[0] & 0xFFFFFFFFull);
+    sl.n_send[1] = (uint32_t)(cnt[0] >> 32);
+    if ((uint32_t)(cnt[1] & 0xFFFFFFFFull) != sl.n_ghost[0] || (uint32_t)(cnt[1] >> 32) != sl.n_ghost[1])
+        return fail(c, YASPH_ERR_STATE, "rank %d: ghost lists (%llu | %llu) disagree with the exchanged ghosts (%u | %u)", sl.rank, cnt[1] & 0xFFFFFFFFull, cnt[1] >> 32,
+                    sl.n_ghost[0], sl.n_ghost[1]);
+    if (sl.n_send[0] > sl.max_halo || sl.n_send[1] > sl.max_halo)
+        return fail(c, YASPH_ERR_CAPACITY, "rank %d: %u | %u particles in the halo send lists exceed max_halo=%u", sl.rank, sl.n_send[0], sl.n_send[1], sl.max_halo);
+    sl.halo_lists_valid = true;
+    sl.own_idx_valid = false;  // the selection above borrowed Control::slab_own
     return YASPH_OK;
 }
 
@@ -991,6 +1007,7 @@ static int32_t exchange_counts(yasph_ctx* c, const unsigned long long* packed) {
 template <typename T>
 static int32_t halo_exchange(yasph_ctx* c, T* field) {
     if (!c->slab.active || c->slab.world < 2) return YASPH_OK;
+    TRY(ensure_halo_lists(c));
     pass_begin(c, YASPH_PASS_HALO);
     auto& sl = c->slab;
     const uint32_t ns = sl.n_send[0] + sl.n_send[1], ng = sl.n_ghost[0] + sl.n_ghost[1];
@@ -1097,138 +1114,143 @@ static RecordArrays record_arrays(const GatherPlan& gp) {
     return r;
 }
 
-// Slab mode, between key generation and the sort: particles that left the slab migrate to the adjacent rank, the ghosts of
-// the previous structure are dropped, and the first / last owned columns are exchanged as the new ghosts.  On return
-// *n_sort particles (old local + arrivals) carry sort keys (dropped ones YASPH_KEY_DROPPED) and *n_keep of them survive.
-// Peer transport: the records picked by the last ordered selection (index lists sel[0] / sel[1], counts in *d_counts on the
-// device) go to the left / right neighbour's mailbox, the neighbours' records are appended at `first`; out / in = the counts.
-static int32_t peer_exchange_records(yasph_ctx* c, const RecordArrays& ra, const unsigned long long* d_counts, uint32_t first, uint32_t out[2], uint32_t in[2]) {
-    auto& sl = c->slab;
-    const uint64_t seq = ++sl.halo_seq;
-    const unsigned par = (unsigned)(seq & 1u);
-    const bool hl = has_left(c), hr = has_right(c);
-    void* bl = hl ? sl.peer_box[sl.rank - 1] : nullptr;
-    void* br = hr ? sl.peer_box[sl.rank + 1] : nullptr;
-    PeerBoxHeader* me = reinterpret_cast<PeerBoxHeader*>(sl.box);
-    const int grid = 64;  // grid-stride: the counts are known on the device only
-    k_records_push<<<grid, 256, 0, c->stream>>>(ra, sl.sel[0], sl.sel[1], d_counts, sl.max_halo, hl ? peer_payload(bl, sl.max_halo, par, 1) : nullptr,
-                                                hr ? peer_payload(br, sl.max_halo, par, 0) : nullptr,
-                                                hl ? &reinterpret_cast<PeerBoxHeader*>(bl)->halo_flag[1] : nullptr,
-                                                hr ? &reinterpret_cast<PeerBoxHeader*>(br)->halo_flag[0] : nullptr, seq, sl.d_ticket);
-    CHECK_LAUNCH();
-    const uint32_t hseq = ++sl.pcounts_seq;
-    k_records_pull<<<grid, 256, 0, c->stream>>>(ra, first, c->cap_n, sl.max_halo, peer_payload(sl.box, sl.max_halo, par, 0), peer_payload(sl.box, sl.max_halo, par, 1),
-                                                hl ? &me->halo_flag[0] : nullptr, hr ? &me->halo_flag[1] : nullptr, seq, sl.pflag, d_counts, sl.d_pcounts, hseq,
-                                                c->ctl);
-    CHECK_LAUNCH();
-    TRY(wait_published(c, &sl.h_pcounts->seq, hseq, c->stream));
-    for (int sd = 0; sd < 2; ++sd) {
-        out[sd] = sl.h_pcounts->out[sd];
-        in[sd] = sl.h_pcounts->in[sd];
-    }
-    sl.halo_exchanges++;
-    return YASPH_OK;
-}
-
+// Slab mode, between key generation and the sort: particles that left the slab migrate to the adjacent rank, the ghosts of the
+// previous structure are dropped, and the first / last W owned columns are sent as the neighbours' new ghost layers -- ONE ordered
+// four-way selection, ONE message per neighbour, one wait of the host (slab.cuh).  On return *n_sort particles (old local set +
+// arrivals) carry sort keys (dropped ones YASPH_KEY_DROPPED) and *n_keep of them survive the sort.
 static int32_t slab_exchange_particles(yasph_ctx* c, const GatherPlan& gp, uint32_t n_old, uint32_t* n_sort, uint32_t* n_keep) {
     auto& sl = c->slab;
     const RecordArrays ra = record_arrays(gp);
     const size_t rec = record_bytes(gp.n2, gp.n1);
     const SlabParams sp = slab_params(c);
     const uint32_t ghosts_old = sl.n_ghost[0] + sl.n_ghost[1];
-    // (1) migrants: ordered selection by classification flag, counts to both neighbours
-    TRY(select_pair(c, FlagSelIn{sl.pflag, (uint8_t)SLAB_MIG_LEFT, (uint8_t)SLAB_MIG_RIGHT}, n_old, sl.sel[0], sl.sel[1], nullptr, sl.max_halo, &c->ctl->slab_migrants));
-    uint32_t out[2], in[2];
-    if (sl.peer) {
-        TRY(peer_exchange_records(c, ra, &c->ctl->slab_migrants, n_old, out, in));
-    } else {
-        TRY(exchange_counts(c, &c->ctl->slab_migrants));
-        out[0] = sl.h_cnt[0], out[1] = sl.h_cnt[1], in[0] = sl.h_cnt[2], in[1] = sl.h_cnt[3];
-    }
-    // a particle that leaves through an end of the domain has no rank to go to
-    if ((out[0] && !has_left(c)) || (out[1] && !has_right(c)))
-        return fail(c, YASPH_ERR_STATE, "rank %d: %u / %u particles left the domain's first / last slab [%u, %u)", sl.rank, out[0], out[1], sl.col_lo, sl.col_hi);
-    sl.mig_out[0] = out[0];
-    sl.mig_out[1] = out[1];
-    for (int sd = 0; sd < 2; ++sd)
-        if (out[sd] > sl.max_halo || in[sd] > sl.max_halo)
-            return fail(c, YASPH_ERR_CAPACITY, "rank %d: %u migrants out / %u in on side %d exceed max_halo=%u", sl.rank, out[sd], in[sd], sd, sl.max_halo);
-    uint32_t n1 = n_old + in[0] + in[1];
-    if (n1 > c->cap_n) return fail(c, YASPH_ERR_CAPACITY, "rank %d: %u local particles after migration > max_particles=%u", sl.rank, n1, c->cap_n);
-    if (out[0] + out[1] + in[0] + in[1]) {
-        for (int sd = 0; sd < 2 && !sl.peer; ++sd)
-            if (out[sd]) {
-                k_pack_records<<<blocks_for(out[sd], 256), 256, 0, c->stream>>>(ra, sl.sel[sd], out[sd], sl.sbuf[sd]);
-                CHECK_LAUNCH();
-            }
-        const void* sb[2] = {sl.sbuf[0], sl.sbuf[1]};
-        void* rb[2] = {sl.rbuf[0], sl.rbuf[1]};
-        const size_t sby[2] = {out[0] * rec, out[1] * rec}, rby[2] = {in[0] * rec, in[1] * rec};
-        if (!sl.peer) TRY(neighbor_sendrecv(c, sb, sby, rb, rby));
-        uint32_t first = n_old;
-        for (int sd = 0; sd < 2 && !sl.peer; ++sd)
-            if (in[sd]) {
-                k_unpack_records<<<blocks_for(in[sd], 256), 256, 0, c->stream>>>(ra, first, in[sd], sl.rbuf[sd], sl.pflag);
-                CHECK_LAUNCH();
-                first += in[sd];
-            }
-        const uint32_t nin = in[0] + in[1];
-        if (nin) {
-            k_keygen<<<keygen_grid(nin, c->num_sms), KG_THREADS, 0, c->stream>>>(c->pos, n_old, n1, c->grid, c->keys[0], c->idx[0], c->radix_scratch, sp);
-            CHECK_LAUNCH();
-            k_check_arrivals<<<blocks_for(nin, 256), 256, 0, c->stream>>>(sl.pflag, n_old, n1, c->ctl);
-            CHECK_LAUNCH();
-        }
-    }
-    sl.mig_in = in[0] + in[1];
-    // (2) ghosts: the owned particles of the first / last owned column, in pre-sort order, to the left / right rank
-    // the first / last W owned columns (W = ghost_cols) go to the left / right rank; an empty range disables a side
+    const bool hl = has_left(c), hr = has_right(c);
+    SlabCounts* dcnt = reinterpret_cast<SlabCounts*>(c->ctl->slab_cnt);
+    static_assert(sizeof(SlabCounts) == sizeof(((Control*)nullptr)->slab_cnt), "SlabCounts lives in Control::slab_cnt");
+    // (1) the four lists: migrants left | right, stayers of the first | last W owned columns (W = ghost_cols; an empty range disables a side)
     const uint32_t W = sl.ghost_cols;
-    const uint32_t a_lo = sl.col_lo, a_hi = has_left(c) ? std::min(sl.col_lo + W, sl.col_hi) : sl.col_lo;
-    const uint32_t b_hi = sl.col_hi, b_lo = has_right(c) ? (sl.col_hi - sl.col_lo > W ? sl.col_hi - W : sl.col_lo) : sl.col_hi;
-    TRY(select_pair(c, ColumnSelIn{c->keys[0], sl.pflag, a_lo, a_hi, b_lo, b_hi}, n1, sl.sel[0], sl.sel[1], nullptr, sl.max_halo, &c->ctl->slab_ghost_send));
-    uint32_t gout[2], gin[2];
-    if (sl.peer) {
-        TRY(peer_exchange_records(c, ra, &c->ctl->slab_ghost_send, n1, gout, gin));
+    const uint32_t a_lo = sl.col_lo, a_hi = hl ? std::min(sl.col_lo + W, sl.col_hi) : sl.col_lo;
+    const uint32_t b_hi = sl.col_hi, b_lo = hr ? (sl.col_hi - sl.col_lo > W ? sl.col_hi - W : sl.col_lo) : sl.col_hi;
+    if (n_old) {
+        const uint32_t nch = scan_num_chunks(n_old);
+        const Select4In in{c->keys[0], sl.pflag, a_lo, a_hi, b_lo, b_hi};
+        k_select4_reduce<<<nch, SCAN_THREADS, 0, c->stream>>>(in, n_old, sl.sel4_chunks);
+        CHECK_LAUNCH();
+        k_select4_chunks<<<1, SCAN_THREADS, 0, c->stream>>>(sl.sel4_chunks, nch, c->ctl->slab_sel4);
+        CHECK_LAUNCH();
+        k_select4_apply<<<nch, SCAN_THREADS, 0, c->stream>>>(in, n_old, sl.sel4_chunks, sl.sel[0], sl.sel[1], sl.sel_g[0], sl.sel_g[1], sl.max_halo);
+        CHECK_LAUNCH();
     } else {
-        TRY(exchange_counts(c, &c->ctl->slab_ghost_send));
-        gout[0] = sl.h_cnt[0], gout[1] = sl.h_cnt[1], gin[0] = sl.h_cnt[2], gin[1] = sl.h_cnt[3];
+        CU(cudaMemsetAsync(c->ctl->slab_sel4, 0, 4 * sizeof(uint32_t), c->stream));
     }
-    for (int sd = 0; sd < 2; ++sd)
-        if (gout[sd] > sl.max_halo || gin[sd] > sl.max_halo)
-            return fail(c, YASPH_ERR_CAPACITY, "rank %d: %u ghosts out / %u in on side %d exceed max_halo=%u", sl.rank, gout[sd], gin[sd], sd, sl.max_halo);
-    const uint32_t n2 = n1 + gin[0] + gin[1];
-    if (n2 > c->cap_n) return fail(c, YASPH_ERR_CAPACITY, "rank %d: %u local particles with ghosts > max_particles=%u", sl.rank, n2, c->cap_n);
-    if (gout[0] + gout[1] + gin[0] + gin[1]) {
-        for (int sd = 0; sd < 2 && !sl.peer; ++sd)
-            if (gout[sd]) {
-                k_pack_records<<<blocks_for(gout[sd], 256), 256, 0, c->stream>>>(ra, sl.sel[sd], gout[sd], sl.sbuf[sd]);
-                CHECK_LAUNCH();
-            }
-        const void* sb[2] = {sl.sbuf[0], sl.sbuf[1]};
-        void* rb[2] = {sl.rbuf[0], sl.rbuf[1]};
-        const size_t sby[2] = {gout[0] * rec, gout[1] * rec}, rby[2] = {gin[0] * rec, gin[1] * rec};
-        if (!sl.peer) TRY(neighbor_sendrecv(c, sb, sby, rb, rby));
-        uint32_t first = n1;
-        for (int sd = 0; sd < 2 && !sl.peer; ++sd)
-            if (gin[sd]) {
-                k_unpack_records<<<blocks_for(gin[sd], 256), 256, 0, c->stream>>>(ra, first, gin[sd], sl.rbuf[sd], sl.pflag);
-                CHECK_LAUNCH();
-                first += gin[sd];
-            }
-        const uint32_t ngin = gin[0] + gin[1];
-        if (ngin) {  // ghosts keep their keys (they lie outside the slab by construction): no classification
-            k_keygen<<<keygen_grid(ngin, c->num_sms), KG_THREADS, 0, c->stream>>>(c->pos, n1, n2, c->grid, c->keys[0], c->idx[0], c->radix_scratch,
-                                                                               SlabParams{0u, 0u, nullptr, 0});
-            CHECK_LAUNCH();
+    // (2) the exchange
+    const uint32_t hseq = ++sl.pcounts_seq;
+    if (sl.peer) {
+        const uint64_t seq = ++sl.halo_seq;
+        const unsigned par = (unsigned)(seq & 1u);
+        void* bl = hl ? sl.peer_box[sl.rank - 1] : nullptr;
+        void* br = hr ? sl.peer_box[sl.rank + 1] : nullptr;
+        PeerBoxHeader* me = reinterpret_cast<PeerBoxHeader*>(sl.box);
+        const int grid = 64;  // grid-stride: the counts are known on the device only
+        k_records_push<<<grid, 256, 0, c->stream>>>(ra, sl.sel[0], sl.sel[1], sl.sel_g[0], sl.sel_g[1], c->ctl->slab_sel4, sl.max_halo,
+                                                    hl ? peer_payload(bl, sl.max_halo, par, 1) : nullptr, hr ? peer_payload(br, sl.max_halo, par, 0) : nullptr,
+                                                    hl ? &reinterpret_cast<PeerBoxHeader*>(bl)->halo_flag[1] : nullptr,
+                                                    hr ? &reinterpret_cast<PeerBoxHeader*>(br)->halo_flag[0] : nullptr, seq, sl.d_ticket);
+        CHECK_LAUNCH();
+        k_records_pull<<<grid, 256, 0, c->stream>>>(ra, n_old, c->cap_n, sl.max_halo, peer_payload(sl.box, sl.max_halo, par, 0), peer_payload(sl.box, sl.max_halo, par, 1),
+                                                    hl ? &me->halo_flag[0] : nullptr, hr ? &me->halo_flag[1] : nullptr, seq, sl.pflag, c->ctl->slab_sel4, dcnt, c->ctl);
+        CHECK_LAUNCH();
+    } else {
+        // host-mediated transports (NCCL send / recv, loopback): counts first, then the records
+        uint32_t mine[4];
+        CU(cudaMemcpyAsync(mine, c->ctl->slab_sel4, sizeof(mine), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        uint32_t* d = sl.d_cnt;  // [0..1] to the left: migrants, ghosts; [2..3] to the right; [4..5] from the left; [6..7] from the right
+        const uint32_t snd[4] = {hl ? mine[0] : 0u, hl ? mine[2] : 0u, hr ? mine[1] : 0u, hr ? mine[3] : 0u};
+        memcpy(sl.h_cnt, snd, sizeof(snd));
+        CU(cudaMemcpyAsync(d, sl.h_cnt, 4 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemsetAsync(d + 4, 0, 4 * sizeof(uint32_t), c->stream));
+        {
+            const void* sb[2] = {d, d + 2};
+            void* rb[2] = {d + 4, d + 6};
+            const size_t by[2] = {2 * sizeof(uint32_t), 2 * sizeof(uint32_t)};
+            TRY(neighbor_sendrecv(c, sb, by, rb, by));
         }
+        CU(cudaMemcpyAsync(sl.h_cnt + 4, d + 4, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        const uint32_t in_m[2] = {sl.h_cnt[4], sl.h_cnt[6]}, in_g[2] = {sl.h_cnt[5], sl.h_cnt[7]};
+        const uint32_t out_m[2] = {snd[0], snd[2]}, out_g[2] = {snd[1], snd[3]};
+        for (int sd = 0; sd < 2; ++sd)
+            if (out_m[sd] + out_g[sd] > sl.max_halo || in_m[sd] + in_g[sd] > sl.max_halo)
+                return fail(c, YASPH_ERR_CAPACITY, "rank %d: %u + %u particles out / %u + %u in on side %d exceed max_halo=%u", sl.rank, out_m[sd], out_g[sd], in_m[sd],
+                            in_g[sd], sd, sl.max_halo);
+        if ((uint64_t)n_old + in_m[0] + in_m[1] + in_g[0] + in_g[1] > c->cap_n)
+            return fail(c, YASPH_ERR_CAPACITY, "rank %d: %u local particles with arrivals > max_particles=%u", sl.rank, n_old + in_m[0] + in_m[1] + in_g[0] + in_g[1], c->cap_n);
+        for (int sd = 0; sd < 2; ++sd)
+            if (out_m[sd] + out_g[sd]) {
+                k_pack_records<<<blocks_for(out_m[sd] + out_g[sd], 256), 256, 0, c->stream>>>(ra, sl.sel[sd], out_m[sd], sl.sel_g[sd], out_g[sd], sl.sbuf[sd]);
+                CHECK_LAUNCH();
+            }
+        {
+            const void* sb[2] = {sl.sbuf[0], sl.sbuf[1]};
+            void* rb[2] = {sl.rbuf[0], sl.rbuf[1]};
+            const size_t sby[2] = {(out_m[0] + out_g[0]) * rec, (out_m[1] + out_g[1]) * rec}, rby[2] = {(in_m[0] + in_g[0]) * rec, (in_m[1] + in_g[1]) * rec};
+            if (sby[0] + sby[1] + rby[0] + rby[1]) TRY(neighbor_sendrecv(c, sb, sby, rb, rby));
+        }
+        // the same layout as k_records_pull: migrants from the left | right, then ghosts from the left | right
+        uint32_t first = n_old;
+        for (int sd = 0; sd < 2; ++sd)
+            if (in_m[sd]) {
+                k_unpack_records<<<blocks_for(in_m[sd], 256), 256, 0, c->stream>>>(ra, first, in_m[sd], sl.rbuf[sd], in_m[sd] + in_g[sd], 0u, sl.pflag);
+                CHECK_LAUNCH();
+                first += in_m[sd];
+            }
+        for (int sd = 0; sd < 2; ++sd)
+            if (in_g[sd]) {
+                k_unpack_records<<<blocks_for(in_g[sd], 256), 256, 0, c->stream>>>(ra, first, in_g[sd], sl.rbuf[sd], in_m[sd] + in_g[sd], in_m[sd], sl.pflag);
+                CHECK_LAUNCH();
+                first += in_g[sd];
+            }
+        const uint32_t all[10] = {mine[0], mine[1], mine[2], mine[3], in_m[0], in_m[1], in_g[0], in_g[1], 0u, 0u};  // SlabCounts: out_m, out_g, in_m, in_g
+        memcpy(sl.h_cnt + 8, all, sizeof(all));
+        CU(cudaMemcpyAsync(dcnt, sl.h_cnt + 8, sizeof(all), cudaMemcpyHostToDevice, c->stream));
     }
-    sl.n_send[0] = gout[0];
-    sl.n_send[1] = gout[1];
-    sl.n_ghost[0] = gin[0];
-    sl.n_ghost[1] = gin[1];
-    *n_sort = n2;
-    *n_keep = n2 - ghosts_old - sl.mig_out[0] - sl.mig_out[1];
+    // (3) this rank's out-migrants that are now part of a neighbour's first W columns stay here as ghosts; the counts reach the host
+    k_slab_retain<<<1, 32, 0, c->stream>>>(ra, c->grid, sl.sel[0], sl.sel[1], dcnt, n_old, c->cap_n, sl.max_halo, sl.col_lo, sl.col_hi, W, sl.pflag, sl.d_pcounts, hseq);
+    CHECK_LAUNCH();
+    TRY(wait_published(c, &sl.h_pcounts->seq, hseq, c->stream));
+    const SlabCounts cnt = const_cast<const PeerCounts*>(sl.h_pcounts)->cnt;
+    // a particle that leaves through an end of the domain has no rank to go to
+    if ((cnt.out_m[0] && !hl) || (cnt.out_m[1] && !hr))
+        return fail(c, YASPH_ERR_STATE, "rank %d: %u / %u particles left the domain's first / last slab [%u, %u)", sl.rank, cnt.out_m[0], cnt.out_m[1], sl.col_lo, sl.col_hi);
+    for (int sd = 0; sd < 2; ++sd)
+        if (cnt.out_m[sd] + cnt.out_g[sd] > sl.max_halo || cnt.in_m[sd] + cnt.in_g[sd] > sl.max_halo)
+            return fail(c, YASPH_ERR_CAPACITY, "rank %d: %u + %u particles out / %u + %u in on side %d exceed max_halo=%u", sl.rank, cnt.out_m[sd], cnt.out_g[sd],
+                        cnt.in_m[sd], cnt.in_g[sd], sd, sl.max_halo);
+    const uint32_t n_mig_in = cnt.in_m[0] + cnt.in_m[1], n_ghost_in = cnt.in_g[0] + cnt.in_g[1] + cnt.retained[0] + cnt.retained[1];
+    const uint64_t n2 = (uint64_t)n_old + n_mig_in + n_ghost_in;
+    if (n2 > c->cap_n) return fail(c, YASPH_ERR_CAPACITY, "rank %d: %llu local particles with arrivals and ghosts > max_particles=%u", sl.rank, (unsigned long long)n2, c->cap_n);
+    // (4) sort keys of the arrivals: migrants are classified (they must lie inside the slab: particles move less than a cell per step and
+    // a slab is many cells wide); ghosts keep their keys, they lie outside the slab by construction
+    if (n_mig_in) {
+        k_keygen<<<keygen_grid(n_mig_in, c->num_sms), KG_THREADS, 0, c->stream>>>(c->pos, n_old, n_old + n_mig_in, c->grid, c->keys[0], c->idx[0], c->radix_scratch, sp);
+        CHECK_LAUNCH();
+        k_check_arrivals<<<blocks_for(n_mig_in, 256), 256, 0, c->stream>>>(sl.pflag, n_old, n_old + n_mig_in, c->ctl);
+        CHECK_LAUNCH();
+    }
+    if (n_ghost_in) {
+        k_keygen<<<keygen_grid(n_ghost_in, c->num_sms), KG_THREADS, 0, c->stream>>>(c->pos, n_old + n_mig_in, (uint32_t)n2, c->grid, c->keys[0], c->idx[0],
+                                                                                  c->radix_scratch, SlabParams{0u, 0u, nullptr, 0});
+        CHECK_LAUNCH();
+    }
+    sl.mig_out[0] = cnt.out_m[0];
+    sl.mig_out[1] = cnt.out_m[1];
+    sl.mig_in = n_mig_in;
+    sl.n_ghost[0] = cnt.in_g[0] + cnt.retained[0];
+    sl.n_ghost[1] = cnt.in_g[1] + cnt.retained[1];
+    sl.halo_exchanges++;
+    *n_sort = (uint32_t)n2;
+    *n_keep = (uint32_t)n2 - ghosts_old - sl.mig_out[0] - sl.mig_out[1];
     return YASPH_OK;
 }
 
@@ -1321,6 +1343,14 @@ static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp
             ga.in1[q] = *gp.a1[q];
             ga.out1[q] = *gp.alt1[q];
         }
+        if (c->slab.active) {
+            CU(cudaMemsetAsync(&c->ctl->slab_ghost, 0, sizeof(unsigned long long), c->stream));
+            ga.keys = c->keys[0];
+            ga.ghost = c->slab.pflag;
+            ga.ghost_count = &c->ctl->slab_ghost;
+            ga.col_lo = c->slab.col_lo;
+            ga.col_hi = c->slab.col_hi;
+        }
         k_gather<<<blocks_for(n, 256), 256, 0, c->stream>>>(c->idx[0], n, ga);
         CHECK_LAUNCH();
         for (int q = 0; q < gp.n2; ++q) std::swap(*gp.a2[q], *gp.alt2[q]);
@@ -1336,16 +1366,7 @@ static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp
         k_tile_tables<<<c->num_sms * 16, TT_WARPS * 32, 0, c->stream>>>(ta, c->ctl);
         CHECK_LAUNCH();
     }
-    if (c->slab.active) {
-        // per-pass halo lists of the new structure, in sorted order: what this rank sends (its first / last owned column) and
-        // where its ghosts sit; the ghost flags; counts come back with the control block below
-        auto& sl = c->slab;
-        const uint32_t W = sl.ghost_cols;
-        const uint32_t a_lo = sl.col_lo, a_hi = has_left(c) ? std::min(sl.col_lo + W, sl.col_hi) : sl.col_lo;
-        const uint32_t b_hi = sl.col_hi, b_lo = has_right(c) ? (sl.col_hi - sl.col_lo > W ? sl.col_hi - W : sl.col_lo) : sl.col_hi;
-        TRY(select_pair(c, ColumnSelIn{c->keys[0], nullptr, a_lo, a_hi, b_lo, b_hi}, n, sl.send_idx[0], sl.send_idx[1], nullptr, sl.max_halo, &c->ctl->slab_send));
-        TRY(select_pair(c, GhostSelIn{c->keys[0], sl.col_lo, sl.col_hi}, n, sl.ghost_idx[0], sl.ghost_idx[1], sl.pflag, sl.max_halo, &c->ctl->slab_ghost));
-    }
+    c->slab.halo_lists_valid = false;  // per-pass halo lists of the new structure are built when a pass needs an exchange (ensure_halo_lists)
     pass_end(c);
     // The one host round trip of the neighbourhood update: tile count (grid of every tile kernel until the next update) and
     // the largest tile (their shared-memory size).  The list build does not wait for it when the previous structure's sizes are
@@ -1382,12 +1403,10 @@ static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp
     if (c->slab.active) {
         auto& sl = c->slab;
         const Control& h = *c->h_ctl;
-        const uint32_t s0 = (uint32_t)(h.slab_send & 0xFFFFFFFFull), s1 = (uint32_t)(h.slab_send >> 32);
         const uint32_t g0 = (uint32_t)(h.slab_ghost & 0xFFFFFFFFull), g1 = (uint32_t)(h.slab_ghost >> 32);
         if (h.err_slab) return fail(c, YASPH_ERR_STATE, "rank %d: %u migrants arrived outside the slab [%u, %u) (a particle crossed more than one slab in a step)", sl.rank, h.err_slab, sl.col_lo, sl.col_hi);
-        if (s0 != sl.n_send[0] || s1 != sl.n_send[1] || g0 != sl.n_ghost[0] || g1 != sl.n_ghost[1])
-            return fail(c, YASPH_ERR_STATE, "rank %d: halo lists (%u,%u | %u,%u) disagree with the exchanged ghosts (%u,%u | %u,%u)", sl.rank, s0, s1, g0, g1,
-                        sl.n_send[0], sl.n_send[1], sl.n_ghost[0], sl.n_ghost[1]);
+        if (g0 != sl.n_ghost[0] || g1 != sl.n_ghost[1])
+            return fail(c, YASPH_ERR_STATE, "rank %d: %u | %u ghosts in the sorted structure, %u | %u were exchanged", sl.rank, g0, g1, sl.n_ghost[0], sl.n_ghost[1]);
         sl.n_own = n - g0 - g1;
     }
     c->num_tiles = n ? c->h_ctl->num_tiles : 0u;
@@ -2390,9 +2409,6 @@ static int32_t peer_setup(yasph_ctx* c) {
         CU(cudaMemcpy(sl.d_boxes, sl.peer_box, sizeof(void*) * PEER_MAX_RANKS, cudaMemcpyHostToDevice));
         CU(cudaMalloc((void**)&sl.d_ticket, sizeof(unsigned int)));
         CU(cudaMemset(sl.d_ticket, 0, sizeof(unsigned int)));
-        CU(cudaHostAlloc((void**)&sl.h_pcounts, sizeof(PeerCounts), cudaHostAllocMapped));
-        memset(sl.h_pcounts, 0, sizeof(PeerCounts));
-        CU(cudaHostGetDevicePointer((void**)&sl.d_pcounts, sl.h_pcounts, 0));
         sl.peer = true;
     } else {
         for (int r = 0; r < sl.world; ++r)
@@ -2412,9 +2428,6 @@ static void peer_teardown(yasph_ctx* c) {
     if (sl.box) cudaFree(sl.box);
     if (sl.d_boxes) cudaFree(sl.d_boxes);
     if (sl.d_ticket) cudaFree(sl.d_ticket);
-    if (sl.h_pcounts) cudaFreeHost(sl.h_pcounts);
-    sl.h_pcounts = nullptr;
-    sl.d_pcounts = nullptr;
     sl.box = nullptr;
     sl.d_boxes = nullptr;
     sl.d_ticket = nullptr;
@@ -2435,20 +2448,26 @@ extern "C" int32_t yasph_slab_set(yasph_ctx* c, uint32_t col_lo, uint32_t col_hi
     sl.id_base = id_base;
     sl.max_halo = c->cfg.max_halo;
     sl.ghost_cols = c->cfg.ghost_columns ? c->cfg.ghost_columns : 1u;
-    if (sl.world > 1 && sl.rank > 0 && sl.rank + 1 < sl.world && col_hi - col_lo < sl.ghost_cols)
-        return fail(c, YASPH_ERR_INVALID_ARGUMENT, "yasph_slab_set: slab [%u, %u) is narrower than the ghost layer (ghost_columns = %u)", col_lo, col_hi, sl.ghost_cols);
+    if (sl.world > 1 && sl.rank > 0 && sl.rank + 1 < sl.world && col_hi - col_lo < sl.ghost_cols + 1u)
+        return fail(c, YASPH_ERR_INVALID_ARGUMENT, "yasph_slab_set: slab [%u, %u) between two others must be wider than the ghost layer (ghost_columns = %u)", col_lo, col_hi,
+                    sl.ghost_cols);
     if (!sl.pflag) {
         CU(dmalloc(&sl.pflag, (size_t)c->cap_n));
         CU(cudaMemsetAsync(sl.pflag, 0, c->cap_n, c->stream));
         for (int sd = 0; sd < 2; ++sd) {
             CU(dmalloc(&sl.sel[sd], (size_t)sl.max_halo));
+            CU(dmalloc(&sl.sel_g[sd], (size_t)sl.max_halo));
             CU(dmalloc(&sl.send_idx[sd], (size_t)sl.max_halo));
             CU(dmalloc(&sl.ghost_idx[sd], (size_t)sl.max_halo));
             CU(dmalloc(&sl.sbuf[sd], (size_t)sl.max_halo * RECORD_MAX_BYTES));
             CU(dmalloc(&sl.rbuf[sd], (size_t)sl.max_halo * RECORD_MAX_BYTES));
         }
-        CU(dmalloc(&sl.d_cnt, 4));
-        CU(cudaMallocHost((void**)&sl.h_cnt, 4 * sizeof(uint32_t)));
+        CU(dmalloc(&sl.sel4_chunks, (size_t)scan_num_chunks(c->cap_n) + 1));
+        CU(dmalloc(&sl.d_cnt, 8));
+        CU(cudaMallocHost((void**)&sl.h_cnt, 32 * sizeof(uint32_t)));
+        CU(cudaHostAlloc((void**)&sl.h_pcounts, sizeof(PeerCounts), cudaHostAllocMapped));
+        memset(sl.h_pcounts, 0, sizeof(PeerCounts));
+        CU(cudaHostGetDevicePointer((void**)&sl.d_pcounts, sl.h_pcounts, 0));
     }
     TRY(peer_setup(c));
     sl.active = true;

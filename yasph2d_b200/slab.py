@@ -13,7 +13,7 @@ from . import _capi as capi
 from .host import GpuContext, _f32p
 
 f32 = np.float32
-GHOST_COLUMNS = 8  # default width of the ghost layer (cell columns): no per-pass halo exchange in a DFSPH step of up to 2 + 2 Jacobi iterations
+GHOST_COLUMNS = 12  # default width of the ghost layer (cell columns): no per-pass halo exchange in a DFSPH step of up to ~4 Jacobi iterations + warm start
 
 
 def cell_columns(x, smoothing_length, grid_min_x=-100.0):
@@ -164,8 +164,11 @@ def make_slab_context(base_cfg, rank, world, comm, positions, velocities, bounda
     positions = np.ascontiguousarray(positions, np.float32).reshape(-1, 2)
     ranges, own = scatter_scene(positions, base_cfg.smoothing_length, base_cfg.grid_min[0], world, ranges)
     cfg = capi.Config.from_buffer_copy(base_cfg)
-    if cfg.ghost_columns == 0:  # as wide a ghost layer as the narrowest slab allows, at most GHOST_COLUMNS (see yasph_config.ghost_columns)
-        cfg.ghost_columns = max(1, min(GHOST_COLUMNS, min(hi - lo for lo, hi in ranges)))
+    if cfg.ghost_columns == 0:
+        # as wide a ghost layer as the narrowest slab between two others allows (W <= width - 1: a migrant that arrives from one side must not
+        # belong to the ghost layer of the OTHER side), at most GHOST_COLUMNS (see yasph_config.ghost_columns)
+        inner = [hi - lo for lo, hi in ranges[1:-1]]
+        cfg.ghost_columns = max(1, min([GHOST_COLUMNS] + [w - 1 for w in inner]))
     id_base = int(sum(len(o) for o in own[:rank]))
     ctx = SlabContext(cfg, rank, world, comm, ranges[rank], len(positions), id_base)
     ctx.set_boundary(boundary)
