@@ -586,8 +586,6 @@ struct ListSmem {
     uint32_t ncand[2][TILE_CELLS];    // per own cell: total candidates
     unsigned long long wtotal[NB_THREADS / 32];
     uint32_t nk_max;
-    uint32_t wk[NB_THREADS / 32][LIST_WORDS];  // particles per (warp, list-word count): the tile's work order
-    uint32_t wk_bin[LIST_WORDS];
     uint16_t sl[NB_ROWS][NB_THREADS];
 };
 inline size_t list_smem_bytes(uint32_t cap_dyn, uint32_t cap_stat) { return sizeof(ListSmem) + 2 * ((size_t)cap_dyn + cap_stat) * sizeof(float2); }
@@ -604,7 +602,7 @@ struct ListArgs {
     GridParams g;
     Control* ctl;
     unsigned long long* lists;
-    uint32_t* counts;   // low half: count_dynamic | count_total << 8 of particle i; high half: work order of i's tile (see k_build_lists)
+    uint32_t* counts;   // count_dynamic | count_total << 8 of particle i
     uint32_t* tile_nk;  // [tile] most list words of any particle of the tile
     uint32_t cap_dyn, cap_stat;
     uint32_t* apron_idx;  // [tile][APRON_TABLE]
@@ -760,11 +758,9 @@ __global__ void __launch_bounds__(NB_THREADS) k_build_lists(ListArgs a) {
             S.ncand[which][lc] = tot;
         }
         if (tid == 0) S.nk_max = 0u;
-        if (tid < (NB_THREADS / 32) * LIST_WORDS) (&S.wk[0][0])[tid] = 0u;
         __syncthreads();
         LT_MARK(2)  // cell phase (incl. its barrier)
-        uint32_t my_nk = 0, my_words = 0xFFu;
-        uint16_t* const counts16 = reinterpret_cast<uint16_t*>(a.counts);
+        uint32_t my_nk = 0;
         if (mine) {
             for (uint32_t tl = tid; tl < h.pcount; tl += NB_THREADS) {
                 const uint32_t i = h.pstart + tl;
@@ -802,55 +798,21 @@ __global__ void __launch_bounds__(NB_THREADS) k_build_lists(ListArgs a) {
                         if (cd + kb * 4 + e < ct) w |= (unsigned long long)col[(cd + kb * 4 + e) * NB_THREADS] << (16 * e);
                     a.lists[list_word_index(h.pstart, h.pcount, nkd + kb, tl)] = w;
                 }
-                counts16[2 * (size_t)i] = (uint16_t)(cd | (ct << 8));
-                my_words = nkd + nks;
-                my_nk = max(my_nk, my_words);
+                a.counts[i] = cd | (ct << 8);
+                my_nk = max(my_nk, nkd + nks);
                 my_total += ct;
             }
         }
         LT_MARK(3)  // candidate scan + packing + stores
         my_nk = __reduce_max_sync(0xffffffffu, my_nk);
         if (lane_id() == 0 && my_nk) atomicMax(&S.nk_max, my_nk);
-        // Work order of the tile: its particles sorted (stably) by their number of list words.  The sweeps hand 32 consecutive
-        // entries of this order to one warp, so the lanes of a warp walk lists of (nearly) equal length.  Stored in the high
-        // half of counts[pstart + position].  Tiles of more than NB_THREADS particles keep the identity order.
-        const bool sortable = mine && h.pcount <= NB_THREADS;
-        const unsigned same = __match_any_sync(0xffffffffu, my_words);
-        if (sortable && my_words != 0xFFu && lane_id() == (unsigned)(__ffs(same) - 1)) S.wk[tid >> 5][my_words] = (uint32_t)__popc(same);
-        __syncthreads();  // also orders this tile's reads of S.crun / S.ncand before the next tile's writes
-        if (tid < 32) {
-            uint32_t tot = 0;
-            if (tid < LIST_WORDS) {
-#pragma unroll
-                for (int w = 0; w < NB_THREADS / 32; ++w) {
-                    const uint32_t v = S.wk[w][tid];
-                    S.wk[w][tid] = tot;  // exclusive over the warps
-                    tot += v;
-                }
-            }
-            uint32_t inc = tot;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
-                if (tid >= (uint32_t)o) inc += u;
-            }
-            if (tid < LIST_WORDS) S.wk_bin[tid] = inc - tot;
-        }
-        __syncthreads();
-        if (sortable) {
-            if (my_words != 0xFFu) {
-                const uint32_t position = S.wk_bin[my_words] + S.wk[tid >> 5][my_words] + (uint32_t)__popc(same & lanemask_lt());
-                counts16[2 * (size_t)(h.pstart + position) + 1] = (uint16_t)tid;
-            }
-        } else if (mine) {
-            for (uint32_t tl = tid; tl < h.pcount; tl += NB_THREADS) counts16[2 * (size_t)(h.pstart + tl) + 1] = (uint16_t)tl;
-        }
+        __syncthreads();  // S.nk_max is complete; also orders this tile's reads of S.crun / S.ncand before the next tile's writes
         if (tid == 0 && mine) {
             a.tile_nk[t] = S.nk_max;
             cta_nk = max(cta_nk, S.nk_max);
         }
         pre.store(S.runs[(k + 2) % 3u], have2);
-        LT_MARK(4)  // work order (two barriers)
+        LT_MARK(4)  // closing barrier
     }
 #ifdef YASPH_LIST_TIMING
     if (lane_id() == 0 && a.dbg) {

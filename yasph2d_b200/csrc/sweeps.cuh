@@ -517,9 +517,9 @@ __global__ void __launch_bounds__(SW_THREADS, YASPH_SWEEP_MIN_CTAS) k_sweep(Swee
             const uint32_t od = h.pstart & 3u;  // the per-particle operand arrays are staged from the 4-element-aligned index below pstart
             if (nk_st != 0xFFFFFFFFu) {
                 for (uint32_t j = (cw + SW_CONSUMER_WARPS - chunk_base % SW_CONSUMER_WARPS) % SW_CONSUMER_WARPS; j < nchunks; j += SW_CONSUMER_WARPS) {
-                    const uint32_t wo = j * 32u + lane;  // entry of the tile's work order: its particles sorted by list length
+                    const uint32_t wo = j * 32u + lane;  // particle of the tile (a per-tile order by list length was measured to change nothing)
                     if (wo < h.pcount) {
-                        const uint32_t tl = st.cnt[od + wo] >> 16;
+                        const uint32_t tl = wo;
                         const uint32_t i = h.pstart + tl;
                         const uint32_t own = h.own_lo + tl;
                         const float2 pi = st.pos[own];
