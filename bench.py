@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--cpu-columns", type=int, default=250, help="fluid columns of the bounded CPU sample (rows as the workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="multi-GPU: skip the N-rank-vs-one-context equivalence check that precedes the timing")
     ap.add_argument("--no-peer-transport", action="store_true", help="multi-GPU: keep halo exchanges and all-reduces on NCCL (A/B of the peer-memory transport)")
     return ap.parse_args()
 
@@ -225,6 +226,125 @@ def neighbor_sweep(args):
     return 0
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Pins this process to the CPU cores next to its GPU (the GPU's NUMA node) BEFORE any pinned host memory is allocated, so that the
+    e2e arm's host buffers are first-touched on that node: with one process per GPU the uploads / downloads of all ranks then do not
+    funnel through one socket's memory controllers.  Best effort: returns a note for the JSON line."""
+    try:
+        import pynvml as nv
+
+        nv.nvmlInit()
+        bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(device_index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:  # NVML prints an 8-digit PCI domain, sysfs a 4-digit one
+            bus = bus[4:]
+        base = "/sys/bus/pci/devices/" + bus
+        node = int(open(base + "/numa_node").read().strip())
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if node < 0 or not cpus:
+            return "no NUMA information for %s" % bus
+        os.sched_setaffinity(0, cpus)
+        return "bound to NUMA node %d (%d cores) of GPU %s" % (node, len(cpus), bus)
+    except Exception as e:  # noqa: BLE001
+        return "not bound (%r)" % (e,)
+
+
+def verify_slabs(args, dist, rank, world, local_rank):
+    """N-rank equivalence on the hardware of this very run: a small tank stepped by the `world` slab contexts of
+    this job (peer-memory transport, ghost layers, migration) against ONE context on rank 0.  Bars as in tests/test_gpu_slab.py: every
+    particle is owned by exactly one rank at every step; bit-identical states, dt, iteration counts and residuals until the first
+    particle migrates (same arithmetic, same neighbour order); afterwards only the summation order inside cells that received a
+    migrant differs -- fields within 1e-4 relative for the next three steps, then global quantities (kinetic energy 2 %, mean density 0.1 %)."""
+    import yasph2d_b200 as y
+    from yasph2d_b200 import slab
+
+    capi = y.capi
+    steps, columns, rows = 50, 128 * world, 160
+    hw = y.tank_scene(y.FluidParticleWorld(2.0, 10000.0, 100.0), columns, rows)
+    pos, vel, bnd = hw.particles.positions, hw.particles.velocities.copy(), hw.particles.boundary_particles
+    vel[:, 0] = 0.4  # a drift towards +x: particles cross the slab boundaries within the first steps
+    n = len(pos)
+    cfg = capi.default_config(2.0, 10000.0, 100.0, capi.SOLVER_DFSPH if args.solver == "dfsph" else capi.SOLVER_WCSPH)
+    cfg.device = local_rank
+    cfg.max_particles, cfg.max_boundary = 2 * n // world + 65536, len(bnd)
+    cfg.flags = capi.FLAG_PERMUTE_WARMSTART | capi.FLAG_TRACK_IDS | (capi.FLAG_NO_PEER_TRANSPORT if args.no_peer_transport else 0)
+    uid = slab.broadcast_unique_id(dist)
+    ctx, ranges, id_map = slab.make_slab_context(cfg, rank, world, uid, pos, vel, bnd)
+    snaps, reps, migs = [], [], []
+    for _ in range(steps):
+        r = ctx.step()
+        info = ctx.info()
+        p, v, d = ctx.download_particles()
+        snaps.append((id_map[ctx.ids()].astype(np.int64), p, v, d))
+        reps.append((int(r.dt_ns), int(r.iters_density), int(r.iters_divergence), float(r.avg_density_error), float(r.avg_divergence)))
+        migs.append(int(info.migrated_in + info.migrated_out_left + info.migrated_out_right))
+    peer = int(ctx.info().peer_transport)
+    ghost_cols = int(ctx.cfg.ghost_columns)
+    halos = int(ctx.info().halo_exchanges)
+    ctx.close()
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object((snaps, reps, migs), gathered, dst=0)
+    if rank != 0:
+        return None
+    cfg1 = capi.default_config(2.0, 10000.0, 100.0, cfg.solver)
+    cfg1.device = local_rank
+    cfg1.max_particles, cfg1.max_boundary = n, len(bnd)
+    cfg1.flags = capi.FLAG_PERMUTE_WARMSTART | capi.FLAG_TRACK_IDS
+    one = y.GpuContext(cfg1)
+    one.set_boundary(bnd)
+    one.upload_particles(pos, vel)
+    first_mig = next((s for s in range(steps) if any(g[2][s] for g in gathered)), steps)
+    res = {"ok": True, "steps": steps, "particles": n, "ranks": world, "first_migration_step": first_mig, "bit_identical_steps": 0, "max_rel_dev_after_migration": 0.0,
+           "peer_transport": peer, "ghost_columns": ghost_cols, "halo_exchanges_rank0": halos, "problems": []}
+    for s in range(steps):
+        r1 = one.step()
+        ids1 = one.field(capi.FIELD_ID).astype(np.int64)
+        p1, v1, d1 = one.download_particles()
+        ref = {"pos": np.empty_like(p1), "vel": np.empty_like(v1), "dens": np.empty_like(d1)}
+        ref["pos"][ids1], ref["vel"][ids1], ref["dens"][ids1] = p1, v1, d1
+        got = {"pos": np.full_like(p1, np.nan), "vel": np.full_like(v1, np.nan), "dens": np.full_like(d1, np.nan)}
+        seen = np.zeros(n, np.int32)
+        for g in gathered:
+            ids, p, v, d = g[0][s]
+            np.add.at(seen, ids, 1)
+            got["pos"][ids], got["vel"][ids], got["dens"][ids] = p, v, d
+        if not (seen == 1).all():
+            res["problems"].append("step %d: %d particles unowned, %d owned twice" % (s, int((seen == 0).sum()), int((seen > 1).sum())))
+            break
+        rep1 = (int(r1.dt_ns), int(r1.iters_density), int(r1.iters_divergence), float(r1.avg_density_error), float(r1.avg_divergence))
+        if len({g[1][s] for g in gathered}) != 1:
+            res["problems"].append("step %d: the ranks disagree on dt / iteration counts / residuals" % s)
+        if s < first_mig:
+            same = all(np.array_equal(got[k], ref[k]) for k in ref) and gathered[0][1][s] == rep1
+            if same:
+                res["bit_identical_steps"] += 1
+            else:
+                res["problems"].append("step %d: differs from the single context before any migration" % s)
+        else:
+            dev = 0.0
+            for k in ("vel", "dens"):
+                a, b = got[k].astype(np.float64), ref[k].astype(np.float64)
+                dev = max(dev, float((np.abs(a - b) / np.maximum(np.abs(b), 0.1 * np.abs(b).mean() + 1e-30)).max()))
+            if s < first_mig + 3:
+                res["max_rel_dev_after_migration"] = max(res["max_rel_dev_after_migration"], dev)
+                if dev > 1e-4:
+                    res["problems"].append("step %d: relative deviation %.2e > 1e-4 within three steps of the first migration" % (s, dev))
+            else:
+                ea, eb = float((got["vel"].astype(np.float64) ** 2).sum()), float((ref["vel"].astype(np.float64) ** 2).sum())
+                if abs(ea - eb) > 0.02 * max(eb, 1e-12) or abs(float(got["dens"].mean()) - float(ref["dens"].mean())) > 1e-3 * float(ref["dens"].mean()):
+                    res["problems"].append("step %d: kinetic energy / mean density left the bounds" % s)
+            if abs(gathered[0][1][s][0] - rep1[0]) > 2e-3 * rep1[0]:
+                res["problems"].append("step %d: dt %d vs %d" % (s, gathered[0][1][s][0], rep1[0]))
+    one.close()
+    res["ok"] = not res["problems"]
+    res["problems"] = res["problems"][:5]
+    return res
+
+
 def pass_groups(solver, pt, B, K, it_rho, it_div, w_rho, w_div):
     """(us per step, algorithmic bytes per particle and step) of every timed pass group.  The density / alpha sweep also carries
     iteration 0's density-change pass of the divergence solver whenever that solver's warm start does not run (OpDensityAlphaDiv):
@@ -303,6 +423,7 @@ def main():
     capi = y.capi
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    numa_note = bind_to_gpu_numa_node(local_rank) if world > 1 else "single process: not bound"
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
@@ -313,6 +434,8 @@ def main():
     def barrier():
         if dist is not None:
             dist.barrier()
+
+    verify = verify_slabs(args, dist, rank, world, local_rank) if (world > 1 and not args.no_verify) else None
 
     # ---- scene (host): every rank builds the whole scene (the jitter stream is sequential), then keeps its slab ----
     hw = y.FluidParticleWorld(2.0, 10000.0, 100.0)
@@ -522,7 +645,7 @@ def main():
             no_upload = {"value": n_total * args.steps / (ums * 1e-3), "ms_per_step": ums / args.steps, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(n_total * 20),
                          "api": "yasph_step_host_ex(YASPH_HOST_INPUT_UNCHANGED)"}
         e2e = {"value": n_total * args.steps / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(n_total * 16), "d2h_bytes_per_step": int(n_total * 20),
-               "ms_per_step": ems / args.steps, "device_timeline_us": timeline, "input_unchanged": no_upload,
+               "ms_per_step": ems / args.steps, "device_timeline_us": timeline, "input_unchanged": no_upload, "host_affinity": numa_note,
                "api": "yasph_step_host%s (upload pos+vel, simulation_step, download pos+vel+densities; bytes summed over ranks)" % ("" if world == 1 else "_slab")}
 
     # ---- regime "collapse": further into the run, where the divergence solver iterates and warm-starts ----
@@ -563,6 +686,8 @@ def main():
         if collapse is not None:
             line["regimes"] = {"early": {k: early[k] for k in ("first_timed_step", "value", "ms_per_step", "iters_density", "iters_divergence", "warm_density", "warm_divergence", "mean_neighbors")},
                                "collapse": collapse}
+        if verify is not None:
+            line["verify"] = verify
         if e2e:
             line["e2e"] = e2e
         if cpu:
