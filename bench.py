@@ -570,8 +570,14 @@ def main():
         traffic, traffic_src = None, None
         if traffic_file and world == 1 and n_loc == traffic_file.get("particles") and args.solver == traffic_file.get("solver", "dfsph"):
             if traffic_file.get("kernel_source_hash") == kernel_source_hash():
+                def entry(kname):  # ncu prints template arguments its own way (k_build_lists<0>): match by prefix
+                    hits = [v for k, v in traffic_file["kernels"].items() if k == kname or k.startswith(kname + "<")]
+                    if not hits:
+                        raise KeyError(kname)
+                    return max(hits, key=lambda v: v["us"])
+
                 try:
-                    traffic = sum(traffic_file["kernels"][k]["dram_bytes_read"] + traffic_file["kernels"][k]["dram_bytes_write"] for k in PASS_KERNELS[dominant])
+                    traffic = sum(entry(k)["dram_bytes_read"] + entry(k)["dram_bytes_write"] for k in PASS_KERNELS[dominant])
                     traffic_src = traffic_file.get("source")
                 except KeyError:
                     traffic_src = "profiles/r02/traffic.json has no entry for %s" % PASS_KERNELS[dominant]
