@@ -1853,12 +1853,13 @@ static int32_t jacobi_solve(yasph_ctx* c, bool first_a_done = false) {
     sp.max_error = SOLVER == 0 ? c->cfg.dfsph_max_avg_density_error : c->cfg.dfsph_max_divergence_error;
     sp.max_iters = SOLVER == 0 ? c->cfg.dfsph_max_density_iters : c->cfg.dfsph_max_divergence_iters;
     uint32_t it = 0;
-    // slab mode: every iteration carries collectives that cannot be skipped on the device, so nothing is launched speculatively
     const bool slab = c->slab.active && c->slab.world > 1;
-    // Iterations launched before the first read-back: as many as the previous solve needed (the count changes slowly from
-    // step to step), at most `speculative_iterations`; later chunks launch `speculative_iterations` at a time.
+    // Iterations launched before the first read-back: as many as the previous solve needed (the count changes slowly from step to
+    // step; at most 8); later chunks launch `speculative_iterations` at a time.  Sweeps past the converged iteration exit on the
+    // device-side stop_iter.  Slab mode: the all-reduce (and any halo exchange) of such an iteration still runs on every rank -- all
+    // ranks take the same decision from the same all-reduced residual, so the exchanges stay matched; they just move stale values.
     const uint32_t spec = c->cfg.speculative_iterations;
-    uint32_t chunk = slab ? 1u : (prev_iters < 1u ? 1u : (prev_iters > spec ? spec : prev_iters));
+    uint32_t chunk = prev_iters < 1u ? 1u : std::min(prev_iters, std::max(spec, 8u));
     const int solve_pass = SOLVER == 0 ? YASPH_PASS_DENSITY_SOLVE : YASPH_PASS_DIVERGENCE_SOLVE;
     while (true) {
         pass_begin(c, solve_pass);
@@ -1932,7 +1933,7 @@ static int32_t jacobi_solve(yasph_ctx* c, bool first_a_done = false) {
         }
         if (SOLVER == 1) c->early_vel_stale = true;
         if (it > sp.max_iters + spec + 1) return fail(c, YASPH_ERR_STATE, "jacobi_solve: device loop control did not terminate");
-        chunk = slab ? 1u : spec;
+        chunk = spec;
     }
     return YASPH_OK;
 }
