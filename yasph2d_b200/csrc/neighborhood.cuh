@@ -218,11 +218,15 @@ struct HeadCompactOut {
         }
     }
 };
-// sentinel cell {first_particle = N, cidx = u32::MAX} (neighborhood_search.rs:161-164), tile sentinels and the counts
-__global__ void k_finish_cells(const unsigned long long* __restrict__ total, uint32_t n, uint32_t* cell_key, uint32_t* cell_start,
-                               uint32_t* tile_pstart, uint32_t* tile_cstart, uint32_t max_tiles, Control* ctl, int is_static) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        unsigned long long t = n ? *total : 0ull;
+// sentinel cell {first_particle = N, cidx = u32::MAX} (neighborhood_search.rs:161-164), tile sentinels and the counts, from the
+// scan's grand total (cells | tiles << 32): called by the thread of the fused scan that holds it
+struct FinishCells {
+    uint32_t n;
+    uint32_t *cell_key, *cell_start, *tile_pstart, *tile_cstart;
+    uint32_t max_tiles;
+    Control* ctl;
+    int is_static;
+    __device__ __forceinline__ void operator()(unsigned long long t) const {
         uint32_t c = (uint32_t)(t & 0xFFFFFFFFull), nt = (uint32_t)(t >> 32);
         cell_key[c] = 0xFFFFFFFFu;
         cell_start[c] = n;
@@ -244,6 +248,10 @@ __global__ void k_finish_cells(const unsigned long long* __restrict__ total, uin
             ctl->max_nk = 0u;
         }
     }
+};
+// the same for an empty particle set
+__global__ void k_finish_cells(FinishCells f) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) f(0ull);
 }
 
 // first index in [lo, hi) whose key is >= `key` (the role of find_next_cell, neighborhood_search.rs:169-189)

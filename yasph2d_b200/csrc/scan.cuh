@@ -118,6 +118,65 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(In in, uint32_t n, 
     }
 }
 
+// ---- the same scan in ONE kernel ---------------------------------------------------------------------------------------------
+// Chunks are taken in ticket order; a chunk publishes its total as soon as it has counted its flags, and obtains its exclusive prefix
+// by summing the totals of ALL earlier chunks (one warp, coalesced loads, spinning on the few that are not published yet) -- no
+// serial chain of inclusive prefixes, and the input is read once.  The chunk that holds the last element also hands the grand total to
+// `fin` (sentinels, counts), so no extra launch follows.  status[0] = ticket counter, status[1 + b] = total of chunk b | 1 << 63
+// (a total's tile half is <= 4096, so bit 63 is free); the caller zeroes 1 + nchunks words before the launch.
+template <typename In, typename Out, typename Fin>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_fused(In in, uint32_t n, unsigned long long* __restrict__ status, Out out, Fin fin) {
+    typedef unsigned long long T;
+    __shared__ T wsum[SCAN_WARPS];
+    __shared__ T off_s;
+    __shared__ uint32_t chunk_s;
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    const unsigned lt = lanemask_lt();
+    if (threadIdx.x == 0) chunk_s = atomicAdd(reinterpret_cast<unsigned int*>(status), 1u);
+    __syncthreads();
+    const uint32_t b = chunk_s;
+    const uint32_t base = b * SCAN_CHUNK + warp * (32 * SCAN_ITEMS);
+    T v[SCAN_ITEMS], ex[SCAN_ITEMS];
+    T carry = 0;  // warp-uniform
+#pragma unroll
+    for (int r = 0; r < SCAN_ITEMS; ++r) {
+        const uint32_t i = base + r * 32 + lane;
+        v[r] = i < n ? in(i) : (T)0;
+        T e, tot;
+        warp_flag_scan(v[r], lt, e, tot);
+        ex[r] = carry + e;
+        carry += tot;
+    }
+    if (lane == 0) wsum[warp] = carry;
+    __syncthreads();
+    volatile T* st = status + 1;
+    if (warp == 0) {
+        T total = 0;
+#pragma unroll
+        for (int w = 0; w < SCAN_WARPS; ++w) total += wsum[w];
+        if (lane == 0) st[b] = total | (1ull << 63);
+        // exclusive prefix over the chunks: every lane sums a strided share of the earlier totals
+        T acc = 0;
+        for (uint32_t j = lane; j < b; j += 32) {
+            T s;
+            while (((s = st[j]) >> 63) == 0ull) {
+            }
+            acc += s & ~(1ull << 63);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) off_s = acc;
+    }
+    __syncthreads();
+    T off = off_s;
+    for (uint32_t w = 0; w < warp; ++w) off += wsum[w];
+#pragma unroll
+    for (int r = 0; r < SCAN_ITEMS; ++r) {
+        const uint32_t i = base + r * 32 + lane;
+        if (i < n) out(i, off + ex[r], v[r]);
+    }
+    if (threadIdx.x == SCAN_THREADS - 1 && (uint64_t)(b + 1) * SCAN_CHUNK >= n) fin(off + carry);  // the last warp's offset + its total = the grand total
+}
+
 struct U32In {
     const uint32_t* p;
     __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return p[i]; }

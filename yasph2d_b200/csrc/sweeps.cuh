@@ -1087,6 +1087,9 @@ __global__ void k_begin_step(Control* ctl) {
         ctl->max_v2_bits = 0u;
         ctl->not_converged = 0u;
         ctl->nonfinite = 0u;
+        // set up the divergence solver (dfsph.rs:354,368): its iteration count of the previous step does not change until it runs
+        ctl->warm[1] = ctl->iters[1] > 1u ? 1u : 0u;
+        ctl->stop_iter[1] = 0xFFFFFFFFu;
     }
 }
 // update_simulation_step (timemanager.rs:252-279) evaluated redundantly by every thread from the reduced maximum, then
@@ -1114,12 +1117,4 @@ __global__ void k_timestep_apply(Control* ctl, TimeParams tp, float particle_dia
             vel_out[i] = vel_in[i] + 0.5f * dt * accel[i];
     }
 }
-// set up the divergence solver (dfsph.rs:354,368)
-__global__ void k_begin_divergence(Control* ctl) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        ctl->warm[1] = ctl->iters[1] > 1u ? 1u : 0u;
-        ctl->stop_iter[1] = 0xFFFFFFFFu;
-    }
-}
-
 }  // namespace yasph

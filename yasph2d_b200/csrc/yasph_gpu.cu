@@ -65,7 +65,7 @@ struct yasph_ctx {
     uint32_t* apron_idx = nullptr;  // per tile: global index of its first APRON_TABLE apron slots (list build -> sweeps)
     // scratch
     uint32_t* radix_scratch = nullptr;
-    unsigned long long *scan_chunks = nullptr, *scan_total = nullptr;
+    unsigned long long *scan_chunks = nullptr, *scan_total = nullptr, *scan_status = nullptr;
     double* partials = nullptr;
 #if defined(YASPH_SWEEP_TIMING) || defined(YASPH_LIST_TIMING)
     unsigned long long* sweep_dbg = nullptr;
@@ -411,7 +411,7 @@ static void free_all(yasph_ctx* c) {
                     c->f_alt0, c->f_alt1, c->keys[0], c->keys[1], c->idx[0], c->idx[1], c->cell_key, c->cell_start, c->tile_key, c->tile_pstart,
                     c->tile_cstart, c->bpos, c->bpos_alt, c->scell_key, c->scell_start, c->stile_key, c->stile_cstart, c->tile_runs, c->cslot_d,
                     c->cslot_s, c->lists, c->counts, c->tile_nk, c->apron_idx,
-                    c->radix_scratch, c->scan_chunks, c->scan_total, c->partials, c->ctl, c->exp_cd, c->exp_ct, c->exp_lists,
+                    c->radix_scratch, c->scan_chunks, c->scan_total, c->scan_status, c->partials, c->ctl, c->exp_cd, c->exp_ct, c->exp_lists,
                     c->ids, c->ids_alt, c->slab.pflag, c->slab.sel[0], c->slab.sel[1], c->slab.sel_g[0], c->slab.sel_g[1], c->slab.sel4_chunks, c->slab.send_idx[0], c->slab.send_idx[1],
                     c->slab.ghost_idx[0], c->slab.ghost_idx[1], c->slab.own_idx, c->slab.sbuf[0], c->slab.sbuf[1], c->slab.rbuf[0],
                     c->slab.rbuf[1], c->slab.d_cnt};
@@ -561,6 +561,7 @@ extern "C" int32_t yasph_create(const yasph_config* cfg, yasph_ctx** out) {
     CUC(dmalloc(&c->radix_scratch, radix_scratch_words((uint32_t)NM)));
     CUC(dmalloc(&c->scan_chunks, (size_t)scan_num_chunks((uint32_t)NM) + 1));
     CUC(dmalloc(&c->scan_total, 1));
+    CUC(dmalloc(&c->scan_status, (size_t)scan_num_chunks((uint32_t)NM) + 2));
     CUC(dmalloc(&c->ctl, 1));
     CUC(cudaMallocHost((void**)&c->h_ctl, sizeof(Control)));
     CUC(cudaHostAlloc((void**)&c->h_pub, sizeof(yasph_ctx::Published), cudaHostAllocMapped));
@@ -691,21 +692,20 @@ static int32_t radix_sort(yasph_ctx* c, uint32_t n) {
 static int32_t build_cells(yasph_ctx* c, uint32_t n, bool is_static) {
     uint32_t* ck = is_static ? c->scell_key : c->cell_key;
     uint32_t* cs = is_static ? c->scell_start : c->cell_start;
+    const FinishCells fin{n, ck, cs, c->tile_pstart, is_static ? c->stile_cstart : c->tile_cstart, is_static ? c->cap_m : c->max_tiles, c->ctl, is_static ? 1 : 0};
     if (n) {
+        // head flags -> prefix -> compaction -> sentinels and counts in ONE kernel (scan.cuh: k_scan_fused)
         const uint32_t nch = scan_num_chunks(n);
         HeadFlagsIn in{c->keys[0]};
         HeadCompactOut out{c->keys[0], ck, cs, is_static ? c->stile_key : c->tile_key, is_static ? nullptr : c->tile_pstart,
                            is_static ? c->stile_cstart : c->tile_cstart, is_static ? c->cap_m : c->max_tiles};
-        k_scan_reduce<unsigned long long, HeadFlagsIn><<<nch, SCAN_THREADS, 0, c->stream>>>(in, n, c->scan_chunks);
+        CU(cudaMemsetAsync(c->scan_status, 0, ((size_t)nch + 1) * sizeof(unsigned long long), c->stream));
+        k_scan_fused<HeadFlagsIn, HeadCompactOut, FinishCells><<<nch, SCAN_THREADS, 0, c->stream>>>(in, n, c->scan_status, out, fin);
         CHECK_LAUNCH();
-        k_scan_chunks<unsigned long long><<<1, SCAN_THREADS, 0, c->stream>>>(c->scan_chunks, nch, c->scan_total);
-        CHECK_LAUNCH();
-        k_scan_apply<unsigned long long, HeadFlagsIn, HeadCompactOut><<<nch, SCAN_THREADS, 0, c->stream>>>(in, n, c->scan_chunks, out);
+    } else {
+        k_finish_cells<<<1, 32, 0, c->stream>>>(fin);
         CHECK_LAUNCH();
     }
-    k_finish_cells<<<1, 32, 0, c->stream>>>(c->scan_total, n, ck, cs, c->tile_pstart, is_static ? c->stile_cstart : c->tile_cstart,
-                                            is_static ? c->cap_m : c->max_tiles, c->ctl, is_static ? 1 : 0);
-    CHECK_LAUNCH();
     return YASPH_OK;
 }
 
@@ -2024,8 +2024,6 @@ static int32_t dfsph_step(yasph_ctx* c) {
         TRY(neighborhood_update(c, true, gp, true, sorted_ready));  // positions are final (dfsph.rs:502-512)
     }
     pass_begin(c, YASPH_PASS_DENSITY_ALPHA);
-    k_begin_divergence<<<1, 32, 0, c->stream>>>(c->ctl);
-    CHECK_LAUNCH();
     // The divergence warm start runs iff the previous divergence solve took more than one iteration (dfsph.rs:354); the
     // host mirror still holds that count.  Without a warm start, iteration 0's density-change pass reads the same v* and
     // positions as the density / alpha passes and is fused into their sweep.
