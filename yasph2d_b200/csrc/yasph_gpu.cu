@@ -90,6 +90,8 @@ struct yasph_ctx {
     // density sweep) leave on a second stream while the rest of the step computes; only the velocities wait for the last pass
     cudaStream_t copy_stream = nullptr;
     cudaStream_t ctl_stream = nullptr;  // publishes the control block while the early list build runs (never carries copies)
+    cudaStream_t aux_stream = nullptr;  // the gather of a neighbourhood update, next to the cell / tile tables
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_early[2] = {nullptr, nullptr};
     float *early_pos_out = nullptr, *early_dens_out = nullptr, *early_vel_out = nullptr;  // pinned host destinations of the current yasph_step_host call
     bool early_vel_stale = false;  // the velocities changed after their speculative download (the solve needed more iterations)
@@ -435,6 +437,9 @@ static void free_all(yasph_ctx* c) {
     }
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->ctl_stream) cudaStreamDestroy(c->ctl_stream);
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     for (int i = 0; i < 2; ++i)
         if (c->ev_early[i]) cudaEventDestroy(c->ev_early[i]);
     for (int i = 0; i < 6; ++i)
@@ -486,6 +491,9 @@ extern "C" int32_t yasph_create(const yasph_config* cfg, yasph_ctx** out) {
         CUC(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
         CUC(cudaStreamCreateWithPriority(&c->ctl_stream, cudaStreamNonBlocking, prio_hi));
     }
+    CUC(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    CUC(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CUC(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) CUC(cudaEventCreateWithFlags(&c->ev_early[i], cudaEventDisableTiming));
     for (int i = 0; i < 6; ++i) CUC(cudaEventCreate(&c->ev_host[i]));
     CUC(cudaEventCreateWithFlags(&c->ev_tables, cudaEventDisableTiming));
@@ -1330,6 +1338,7 @@ static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp
     if (!sorted_ready) TRY(radix_sort(c, n_sort));
     pass_end(c);
     pass_begin(c, YASPH_PASS_GATHER);
+    bool gather_aside = false;
     if (n) {
         GatherArgs ga;
         memset(&ga, 0, sizeof(ga));
@@ -1343,16 +1352,25 @@ static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp
             ga.in1[q] = *gp.a1[q];
             ga.out1[q] = *gp.alt1[q];
         }
+        // The gather (permuted arrays) and the cell / tile tables (sorted keys only) do not depend on each other: the gather runs on a
+        // side stream next to them and is joined before the list build.  Not under YASPH_FLAG_PROFILE_PASSES (per-pass times).
+        gather_aside = !(c->cfg.flags & YASPH_FLAG_PROFILE_PASSES);
+        cudaStream_t gs = gather_aside ? c->aux_stream : c->stream;
+        if (gather_aside) {
+            CU(cudaEventRecord(c->ev_fork, c->stream));
+            CU(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
+        }
         if (c->slab.active) {
-            CU(cudaMemsetAsync(&c->ctl->slab_ghost, 0, sizeof(unsigned long long), c->stream));
+            CU(cudaMemsetAsync(&c->ctl->slab_ghost, 0, sizeof(unsigned long long), gs));
             ga.keys = c->keys[0];
             ga.ghost = c->slab.pflag;
             ga.ghost_count = &c->ctl->slab_ghost;
             ga.col_lo = c->slab.col_lo;
             ga.col_hi = c->slab.col_hi;
         }
-        k_gather<<<blocks_for(n, 256), 256, 0, c->stream>>>(c->idx[0], n, ga);
+        k_gather<<<blocks_for(n, 256), 256, 0, gs>>>(c->idx[0], n, ga);
         CHECK_LAUNCH();
+        if (gather_aside) CU(cudaEventRecord(c->ev_join, c->aux_stream));
         for (int q = 0; q < gp.n2; ++q) std::swap(*gp.a2[q], *gp.alt2[q]);
         for (int q = 0; q < gp.n1; ++q) std::swap(*gp.a1[q], *gp.alt1[q]);
     }
@@ -1367,6 +1385,7 @@ static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp
         CHECK_LAUNCH();
     }
     c->slab.halo_lists_valid = false;  // per-pass halo lists of the new structure are built when a pass needs an exchange (ensure_halo_lists)
+    if (gather_aside) CU(cudaStreamWaitEvent(c->stream, c->ev_join, 0));  // the permuted arrays are in place from here on
     pass_end(c);
     // The one host round trip of the neighbourhood update: tile count (grid of every tile kernel until the next update) and
     // the largest tile (their shared-memory size).  The list build does not wait for it when the previous structure's sizes are
