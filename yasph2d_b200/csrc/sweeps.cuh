@@ -1097,24 +1097,35 @@ __global__ void k_begin_step(Control* ctl) {
 template <int MODE>
 __global__ void k_timestep_apply(Control* ctl, TimeParams tp, float particle_diameter, const float2* vel_in,
                                  const float2* __restrict__ accel, float2* vel_out, uint32_t n) {
-    const float max_velocity = sqrtf(__uint_as_float(ctl->max_v2_bits));
-    const unsigned long long step = update_simulation_step(tp, ctl->step_prev_ns, particle_diameter, max_velocity, ctl->total_simulated_ns);
-    const float dt = duration_as_secs_f32(step);
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) {
-        ctl->step_ns = step;
-        ctl->dt = dt;
-        ctl->max_velocity = max_velocity;
-        if (MODE == 0) {  // set up the density solver (dfsph.rs:199,213)
-            ctl->warm[0] = ctl->iters[0] > 1u ? 1u : 0u;
-            ctl->stop_iter[0] = 0xFFFFFFFFu;
+    // one thread per CTA evaluates the rule (64-bit integer and f64 arithmetic); every CTA gets the same result
+    __shared__ float dt_s;
+    if (threadIdx.x == 0) {
+        const float max_velocity = sqrtf(__uint_as_float(ctl->max_v2_bits));
+        const unsigned long long step = update_simulation_step(tp, ctl->step_prev_ns, particle_diameter, max_velocity, ctl->total_simulated_ns);
+        const float dt0 = duration_as_secs_f32(step);
+        dt_s = dt0;
+        if (blockIdx.x == 0) {
+            ctl->step_ns = step;
+            ctl->dt = dt0;
+            ctl->max_velocity = max_velocity;
+            if (MODE == 0) {  // set up the density solver (dfsph.rs:199,213)
+                ctl->warm[0] = ctl->iters[0] > 1u ? 1u : 0u;
+                ctl->stop_iter[0] = 0xFFFFFFFFu;
+            }
         }
     }
-    if (i < n) {
-        if (MODE == 0)
-            vel_out[i] = vel_in[i] + accel[i] * dt;
-        else
-            vel_out[i] = vel_in[i] + 0.5f * dt * accel[i];
+    __syncthreads();
+    const float dt = dt_s;
+    // two particles per thread (16-byte accesses)
+    const uint32_t i = 2u * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (i + 1 < n) {
+        const float4 v = *reinterpret_cast<const float4*>(vel_in + i), a = *reinterpret_cast<const float4*>(accel + i);
+        const float2 o0 = MODE == 0 ? f2(v.x, v.y) + f2(a.x, a.y) * dt : f2(v.x, v.y) + 0.5f * dt * f2(a.x, a.y);
+        const float2 o1 = MODE == 0 ? f2(v.z, v.w) + f2(a.z, a.w) * dt : f2(v.z, v.w) + 0.5f * dt * f2(a.z, a.w);
+        *reinterpret_cast<float4*>(vel_out + i) = make_float4(o0.x, o0.y, o1.x, o1.y);
+    } else if (i < n) {
+        vel_out[i] = MODE == 0 ? vel_in[i] + accel[i] * dt : vel_in[i] + 0.5f * dt * accel[i];
     }
 }
+
 }  // namespace yasph

@@ -2013,7 +2013,7 @@ static int32_t dfsph_step(yasph_ctx* c) {
     TRY(allreduce_scalar(c, &c->ctl->max_v2_bits, ncclFloat, ncclMax));  // CFL maximum over all ranks (values are >= 0)
     // update timestep + velocity prediction (dfsph.rs:478-491)
     pass_begin(c, YASPH_PASS_PREDICT);
-    k_timestep_apply<0><<<blocks_for(n, 256), 256, 0, c->stream>>>(c->ctl, c->tp, c->radius * 2.0f, c->vel, c->accel, c->vstar, n);
+    k_timestep_apply<0><<<std::max(1u, blocks_for((n + 1) / 2, 256)), 256, 0, c->stream>>>(c->ctl, c->tp, c->radius * 2.0f, c->vel, c->accel, c->vstar, n);
     CHECK_LAUNCH();
     pass_end(c);
     c->slab.valid[SF_VSTAR] = slab_own_valid(c, {SF_VEL, SF_ACCEL});  // the ghosts predict with their own (recomputed) accelerations
@@ -2119,7 +2119,7 @@ static int32_t wcsph_step(yasph_ctx* c) {
     TRY(allreduce_scalar(c, &c->ctl->max_v2_bits, ncclFloat, ncclMax));
     // update timestep + leap frog 2 (wscsph.rs:160-177)
     pass_begin(c, YASPH_PASS_WCSPH_KICK);
-    k_timestep_apply<1><<<blocks_for(n, 256), 256, 0, c->stream>>>(c->ctl, c->tp, c->radius * 2.0f, c->vel, c->accel, c->vel, n);
+    k_timestep_apply<1><<<std::max(1u, blocks_for((n + 1) / 2, 256)), 256, 0, c->stream>>>(c->ctl, c->tp, c->radius * 2.0f, c->vel, c->accel, c->vel, n);
     CHECK_LAUNCH();
     pass_end(c);
     c->slab.valid[SF_VEL] = slab_own_valid(c, {SF_VEL, SF_ACCEL});
