@@ -25,7 +25,7 @@ sys.path.insert(0, ROOT)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--solver", default="dfsph")
-    ap.add_argument("--skip", type=int, default=4400)
+    ap.add_argument("--skip", type=int, default=3600)
     ap.add_argument("--count", type=int, default=120)
     args = ap.parse_args()
     import bench

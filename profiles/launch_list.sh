@@ -1,6 +1,6 @@
 #!/bin/bash
 # per-launch durations of a few steady-state steps: launch_list.sh <tag> [launch-skip] [count] [extra bench args]
-TAG="$1"; SKIP="${2:-4400}"; CNT="${3:-160}"; shift 3
+TAG="$1"; SKIP="${2:-3600}"; CNT="${3:-160}"; shift 3
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip "$SKIP" -c "$CNT" --csv --log-file "gpurun_out/launches_$TAG.csv" \
     python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-e2e --collapse-presteps 0 "$@" > "gpurun_out/launches_$TAG.log" 2>&1 || tail -5 "gpurun_out/launches_$TAG.log"
 python - "$TAG" <<'PY'
