@@ -82,14 +82,17 @@ inline uint32_t keygen_grid(uint32_t n, int num_sms) {
 // neighborhood_search.rs:111-114 (sequential in the reference)
 __global__ void __launch_bounds__(KG_THREADS)
     k_keygen(const float2* __restrict__ pos, uint32_t first, uint32_t n, GridParams g, uint32_t* __restrict__ keys, uint32_t* __restrict__ idx,
-             uint32_t* __restrict__ sort_scratch, SlabParams sp) {
+             uint32_t* __restrict__ sort_scratch, SlabParams sp, uint32_t classify_end) {
+    // classify_end: particles from this index on are not classified (the ghost arrivals of a slab exchange, which lie outside the slab
+    // by construction, behind the migrant arrivals, which must lie inside)
     __shared__ RadixHistSmem sh;
     radix_hist_init(sh);
     for (uint32_t base = first + blockIdx.x * KG_THREADS; base < n; base += gridDim.x * KG_THREADS) {
         const uint32_t i = base + threadIdx.x;
         uint32_t key = 0;
         if (i < n) {
-            key = slab_classify(sp, i, position_to_cidx(g, pos[i]));
+            key = position_to_cidx(g, pos[i]);
+            if (i < classify_end) key = slab_classify(sp, i, key);
             keys[i] = key;
             idx[i] = i;
         }

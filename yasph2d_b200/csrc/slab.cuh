@@ -88,67 +88,22 @@ __device__ __forceinline__ void warp_flag_scan4(uint32_t m, unsigned lt, uint4& 
     excl = make_uint4(__popc(b0 & lt), __popc(b1 & lt), __popc(b2 & lt), __popc(b3 & lt));
     total = make_uint4(__popc(b0), __popc(b1), __popc(b2), __popc(b3));
 }
-__global__ void __launch_bounds__(SCAN_THREADS) k_select4_reduce(Select4In in, uint32_t n, uint4* __restrict__ chunk_sums) {
+// One kernel (the scheme of scan.cuh's k_scan_fused): a chunk publishes its four counts early -- 15 bits each in one
+// 64-bit status word, bit 63 = published -- and sums the counts of all earlier chunks itself.  status[0] = ticket counter,
+// status[1 + b] = counts of chunk b; the caller zeroes 1 + nchunks words.  The chunk that holds the last element writes the totals.
+static_assert(SCAN_CHUNK < (1 << 15), "four 15-bit counts per status word");
+__global__ void __launch_bounds__(SCAN_THREADS) k_select4_fused(Select4In in, uint32_t n, unsigned long long* __restrict__ status, uint32_t* __restrict__ out0,
+                                                                uint32_t* __restrict__ out1, uint32_t* __restrict__ out2, uint32_t* __restrict__ out3, uint32_t cap,
+                                                                uint32_t* __restrict__ totals_out) {
     __shared__ uint4 wsum[SCAN_WARPS];
+    __shared__ uint4 off_s;
+    __shared__ uint32_t chunk_s;
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
     const unsigned lt = lanemask_lt();
-    const uint32_t base = blockIdx.x * SCAN_CHUNK + warp * (32 * SCAN_ITEMS);
-    uint4 s = make_uint4(0, 0, 0, 0);
-#pragma unroll 4
-    for (int r = 0; r < SCAN_ITEMS; ++r) {
-        const uint32_t i = base + r * 32 + lane;
-        uint4 ex, tot;
-        warp_flag_scan4(i < n ? in(i) : 0u, lt, ex, tot);
-        s = s + tot;
-    }
-    if (lane == 0) wsum[warp] = s;
+    if (threadIdx.x == 0) chunk_s = atomicAdd(reinterpret_cast<unsigned int*>(status), 1u);
     __syncthreads();
-    if (threadIdx.x == 0) {
-        uint4 t = wsum[0];
-        for (int w = 1; w < SCAN_WARPS; ++w) t = t + wsum[w];
-        chunk_sums[blockIdx.x] = t;
-    }
-}
-// in-place exclusive scan of chunk_sums[0..nchunks) by ONE block; totals -> totals_out[4]
-__global__ void __launch_bounds__(SCAN_THREADS) k_select4_chunks(uint4* __restrict__ chunk_sums, uint32_t nchunks, uint32_t* __restrict__ totals_out) {
-    __shared__ uint4 wsum[SCAN_WARPS];
-    __shared__ uint4 carry_s;
-    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
-    if (threadIdx.x == 0) carry_s = make_uint4(0, 0, 0, 0);
-    __syncthreads();
-    for (uint32_t base = 0; base < nchunks; base += SCAN_THREADS) {
-        const uint32_t i = base + threadIdx.x;
-        const uint4 v = i < nchunks ? chunk_sums[i] : make_uint4(0, 0, 0, 0);
-        uint4 inc = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint4 u = make_uint4(__shfl_up_sync(0xffffffffu, inc.x, o), __shfl_up_sync(0xffffffffu, inc.y, o), __shfl_up_sync(0xffffffffu, inc.z, o),
-                                       __shfl_up_sync(0xffffffffu, inc.w, o));
-            if (lane >= (uint32_t)o) inc = inc + u;
-        }
-        if (lane == 31) wsum[warp] = inc;
-        __syncthreads();
-        uint4 off = carry_s;
-        for (uint32_t w = 0; w < warp; ++w) off = off + wsum[w];
-        if (i < nchunks) chunk_sums[i] = make_uint4(off.x + inc.x - v.x, off.y + inc.y - v.y, off.z + inc.z - v.z, off.w + inc.w - v.w);
-        __syncthreads();
-        if (threadIdx.x == SCAN_THREADS - 1) carry_s = off + inc;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        totals_out[0] = carry_s.x;
-        totals_out[1] = carry_s.y;
-        totals_out[2] = carry_s.z;
-        totals_out[3] = carry_s.w;
-    }
-}
-// out[q][prefix_q(i)] = i for every i with flag q set (q = 0..3), up to `cap` entries per list
-__global__ void __launch_bounds__(SCAN_THREADS) k_select4_apply(Select4In in, uint32_t n, const uint4* __restrict__ chunk_offsets, uint32_t* __restrict__ out0,
-                                                                uint32_t* __restrict__ out1, uint32_t* __restrict__ out2, uint32_t* __restrict__ out3, uint32_t cap) {
-    __shared__ uint4 wsum[SCAN_WARPS];
-    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
-    const uint32_t base = blockIdx.x * SCAN_CHUNK + warp * (32 * SCAN_ITEMS);
-    const unsigned lt = lanemask_lt();
+    const uint32_t b = chunk_s;
+    const uint32_t base = b * SCAN_CHUNK + warp * (32 * SCAN_ITEMS);
     uint32_t m[SCAN_ITEMS];
     uint4 ex[SCAN_ITEMS];
     uint4 carry = make_uint4(0, 0, 0, 0);  // warp-uniform
@@ -163,7 +118,28 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_select4_apply(Select4In in, ui
     }
     if (lane == 0) wsum[warp] = carry;
     __syncthreads();
-    uint4 off = chunk_offsets[blockIdx.x];
+    volatile unsigned long long* st = status + 1;
+    if (warp == 0) {
+        uint4 total = wsum[0];
+#pragma unroll
+        for (int w = 1; w < SCAN_WARPS; ++w) total = total + wsum[w];
+        if (lane == 0)
+            st[b] = (unsigned long long)total.x | ((unsigned long long)total.y << 15) | ((unsigned long long)total.z << 30) | ((unsigned long long)total.w << 45) | (1ull << 63);
+        uint4 acc = make_uint4(0, 0, 0, 0);
+        for (uint32_t j = lane; j < b; j += 32) {
+            unsigned long long v;
+            while (((v = st[j]) >> 63) == 0ull) {
+            }
+            acc = acc + make_uint4((uint32_t)v & 0x7FFFu, (uint32_t)(v >> 15) & 0x7FFFu, (uint32_t)(v >> 30) & 0x7FFFu, (uint32_t)(v >> 45) & 0x7FFFu);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            acc = acc + make_uint4(__shfl_xor_sync(0xffffffffu, acc.x, o), __shfl_xor_sync(0xffffffffu, acc.y, o), __shfl_xor_sync(0xffffffffu, acc.z, o),
+                                   __shfl_xor_sync(0xffffffffu, acc.w, o));
+        if (lane == 0) off_s = acc;
+    }
+    __syncthreads();
+    uint4 off = off_s;
     for (uint32_t w = 0; w < warp; ++w) off = off + wsum[w];
 #pragma unroll
     for (int r = 0; r < SCAN_ITEMS; ++r) {
@@ -172,6 +148,13 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_select4_apply(Select4In in, ui
         if (m[r] & 2u) { const uint32_t e = off.y + ex[r].y; if (e < cap) out1[e] = i; }
         if (m[r] & 4u) { const uint32_t e = off.z + ex[r].z; if (e < cap) out2[e] = i; }
         if (m[r] & 8u) { const uint32_t e = off.w + ex[r].w; if (e < cap) out3[e] = i; }
+    }
+    if (threadIdx.x == SCAN_THREADS - 1 && (uint64_t)(b + 1) * SCAN_CHUNK >= n) {
+        const uint4 t = off + carry;
+        totals_out[0] = t.x;
+        totals_out[1] = t.y;
+        totals_out[2] = t.z;
+        totals_out[3] = t.w;
     }
 }
 
@@ -333,10 +316,10 @@ __global__ void k_halo_exchange(T* __restrict__ field, const uint32_t* __restric
 
 // ---- particle records (migrants + ghost layers) through the mailboxes: the COUNTS stay on the device ------------------------
 // One message per neighbour and update: [count of migrants, count of ghost-layer particles | SoA block of both, migrants first].
-// k_records_push reads how many particles the ordered selection picked (device memory), packs them straight into the neighbours'
-// mailboxes and publishes the sequence number.  k_records_pull waits for both neighbours and appends their records behind the old
-// local set: [migrants from the left | migrants from the right | ghosts from the left | ghosts from the right].  k_slab_retain then
-// appends copies of this rank's own OUT-migrants that landed in a neighbour's first W columns: the neighbour owns them now, and they
+// k_records_exchange reads how many particles the ordered selection picked (device memory), packs them straight into the neighbours'
+// mailboxes and publishes the sequence number, waits for both neighbours and appends their records behind the old local set:
+// [migrants from the left | migrants from the right | ghosts from the left | ghosts from the right].  Its last part (k_slab_retain
+// for the host-mediated transports) appends copies of this rank's own OUT-migrants that landed in a neighbour's first W columns: the neighbour owns them now, and they
 // are part of the ghost layer this rank keeps of that neighbour (behind the received ghosts: the same order the neighbour's own sort
 // gives them, after its stayers of the same cell).  It hands all counts to the host through mapped memory -- the ONE thing the host
 // waits for in the exchange, to size the sort.
@@ -349,96 +332,12 @@ struct PeerCounts {  // mapped host memory
     SlabCounts cnt;
     uint32_t seq;
 };
-__global__ void k_records_push(RecordArrays arr, const uint32_t* __restrict__ idx_ml, const uint32_t* __restrict__ idx_mr, const uint32_t* __restrict__ idx_gl,
-                               const uint32_t* __restrict__ idx_gr, const uint32_t* __restrict__ counts4, uint32_t cap, unsigned char* dst_l, unsigned char* dst_r,
-                               unsigned long long* flag_l, unsigned long long* flag_r, unsigned long long seq, unsigned int* ticket) {
-    const uint32_t nml = dst_l ? min(counts4[0], cap) : 0u, ngl = dst_l ? min(counts4[2], cap - nml) : 0u;
-    const uint32_t nmr = dst_r ? min(counts4[1], cap) : 0u, ngr = dst_r ? min(counts4[3], cap - nmr) : 0u;
-    const uint32_t tl = nml + ngl, tr = nmr + ngr;
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < tl + tr; k += gridDim.x * blockDim.x) {
-        const bool right = k >= tl;
-        const uint32_t kk = right ? k - tl : k, cnt = right ? tr : tl, nm = right ? nmr : nml;
-        const uint32_t s = kk < nm ? (right ? idx_mr : idx_ml)[kk] : (right ? idx_gr : idx_gl)[kk - nm];
-        unsigned char* buf = (right ? dst_r : dst_l) + PEER_MSG_HEADER_BYTES;
-        float2* b2 = reinterpret_cast<float2*>(buf);
-#pragma unroll
-        for (int q = 0; q < 3; ++q)
-            if (q < arr.n2) b2[(size_t)q * cnt + kk] = arr.a2[q][s];
-        float* b1 = reinterpret_cast<float*>(buf + (size_t)arr.n2 * 8 * cnt);
-#pragma unroll
-        for (int q = 0; q < 3; ++q)
-            if (q < arr.n1) b1[(size_t)q * cnt + kk] = arr.a1[q][s];
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        if (dst_l) {
-            reinterpret_cast<uint32_t*>(dst_l)[0] = nml;
-            reinterpret_cast<uint32_t*>(dst_l)[1] = ngl;
-        }
-        if (dst_r) {
-            reinterpret_cast<uint32_t*>(dst_r)[0] = nmr;
-            reinterpret_cast<uint32_t*>(dst_r)[1] = ngr;
-        }
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int t = atomicAdd(ticket, 1u);
-        if (t == gridDim.x - 1) {
-            *ticket = 0u;
-            __threadfence_system();
-            if (flag_l) st_release_sys(flag_l, seq);
-            if (flag_r) st_release_sys(flag_r, seq);
-        }
-    }
-}
-__global__ void k_records_pull(RecordArrays arr, uint32_t first, uint32_t cap_n, uint32_t cap_halo, const unsigned char* src_l, const unsigned char* src_r,
-                               const unsigned long long* flag_l, const unsigned long long* flag_r, unsigned long long seq, uint8_t* __restrict__ pflag,
-                               const uint32_t* __restrict__ counts4, SlabCounts* dc, Control* ctl) {
-    __shared__ int ok;
-    if (threadIdx.x == 0) {
-        ok = 1;
-        if (flag_l && !peer_wait(flag_l, seq)) ok = 0;
-        if (flag_r && !peer_wait(flag_r, seq)) ok = 0;
-        if (!ok) atomicOr(&ctl->err_comm, 4u);
-    }
-    __syncthreads();
-    const uint32_t nml = (ok && flag_l) ? __ldcg(reinterpret_cast<const uint32_t*>(src_l)) : 0u, ngl = (ok && flag_l) ? __ldcg(reinterpret_cast<const uint32_t*>(src_l) + 1) : 0u;
-    const uint32_t nmr = (ok && flag_r) ? __ldcg(reinterpret_cast<const uint32_t*>(src_r)) : 0u, ngr = (ok && flag_r) ? __ldcg(reinterpret_cast<const uint32_t*>(src_r) + 1) : 0u;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        dc->out_m[0] = counts4[0];
-        dc->out_m[1] = counts4[1];
-        dc->out_g[0] = counts4[2];
-        dc->out_g[1] = counts4[3];
-        dc->in_m[0] = nml;
-        dc->in_m[1] = nmr;
-        dc->in_g[0] = ngl;
-        dc->in_g[1] = ngr;
-    }
-    const uint32_t tl = nml + ngl, tr = nmr + ngr;
-    if (tl > cap_halo || tr > cap_halo || (unsigned long long)first + tl + tr > cap_n) return;  // the host fails the step on these counts
-    const uint32_t base_g = first + nml + nmr;
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < tl + tr; k += gridDim.x * blockDim.x) {
-        const bool right = k >= tl;
-        const uint32_t kk = right ? k - tl : k, cnt = right ? tr : tl, nm = right ? nmr : nml;
-        const uint32_t dst = kk < nm ? first + (right ? nml : 0u) + kk : base_g + (right ? ngl : 0u) + (kk - nm);
-        const unsigned char* buf = (right ? src_r : src_l) + PEER_MSG_HEADER_BYTES;
-        const float2* b2 = reinterpret_cast<const float2*>(buf);
-#pragma unroll
-        for (int q = 0; q < 3; ++q)
-            if (q < arr.n2) arr.a2[q][dst] = __ldcg(&b2[(size_t)q * cnt + kk]);
-        const float* b1 = reinterpret_cast<const float*>(buf + (size_t)arr.n2 * 8 * cnt);
-#pragma unroll
-        for (int q = 0; q < 3; ++q)
-            if (q < arr.n1) arr.a1[q][dst] = __ldcg(&b1[(size_t)q * cnt + kk]);
-        pflag[dst] = 0;
-    }
-}
 // one warp: ordered copies of the out-migrants that stay visible as ghosts, then the counts for the host (see above).
 // arr.a2[0] are the positions (already advanced): the migrant's new cell column decides.
-__global__ void k_slab_retain(RecordArrays arr, GridParams g, const uint32_t* __restrict__ idx_ml, const uint32_t* __restrict__ idx_mr, SlabCounts* dc, uint32_t n_old,
-                              uint32_t cap_n, uint32_t cap_halo, uint32_t col_lo, uint32_t col_hi, uint32_t W, uint8_t* __restrict__ pflag, PeerCounts* host_counts,
-                              uint32_t host_seq) {
-    const uint32_t lane = threadIdx.x;
+__device__ __forceinline__ void slab_retain_warp(const RecordArrays& arr, const GridParams& g, const uint32_t* __restrict__ idx_ml, const uint32_t* __restrict__ idx_mr,
+                                                 SlabCounts* dc, uint32_t n_old, uint32_t cap_n, uint32_t cap_halo, uint32_t col_lo, uint32_t col_hi, uint32_t W,
+                                                 uint8_t* __restrict__ pflag, PeerCounts* host_counts, uint32_t host_seq) {
+    const uint32_t lane = threadIdx.x & 31u;
     const unsigned lt = lanemask_lt();
     uint32_t dst = n_old + dc->in_m[0] + dc->in_m[1] + dc->in_g[0] + dc->in_g[1];
     uint32_t kept[2] = {0u, 0u};
@@ -485,6 +384,122 @@ __global__ void k_slab_retain(RecordArrays arr, GridParams g, const uint32_t* __
         __threadfence_system();
         h->seq = host_seq;
         __threadfence_system();
+    }
+}
+__global__ void k_slab_retain(RecordArrays arr, GridParams g, const uint32_t* __restrict__ idx_ml, const uint32_t* __restrict__ idx_mr, SlabCounts* dc, uint32_t n_old,
+                              uint32_t cap_n, uint32_t cap_halo, uint32_t col_lo, uint32_t col_hi, uint32_t W, uint8_t* __restrict__ pflag, PeerCounts* host_counts,
+                              uint32_t host_seq) {
+    slab_retain_warp(arr, g, idx_ml, idx_mr, dc, n_old, cap_n, cap_halo, col_lo, col_hi, W, pflag, host_counts, host_seq);
+}
+// The whole exchange of the peer-memory transport in ONE launch (the scheme of k_halo_exchange): every CTA pushes its share of the
+// outgoing records into the neighbours' mailboxes, the last one to finish publishes the sequence number; then every CTA waits for the
+// neighbours' numbers and pulls its share of what they stored here; CTA 0 finally keeps the out-migrants that stay visible as ghosts
+// and hands the counts to the host.  Grid of at most one CTA per SM: all CTAs are resident, so a CTA that already waits for the other
+// rank never keeps a CTA that still has to push from running.
+struct RecordExchangeArgs {
+    RecordArrays arr;
+    const uint32_t *idx_ml, *idx_mr, *idx_gl, *idx_gr;  // the four selections
+    const uint32_t* counts4;                            // their sizes (device)
+    uint32_t cap_halo, cap_n, n_old;
+    unsigned char *dst_l, *dst_r;                       // the neighbours' mailbox slots for this exchange (null: no neighbour)
+    unsigned long long *pflag_l, *pflag_r;              // ... and their flags
+    const unsigned char *src_l, *src_r;                 // the own mailbox slots the neighbours fill
+    const unsigned long long *flag_l, *flag_r;
+    unsigned long long seq;
+    unsigned int* ticket;
+    uint8_t* pflag;
+    SlabCounts* dc;
+    Control* ctl;
+    GridParams g;
+    uint32_t col_lo, col_hi, W;
+    PeerCounts* host_counts;
+    uint32_t host_seq;
+};
+__global__ void __launch_bounds__(256) k_records_exchange(RecordExchangeArgs a) {
+    const RecordArrays& arr = a.arr;
+    {   // ---- push
+        const uint32_t nml = a.dst_l ? min(a.counts4[0], a.cap_halo) : 0u, ngl = a.dst_l ? min(a.counts4[2], a.cap_halo - nml) : 0u;
+        const uint32_t nmr = a.dst_r ? min(a.counts4[1], a.cap_halo) : 0u, ngr = a.dst_r ? min(a.counts4[3], a.cap_halo - nmr) : 0u;
+        const uint32_t tl = nml + ngl, tr = nmr + ngr;
+        for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < tl + tr; k += gridDim.x * blockDim.x) {
+            const bool right = k >= tl;
+            const uint32_t kk = right ? k - tl : k, cnt = right ? tr : tl, nm = right ? nmr : nml;
+            const uint32_t s = kk < nm ? (right ? a.idx_mr : a.idx_ml)[kk] : (right ? a.idx_gr : a.idx_gl)[kk - nm];
+            unsigned char* buf = (right ? a.dst_r : a.dst_l) + PEER_MSG_HEADER_BYTES;
+            float2* b2 = reinterpret_cast<float2*>(buf);
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+                if (q < arr.n2) b2[(size_t)q * cnt + kk] = arr.a2[q][s];
+            float* b1 = reinterpret_cast<float*>(buf + (size_t)arr.n2 * 8 * cnt);
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+                if (q < arr.n1) b1[(size_t)q * cnt + kk] = arr.a1[q][s];
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            if (a.dst_l) {
+                reinterpret_cast<uint32_t*>(a.dst_l)[0] = nml;
+                reinterpret_cast<uint32_t*>(a.dst_l)[1] = ngl;
+            }
+            if (a.dst_r) {
+                reinterpret_cast<uint32_t*>(a.dst_r)[0] = nmr;
+                reinterpret_cast<uint32_t*>(a.dst_r)[1] = ngr;
+            }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ int ok;
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(a.ticket, 1u);
+        if (t == gridDim.x - 1) {
+            *a.ticket = 0u;
+            __threadfence_system();
+            if (a.pflag_l) st_release_sys(a.pflag_l, a.seq);
+            if (a.pflag_r) st_release_sys(a.pflag_r, a.seq);
+        }
+        ok = 1;
+        if (a.flag_l && !peer_wait(a.flag_l, a.seq)) ok = 0;
+        if (a.flag_r && !peer_wait(a.flag_r, a.seq)) ok = 0;
+        if (!ok) atomicOr(&a.ctl->err_comm, 4u);
+    }
+    __syncthreads();
+    // ---- pull
+    const uint32_t nml = (ok && a.flag_l) ? __ldcg(reinterpret_cast<const uint32_t*>(a.src_l)) : 0u, ngl = (ok && a.flag_l) ? __ldcg(reinterpret_cast<const uint32_t*>(a.src_l) + 1) : 0u;
+    const uint32_t nmr = (ok && a.flag_r) ? __ldcg(reinterpret_cast<const uint32_t*>(a.src_r)) : 0u, ngr = (ok && a.flag_r) ? __ldcg(reinterpret_cast<const uint32_t*>(a.src_r) + 1) : 0u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        a.dc->out_m[0] = a.counts4[0];
+        a.dc->out_m[1] = a.counts4[1];
+        a.dc->out_g[0] = a.counts4[2];
+        a.dc->out_g[1] = a.counts4[3];
+        a.dc->in_m[0] = nml;
+        a.dc->in_m[1] = nmr;
+        a.dc->in_g[0] = ngl;
+        a.dc->in_g[1] = ngr;
+    }
+    const uint32_t tl = nml + ngl, tr = nmr + ngr;
+    const bool room = tl <= a.cap_halo && tr <= a.cap_halo && (unsigned long long)a.n_old + tl + tr <= a.cap_n;  // else the host fails the step on the counts
+    if (room) {
+        const uint32_t first = a.n_old, base_g = first + nml + nmr;
+        for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < tl + tr; k += gridDim.x * blockDim.x) {
+            const bool right = k >= tl;
+            const uint32_t kk = right ? k - tl : k, cnt = right ? tr : tl, nm = right ? nmr : nml;
+            const uint32_t dst = kk < nm ? first + (right ? nml : 0u) + kk : base_g + (right ? ngl : 0u) + (kk - nm);
+            const unsigned char* buf = (right ? a.src_r : a.src_l) + PEER_MSG_HEADER_BYTES;
+            const float2* b2 = reinterpret_cast<const float2*>(buf);
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+                if (q < arr.n2) arr.a2[q][dst] = __ldcg(&b2[(size_t)q * cnt + kk]);
+            const float* b1 = reinterpret_cast<const float*>(buf + (size_t)arr.n2 * 8 * cnt);
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+                if (q < arr.n1) arr.a1[q][dst] = __ldcg(&b1[(size_t)q * cnt + kk]);
+            a.pflag[dst] = 0;
+        }
+    }
+    // ---- the out-migrants that stay here as ghosts go behind everything received (their places depend on the counts only)
+    if (blockIdx.x == 0) {
+        __syncthreads();  // thread 0's counts in a.dc
+        if (threadIdx.x < 32) slab_retain_warp(arr, a.g, a.idx_ml, a.idx_mr, a.dc, a.n_old, a.cap_n, a.cap_halo, a.col_lo, a.col_hi, a.W, a.pflag, a.host_counts, a.host_seq);
     }
 }
 

@@ -116,7 +116,6 @@ struct yasph_ctx {
         uint8_t* pflag = nullptr;        // [cap_n] ghost flag of the current structure / classification during an update
         uint32_t* sel[2] = {nullptr, nullptr};    // index lists of an update's four-way selection: migrants to the left | right rank [max_halo]
         uint32_t* sel_g[2] = {nullptr, nullptr};  // ... and the stayers in the first | last W owned columns (ghost layer of the left | right rank)
-        uint4* sel4_chunks = nullptr;             // per-chunk counts of that selection
         bool halo_lists_valid = false;            // send_idx / ghost_idx describe the current structure (built on demand: ensure_halo_lists)
         uint32_t* send_idx[2] = {nullptr, nullptr};   // per-pass halo send lists (left, right), sorted order [max_halo]
         uint32_t* ghost_idx[2] = {nullptr, nullptr};  // ghosts from the left / right rank, sorted order [max_halo]
@@ -414,7 +413,7 @@ static void free_all(yasph_ctx* c) {
                     c->tile_cstart, c->bpos, c->bpos_alt, c->scell_key, c->scell_start, c->stile_key, c->stile_cstart, c->tile_runs, c->cslot_d,
                     c->cslot_s, c->lists, c->counts, c->tile_nk, c->apron_idx,
                     c->radix_scratch, c->scan_chunks, c->scan_total, c->scan_status, c->partials, c->ctl, c->exp_cd, c->exp_ct, c->exp_lists,
-                    c->ids, c->ids_alt, c->slab.pflag, c->slab.sel[0], c->slab.sel[1], c->slab.sel_g[0], c->slab.sel_g[1], c->slab.sel4_chunks, c->slab.send_idx[0], c->slab.send_idx[1],
+                    c->ids, c->ids_alt, c->slab.pflag, c->slab.sel[0], c->slab.sel[1], c->slab.sel_g[0], c->slab.sel_g[1], c->slab.send_idx[0], c->slab.send_idx[1],
                     c->slab.ghost_idx[0], c->slab.ghost_idx[1], c->slab.own_idx, c->slab.sbuf[0], c->slab.sbuf[1], c->slab.rbuf[0],
                     c->slab.rbuf[1], c->slab.d_cnt};
     for (void* p : ptrs)
@@ -1142,11 +1141,8 @@ static int32_t slab_exchange_particles(yasph_ctx* c, const GatherPlan& gp, uint3
     if (n_old) {
         const uint32_t nch = scan_num_chunks(n_old);
         const Select4In in{c->keys[0], sl.pflag, a_lo, a_hi, b_lo, b_hi};
-        k_select4_reduce<<<nch, SCAN_THREADS, 0, c->stream>>>(in, n_old, sl.sel4_chunks);
-        CHECK_LAUNCH();
-        k_select4_chunks<<<1, SCAN_THREADS, 0, c->stream>>>(sl.sel4_chunks, nch, c->ctl->slab_sel4);
-        CHECK_LAUNCH();
-        k_select4_apply<<<nch, SCAN_THREADS, 0, c->stream>>>(in, n_old, sl.sel4_chunks, sl.sel[0], sl.sel[1], sl.sel_g[0], sl.sel_g[1], sl.max_halo);
+        CU(cudaMemsetAsync(c->scan_status, 0, ((size_t)nch + 1) * sizeof(unsigned long long), c->stream));
+        k_select4_fused<<<nch, SCAN_THREADS, 0, c->stream>>>(in, n_old, c->scan_status, sl.sel[0], sl.sel[1], sl.sel_g[0], sl.sel_g[1], sl.max_halo, c->ctl->slab_sel4);
         CHECK_LAUNCH();
     } else {
         CU(cudaMemsetAsync(c->ctl->slab_sel4, 0, 4 * sizeof(uint32_t), c->stream));
@@ -1159,14 +1155,23 @@ static int32_t slab_exchange_particles(yasph_ctx* c, const GatherPlan& gp, uint3
         void* bl = hl ? sl.peer_box[sl.rank - 1] : nullptr;
         void* br = hr ? sl.peer_box[sl.rank + 1] : nullptr;
         PeerBoxHeader* me = reinterpret_cast<PeerBoxHeader*>(sl.box);
-        const int grid = 64;  // grid-stride: the counts are known on the device only
-        k_records_push<<<grid, 256, 0, c->stream>>>(ra, sl.sel[0], sl.sel[1], sl.sel_g[0], sl.sel_g[1], c->ctl->slab_sel4, sl.max_halo,
-                                                    hl ? peer_payload(bl, sl.max_halo, par, 1) : nullptr, hr ? peer_payload(br, sl.max_halo, par, 0) : nullptr,
-                                                    hl ? &reinterpret_cast<PeerBoxHeader*>(bl)->halo_flag[1] : nullptr,
-                                                    hr ? &reinterpret_cast<PeerBoxHeader*>(br)->halo_flag[0] : nullptr, seq, sl.d_ticket);
-        CHECK_LAUNCH();
-        k_records_pull<<<grid, 256, 0, c->stream>>>(ra, n_old, c->cap_n, sl.max_halo, peer_payload(sl.box, sl.max_halo, par, 0), peer_payload(sl.box, sl.max_halo, par, 1),
-                                                    hl ? &me->halo_flag[0] : nullptr, hr ? &me->halo_flag[1] : nullptr, seq, sl.pflag, c->ctl->slab_sel4, dcnt, c->ctl);
+        RecordExchangeArgs xa;
+        xa.arr = ra;
+        xa.idx_ml = sl.sel[0], xa.idx_mr = sl.sel[1], xa.idx_gl = sl.sel_g[0], xa.idx_gr = sl.sel_g[1];
+        xa.counts4 = c->ctl->slab_sel4;
+        xa.cap_halo = sl.max_halo, xa.cap_n = c->cap_n, xa.n_old = n_old;
+        xa.dst_l = hl ? peer_payload(bl, sl.max_halo, par, 1) : nullptr;
+        xa.dst_r = hr ? peer_payload(br, sl.max_halo, par, 0) : nullptr;
+        xa.pflag_l = hl ? &reinterpret_cast<PeerBoxHeader*>(bl)->halo_flag[1] : nullptr;
+        xa.pflag_r = hr ? &reinterpret_cast<PeerBoxHeader*>(br)->halo_flag[0] : nullptr;
+        xa.src_l = peer_payload(sl.box, sl.max_halo, par, 0);
+        xa.src_r = peer_payload(sl.box, sl.max_halo, par, 1);
+        xa.flag_l = hl ? &me->halo_flag[0] : nullptr;
+        xa.flag_r = hr ? &me->halo_flag[1] : nullptr;
+        xa.seq = seq, xa.ticket = sl.d_ticket, xa.pflag = sl.pflag, xa.dc = dcnt, xa.ctl = c->ctl, xa.g = c->grid;
+        xa.col_lo = sl.col_lo, xa.col_hi = sl.col_hi, xa.W = W;
+        xa.host_counts = sl.d_pcounts, xa.host_seq = hseq;
+        k_records_exchange<<<64, 256, 0, c->stream>>>(xa);  // grid-stride (the counts are known on the device only); all CTAs resident
         CHECK_LAUNCH();
     } else {
         // host-mediated transports (NCCL send / recv, loopback): counts first, then the records
@@ -1222,10 +1227,11 @@ static int32_t slab_exchange_particles(yasph_ctx* c, const GatherPlan& gp, uint3
         const uint32_t all[10] = {mine[0], mine[1], mine[2], mine[3], in_m[0], in_m[1], in_g[0], in_g[1], 0u, 0u};  // SlabCounts: out_m, out_g, in_m, in_g
         memcpy(sl.h_cnt + 8, all, sizeof(all));
         CU(cudaMemcpyAsync(dcnt, sl.h_cnt + 8, sizeof(all), cudaMemcpyHostToDevice, c->stream));
+        // (3) this rank's out-migrants that are now part of a neighbour's first W columns stay here as ghosts; the counts reach the host
+        // (the peer transport does this at the end of k_records_exchange)
+        k_slab_retain<<<1, 32, 0, c->stream>>>(ra, c->grid, sl.sel[0], sl.sel[1], dcnt, n_old, c->cap_n, sl.max_halo, sl.col_lo, sl.col_hi, W, sl.pflag, sl.d_pcounts, hseq);
+        CHECK_LAUNCH();
     }
-    // (3) this rank's out-migrants that are now part of a neighbour's first W columns stay here as ghosts; the counts reach the host
-    k_slab_retain<<<1, 32, 0, c->stream>>>(ra, c->grid, sl.sel[0], sl.sel[1], dcnt, n_old, c->cap_n, sl.max_halo, sl.col_lo, sl.col_hi, W, sl.pflag, sl.d_pcounts, hseq);
-    CHECK_LAUNCH();
     TRY(wait_published(c, &sl.h_pcounts->seq, hseq, c->stream));
     const SlabCounts cnt = const_cast<const PeerCounts*>(sl.h_pcounts)->cnt;
     // a particle that leaves through an end of the domain has no rank to go to
@@ -1240,15 +1246,13 @@ static int32_t slab_exchange_particles(yasph_ctx* c, const GatherPlan& gp, uint3
     if (n2 > c->cap_n) return fail(c, YASPH_ERR_CAPACITY, "rank %d: %llu local particles with arrivals and ghosts > max_particles=%u", sl.rank, (unsigned long long)n2, c->cap_n);
     // (4) sort keys of the arrivals: migrants are classified (they must lie inside the slab: particles move less than a cell per step and
     // a slab is many cells wide); ghosts keep their keys, they lie outside the slab by construction
-    if (n_mig_in) {
-        k_keygen<<<keygen_grid(n_mig_in, c->num_sms), KG_THREADS, 0, c->stream>>>(c->pos, n_old, n_old + n_mig_in, c->grid, c->keys[0], c->idx[0], c->radix_scratch, sp);
-        CHECK_LAUNCH();
-        k_check_arrivals<<<blocks_for(n_mig_in, 256), 256, 0, c->stream>>>(sl.pflag, n_old, n_old + n_mig_in, c->ctl);
+    if (n_mig_in + n_ghost_in) {
+        k_keygen<<<keygen_grid(n_mig_in + n_ghost_in, c->num_sms), KG_THREADS, 0, c->stream>>>(c->pos, n_old, (uint32_t)n2, c->grid, c->keys[0], c->idx[0], c->radix_scratch, sp,
+                                                                                               n_old + n_mig_in);
         CHECK_LAUNCH();
     }
-    if (n_ghost_in) {
-        k_keygen<<<keygen_grid(n_ghost_in, c->num_sms), KG_THREADS, 0, c->stream>>>(c->pos, n_old + n_mig_in, (uint32_t)n2, c->grid, c->keys[0], c->idx[0],
-                                                                                  c->radix_scratch, SlabParams{0u, 0u, nullptr, 0});
+    if (n_mig_in) {
+        k_check_arrivals<<<blocks_for(n_mig_in, 256), 256, 0, c->stream>>>(sl.pflag, n_old, n_old + n_mig_in, c->ctl);
         CHECK_LAUNCH();
     }
     sl.mig_out[0] = cnt.out_m[0];
@@ -1315,7 +1319,7 @@ static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp
     pass_begin(c, YASPH_PASS_SORT);
     if (!keys_ready && n) {
         TRY(radix_prepare(c, n));
-        k_keygen<<<keygen_grid(n, c->num_sms), KG_THREADS, 0, c->stream>>>(c->pos, 0u, n, c->grid, c->keys[0], c->idx[0], c->radix_scratch, slab_params(c));
+        k_keygen<<<keygen_grid(n, c->num_sms), KG_THREADS, 0, c->stream>>>(c->pos, 0u, n, c->grid, c->keys[0], c->idx[0], c->radix_scratch, slab_params(c), n);
         CHECK_LAUNCH();
     }
     uint32_t n_sort = n;
@@ -1573,7 +1577,7 @@ extern "C" int32_t yasph_set_boundary(yasph_ctx* c, const float* xy, uint32_t m)
         CU(cudaMemcpyAsync(c->bpos, xy, (size_t)m * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
         // update_static (neighborhood_search.rs:488-491): sort the boundary particles in place, build the static cells
         TRY(radix_prepare(c, m));
-        k_keygen<<<keygen_grid(m, c->num_sms), KG_THREADS, 0, c->stream>>>(c->bpos, 0u, m, c->grid, c->keys[0], c->idx[0], c->radix_scratch, SlabParams{0u, 0u, nullptr, 0});
+        k_keygen<<<keygen_grid(m, c->num_sms), KG_THREADS, 0, c->stream>>>(c->bpos, 0u, m, c->grid, c->keys[0], c->idx[0], c->radix_scratch, SlabParams{0u, 0u, nullptr, 0}, 0u);
         CHECK_LAUNCH();
         TRY(radix_sort(c, m));
         GatherArgs ga;
@@ -2480,7 +2484,6 @@ extern "C" int32_t yasph_slab_set(yasph_ctx* c, uint32_t col_lo, uint32_t col_hi
             CU(dmalloc(&sl.sbuf[sd], (size_t)sl.max_halo * RECORD_MAX_BYTES));
             CU(dmalloc(&sl.rbuf[sd], (size_t)sl.max_halo * RECORD_MAX_BYTES));
         }
-        CU(dmalloc(&sl.sel4_chunks, (size_t)scan_num_chunks(c->cap_n) + 1));
         CU(dmalloc(&sl.d_cnt, 8));
         CU(cudaMallocHost((void**)&sl.h_cnt, 32 * sizeof(uint32_t)));
         CU(cudaHostAlloc((void**)&sl.h_pcounts, sizeof(PeerCounts), cudaHostAllocMapped));
