@@ -464,7 +464,8 @@ def main():
         # 1-D slab decomposition over cell columns: migration + ghost columns + per-pass halo exchange, all-reduced residual
         cfg.max_particles, cfg.max_boundary = int(n_global / world * 1.3) + 65536, m
         uid = slab.broadcast_unique_id(dist)
-        ctx, ranges, _ = slab.make_slab_context(cfg, rank, world, uid, hw.particles.positions, hw.particles.velocities, hw.particles.boundary_particles)
+        ctx, ranges, _ = slab.make_slab_context(cfg, rank, world, uid, hw.particles.positions, hw.particles.velocities, hw.particles.boundary_particles,
+                                                track_ids=False)
         n = ctx.counts()[0]
     del hw
     stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=torch.device("cuda", local_rank))

@@ -98,8 +98,9 @@ class SlabContext(GpuContext):
     comm: bytes (NCCL unique id shared by all ranks) or a LoopbackFabric.
     """
 
-    def __init__(self, cfg, rank, world, comm, col_range, n_global, id_base=0):
-        cfg.flags |= capi.FLAG_TRACK_IDS
+    def __init__(self, cfg, rank, world, comm, col_range, n_global, id_base=0, track_ids=True):
+        if track_ids:  # ids travel with the particles (tests, verification); a production run does not need them
+            cfg.flags |= capi.FLAG_TRACK_IDS
         super().__init__(cfg)
         self.rank, self.world = rank, world
         if isinstance(comm, LoopbackFabric):
@@ -155,7 +156,7 @@ def scatter_scene(positions, smoothing_length, grid_min_x, world, ranges=None):
     return ranges, own
 
 
-def make_slab_context(base_cfg, rank, world, comm, positions, velocities, boundary, ranges=None):
+def make_slab_context(base_cfg, rank, world, comm, positions, velocities, boundary, ranges=None, track_ids=True):
     """Partitions a scene (identical arrays on every rank), creates this rank's SlabContext and uploads its particles.
 
     Particle ids (YASPH_FIELD_ID) are positions in the concatenation own[0] ++ own[1] ++ ...; the returned `id_to_global`
@@ -170,7 +171,7 @@ def make_slab_context(base_cfg, rank, world, comm, positions, velocities, bounda
         inner = [hi - lo for lo, hi in ranges[1:-1]]
         cfg.ghost_columns = max(1, min([GHOST_COLUMNS] + [w - 1 for w in inner]))
     id_base = int(sum(len(o) for o in own[:rank]))
-    ctx = SlabContext(cfg, rank, world, comm, ranges[rank], len(positions), id_base)
+    ctx = SlabContext(cfg, rank, world, comm, ranges[rank], len(positions), id_base, track_ids)
     ctx.set_boundary(boundary)
     mine = own[rank]
     vel = None if velocities is None else np.ascontiguousarray(velocities, np.float32).reshape(-1, 2)[mine]
