@@ -302,6 +302,16 @@ __device__ __forceinline__ uint32_t slab_classify(const SlabParams& sp, uint32_t
     return out ? YASPH_KEY_DROPPED : key;
 }
 
+// Programmatic dependent launch (sm_90+): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may become
+// resident while its predecessor in the stream still runs; pdl_enter() blocks until that predecessor has completed and its memory
+// is visible, then lets the kernel's own successor become resident the same way.  Everything ahead of pdl_enter() in a kernel
+// touches registers and shared memory only.  Launch latency, CTA placement and the shared-memory set-up of kernel N + 1 thus
+// overlap the tail of kernel N.  In a kernel launched without the attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // warp helpers
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 __device__ __forceinline__ unsigned lanemask_lt() {

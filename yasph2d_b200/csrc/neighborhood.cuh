@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(KG_THREADS)
     // by construction, behind the migrant arrivals, which must lie inside)
     __shared__ RadixHistSmem sh;
     radix_hist_init(sh);
+    pdl_enter();
     for (uint32_t base = first + blockIdx.x * KG_THREADS; base < n; base += gridDim.x * KG_THREADS) {
         const uint32_t i = base + threadIdx.x;
         uint32_t key = 0;
@@ -104,10 +105,11 @@ __global__ void __launch_bounds__(KG_THREADS)
 __global__ void __launch_bounds__(KG_THREADS)
     k_advect_keygen(float2* __restrict__ pos, const float2* __restrict__ vstar, uint32_t n, const Control* __restrict__ ctl, GridParams g,
                     uint32_t* __restrict__ keys, uint32_t* __restrict__ idx, uint32_t* __restrict__ sort_scratch, SlabParams sp, uint32_t only_if_converged) {
-    // launched ahead of the density solver's read-back (dfsph_step): nothing may move unless that solve has finished
-    if (only_if_converged && ctl->stop_iter[0] == 0xFFFFFFFFu) return;
     __shared__ RadixHistSmem sh;
     radix_hist_init(sh);
+    pdl_enter();
+    // launched ahead of the density solver's read-back (dfsph_step): nothing may move unless that solve has finished
+    if (only_if_converged && ctl->stop_iter[0] == 0xFFFFFFFFu) return;
     const float dt = ctl->dt;
     for (uint32_t base = blockIdx.x * KG_THREADS; base < n; base += gridDim.x * KG_THREADS) {
         const uint32_t i = base + threadIdx.x;
@@ -129,6 +131,7 @@ __global__ void __launch_bounds__(KG_THREADS)
                        GridParams g, uint32_t* __restrict__ keys, uint32_t* __restrict__ idx, uint32_t* __restrict__ sort_scratch, SlabParams sp) {
     __shared__ RadixHistSmem sh;
     radix_hist_init(sh);
+    pdl_enter();
     const float dt = ctl->dt_prev;
     for (uint32_t base = blockIdx.x * KG_THREADS; base < n; base += gridDim.x * KG_THREADS) {
         const uint32_t i = base + threadIdx.x;
@@ -162,6 +165,7 @@ struct GatherArgs {
     uint32_t col_lo, col_hi;
 };
 __global__ void k_gather(const uint32_t* __restrict__ perm, uint32_t n, GatherArgs a) {
+    pdl_enter();
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     bool gl = false, gr = false;
     if (k < n) {
@@ -249,6 +253,9 @@ struct FinishCells {
             ctl->max_stat_total = 0u;
             ctl->max_pcount = 0u;
             ctl->max_nk = 0u;
+            ctl->total_neighbors = 0ull;  // the list build's statistics
+            ctl->capped = 0u;
+            ctl->dropped = 0u;
         }
     }
 };
@@ -310,6 +317,7 @@ __global__ void __launch_bounds__(TT_WARPS * 32) k_tile_tables(TileTableArgs a, 
     TTScratch& S = scratch[threadIdx.x >> 5];
     const uint32_t lane = lane_id();
     const unsigned lt = lanemask_lt();
+    pdl_enter();
     const uint32_t ntiles = ctl->num_tiles, nstiles = ctl->num_tiles_static;
     uint32_t wmax_d = 0, wmax_s = 0, wmax_p = 0;
     for (uint32_t t = blockIdx.x * TT_WARPS + (threadIdx.x >> 5); t < ntiles; t += gridDim.x * TT_WARPS) {
@@ -695,6 +703,7 @@ __global__ void __launch_bounds__(NB_THREADS) k_build_lists(ListArgs a) {
     ListSmem& S = *reinterpret_cast<ListSmem*>(smem_raw);
     float2* const sdyn[2] = {reinterpret_cast<float2*>(smem_raw + sizeof(ListSmem)),
                              reinterpret_cast<float2*>(smem_raw + sizeof(ListSmem)) + a.cap_dyn + a.cap_stat};
+    pdl_enter();
     const uint32_t ntiles = a.ctl->num_tiles;
     const uint32_t tid = threadIdx.x, G = gridDim.x;
     unsigned long long my_total = 0;

@@ -123,7 +123,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(In in, uint32_t n, 
 // by summing the totals of ALL earlier chunks (one warp, coalesced loads, spinning on the few that are not published yet) -- no
 // serial chain of inclusive prefixes, and the input is read once.  The chunk that holds the last element also hands the grand total to
 // `fin` (sentinels, counts), so no extra launch follows.  status[0] = ticket counter, status[1 + b] = total of chunk b | 1 << 63
-// (a total's tile half is <= 4096, so bit 63 is free); the caller zeroes 1 + nchunks words before the launch.
+// (a total's tile half is <= 4096, so bit 63 is free), status[1 + nchunks] = chunks that are done.  The words are zero at launch and
+// the chunk that finishes last zeroes them again, so back-to-back uses need no memset between them.
 template <typename In, typename Out, typename Fin>
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_fused(In in, uint32_t n, unsigned long long* __restrict__ status, Out out, Fin fin) {
     typedef unsigned long long T;
@@ -132,6 +133,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_fused(In in, uint32_t n, 
     __shared__ uint32_t chunk_s;
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
     const unsigned lt = lanemask_lt();
+    pdl_enter();
     if (threadIdx.x == 0) chunk_s = atomicAdd(reinterpret_cast<unsigned int*>(status), 1u);
     __syncthreads();
     const uint32_t b = chunk_s;
@@ -175,6 +177,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_fused(In in, uint32_t n, 
         if (i < n) out(i, off + ex[r], v[r]);
     }
     if (threadIdx.x == SCAN_THREADS - 1 && (uint64_t)(b + 1) * SCAN_CHUNK >= n) fin(off + carry);  // the last warp's offset + its total = the grand total
+    // clean-up by the chunk that finishes last: nobody reads a status word any more
+    __shared__ bool last_s;
+    __syncthreads();
+    const uint32_t nch = gridDim.x;
+    if (threadIdx.x == 0) last_s = atomicAdd(reinterpret_cast<unsigned int*>(status + 1 + nch), 1u) == nch - 1u;
+    __syncthreads();
+    if (last_s)
+        for (uint32_t q = threadIdx.x; q < nch + 2u; q += SCAN_THREADS) status[q] = 0ull;
 }
 
 struct U32In {

@@ -115,11 +115,12 @@ __global__ void __launch_bounds__(RS_THREADS)
 #ifdef YASPH_RADIX_TIMING
     long long rz = clock64();
 #endif
+    for (uint32_t q = tid; q < RS_WARPS * RS_BINS; q += RS_THREADS) (&S.cnt[0][0])[q] = 0u;
+    pdl_enter();
     if (tid == 0) {
         S.tile = atomicAdd(&scratch[pass], 1u);
         S.trivial = 0u;
     }
-    for (uint32_t q = tid; q < RS_WARPS * RS_BINS; q += RS_THREADS) (&S.cnt[0][0])[q] = 0u;
     __syncthreads();
     const uint32_t tile = S.tile;
     const bool owner = tid < RS_BINS;

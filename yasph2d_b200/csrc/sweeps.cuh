@@ -379,10 +379,6 @@ __global__ void __launch_bounds__(SW_THREADS, YASPH_SWEEP_MIN_CTAS) k_sweep(Swee
     typedef typename Op::P0 P0;
     typedef typename Op::P1 P1;
     typedef SweepLayout<Op> L;
-    if (op.skip(c.ctl)) return;
-#ifdef YASPH_SWEEP_TIMING
-    if (threadIdx.x == 0 && c.dbg) atomicMin(&c.dbg[8], global_timer_ns_sweep());
-#endif
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* full_bar = reinterpret_cast<unsigned long long*>(smem_raw);
     unsigned long long* empty_bar = full_bar + SW_STAGES;
@@ -398,6 +394,11 @@ __global__ void __launch_bounds__(SW_THREADS, YASPH_SWEEP_MIN_CTAS) k_sweep(Swee
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    pdl_enter();  // the barriers above are set up while the previous kernel of the stream drains
+    if (op.skip(c.ctl)) return;
+#ifdef YASPH_SWEEP_TIMING
+    if (threadIdx.x == 0 && c.dbg) atomicMin(&c.dbg[8], global_timer_ns_sweep());
+#endif
     op.prepare(c);
     __syncthreads();
     const uint32_t ntiles = c.ctl->num_tiles;
@@ -1076,6 +1077,7 @@ struct OpWcsphAccel {
 // ---------------------------------------------------------------------------------------------------------------------
 // TimeManager::simulation_step at step entry (dfsph.rs:433 / wscsph.rs:133)
 __global__ void k_begin_step(Control* ctl) {
+    pdl_enter();
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         ctl->step_prev_ns = ctl->step_ns;
         ctl->dt_prev = duration_as_secs_f32(ctl->step_ns);
@@ -1099,6 +1101,7 @@ __global__ void k_timestep_apply(Control* ctl, TimeParams tp, float particle_dia
                                  const float2* __restrict__ accel, float2* vel_out, uint32_t n) {
     // one thread per CTA evaluates the rule (64-bit integer and f64 arithmetic); every CTA gets the same result
     __shared__ float dt_s;
+    pdl_enter();
     if (threadIdx.x == 0) {
         const float max_velocity = sqrtf(__uint_as_float(ctl->max_v2_bits));
         const unsigned long long step = update_simulation_step(tp, ctl->step_prev_ns, particle_diameter, max_velocity, ctl->total_simulated_ns);

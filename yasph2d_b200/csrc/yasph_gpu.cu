@@ -64,7 +64,13 @@ struct yasph_ctx {
     uint32_t* tile_nk = nullptr;  // per tile: most list words of any of its particles
     uint32_t* apron_idx = nullptr;  // per tile: global index of its first APRON_TABLE apron slots (list build -> sweeps)
     // scratch
-    uint32_t* radix_scratch = nullptr;
+    // Radix sort scratch (tile tickets, digit histograms, look-back status): two areas used alternately.  The area of the NEXT sort is
+    // zeroed on the side stream while the cell / tile tables of the current update are built (neighborhood_update), so no memset
+    // sits between the kernels of the step's chain; radix_prepare falls back to a memset in the main stream when that has not happened.
+    uint32_t* radix_base[2] = {nullptr, nullptr};
+    uint32_t* radix_scratch = nullptr;   // the area of the running / next sort (radix_prepare)
+    int radix_cur = 0;
+    uint32_t radix_clean_n[2] = {0u, 0u};  // pairs the area is known to be zeroed for (0: dirty)
     unsigned long long *scan_chunks = nullptr, *scan_total = nullptr, *scan_status = nullptr;
     double* partials = nullptr;
 #if defined(YASPH_SWEEP_TIMING) || defined(YASPH_LIST_TIMING)
@@ -150,6 +156,8 @@ struct yasph_ctx {
     bool have_particles = false, lists_valid = false, dfsph_ready = false;
     uint32_t dfsph_n = 0;  // length of the DFSPH solver arrays (alpha / kappa / stiffness) as of their last resize (dfsph.rs:419-423)
     int list_margin_pct = 12;
+    bool scan_status_clean = false;  // scan_status is all zero (k_scan_fused cleans up after itself)
+    bool pdl = true;  // programmatic dependent launch of the step's kernel chain (YASPH_DEBUG_NO_PDL=1 turns it off for A/B timing)
     bool spec_advect = false, spec_advect_done = false;  // advect + sort enqueued ahead of the density solver's read-back (dfsph_step)
     uint64_t list_rebuilds = 0;     // early list builds that had to be repeated
     bool unstaged_tiles = false;    // the current structure has tiles beyond the (clipped) staging capacities: every tile kernel is followed / preceded by its unstaged twin
@@ -412,7 +420,7 @@ static void free_all(yasph_ctx* c) {
                     c->f_alt0, c->f_alt1, c->keys[0], c->keys[1], c->idx[0], c->idx[1], c->cell_key, c->cell_start, c->tile_key, c->tile_pstart,
                     c->tile_cstart, c->bpos, c->bpos_alt, c->scell_key, c->scell_start, c->stile_key, c->stile_cstart, c->tile_runs, c->cslot_d,
                     c->cslot_s, c->lists, c->counts, c->tile_nk, c->apron_idx,
-                    c->radix_scratch, c->scan_chunks, c->scan_total, c->scan_status, c->partials, c->ctl, c->exp_cd, c->exp_ct, c->exp_lists,
+                    c->radix_base[0], c->scan_chunks, c->scan_total, c->scan_status, c->partials, c->ctl, c->exp_cd, c->exp_ct, c->exp_lists,
                     c->ids, c->ids_alt, c->slab.pflag, c->slab.sel[0], c->slab.sel[1], c->slab.sel_g[0], c->slab.sel_g[1], c->slab.send_idx[0], c->slab.send_idx[1],
                     c->slab.ghost_idx[0], c->slab.ghost_idx[1], c->slab.own_idx, c->slab.sbuf[0], c->slab.sbuf[1], c->slab.rbuf[0],
                     c->slab.rbuf[1], c->slab.d_cnt};
@@ -497,6 +505,7 @@ extern "C" int32_t yasph_create(const yasph_config* cfg, yasph_ctx** out) {
     for (int i = 0; i < 6; ++i) CUC(cudaEventCreate(&c->ev_host[i]));
     CUC(cudaEventCreateWithFlags(&c->ev_tables, cudaEventDisableTiming));
     if (const char* e = getenv("YASPH_DEBUG_LIST_MARGIN_PCT")) c->list_margin_pct = atoi(e);
+    if (const char* e = getenv("YASPH_DEBUG_NO_PDL")) c->pdl = atoi(e) == 0;
 
     c->cap_n = cfg->max_particles;
     c->cap_m = cfg->max_boundary;
@@ -565,10 +574,12 @@ extern "C" int32_t yasph_create(const yasph_config* cfg, yasph_ctx** out) {
     CUC(dmalloc(&c->counts, N));
     CUC(dmalloc(&c->tile_nk, (size_t)c->max_tiles + 1));
     CUC(dmalloc(&c->apron_idx, ((size_t)c->max_tiles + 1) * APRON_TABLE));
-    CUC(dmalloc(&c->radix_scratch, radix_scratch_words((uint32_t)NM)));
+    CUC(dmalloc(&c->radix_base[0], 2 * radix_scratch_words((uint32_t)NM)));
+    c->radix_base[1] = c->radix_base[0] + radix_scratch_words((uint32_t)NM);
+    c->radix_scratch = c->radix_base[0];
     CUC(dmalloc(&c->scan_chunks, (size_t)scan_num_chunks((uint32_t)NM) + 1));
     CUC(dmalloc(&c->scan_total, 1));
-    CUC(dmalloc(&c->scan_status, (size_t)scan_num_chunks((uint32_t)NM) + 2));
+    CUC(dmalloc(&c->scan_status, (size_t)scan_num_chunks((uint32_t)NM) + 3));
     CUC(dmalloc(&c->ctl, 1));
     CUC(cudaMallocHost((void**)&c->h_ctl, sizeof(Control)));
     CUC(cudaHostAlloc((void**)&c->h_pub, sizeof(yasph_ctx::Published), cudaHostAllocMapped));
@@ -672,14 +683,51 @@ extern "C" int32_t yasph_pass_times(yasph_ctx* c, float* out_us) {
 // ---------------------------------------------------------------------------------------------------------------------
 static inline uint32_t blocks_for(uint32_t n, uint32_t threads) { return (n + threads - 1) / threads; }
 
+// Launch of a kernel of the step's chain.  With programmatic stream serialization the kernel may become resident while its
+// predecessor in the stream drains; it must (and every kernel launched through here does) call pdl_enter() before it touches
+// global memory (common.cuh).
+template <class... P, class... A>
+static inline void launch_chain(const yasph_ctx* c, void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = c->pdl ? 1u : 0u;
+    cudaLaunchKernelEx(&cfg, kernel, P(std::forward<A>(args))...);  // errors surface through CHECK_LAUNCH (cudaGetLastError)
+}
+
 // Stable LSD radix sort of (keys[0], idx[0]) over n elements; result back in buffer 0 (4 passes).  radix_prepare must be
 // enqueued BEFORE the kernel that generates the keys, because that kernel accumulates the digit histograms.
+static uint32_t radix_bound(const yasph_ctx* c, uint32_t n) {
+    if (c->slab.active) n = (uint32_t)std::min<uint64_t>(c->cap_n, (uint64_t)n + 4ull * c->slab.max_halo);
+    return n;
+}
 static int32_t radix_prepare(yasph_ctx* c, uint32_t n) {
     // Slab mode: migrants and ghosts are appended between key generation and the sort (slab_exchange_particles), so the sort runs
     // over up to n + 4 * max_halo pairs and its status area [pass][tiles(n_sort)][bins] is larger than tiles(n) suggests: zero
     // the area of the largest count the exchange can produce (the layout is addressed with the tile count of the sort's launch).
-    if (c->slab.active) n = (uint32_t)std::min<uint64_t>(c->cap_n, (uint64_t)n + 4ull * c->slab.max_halo);
-    if (n) CU(cudaMemsetAsync(c->radix_scratch, 0, radix_scratch_words(n) * sizeof(uint32_t), c->stream));
+    n = radix_bound(c, n);
+    c->radix_cur ^= 1;
+    c->radix_scratch = c->radix_base[c->radix_cur];
+    if (n && c->radix_clean_n[c->radix_cur] < n) CU(cudaMemsetAsync(c->radix_scratch, 0, radix_scratch_words(n) * sizeof(uint32_t), c->stream));
+    c->radix_clean_n[c->radix_cur] = 0u;  // about to be used
+    return YASPH_OK;
+}
+// zeroes the area of the NEXT sort in `stream` (the caller orders that stream ahead of the next key generation)
+static int32_t radix_clean_next(yasph_ctx* c, uint32_t n, cudaStream_t stream) {
+    const int nxt = c->radix_cur ^ 1;
+    n = radix_bound(c, n);
+    // a few tiles of margin: the particle count of the next sort may differ slightly (slab mode: migration)
+    n = (uint32_t)std::min<uint64_t>(std::max(c->cap_n, c->cap_m), (uint64_t)n + 4ull * RS_TILE);
+    if (n == 0) return YASPH_OK;
+    CU(cudaMemsetAsync(c->radix_base[nxt], 0, radix_scratch_words(n) * sizeof(uint32_t), stream));
+    c->radix_clean_n[nxt] = n;
     return YASPH_OK;
 }
 static int32_t radix_sort(yasph_ctx* c, uint32_t n) {
@@ -687,8 +735,8 @@ static int32_t radix_sort(yasph_ctx* c, uint32_t n) {
     const uint32_t ntiles = radix_num_tiles(n);
     int src = 0;
     for (int pass = 0; pass < RS_PASSES; ++pass) {
-        k_radix_pass<<<ntiles, RS_THREADS, sizeof(RadixPassSmem), c->stream>>>(c->keys[src], c->idx[src], c->keys[src ^ 1], c->idx[src ^ 1], n, pass,
-                                                                             c->radix_scratch, ntiles);
+        launch_chain(c, k_radix_pass, ntiles, RS_THREADS, sizeof(RadixPassSmem), c->stream, c->keys[src], c->idx[src], c->keys[src ^ 1], c->idx[src ^ 1], n, pass,
+                     c->radix_scratch, ntiles);
         CHECK_LAUNCH();
         src ^= 1;
     }
@@ -706,8 +754,10 @@ static int32_t build_cells(yasph_ctx* c, uint32_t n, bool is_static) {
         HeadFlagsIn in{c->keys[0]};
         HeadCompactOut out{c->keys[0], ck, cs, is_static ? c->stile_key : c->tile_key, is_static ? nullptr : c->tile_pstart,
                            is_static ? c->stile_cstart : c->tile_cstart, is_static ? c->cap_m : c->max_tiles};
-        CU(cudaMemsetAsync(c->scan_status, 0, ((size_t)nch + 1) * sizeof(unsigned long long), c->stream));
-        k_scan_fused<HeadFlagsIn, HeadCompactOut, FinishCells><<<nch, SCAN_THREADS, 0, c->stream>>>(in, n, c->scan_status, out, fin);
+        // k_scan_fused leaves its status words zeroed (its last chunk cleans up); other users of the area (slab mode's selections) do not
+        if (c->slab.active || !c->scan_status_clean) CU(cudaMemsetAsync(c->scan_status, 0, ((size_t)nch + 2) * sizeof(unsigned long long), c->stream));
+        c->scan_status_clean = true;
+        launch_chain(c, k_scan_fused<HeadFlagsIn, HeadCompactOut, FinishCells>, nch, SCAN_THREADS, 0, c->stream, in, n, c->scan_status, out, fin);
         CHECK_LAUNCH();
     } else {
         k_finish_cells<<<1, 32, 0, c->stream>>>(fin);
@@ -778,7 +828,7 @@ static int32_t launch_sweep(yasph_ctx* c, Op op) {
         sc.nk_stage = sweep_nk_stage<Op>(c->cap_dyn, c->cap_stat, c->cap_pc, hint, sc.nstages, c->smem_optin);
     }
     const size_t bytes = L::total_bytes(c->cap_dyn, c->cap_stat, c->cap_pc, sc.nk_stage, sc.nstages);
-    k_sweep<Op><<<persistent_grid(c, k_sweep<Op>, bytes, SW_THREADS), SW_THREADS, bytes, c->stream>>>(sc, op);
+    launch_chain(c, k_sweep<Op>, persistent_grid(c, k_sweep<Op>, bytes, SW_THREADS), SW_THREADS, bytes, c->stream, sc, op);
     CHECK_LAUNCH();
     return YASPH_OK;
 }
@@ -787,6 +837,7 @@ static int32_t launch_sweep(yasph_ctx* c, Op op) {
 // travels as zero-copy stores of a one-warp kernel into mapped host memory, published by a sequence number the host polls:
 // a few microseconds less per read-back than a DMA copy plus a stream synchronisation, four or more times per step.
 __global__ void k_publish_control(const Control* __restrict__ ctl, uint32_t* __restrict__ dst_words, unsigned int* seq_out, unsigned int seq) {
+    pdl_enter();
     const uint32_t* src = reinterpret_cast<const uint32_t*>(ctl);
     for (uint32_t q = threadIdx.x; q < sizeof(Control) / 4; q += blockDim.x) dst_words[q] = src[q];
     __threadfence_system();
@@ -818,7 +869,7 @@ static int32_t wait_published(yasph_ctx* c, volatile unsigned int* vs, unsigned 
 static int32_t read_control(yasph_ctx* c, cudaStream_t stream = nullptr) {
     static_assert(sizeof(Control) % 4 == 0, "Control is published word by word");
     const unsigned int seq = ++c->pub_seq;
-    k_publish_control<<<1, 64, 0, stream ? stream : c->stream>>>(c->ctl, reinterpret_cast<uint32_t*>(&c->d_pub->ctl), &c->d_pub->seq, seq);
+    launch_chain(c, k_publish_control, 1, 64, 0, stream ? stream : c->stream, c->ctl, reinterpret_cast<uint32_t*>(&c->d_pub->ctl), &c->d_pub->seq, seq);
     CHECK_LAUNCH();
     TRY(wait_published(c, &c->h_pub->seq, seq, stream ? stream : c->stream));
     memcpy(c->h_ctl, const_cast<const Control*>(&c->h_pub->ctl), sizeof(Control));
@@ -1374,18 +1425,18 @@ static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp
         }
         k_gather<<<blocks_for(n, 256), 256, 0, gs>>>(c->idx[0], n, ga);
         CHECK_LAUNCH();
+        TRY(radix_clean_next(c, n, gs));  // the scratch of the next step's sort, off the main stream's kernel chain
         if (gather_aside) CU(cudaEventRecord(c->ev_join, c->aux_stream));
         for (int q = 0; q < gp.n2; ++q) std::swap(*gp.a2[q], *gp.alt2[q]);
         for (int q = 0; q < gp.n1; ++q) std::swap(*gp.a1[q], *gp.alt1[q]);
     }
     pass_end(c);
     pass_begin(c, YASPH_PASS_CELLS_TILES);
-    TRY(build_cells(c, n, false));
-    CU(cudaMemsetAsync(&c->ctl->total_neighbors, 0, sizeof(unsigned long long) + 2 * sizeof(unsigned int), c->stream));
+    TRY(build_cells(c, n, false));  // also zeroes the list statistics (FinishCells)
     if (n) {
         TileTableArgs ta{c->tile_key, c->tile_pstart, c->tile_cstart, c->cell_key, c->cell_start, c->stile_key, c->stile_cstart,
                          c->scell_key, c->scell_start, c->tile_runs, c->cslot_d, c->cslot_s};
-        k_tile_tables<<<c->num_sms * 16, TT_WARPS * 32, 0, c->stream>>>(ta, c->ctl);
+        launch_chain(c, k_tile_tables, c->num_sms * 16, TT_WARPS * 32, 0, c->stream, ta, c->ctl);
         CHECK_LAUNCH();
     }
     c->slab.halo_lists_valid = false;  // per-pass halo lists of the new structure are built when a pass needs an exchange (ensure_halo_lists)
@@ -1414,7 +1465,7 @@ static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp
             CU(cudaEventRecord(c->ev_tables, c->stream));
             pass_begin(c, YASPH_PASS_LISTS);
             ListArgs la{tile_tables(c), c->pos, c->bpos, c->keys[0], c->grid, c->ctl, c->lists, c->counts, c->tile_nk, spec_dyn, spec_stat, c->apron_idx};
-            k_build_lists<false><<<persistent_grid(c, k_build_lists<false>, bytes, NB_THREADS), NB_THREADS, bytes, c->stream>>>(la);
+            launch_chain(c, k_build_lists<false>, persistent_grid(c, k_build_lists<false>, bytes, NB_THREADS), NB_THREADS, bytes, c->stream, la);
             CHECK_LAUNCH();
             pass_end(c);
             lists_launched = true;
@@ -1462,7 +1513,7 @@ static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp
 #ifdef YASPH_LIST_TIMING
         la.dbg = c->sweep_dbg;
 #endif
-        k_build_lists<false><<<persistent_grid(c, k_build_lists<false>, bytes, NB_THREADS), NB_THREADS, bytes, c->stream>>>(la);
+        launch_chain(c, k_build_lists<false>, persistent_grid(c, k_build_lists<false>, bytes, NB_THREADS), NB_THREADS, bytes, c->stream, la);
         CHECK_LAUNCH();
         spec_dyn = c->cap_dyn;
         spec_stat = c->cap_stat;
@@ -1836,8 +1887,8 @@ static int32_t enqueue_advect_sort(yasph_ctx* c, bool only_if_converged) {
     const uint32_t n = c->n;
     pass_begin(c, YASPH_PASS_ADVECT_KEYGEN);
     TRY(radix_prepare(c, n));
-    k_advect_keygen<<<keygen_grid(n, c->num_sms), KG_THREADS, 0, c->stream>>>(c->pos, c->vstar, n, c->ctl, c->grid, c->keys[0], c->idx[0], c->radix_scratch,
-                                                                            slab_params(c), only_if_converged ? 1u : 0u);
+    launch_chain(c, k_advect_keygen, keygen_grid(n, c->num_sms), KG_THREADS, 0, c->stream, c->pos, c->vstar, n, c->ctl, c->grid, c->keys[0], c->idx[0], c->radix_scratch,
+                 slab_params(c), only_if_converged ? 1u : 0u);
     CHECK_LAUNCH();
     pass_end(c);
     if (only_if_converged) {  // the sort too (neighborhood_update skips it then)
@@ -1995,7 +2046,7 @@ static int32_t dfsph_initialize(yasph_ctx* c) {
 static int32_t dfsph_step(yasph_ctx* c) {
     if (!c->dfsph_ready) TRY(dfsph_initialize(c));
     const uint32_t n = c->n;  // local particles (slab mode: owned + ghosts); the neighbourhood update below changes it
-    k_begin_step<<<1, 32, 0, c->stream>>>(c->ctl);
+    launch_chain(c, k_begin_step, 1, 32, 0, c->stream, c->ctl);
     CHECK_LAUNCH();
     // non-pressure forces + CFL maximum (dfsph.rs:436-477); slab mode: v_j and rho_j of the ghosts, if stale
     TRY(slab_refresh(c, SF_VEL, c->vel));
@@ -2017,7 +2068,7 @@ static int32_t dfsph_step(yasph_ctx* c) {
     TRY(allreduce_scalar(c, &c->ctl->max_v2_bits, ncclFloat, ncclMax));  // CFL maximum over all ranks (values are >= 0)
     // update timestep + velocity prediction (dfsph.rs:478-491)
     pass_begin(c, YASPH_PASS_PREDICT);
-    k_timestep_apply<0><<<std::max(1u, blocks_for((n + 1) / 2, 256)), 256, 0, c->stream>>>(c->ctl, c->tp, c->radius * 2.0f, c->vel, c->accel, c->vstar, n);
+    launch_chain(c, k_timestep_apply<0>, std::max(1u, blocks_for((n + 1) / 2, 256)), 256, 0, c->stream, c->ctl, c->tp, c->radius * 2.0f, c->vel, c->accel, c->vstar, n);
     CHECK_LAUNCH();
     pass_end(c);
     c->slab.valid[SF_VSTAR] = slab_own_valid(c, {SF_VEL, SF_ACCEL});  // the ghosts predict with their own (recomputed) accelerations
@@ -2080,15 +2131,15 @@ static int32_t dfsph_step(yasph_ctx* c) {
 
 static int32_t wcsph_step(yasph_ctx* c) {
     uint32_t n = c->n;
-    k_begin_step<<<1, 32, 0, c->stream>>>(c->ctl);
+    launch_chain(c, k_begin_step, 1, 32, 0, c->stream, c->ctl);
     CHECK_LAUNCH();
     // leap frog 1 (wscsph.rs:141-150) fused with key generation
     c->slab.valid[SF_VEL] = slab_own_valid(c, {SF_VEL, SF_ACCEL});
     c->slab.valid[SF_POS] = slab_own_valid(c, {SF_POS, SF_VEL});
     pass_begin(c, YASPH_PASS_ADVECT_KEYGEN);
     TRY(radix_prepare(c, n));
-    k_kickdrift_keygen<<<keygen_grid(n, c->num_sms), KG_THREADS, 0, c->stream>>>(c->pos, c->vel, c->accel, n, c->ctl, c->grid, c->keys[0], c->idx[0],
-                                                                               c->radix_scratch, slab_params(c));
+    launch_chain(c, k_kickdrift_keygen, keygen_grid(n, c->num_sms), KG_THREADS, 0, c->stream, c->pos, c->vel, c->accel, n, c->ctl, c->grid, c->keys[0], c->idx[0],
+                 c->radix_scratch, slab_params(c));
     CHECK_LAUNCH();
     pass_end(c);
     GatherPlan gp;
@@ -2123,7 +2174,7 @@ static int32_t wcsph_step(yasph_ctx* c) {
     TRY(allreduce_scalar(c, &c->ctl->max_v2_bits, ncclFloat, ncclMax));
     // update timestep + leap frog 2 (wscsph.rs:160-177)
     pass_begin(c, YASPH_PASS_WCSPH_KICK);
-    k_timestep_apply<1><<<std::max(1u, blocks_for((n + 1) / 2, 256)), 256, 0, c->stream>>>(c->ctl, c->tp, c->radius * 2.0f, c->vel, c->accel, c->vel, n);
+    launch_chain(c, k_timestep_apply<1>, std::max(1u, blocks_for((n + 1) / 2, 256)), 256, 0, c->stream, c->ctl, c->tp, c->radius * 2.0f, c->vel, c->accel, c->vel, n);
     CHECK_LAUNCH();
     pass_end(c);
     c->slab.valid[SF_VEL] = slab_own_valid(c, {SF_VEL, SF_ACCEL});
