@@ -494,8 +494,12 @@ def main():
         l0 = ctx.launch_count()
         window.setdefault("t0", time.perf_counter())  # the first timed region (device-resident steps) is the one the clocks belong to
         e0.record(stream)
-        for _ in range(steps):
-            reps.append(step_fn())
+        if step_fn is dev_step and not os.environ.get("YASPH_BENCH_SINGLE_STEPS"):  # device-resident steps: ONE call for the whole timed region (yasph_step_n, the application's frame loop)
+            steps_done[0] += steps
+            reps = ctx.step_n(steps)
+        else:
+            for _ in range(steps):
+                reps.append(step_fn())
         e1.record(stream)
         torch.cuda.synchronize()
         window.setdefault("t1", time.perf_counter())

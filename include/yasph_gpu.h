@@ -192,6 +192,10 @@ int32_t yasph_num_particles(const yasph_ctx* ctx, uint32_t* n, uint32_t* m);
 int32_t yasph_clear_cached(yasph_ctx* ctx);
 /* One Solver::simulation_step on the device-resident state.  report may be NULL. */
 int32_t yasph_step(yasph_ctx* ctx, yasph_step_report* report);
+/* `steps` simulation steps in one call -- the application's frame loop (main.rs:339-360 runs several simulation steps per rendered
+ * frame).  Same results as `steps` calls of yasph_step; reports (NULL or [steps]) receives every step's report.  On one GPU the head of
+ * each following step is enqueued ahead of the read-back that ends the running one, so the GPU does not idle between steps. */
+int32_t yasph_step_n(yasph_ctx* ctx, uint32_t steps, yasph_step_report* reports);
 /* The reference-facing call with HOST buffers: upload pos/vel (N particles), one step, download pos/vel/densities
  * into the same arrays (new sorted order) -- what `solver.simulation_step(&mut world, &mut time)` does to the Vecs. */
 int32_t yasph_step_host(yasph_ctx* ctx, float* pos_xy, float* vel_xy, float* densities, uint32_t n, yasph_step_report* report);

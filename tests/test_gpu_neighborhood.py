@@ -66,6 +66,20 @@ def test_coincident_points_and_far_outlier():
     run_pair(pos, 1.0)
 
 
+def test_far_apart_clusters_need_the_top_radix_digit():
+    """Cell coordinates beyond 2^13.5: the sort's fourth pass (key bits 27..31), normally skipped, has to run.  One point sits in the
+    cell whose key has all 27 low bits set (cell (16383, 8191) from grid_min = -100)."""
+    rng = np.random.default_rng(17)
+    a = (rng.random((6000, 2)) * 12.0).astype(np.float32)
+    b = (rng.random((6000, 2)) * 12.0 + np.array([30000.0, 21000.0])).astype(np.float32)
+    c = (rng.random((3000, 2)) * 6.0 + np.array([16280.0, 8088.0])).astype(np.float32)
+    tie = np.array([[16283.5, 8091.5]], np.float32)
+    pos = np.concatenate([a, b, c, tie])[rng.permutation(15001)]
+    ns, w = run_pair(pos, 1.0)
+    keys = ns.ctx.field(capi.FIELD_CELL_KEY)
+    assert keys.max() >= (1 << 27) and (keys & 0x07FFFFFF == 0x07FFFFFF).any() and np.all(np.diff(keys.astype(np.int64)) >= 0)
+
+
 def test_dam_break_scene_lists():
     """The application's scene (main.rs:177-196): 4050 fluid + 6840 boundary particles, h = 0.02."""
     ow = po.dam_break_scene(po.World())

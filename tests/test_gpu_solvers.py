@@ -332,6 +332,36 @@ def test_step_host_pinned_arrays_overlapped_download(solver, tight):
         assert np.array_equal(p1, pos) and np.array_equal(v1, vel) and np.array_equal(d1, den), s
 
 
+@pytest.mark.parametrize("solver,tight", [(capi.SOLVER_DFSPH, False), (capi.SOLVER_DFSPH, True), (capi.SOLVER_WCSPH, False)])
+def test_step_n_equals_single_steps(solver, tight):
+    """yasph_step_n (the application's frame loop, main.rs:339-360) enqueues the head of step s + 1 ahead of the read-back that ends
+    step s, guarded on the device by that step's divergence verdict.  Every report and the final state equal single yasph_step
+    calls bit for bit -- also with tight tolerances, where the guess of the last Jacobi chunk is often wrong and the guarded head is
+    enqueued several times per step."""
+    w, _ = make_worlds()
+    kw = dict(cfl_factor=0.2) if solver == capi.SOLVER_WCSPH else {}
+    if tight:
+        kw = dict(TIGHT_GPU, speculative_iterations=2)
+    one, many = gpu_ctx(w, solver, **kw), gpu_ctx(w, solver, **kw)
+    fields = ("dt_ns", "dt_prev_ns", "max_velocity", "iters_density", "iters_divergence", "avg_density_error", "avg_divergence", "warm_density",
+              "warm_divergence", "not_converged", "num_cells", "total_neighbors")
+    for frame, k in enumerate((1, 7, 30, 2, 40)):
+        singles = [one.step() for _ in range(k)]
+        reps = many.step_n(k)
+        assert len(reps) == k
+        for s, (a, b) in enumerate(zip(singles, reps)):
+            for f in fields:
+                assert getattr(a, f) == getattr(b, f), (frame, s, f, getattr(a, f), getattr(b, f))
+        for x, z in zip(one.download_particles(), many.download_particles()):
+            assert np.array_equal(x, z), frame
+    assert one.total_simulated_ns() == many.total_simulated_ns()
+    if tight:
+        assert max(r.iters_divergence for r in reps) >= 3
+    # a single step after a frame starts from a clean stream (no head left behind)
+    a, b = one.step(), many.step()
+    assert a.dt_ns == b.dt_ns and a.total_neighbors == b.total_neighbors
+
+
 def test_wcsph_trajectory_dam_break():
     """WCSPH (wscsph.rs:126-179), cfl 0.2 (main.rs:116): 300 steps identical to the oracle incl. accelerations."""
     w, ow = make_worlds()

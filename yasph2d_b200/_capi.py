@@ -29,7 +29,7 @@ STATUS_NAMES = {0: "OK", 1: "INVALID_ARGUMENT", 2: "CUDA", 3: "CAPACITY", 4: "ST
 EXPORTED_SYMBOLS = [
     "yasph_config_default", "yasph_create", "yasph_destroy", "yasph_last_error", "yasph_get_config", "yasph_set_flags", "yasph_get_properties",
     "yasph_set_boundary", "yasph_upload_particles", "yasph_download_particles", "yasph_download_field", "yasph_num_particles",
-    "yasph_clear_cached", "yasph_step", "yasph_step_host", "yasph_step_host_ex", "yasph_time_get_step_ns", "yasph_time_set_step_ns", "yasph_time_restart", "yasph_time_set_total_simulated_ns", "yasph_time_get_total_simulated_ns",
+    "yasph_clear_cached", "yasph_step", "yasph_step_n", "yasph_step_host", "yasph_step_host_ex", "yasph_time_get_step_ns", "yasph_time_set_step_ns", "yasph_time_restart", "yasph_time_set_total_simulated_ns", "yasph_time_get_total_simulated_ns",
     "yasph_neighborhood_update", "yasph_neighbors_download", "yasph_update_densities", "yasph_compute_alpha", "yasph_pass_times", "yasph_host_step_times",
     "yasph_solver_state_get", "yasph_solver_state_set", "yasph_upload_field",
     "yasph_launch_count", "yasph_stream", "yasph_scene_fluid_rect", "yasph_scene_boundary_line", "yasph_scene_boundary_thick_line",
@@ -126,6 +126,7 @@ def lib():
     sig("yasph_num_particles", C.c_int32, vp, u32p, u32p)
     sig("yasph_clear_cached", C.c_int32, vp)
     sig("yasph_step", C.c_int32, vp, rp)
+    sig("yasph_step_n", C.c_int32, vp, C.c_uint32, rp)
     sig("yasph_step_host", C.c_int32, vp, f32p, f32p, f32p, C.c_uint32, rp)
     sig("yasph_step_host_ex", C.c_int32, vp, f32p, f32p, f32p, C.c_uint32, C.c_uint32, rp)
     sig("yasph_time_get_step_ns", C.c_int32, vp, u64p)

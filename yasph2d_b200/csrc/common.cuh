@@ -273,7 +273,7 @@ struct Control {
     unsigned int err_slab;               // a particle arrived that this rank does not own (moved more than one slab in a step)
     unsigned long long total_simulated_ns;  // TimeManager::total_simulated_time before the frame loop's addition for the running step
     unsigned int total_is_current;          // 1: the host supplied the total incl. the running step (k_begin_step must not add it again)
-    unsigned int pad_time;
+    unsigned int step_token;                // set by k_begin_step: the step whose head (k_begin_step + first pass) may run (yasph_step_n)
     unsigned int err_comm;               // peer-memory transport: bit 0 a halo message, bit 1 an all-reduce contribution did not arrive in time
     unsigned int slab_sel4[4];           // slab mode: counts of the four-way selection of an update (migrants left | right, ghost layer left | right)
     unsigned int slab_cnt[10];           // SlabCounts (slab.cuh) of the running particle exchange

@@ -24,7 +24,11 @@ constexpr int RS_THREADS = YASPH_RS_THREADS;  // threads of a radix pass CTA (>=
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_ITEMS = YASPH_RS_ITEMS;
 constexpr int KG_THREADS = 256;              // threads of the key-generating kernels
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 pairs per tile
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // pairs per tile of the default shape (the smallest tile: sizes the scratch)
+// A pass is latency-bound per tile (ranking, digit prefix, look-back, reorder: phases in series), so a launch whose tiles do not all
+// fit the GPU at once pays a second, nearly empty wave.  The host picks the smallest items-per-thread of this list whose tile count
+// fits one wave (two CTAs per SM), and the default when none does (many waves: the tail no longer matters).
+constexpr int RS_ITEMS_CHOICES[2] = {RS_ITEMS, RS_ITEMS + 2};  // (+4 spills too much under the 64-register cap: measured slower)
 constexpr int RS_BINS = 256;
 constexpr int RS_PASSES = 4;
 #ifndef YASPH_RS_LOOKBACK
@@ -91,21 +95,24 @@ __device__ unsigned long long g_radix_dbg[8];
 #define RT_MARK(i)
 #endif
 // ---- one pass -------------------------------------------------------------------------------------------------------------
+template <int ITEMS>
 struct RadixPassSmem {
     uint32_t cnt[RS_WARPS][RS_BINS];  // per-warp digit counts, then exclusive prefix over the warps
     uint32_t lbin[RS_BINS];           // first position of the digit in the tile's digit-sorted order
     uint32_t gbin[RS_BINS];           // global position of the tile's first key of the digit, minus lbin
-    uint32_t skey[RS_TILE];
-    uint32_t sval[RS_TILE];
+    uint32_t skey[RS_THREADS * ITEMS];
+    uint32_t sval[RS_THREADS * ITEMS];
     uint32_t wsum[RS_WARPS];
     uint32_t tile;
     uint32_t trivial;
 };
-__global__ void __launch_bounds__(RS_THREADS)
+template <int ITEMS>
+__global__ void __launch_bounds__(RS_THREADS, 2)
     k_radix_pass(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
                  uint32_t* __restrict__ vals_out, uint32_t n, int pass, uint32_t* __restrict__ scratch, uint32_t ntiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    RadixPassSmem& S = *reinterpret_cast<RadixPassSmem*>(smem_raw);
+    constexpr int RS_ITEMS = ITEMS, RS_TILE = RS_THREADS * ITEMS;  // this instance's tile shape
+    RadixPassSmem<ITEMS>& S = *reinterpret_cast<RadixPassSmem<ITEMS>*>(smem_raw);
     const int shift = pass * 8;
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = lane_id();
     const unsigned lt = lanemask_lt();

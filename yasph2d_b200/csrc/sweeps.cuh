@@ -763,9 +763,10 @@ struct OpViscosity {
     float2 base_accel;  // (gravity * m) / m, dfsph.rs:442-444
     ViscParams vp;
     float dt;
+    uint32_t need_token;  // != 0: launched ahead of the previous step's read-back; runs only if k_begin_step began this step
     __device__ __forceinline__ const P0* pay0() const { return vel; }
     __device__ __forceinline__ const P1* pay1() const { return dens; }
-    __device__ __forceinline__ bool skip(const Control*) const { return false; }
+    __device__ __forceinline__ bool skip(const Control* ctl) const { return need_token != 0u && ctl->step_token != need_token; }
     __device__ __forceinline__ void prepare(const SweepCommon& c) { dt = c.ctl->dt_prev; }
     __device__ __forceinline__ bool init(const SweepCommon&, Acc& a, uint32_t, float2, P0, P1, uint32_t) const {
         a = base_accel;
@@ -1076,9 +1077,13 @@ struct OpWcsphAccel {
 // element-wise passes
 // ---------------------------------------------------------------------------------------------------------------------
 // TimeManager::simulation_step at step entry (dfsph.rs:433 / wscsph.rs:133)
-__global__ void k_begin_step(Control* ctl) {
+// guarded != 0: enqueued ahead of the read-back that ends the previous step (yasph_step_n) -- the step begins only if that step's
+// divergence solve has finished; the kernels of the step's head then test the token.
+__global__ void k_begin_step(Control* ctl, uint32_t token, uint32_t guarded) {
     pdl_enter();
     if (threadIdx.x == 0 && blockIdx.x == 0) {
+        if (guarded && ctl->stop_iter[1] == 0xFFFFFFFFu) return;
+        ctl->step_token = token;
         ctl->step_prev_ns = ctl->step_ns;
         ctl->dt_prev = duration_as_secs_f32(ctl->step_ns);
         // the frame loop's `total_simulated_time += simulation_step` ahead of the step (timemanager.rs:246)

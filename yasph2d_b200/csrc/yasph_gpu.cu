@@ -159,6 +159,11 @@ struct yasph_ctx {
     bool scan_status_clean = false;  // scan_status is all zero (k_scan_fused cleans up after itself)
     bool pdl = true;  // programmatic dependent launch of the step's kernel chain (YASPH_DEBUG_NO_PDL=1 turns it off for A/B timing)
     bool spec_advect = false, spec_advect_done = false;  // advect + sort enqueued ahead of the density solver's read-back (dfsph_step)
+    // yasph_step_n: the head of the NEXT step (k_begin_step + its first pass) is enqueued ahead of the read-back that ends the
+    // running step, so the GPU does not idle through that round trip
+    bool spec_head = false;      // armed by yasph_step_n for every step but the last
+    bool head_enqueued = false;  // the next step's head is in the stream (and, DFSPH, the device let it run)
+    uint32_t step_token = 0;
     uint64_t list_rebuilds = 0;     // early list builds that had to be repeated
     bool unstaged_tiles = false;    // the current structure has tiles beyond the (clipped) staging capacities: every tile kernel is followed / preceded by its unstaged twin
     bool lists_valid_once = false;  // cap_dyn / cap_stat / num_tiles describe an earlier structure of this particle set
@@ -610,7 +615,8 @@ extern "C" int32_t yasph_create(const yasph_config* cfg, yasph_ctx** out) {
     CUC((prepare_sweep<OpWcsphAccel>(c)));
     CUC(allow_max_smem(c, k_build_lists<false>));
     CUC(allow_max_smem(c, k_build_lists<true>));
-    CUC(allow_max_smem(c, k_radix_pass));
+    CUC(allow_max_smem(c, k_radix_pass<RS_ITEMS_CHOICES[0]>));
+    CUC(allow_max_smem(c, k_radix_pass<RS_ITEMS_CHOICES[1]>));
     CUC(dmalloc(&c->partials, (size_t)c->max_tiles + 1 + UNSTAGED_GRID_MAX));  // per-CTA partials of k_sweep, then of k_sweep_unstaged
 #if defined(YASPH_SWEEP_TIMING) || defined(YASPH_LIST_TIMING)
     CUC(dmalloc(&c->sweep_dbg, 16));
@@ -730,17 +736,24 @@ static int32_t radix_clean_next(yasph_ctx* c, uint32_t n, cudaStream_t stream) {
     c->radix_clean_n[nxt] = n;
     return YASPH_OK;
 }
-static int32_t radix_sort(yasph_ctx* c, uint32_t n) {
-    if (n == 0) return YASPH_OK;
-    const uint32_t ntiles = radix_num_tiles(n);
+template <int ITEMS>
+static int32_t radix_sort_with(yasph_ctx* c, uint32_t n) {
+    const uint32_t ntiles = (n + RS_THREADS * ITEMS - 1) / (RS_THREADS * ITEMS);
     int src = 0;
     for (int pass = 0; pass < RS_PASSES; ++pass) {
-        launch_chain(c, k_radix_pass, ntiles, RS_THREADS, sizeof(RadixPassSmem), c->stream, c->keys[src], c->idx[src], c->keys[src ^ 1], c->idx[src ^ 1], n, pass,
-                     c->radix_scratch, ntiles);
+        launch_chain(c, k_radix_pass<ITEMS>, ntiles, RS_THREADS, sizeof(RadixPassSmem<ITEMS>), c->stream, c->keys[src], c->idx[src], c->keys[src ^ 1], c->idx[src ^ 1], n,
+                     pass, c->radix_scratch, ntiles);
         CHECK_LAUNCH();
         src ^= 1;
     }
     return YASPH_OK;
+}
+static int32_t radix_sort(yasph_ctx* c, uint32_t n) {
+    if (n == 0) return YASPH_OK;
+    // the smallest tile shape whose tiles are all resident at once (two CTAs per SM); the default when none is (sort.cuh)
+    const uint64_t wave = 2ull * (uint64_t)c->num_sms * RS_THREADS;
+    if (n > wave * RS_ITEMS_CHOICES[0] && n <= wave * RS_ITEMS_CHOICES[1]) return radix_sort_with<RS_ITEMS_CHOICES[1]>(c, n);
+    return radix_sort_with<RS_ITEMS_CHOICES[0]>(c, n);
 }
 
 // cells (+ tiles for the dynamic grid) from the sorted keys in keys[0]
@@ -866,14 +879,24 @@ static int32_t wait_published(yasph_ctx* c, volatile unsigned int* vs, unsigned 
     std::atomic_thread_fence(std::memory_order_acquire);
     return YASPH_OK;
 }
-static int32_t read_control(yasph_ctx* c, cudaStream_t stream = nullptr) {
+// the two halves of read_control: enqueue the snapshot / wait for it
+static int32_t publish_control(yasph_ctx* c, cudaStream_t stream, unsigned int* seq_out) {
     static_assert(sizeof(Control) % 4 == 0, "Control is published word by word");
     const unsigned int seq = ++c->pub_seq;
-    launch_chain(c, k_publish_control, 1, 64, 0, stream ? stream : c->stream, c->ctl, reinterpret_cast<uint32_t*>(&c->d_pub->ctl), &c->d_pub->seq, seq);
+    launch_chain(c, k_publish_control, 1, 64, 0, stream, c->ctl, reinterpret_cast<uint32_t*>(&c->d_pub->ctl), &c->d_pub->seq, seq);
     CHECK_LAUNCH();
-    TRY(wait_published(c, &c->h_pub->seq, seq, stream ? stream : c->stream));
+    *seq_out = seq;
+    return YASPH_OK;
+}
+static int32_t await_control(yasph_ctx* c, cudaStream_t stream, unsigned int seq) {
+    TRY(wait_published(c, &c->h_pub->seq, seq, stream));
     memcpy(c->h_ctl, const_cast<const Control*>(&c->h_pub->ctl), sizeof(Control));
     return YASPH_OK;
+}
+static int32_t read_control(yasph_ctx* c, cudaStream_t stream = nullptr) {
+    unsigned int seq = 0;
+    TRY(publish_control(c, stream ? stream : c->stream, &seq));
+    return await_control(c, stream ? stream : c->stream, seq);
 }
 static int32_t check_capacity_flags(yasph_ctx* c) {
     if (c->h_ctl->err_comm)
@@ -1899,6 +1922,31 @@ static int32_t enqueue_advect_sort(yasph_ctx* c, bool only_if_converged) {
     return YASPH_OK;
 }
 
+// The head of a DFSPH step: TimeManager bookkeeping at step entry, then the non-pressure forces + CFL maximum (dfsph.rs:433-477).
+// guarded: enqueued by the previous step ahead of its last read-back (yasph_step_n); `vel` is the velocity array of the step.
+static int32_t dfsph_head(yasph_ctx* c, bool guarded, const float2* vel) {
+    if (++c->step_token == 0u) c->step_token = 1u;
+    launch_chain(c, k_begin_step, 1, 32, 0, c->stream, c->ctl, c->step_token, guarded ? 1u : 0u);
+    CHECK_LAUNCH();
+    // slab mode: v_j and rho_j of the ghosts, if stale (never guarded: yasph_step_n speculates on one GPU only)
+    TRY(slab_refresh(c, SF_VEL, c->vel));
+    TRY(slab_refresh(c, SF_DENS, c->dens));
+    c->slab.valid[SF_ACCEL] = slab_out_valid(c, {SF_POS, SF_VEL, SF_DENS}, {});
+    pass_begin(c, YASPH_PASS_VISCOSITY);
+    OpViscosity v;
+    v.vel = vel;
+    v.dens = c->dens;
+    v.accel = c->accel;
+    const float2 g = make_float2(c->cfg.gravity[0], c->cfg.gravity[1]);
+    v.base_accel = (g * c->mass) / c->mass;  // dfsph.rs:442-444
+    v.vp = visc_params(c);
+    v.dt = 0.f;
+    v.need_token = guarded ? c->step_token : 0u;
+    TRY(launch_sweep(c, v));
+    pass_end(c);
+    return YASPH_OK;
+}
+
 template <int SOLVER>
 static int32_t jacobi_solve(yasph_ctx* c, bool first_a_done = false) {
     const float rho0 = c->cfg.fluid_density;
@@ -2000,10 +2048,23 @@ static int32_t jacobi_solve(yasph_ctx* c, bool first_a_done = false) {
             spec_now = true;
             c->spec_advect = false;  // once per solve
         }
-        TRY(read_control(c, spec_now ? c->ctl_stream : nullptr));
-        if (c->h_ctl->stop_iter[SOLVER] != 0xFFFFFFFFu) {
-            if (spec_now) c->spec_advect_done = true;
-            break;
+        if (SOLVER == 1 && c->spec_head && it >= prev_iters) {
+            // yasph_step_n: snapshot of the control block (this step's report) in stream order, then the head of the next step,
+            // guarded on the device by this solve's verdict; the host waits for the snapshot while the head runs
+            unsigned int seq = 0;
+            TRY(publish_control(c, c->stream, &seq));
+            TRY(dfsph_head(c, true, c->vstar));  // v* becomes the velocity (dfsph.rs:524)
+            TRY(await_control(c, c->stream, seq));
+            if (c->h_ctl->stop_iter[SOLVER] != 0xFFFFFFFFu) {
+                c->head_enqueued = true;
+                break;
+            }
+        } else {
+            TRY(read_control(c, spec_now ? c->ctl_stream : nullptr));
+            if (c->h_ctl->stop_iter[SOLVER] != 0xFFFFFFFFu) {
+                if (spec_now) c->spec_advect_done = true;
+                break;
+            }
         }
         if (SOLVER == 1) c->early_vel_stale = true;
         if (it > sp.max_iters + spec + 1) return fail(c, YASPH_ERR_STATE, "jacobi_solve: device loop control did not terminate");
@@ -2046,25 +2107,11 @@ static int32_t dfsph_initialize(yasph_ctx* c) {
 static int32_t dfsph_step(yasph_ctx* c) {
     if (!c->dfsph_ready) TRY(dfsph_initialize(c));
     const uint32_t n = c->n;  // local particles (slab mode: owned + ghosts); the neighbourhood update below changes it
-    launch_chain(c, k_begin_step, 1, 32, 0, c->stream, c->ctl);
-    CHECK_LAUNCH();
-    // non-pressure forces + CFL maximum (dfsph.rs:436-477); slab mode: v_j and rho_j of the ghosts, if stale
-    TRY(slab_refresh(c, SF_VEL, c->vel));
-    TRY(slab_refresh(c, SF_DENS, c->dens));
-    c->slab.valid[SF_ACCEL] = slab_out_valid(c, {SF_POS, SF_VEL, SF_DENS}, {});
-    pass_begin(c, YASPH_PASS_VISCOSITY);
-    {
-        OpViscosity v;
-        v.vel = c->vel;
-        v.dens = c->dens;
-        v.accel = c->accel;
-        const float2 g = make_float2(c->cfg.gravity[0], c->cfg.gravity[1]);
-        v.base_accel = (g * c->mass) / c->mass;  // dfsph.rs:442-444
-        v.vp = visc_params(c);
-        v.dt = 0.f;
-        TRY(launch_sweep(c, v));
-    }
-    pass_end(c);
+    // step entry + non-pressure forces + CFL maximum (dfsph.rs:433-477) -- unless the previous step of a yasph_step_n call enqueued them
+    if (c->head_enqueued)
+        c->head_enqueued = false;
+    else
+        TRY(dfsph_head(c, false, c->vel));
     TRY(allreduce_scalar(c, &c->ctl->max_v2_bits, ncclFloat, ncclMax));  // CFL maximum over all ranks (values are >= 0)
     // update timestep + velocity prediction (dfsph.rs:478-491)
     pass_begin(c, YASPH_PASS_PREDICT);
@@ -2129,11 +2176,13 @@ static int32_t dfsph_step(yasph_ctx* c) {
     return YASPH_OK;
 }
 
-static int32_t wcsph_step(yasph_ctx* c) {
-    uint32_t n = c->n;
-    launch_chain(c, k_begin_step, 1, 32, 0, c->stream, c->ctl);
+// The head of a WCSPH step: step entry, then leap frog 1 (wscsph.rs:141-150) fused with key generation.  Nothing in it depends on a
+// verdict of the previous step, so yasph_step_n enqueues it ahead of that step's read-back without a guard.
+static int32_t wcsph_head(yasph_ctx* c) {
+    const uint32_t n = c->n;
+    if (++c->step_token == 0u) c->step_token = 1u;
+    launch_chain(c, k_begin_step, 1, 32, 0, c->stream, c->ctl, c->step_token, 0u);
     CHECK_LAUNCH();
-    // leap frog 1 (wscsph.rs:141-150) fused with key generation
     c->slab.valid[SF_VEL] = slab_own_valid(c, {SF_VEL, SF_ACCEL});
     c->slab.valid[SF_POS] = slab_own_valid(c, {SF_POS, SF_VEL});
     pass_begin(c, YASPH_PASS_ADVECT_KEYGEN);
@@ -2142,6 +2191,15 @@ static int32_t wcsph_step(yasph_ctx* c) {
                  c->radix_scratch, slab_params(c));
     CHECK_LAUNCH();
     pass_end(c);
+    return YASPH_OK;
+}
+
+static int32_t wcsph_step(yasph_ctx* c) {
+    uint32_t n = c->n;
+    if (c->head_enqueued)
+        c->head_enqueued = false;
+    else
+        TRY(wcsph_head(c));
     GatherPlan gp;
     gp.n2 = 2;
     gp.a2[0] = &c->pos;
@@ -2270,17 +2328,46 @@ extern "C" int32_t yasph_step(yasph_ctx* c, yasph_step_report* report) {
         TRY(wcsph_step(c));
     else
         TRY(dfsph_step(c));
-    // the divergence solve ends with a read-back and launches nothing after it: the DFSPH step's control block is current
+    // the divergence solve ends with a read-back (the snapshot of the step's control block): the DFSPH step's h_ctl is current
     if (c->cfg.solver == YASPH_SOLVER_WCSPH) {
         TRY(submit_downloads(c));
         TRY(early_velocities(c, c->vel));
-        TRY(read_control(c));
+        if (c->spec_head) {  // yasph_step_n: the next step's head runs while the host waits for the snapshot
+            unsigned int seq = 0;
+            TRY(publish_control(c, c->stream, &seq));
+            TRY(wcsph_head(c));
+            c->head_enqueued = true;
+            TRY(await_control(c, c->stream, seq));
+        } else {
+            TRY(read_control(c));
+        }
     }
     pass_resolve(c);
     TRY(check_capacity_flags(c));
     fill_report(c, report);
     if (c->h_ctl->nonfinite) return fail(c, YASPH_ERR_NONFINITE, "non-finite Jacobi residual (solver mask %u)", c->h_ctl->nonfinite);
     return YASPH_OK;
+}
+
+// `steps` calls of yasph_step (the application's frame loop, main.rs:339-360: several simulation steps per frame); reports, if not
+// null, receives one report per step.  Same results as the single calls; on one GPU with device-resident particles the head of step
+// s + 1 is enqueued ahead of the read-back that ends step s (guarded on the device by step s's own verdict where it depends on one),
+// so the GPU does not idle between the steps.
+extern "C" int32_t yasph_step_n(yasph_ctx* c, uint32_t steps, yasph_step_report* reports) {
+    if (!c) return YASPH_ERR_INVALID_ARGUMENT;
+    const bool can_spec = !c->slab.active && !(c->cfg.flags & YASPH_FLAG_PROFILE_PASSES) && c->early_pos_out == nullptr && c->early_vel_out == nullptr &&
+                          c->early_dens_out == nullptr;
+    int32_t rc = YASPH_OK;
+    for (uint32_t s = 0; s < steps && rc == YASPH_OK; ++s) {
+        c->spec_head = can_spec && s + 1 < steps && (c->cfg.solver == YASPH_SOLVER_WCSPH || c->dfsph_ready);
+        rc = yasph_step(c, reports ? reports + s : nullptr);
+    }
+    c->spec_head = false;
+    if (rc != YASPH_OK && c->head_enqueued) {  // a head that is already in the stream belongs to a step that will not run
+        cudaStreamSynchronize(c->stream);
+        c->head_enqueued = false;
+    }
+    return rc;
 }
 
 static bool is_pinned_host(const void* p) {

@@ -144,6 +144,12 @@ class GpuContext:
         self._ck(capi.lib().yasph_step(self.h, C.byref(rep)))
         return rep
 
+    def step_n(self, steps):
+        """`steps` simulation steps in one call (the application's frame loop); returns the list of their reports."""
+        reps = (capi.StepReport * max(steps, 1))()
+        self._ck(capi.lib().yasph_step_n(self.h, steps, reps))
+        return list(reps)[:steps]
+
     def step_host(self, pos, vel, dens=None, input_unchanged=False):
         """The reference-facing call: HOST arrays in, one simulation_step, HOST arrays out (in place).  input_unchanged: the arrays
         still hold what the previous call handed back (the application only read them), so their upload is skipped."""
