@@ -333,14 +333,15 @@ static cudaEvent_t get_event(yasph_ctx* c) {
     cudaEventCreate(&e);
     return e;
 }
+static const bool g_no_pass_events = getenv("YASPH_DEBUG_NO_PASS_EVENTS") != nullptr;  // host timeline without the per-pass events
 static void pass_begin(yasph_ctx* c, int pass) {
-    if (!(c->cfg.flags & YASPH_FLAG_PROFILE_PASSES)) return;
+    if (!(c->cfg.flags & YASPH_FLAG_PROFILE_PASSES) || g_no_pass_events) return;
     c->cur_pass = pass;
     c->cur_start = get_event(c);
     cudaEventRecord(c->cur_start, c->stream);
 }
 static void pass_end(yasph_ctx* c) {
-    if (!(c->cfg.flags & YASPH_FLAG_PROFILE_PASSES) || c->cur_pass < 0) return;
+    if (!(c->cfg.flags & YASPH_FLAG_PROFILE_PASSES) || g_no_pass_events || c->cur_pass < 0) return;
     cudaEvent_t b = get_event(c);
     cudaEventRecord(b, c->stream);
     c->events.push_back(PassEvent{c->cur_pass, c->cur_start, b});
@@ -1432,7 +1433,7 @@ static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp
         }
         // The gather (permuted arrays) and the cell / tile tables (sorted keys only) do not depend on each other: the gather runs on a
         // side stream next to them and is joined before the list build.  Not under YASPH_FLAG_PROFILE_PASSES (per-pass times).
-        gather_aside = !(c->cfg.flags & YASPH_FLAG_PROFILE_PASSES);
+        gather_aside = !(c->cfg.flags & YASPH_FLAG_PROFILE_PASSES) || g_no_pass_events;
         cudaStream_t gs = gather_aside ? c->aux_stream : c->stream;
         if (gather_aside) {
             CU(cudaEventRecord(c->ev_fork, c->stream));
@@ -2119,7 +2120,7 @@ static int32_t dfsph_step(yasph_ctx* c) {
     CHECK_LAUNCH();
     pass_end(c);
     c->slab.valid[SF_VSTAR] = slab_own_valid(c, {SF_VEL, SF_ACCEL});  // the ghosts predict with their own (recomputed) accelerations
-    c->spec_advect = !c->slab.active && c->early_pos_out == nullptr && c->early_vel_out == nullptr;  // device-resident stepping on one GPU
+    c->spec_advect = !c->slab.active;  // one GPU (also under yasph_step_host: no download is in flight before the positions are final)
     c->spec_advect_done = false;
     TRY(jacobi_solve<0>(c));  // dfsph.rs:496
     c->spec_advect = false;
