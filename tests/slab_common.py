@@ -79,8 +79,9 @@ def neighbor_sets_global(ctx, id_map=None):
     return out
 
 
-def run_slabs_loopback(world, pos, vel, boundary, steps, checkpoints, solver=capi.SOLVER_DFSPH, neighbor_step=None, ranges=None, **kw):
-    """`world` slabs of one scene on cuda:0, one thread per rank, loopback transport."""
+def run_slabs_loopback(world, pos, vel, boundary, steps, checkpoints, solver=capi.SOLVER_DFSPH, neighbor_step=None, ranges=None, frame=None, **kw):
+    """`world` slabs of one scene on cuda:0, one thread per rank, loopback transport.  frame: step through yasph_step_n in frames of
+    that many steps (checkpoints must then fall on the last step of a frame)."""
     fabric = slab.LoopbackFabric(world)
     cfg = base_config(2 * len(pos), len(boundary), solver, **kw)  # room for the ghost layers
     results = [None] * world
@@ -91,7 +92,14 @@ def run_slabs_loopback(world, pos, vel, boundary, steps, checkpoints, solver=cap
             ctx, rngs, id_map = slab.make_slab_context(cfg, rank, world, fabric, pos, vel, boundary, ranges)
             reps, snaps, infos, nsets = [], {}, [], None
             for s in range(steps):
-                reps.append(ctx.step().as_dict())
+                if frame is None:
+                    reps.append(ctx.step().as_dict())
+                elif s % frame == 0:
+                    reps.extend(r.as_dict() for r in ctx.step_n(min(frame, steps - s)))
+                if frame is not None and (s + 1) % frame != 0 and s != steps - 1:
+                    assert s not in checkpoints
+                    infos.append(None)
+                    continue
                 infos.append(ctx.info().as_dict())
                 if s in checkpoints:
                     snaps[s] = snapshot(ctx, id_map)

@@ -71,6 +71,24 @@ def test_dfsph_slabs_match_single_context(world):
     assert sum(r["infos"][-1]["n_own"] for r in results) == len(pos)
 
 
+@pytest.mark.parametrize("solver", [capi.SOLVER_DFSPH, capi.SOLVER_WCSPH])
+def test_slab_frames_equal_single_steps(solver):
+    """yasph_step_n on slabs: the head of the next step is enqueued ahead of the step-end read-back whenever it needs no halo exchange
+    (guarded on every rank by the same all-reduced verdict).  Reports and states equal the step-by-step slab run bit for bit."""
+    pos, vel, boundary = scene_arrays("dam")
+    steps, frame = 60, 6
+    kw = dict(cfl_factor=0.2) if solver == capi.SOLVER_WCSPH else {}
+    cps = [s for s in range(steps) if (s + 1) % frame == 0]
+    res_a, merged_a = run_slabs_loopback(2, pos, vel, boundary, steps, cps, solver=solver, **kw)
+    res_b, merged_b = run_slabs_loopback(2, pos, vel, boundary, steps, cps, solver=solver, frame=frame, **kw)
+    for ra, rb in zip(res_a, res_b):
+        assert ra["reps"] == rb["reps"]
+        assert ra["infos"][-1]["n_own"] == rb["infos"][-1]["n_own"]
+    for s in cps:
+        for k in ("pos", "vel", "dens"):
+            assert np.array_equal(merged_a[s][k], merged_b[s][k]), (s, k)
+
+
 def test_slabs_of_many_sort_tiles_match_single_context():
     """A tank twin of 160 x 192 particles in two slabs of ~15 000 particles: the re-sort of a slab runs over several radix tiles
     (6144 pairs each), and migrants + ghosts appended between key generation and the sort push the count across a tile boundary for

@@ -1929,10 +1929,14 @@ static int32_t dfsph_head(yasph_ctx* c, bool guarded, const float2* vel) {
     if (++c->step_token == 0u) c->step_token = 1u;
     launch_chain(c, k_begin_step, 1, 32, 0, c->stream, c->ctl, c->step_token, guarded ? 1u : 0u);
     CHECK_LAUNCH();
-    // slab mode: v_j and rho_j of the ghosts, if stale (never guarded: yasph_step_n speculates on one GPU only)
-    TRY(slab_refresh(c, SF_VEL, c->vel));
-    TRY(slab_refresh(c, SF_DENS, c->dens));
-    c->slab.valid[SF_ACCEL] = slab_out_valid(c, {SF_POS, SF_VEL, SF_DENS}, {});
+    // slab mode: v_j and rho_j of the ghosts, if stale.  A guarded head is enqueued only when they are fresh (jacobi_solve), and ahead
+    // of the swap that makes v* the velocity (dfsph.rs:524): the field to look at is still called v* then.
+    const SlabField vel_field = guarded ? SF_VSTAR : SF_VEL;
+    if (!guarded) {
+        TRY(slab_refresh(c, SF_VEL, c->vel));
+        TRY(slab_refresh(c, SF_DENS, c->dens));
+    }
+    c->slab.valid[SF_ACCEL] = slab_out_valid(c, {SF_POS, vel_field, SF_DENS}, {});
     pass_begin(c, YASPH_PASS_VISCOSITY);
     OpViscosity v;
     v.vel = vel;
@@ -2049,7 +2053,9 @@ static int32_t jacobi_solve(yasph_ctx* c, bool first_a_done = false) {
             spec_now = true;
             c->spec_advect = false;  // once per solve
         }
-        if (SOLVER == 1 && c->spec_head && it >= prev_iters) {
+        // (slab mode: only if the head needs no halo exchange -- the host cannot guard a rendezvous)
+        const bool head_fresh = !slab || (c->slab.valid[SF_VSTAR] >= 1 && c->slab.valid[SF_DENS] >= 1);
+        if (SOLVER == 1 && c->spec_head && it >= prev_iters && head_fresh) {
             // yasph_step_n: snapshot of the control block (this step's report) in stream order, then the head of the next step,
             // guarded on the device by this solve's verdict; the host waits for the snapshot while the head runs
             unsigned int seq = 0;
@@ -2351,13 +2357,12 @@ extern "C" int32_t yasph_step(yasph_ctx* c, yasph_step_report* report) {
 }
 
 // `steps` calls of yasph_step (the application's frame loop, main.rs:339-360: several simulation steps per frame); reports, if not
-// null, receives one report per step.  Same results as the single calls; on one GPU with device-resident particles the head of step
-// s + 1 is enqueued ahead of the read-back that ends step s (guarded on the device by step s's own verdict where it depends on one),
-// so the GPU does not idle between the steps.
+// null, receives one report per step.  Same results as the single calls; with device-resident particles the head of step s + 1 is
+// enqueued ahead of the read-back that ends step s (guarded on the device by step s's own verdict where it depends on one; on slabs
+// only when that head needs no halo exchange), so the GPU does not idle between the steps.
 extern "C" int32_t yasph_step_n(yasph_ctx* c, uint32_t steps, yasph_step_report* reports) {
     if (!c) return YASPH_ERR_INVALID_ARGUMENT;
-    const bool can_spec = !c->slab.active && !(c->cfg.flags & YASPH_FLAG_PROFILE_PASSES) && c->early_pos_out == nullptr && c->early_vel_out == nullptr &&
-                          c->early_dens_out == nullptr;
+    const bool can_spec = !(c->cfg.flags & YASPH_FLAG_PROFILE_PASSES) && c->early_pos_out == nullptr && c->early_vel_out == nullptr && c->early_dens_out == nullptr;
     int32_t rc = YASPH_OK;
     for (uint32_t s = 0; s < steps && rc == YASPH_OK; ++s) {
         c->spec_head = can_spec && s + 1 < steps && (c->cfg.solver == YASPH_SOLVER_WCSPH || c->dfsph_ready);
