@@ -158,12 +158,17 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_fused(In in, uint32_t n, 
         for (int w = 0; w < SCAN_WARPS; ++w) total += wsum[w];
         if (lane == 0) st[b] = total | (1ull << 63);
         // exclusive prefix over the chunks: every lane sums a strided share of the earlier totals
+        // (eight loads in flight per lane and round trip; a total that is not published yet is polled afterwards)
         T acc = 0;
-        for (uint32_t j = lane; j < b; j += 32) {
-            T s;
-            while (((s = st[j]) >> 63) == 0ull) {
+        for (uint32_t j0 = lane; j0 < b; j0 += 32 * 8) {
+            T s[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s[u] = j0 + 32u * u < b ? st[j0 + 32u * u] : (1ull << 63);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                while ((s[u] >> 63) == 0ull) s[u] = st[j0 + 32u * u];
+                acc += s[u] & ~(1ull << 63);
             }
-            acc += s & ~(1ull << 63);
         }
         acc = warp_sum(acc);
         if (lane == 0) off_s = acc;

@@ -126,11 +126,15 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_select4_fused(Select4In in, ui
         if (lane == 0)
             st[b] = (unsigned long long)total.x | ((unsigned long long)total.y << 15) | ((unsigned long long)total.z << 30) | ((unsigned long long)total.w << 45) | (1ull << 63);
         uint4 acc = make_uint4(0, 0, 0, 0);
-        for (uint32_t j = lane; j < b; j += 32) {
-            unsigned long long v;
-            while (((v = st[j]) >> 63) == 0ull) {
+        for (uint32_t j0 = lane; j0 < b; j0 += 32 * 8) {  // eight loads in flight per lane and round trip (scan.cuh: k_scan_fused)
+            unsigned long long v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = j0 + 32u * u < b ? st[j0 + 32u * u] : (1ull << 63);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                while ((v[u] >> 63) == 0ull) v[u] = st[j0 + 32u * u];
+                acc = acc + make_uint4((uint32_t)v[u] & 0x7FFFu, (uint32_t)(v[u] >> 15) & 0x7FFFu, (uint32_t)(v[u] >> 30) & 0x7FFFu, (uint32_t)(v[u] >> 45) & 0x7FFFu);
             }
-            acc = acc + make_uint4((uint32_t)v & 0x7FFFu, (uint32_t)(v >> 15) & 0x7FFFu, (uint32_t)(v >> 30) & 0x7FFFu, (uint32_t)(v >> 45) & 0x7FFFu);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1)

@@ -431,10 +431,10 @@ __global__ void __launch_bounds__(SW_THREADS, YASPH_SWEEP_MIN_CTAS) k_sweep(Swee
         const bool leader = threadIdx.x == 0;
         auto producers_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(32 * SW_PRODUCER_WARPS) : "memory"); };
         uint32_t t_cur = blockIdx.x, ticket = 0;
+        prefetch(t_cur);  // in flight while the leader fetches the first ticket
         if (leader) next_tile[0] = G + atomicAdd(&c.ctl->tile_next, 1u);
         producers_sync();
         uint32_t t_nxt = next_tile[0];
-        prefetch(t_cur);
         uint32_t k = 0, stage = 0, round = 0;  // round: completed passes over the ring
 #ifdef YASPH_SWEEP_TIMING
         long long t_wait = 0, t_issue = 0, t_total = clock64(), n_tiles = 0, tsplit[2] = {0, 0};
