@@ -596,8 +596,9 @@ __global__ void __launch_bounds__(SW_THREADS, YASPH_SWEEP_MIN_CTAS) k_sweep(Swee
     }
     // the last CTA to get here re-arms the tile queue for the next sweep (nobody fetches a ticket any more: every CTA's
     // producers have seen the queue empty before their CTA counts itself done)
+    // (a reducing sweep does this with the ticket of its reduction below: one atomic round trip less at the end of the launch)
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (Op::REDUCE == REDUCE_NONE && threadIdx.x == 0) {
         __threadfence();
         if (atomicAdd(&c.ctl->cta_done, 1u) == gridDim.x - 1) {
             c.ctl->tile_next = 0u;
@@ -649,6 +650,7 @@ __global__ void __launch_bounds__(SW_THREADS, YASPH_SWEEP_MIN_CTAS) k_sweep(Swee
                 double tot = wred[0];
                 for (int w = 1; w < SW_THREADS / 32; ++w) tot = Op::REDUCE == REDUCE_SUM ? tot + wred[w] : fmax(tot, wred[w]);
                 c.ctl->ticket[Op::TICKET] = 0u;
+                c.ctl->tile_next = 0u;  // re-arm the tile queue (every CTA has left its tile loop)
                 op.finalize(c, tot);
             }
         }
@@ -1079,8 +1081,14 @@ struct OpWcsphAccel {
 // TimeManager::simulation_step at step entry (dfsph.rs:433 / wscsph.rs:133)
 // guarded != 0: enqueued ahead of the read-back that ends the previous step (yasph_step_n) -- the step begins only if that step's
 // divergence solve has finished; the kernels of the step's head then test the token.
-__global__ void k_begin_step(Control* ctl, uint32_t token, uint32_t guarded) {
+// snap != null: the control block as the previous step left it is copied there first (its report; published to the host from a side
+// stream while this step's first pass already runs).
+__global__ void k_begin_step(Control* ctl, uint32_t token, uint32_t guarded, Control* snap) {
     pdl_enter();
+    if (snap != nullptr) {
+        for (uint32_t q = threadIdx.x; q < sizeof(Control) / 4; q += blockDim.x) reinterpret_cast<uint32_t*>(snap)[q] = reinterpret_cast<const uint32_t*>(ctl)[q];
+        __syncthreads();
+    }
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         if (guarded && ctl->stop_iter[1] == 0xFFFFFFFFu) return;
         ctl->step_token = token;

@@ -85,6 +85,7 @@ struct yasph_ctx {
     };
     Published* h_pub = nullptr;  // mapped pinned
     Published* d_pub = nullptr;  // its device address
+    Control* ctl_snap = nullptr; // device copy of the control block taken by k_begin_step (yasph_step_n)
     unsigned int pub_seq = 0;
     // export scratch (allocated on demand)
     uint16_t *exp_cd = nullptr, *exp_ct = nullptr;
@@ -426,7 +427,7 @@ static void free_all(yasph_ctx* c) {
                     c->f_alt0, c->f_alt1, c->keys[0], c->keys[1], c->idx[0], c->idx[1], c->cell_key, c->cell_start, c->tile_key, c->tile_pstart,
                     c->tile_cstart, c->bpos, c->bpos_alt, c->scell_key, c->scell_start, c->stile_key, c->stile_cstart, c->tile_runs, c->cslot_d,
                     c->cslot_s, c->lists, c->counts, c->tile_nk, c->apron_idx,
-                    c->radix_base[0], c->scan_chunks, c->scan_total, c->scan_status, c->partials, c->ctl, c->exp_cd, c->exp_ct, c->exp_lists,
+                    c->radix_base[0], c->scan_chunks, c->scan_total, c->scan_status, c->partials, c->ctl, c->ctl_snap, c->exp_cd, c->exp_ct, c->exp_lists,
                     c->ids, c->ids_alt, c->slab.pflag, c->slab.sel[0], c->slab.sel[1], c->slab.sel_g[0], c->slab.sel_g[1], c->slab.send_idx[0], c->slab.send_idx[1],
                     c->slab.ghost_idx[0], c->slab.ghost_idx[1], c->slab.own_idx, c->slab.sbuf[0], c->slab.sbuf[1], c->slab.rbuf[0],
                     c->slab.rbuf[1], c->slab.d_cnt};
@@ -587,6 +588,7 @@ extern "C" int32_t yasph_create(const yasph_config* cfg, yasph_ctx** out) {
     CUC(dmalloc(&c->scan_total, 1));
     CUC(dmalloc(&c->scan_status, (size_t)scan_num_chunks((uint32_t)NM) + 3));
     CUC(dmalloc(&c->ctl, 1));
+    CUC(dmalloc(&c->ctl_snap, 1));
     CUC(cudaMallocHost((void**)&c->h_ctl, sizeof(Control)));
     CUC(cudaHostAlloc((void**)&c->h_pub, sizeof(yasph_ctx::Published), cudaHostAllocMapped));
     memset(c->h_pub, 0, sizeof(yasph_ctx::Published));
@@ -881,10 +883,10 @@ static int32_t wait_published(yasph_ctx* c, volatile unsigned int* vs, unsigned 
     return YASPH_OK;
 }
 // the two halves of read_control: enqueue the snapshot / wait for it
-static int32_t publish_control(yasph_ctx* c, cudaStream_t stream, unsigned int* seq_out) {
+static int32_t publish_control(yasph_ctx* c, cudaStream_t stream, unsigned int* seq_out, const Control* src = nullptr) {
     static_assert(sizeof(Control) % 4 == 0, "Control is published word by word");
     const unsigned int seq = ++c->pub_seq;
-    launch_chain(c, k_publish_control, 1, 64, 0, stream, c->ctl, reinterpret_cast<uint32_t*>(&c->d_pub->ctl), &c->d_pub->seq, seq);
+    launch_chain(c, k_publish_control, 1, 64, 0, stream, src ? src : c->ctl, reinterpret_cast<uint32_t*>(&c->d_pub->ctl), &c->d_pub->seq, seq);
     CHECK_LAUNCH();
     *seq_out = seq;
     return YASPH_OK;
@@ -1925,10 +1927,16 @@ static int32_t enqueue_advect_sort(yasph_ctx* c, bool only_if_converged) {
 
 // The head of a DFSPH step: TimeManager bookkeeping at step entry, then the non-pressure forces + CFL maximum (dfsph.rs:433-477).
 // guarded: enqueued by the previous step ahead of its last read-back (yasph_step_n); `vel` is the velocity array of the step.
-static int32_t dfsph_head(yasph_ctx* c, bool guarded, const float2* vel) {
+// seq_out != null: the control block of the step that ends here is snapshot by k_begin_step and published from the side stream.
+static int32_t dfsph_head(yasph_ctx* c, bool guarded, const float2* vel, unsigned int* seq_out = nullptr) {
     if (++c->step_token == 0u) c->step_token = 1u;
-    launch_chain(c, k_begin_step, 1, 32, 0, c->stream, c->ctl, c->step_token, guarded ? 1u : 0u);
+    launch_chain(c, k_begin_step, 1, 32, 0, c->stream, c->ctl, c->step_token, guarded ? 1u : 0u, seq_out ? c->ctl_snap : nullptr);
     CHECK_LAUNCH();
+    if (seq_out) {
+        CU(cudaEventRecord(c->ev_tables, c->stream));
+        CU(cudaStreamWaitEvent(c->ctl_stream, c->ev_tables, 0));
+        TRY(publish_control(c, c->ctl_stream, seq_out, c->ctl_snap));
+    }
     // slab mode: v_j and rho_j of the ghosts, if stale.  A guarded head is enqueued only when they are fresh (jacobi_solve), and ahead
     // of the swap that makes v* the velocity (dfsph.rs:524): the field to look at is still called v* then.
     const SlabField vel_field = guarded ? SF_VSTAR : SF_VEL;
@@ -2059,9 +2067,8 @@ static int32_t jacobi_solve(yasph_ctx* c, bool first_a_done = false) {
             // yasph_step_n: snapshot of the control block (this step's report) in stream order, then the head of the next step,
             // guarded on the device by this solve's verdict; the host waits for the snapshot while the head runs
             unsigned int seq = 0;
-            TRY(publish_control(c, c->stream, &seq));
-            TRY(dfsph_head(c, true, c->vstar));  // v* becomes the velocity (dfsph.rs:524)
-            TRY(await_control(c, c->stream, seq));
+            TRY(dfsph_head(c, true, c->vstar, &seq));  // v* becomes the velocity (dfsph.rs:524)
+            TRY(await_control(c, c->ctl_stream, seq));
             if (c->h_ctl->stop_iter[SOLVER] != 0xFFFFFFFFu) {
                 c->head_enqueued = true;
                 break;
@@ -2185,11 +2192,16 @@ static int32_t dfsph_step(yasph_ctx* c) {
 
 // The head of a WCSPH step: step entry, then leap frog 1 (wscsph.rs:141-150) fused with key generation.  Nothing in it depends on a
 // verdict of the previous step, so yasph_step_n enqueues it ahead of that step's read-back without a guard.
-static int32_t wcsph_head(yasph_ctx* c) {
+static int32_t wcsph_head(yasph_ctx* c, unsigned int* seq_out = nullptr) {
     const uint32_t n = c->n;
     if (++c->step_token == 0u) c->step_token = 1u;
-    launch_chain(c, k_begin_step, 1, 32, 0, c->stream, c->ctl, c->step_token, 0u);
+    launch_chain(c, k_begin_step, 1, 32, 0, c->stream, c->ctl, c->step_token, 0u, seq_out ? c->ctl_snap : nullptr);
     CHECK_LAUNCH();
+    if (seq_out) {  // the report of the step that ends here leaves from the side stream while this step's first kernels run
+        CU(cudaEventRecord(c->ev_tables, c->stream));
+        CU(cudaStreamWaitEvent(c->ctl_stream, c->ev_tables, 0));
+        TRY(publish_control(c, c->ctl_stream, seq_out, c->ctl_snap));
+    }
     c->slab.valid[SF_VEL] = slab_own_valid(c, {SF_VEL, SF_ACCEL});
     c->slab.valid[SF_POS] = slab_own_valid(c, {SF_POS, SF_VEL});
     pass_begin(c, YASPH_PASS_ADVECT_KEYGEN);
@@ -2341,10 +2353,9 @@ extern "C" int32_t yasph_step(yasph_ctx* c, yasph_step_report* report) {
         TRY(early_velocities(c, c->vel));
         if (c->spec_head) {  // yasph_step_n: the next step's head runs while the host waits for the snapshot
             unsigned int seq = 0;
-            TRY(publish_control(c, c->stream, &seq));
-            TRY(wcsph_head(c));
+            TRY(wcsph_head(c, &seq));
             c->head_enqueued = true;
-            TRY(await_control(c, c->stream, seq));
+            TRY(await_control(c, c->ctl_stream, seq));
         } else {
             TRY(read_control(c));
         }
