@@ -691,6 +691,8 @@ def main():
                 "mean_neighbors": early["mean_neighbors"], "iters_density": early["iters_density"], "iters_divergence": early["iters_divergence"],
                 "warm_density": early["warm_density"], "warm_divergence": early["warm_divergence"],
                 "arithmetic": "strict f32, no FMA contraction, IEEE div/sqrt (bit-exact vs oracle)",
+                "api": ("yasph_step (one call per step)" if os.environ.get("YASPH_BENCH_SINGLE_STEPS") else
+                        "yasph_step_n: the timed steps in ONE call (the application's frame loop, main.rs:339-360); per-step reports as from yasph_step"),
             },
             "gpu_launches": early["gpu_launches"], "clocks": clocks, "roofline": early["roofline"],
         }

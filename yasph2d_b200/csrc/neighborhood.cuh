@@ -597,7 +597,9 @@ struct RunsPrefetch {
 #endif
 constexpr int NB_THREADS = YASPH_NB_THREADS;  // CTA size of the list build (a multiple of 32, >= 2 * TILE_CELLS)
 static_assert(NB_THREADS % 32 == 0 && NB_THREADS >= 2 * TILE_CELLS && sizeof(TileRuns) / 16 <= NB_THREADS, "list-build CTA size");
-constexpr int NB_ROWS = YASPH_MAXN + 1;  // row 64 absorbs everything past the cap
+constexpr int NB_ROWS = YASPH_MAXN + 2;  // rows 64 and 65 absorb everything past the cap (65: "and then some", see list_scan_candidates)
+constexpr int NB_COL_WORDS = NB_ROWS / 2;  // 33 words of two 16-bit rows
+static_assert(NB_ROWS % 2 == 0 && NB_COL_WORDS % 2 == 1, "odd word stride per thread");
 struct ListSmem {
     TileRuns runs[3];
     uint32_t cs[2][2][REGION_CELLS];  // [buffer][dynamic | static][region cell]: slot_start << 16 | count
@@ -605,7 +607,9 @@ struct ListSmem {
     uint32_t ncand[2][TILE_CELLS];    // per own cell: total candidates
     unsigned long long wtotal[NB_THREADS / 32];
     uint32_t nk_max;
-    uint16_t sl[NB_ROWS][NB_THREADS];
+    // hit columns, thread-major: thread t's rows are the NB_COL_WORDS words from sl[t][0] on.  The odd word stride spreads the lanes of
+    // a warp over all banks whatever rows they are at, and the packing below reads two entries per load.
+    uint32_t sl[NB_THREADS][NB_COL_WORDS];
 };
 inline size_t list_smem_bytes(uint32_t cap_dyn, uint32_t cap_stat) { return sizeof(ListSmem) + 2 * ((size_t)cap_dyn + cap_stat) * sizeof(float2); }
 
@@ -648,31 +652,45 @@ __device__ __forceinline__ void list_issue_stage(const ListArgs& a, uint32_t t, 
     if (fits)
         for (uint32_t s = threadIdx.x; s < h.stat_total; s += NB_THREADS) cp_async<8>(&sstat[s], &a.bpos[run_slot_to_global(tr.rs, s)]);
 }
-// float2 at byte offset `off` of the CTA's dynamic shared memory (every `extern __shared__` array starts at its base): spelled
-// this way the compiler knows the address space and emits LDS instead of a generic load
-__device__ __forceinline__ float2 lds_f2(uint32_t off) {
-    extern __shared__ __align__(16) unsigned char dyn_smem_base[];
-    return *reinterpret_cast<const float2*>(dyn_smem_base + off);
+// Shared-memory accesses of the candidate scan by 32-bit shared address.  The load is a plain asm (no memory clobber): the staged
+// positions are not written while a tile is scanned, so the compiler may schedule it across the hit-column stores, which it could
+// not do with an ordinary load (possible alias), and the address is ONE LEA instead of a window-base computation per candidate.
+__device__ __forceinline__ float2 lds_f2_saddr(uint32_t saddr) {
+    float2 v;
+    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(saddr));
+    return v;
 }
-// candidates of one kind (dynamic / static) for one particle; returns the advanced hit count.
-// cand = byte offset of the staged positions in the CTA's dynamic shared memory.
-__device__ __forceinline__ uint32_t list_scan_candidates(uint32_t cand, const uint32_t* __restrict__ cruns, uint32_t ncand, float2 q, float radius_sq,
-                                                         uint16_t* col, uint32_t c) {
-    uint32_t r = 0, rem = 0, s = 0;
+__device__ __forceinline__ uint32_t lds_u32_saddr(uint32_t saddr) {  // the run table of a cell: written before the tile's barrier
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void sts_u16_saddr(uint32_t saddr, uint32_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(saddr), "h"((unsigned short)v) : "memory");
+}
+constexpr uint32_t NB_ROW_BYTES = sizeof(uint16_t);  // rows of a thread's hit column are adjacent
+// candidates of one kind (dynamic / static) for one particle.  cand: shared address of the staged positions; wp: shared address of
+// the thread's hit-column entry of the current row (row == hits so far); returns the advanced wp.  Every candidate's slot is stored
+// at wp, which advances by one row on a hit and is clamped at row YASPH_MAXN + 1: branch-free, the first 64 hits survive, and the
+// caller still sees whether there were exactly 64 or more (row 64 vs 65 when it starts a scan at row <= 64).
+__device__ __forceinline__ uint32_t list_scan_candidates(uint32_t cand, const uint32_t* __restrict__ cruns, uint32_t ncand, float2 q, float radius_sq, uint32_t wp,
+                                                         uint32_t wp_max) {
+    // sr: slot << 16 | candidates left in the run -- the format of a run entry, so a new run is one load, and "next slot, one
+    // candidate less" is one addition
+    uint32_t rp = (uint32_t)__cvta_generic_to_shared(cruns), sr = 0;
     for (uint32_t j = 0; j < ncand; ++j) {
-        if (rem == 0) {
-            const uint32_t run = cruns[r++];
-            s = run >> 16;
-            rem = run & 0xFFFFu;
+        if ((sr & 0xFFFFu) == 0u) {
+            sr = lds_u32_saddr(rp);
+            rp += 4u;
         }
-        const float2 d = lds_f2(cand + s * 8u) - q;
+        const uint32_t s = sr >> 16;
+        const float2 d = lds_f2_saddr(cand + s * 8u) - q;
         const float d2 = mag2(d);  // fl(fl(dx * dx) + fl(dy * dy)), neighborhood_search.rs:356
-        col[min(c, (uint32_t)YASPH_MAXN) * NB_THREADS] = (uint16_t)s;
-        c += (d2 <= radius_sq && d2 > YASPH_MIN_DISTANCE) ? 1u : 0u;
-        ++s;
-        --rem;
+        sts_u16_saddr(wp, s);
+        wp = min(wp + ((d2 <= radius_sq && d2 > YASPH_MIN_DISTANCE) ? NB_ROW_BYTES : 0u), wp_max);
+        sr += 0xFFFFu;  // slot + 1, left - 1
     }
-    return c;
+    return wp;
 }
 // The same for a tile that is too large to stage: every candidate's position comes from global memory through the tile's copy runs
 // (slot -> global index).  Slow and correct: the reference accepts any particle density (neighborhood_search.rs:353-381).
@@ -688,7 +706,7 @@ __device__ __forceinline__ uint32_t list_scan_candidates_global(const float2* __
         }
         const float2 d = gpos[STATIC ? run_slot_to_global(tr->rs, s) : dyn_slot_to_global(*tr, s)] - q;
         const float d2 = mag2(d);
-        col[min(c, (uint32_t)YASPH_MAXN) * NB_THREADS] = (uint16_t)s;
+        col[min(c, (uint32_t)YASPH_MAXN)] = (uint16_t)s;
         c += (d2 <= radius_sq && d2 > YASPH_MIN_DISTANCE) ? 1u : 0u;
         ++s;
         --rem;
@@ -726,7 +744,7 @@ __global__ void __launch_bounds__(NB_THREADS) k_build_lists(ListArgs a) {
     for (uint32_t t = blockIdx.x; t < ntiles; t += G, ++k) {
         const uint32_t b = k & 1u;
         const float2* cdyn = sdyn[b];
-        const uint32_t cdyn_s = (uint32_t)(reinterpret_cast<const unsigned char*>(cdyn) - smem_raw), cstat_s = cdyn_s + a.cap_dyn * (uint32_t)sizeof(float2);
+        const uint32_t cdyn_s = (uint32_t)__cvta_generic_to_shared(cdyn), cstat_s = cdyn_s + a.cap_dyn * (uint32_t)sizeof(float2);  // shared addresses
         const TileRuns& tr = S.runs[k % 3u];
         RunsPrefetch pre;
         const bool have2 = t + 2 * G < ntiles;
@@ -786,14 +804,22 @@ __global__ void __launch_bounds__(NB_THREADS) k_build_lists(ListArgs a) {
                 const uint32_t i = h.pstart + tl;
                 const float2 q = !UNSTAGED ? cdyn[h.own_lo + tl] : a.pos[i];
                 const uint32_t lc = a.keys[i] & (TILE_CELLS - 1);
-                uint16_t* col = &S.sl[0][tid];
-                // dynamic candidates, ascending slot == ascending sorted index (neighborhood_search.rs:353-366)
-                const uint32_t hits_d = !UNSTAGED ? list_scan_candidates(cdyn_s, S.crun[0][lc], S.ncand[0][lc], q, a.g.radius_sq, col, 0u)
-                                                  : list_scan_candidates_global<false>(a.pos, &tr, S.crun[0][lc], S.ncand[0][lc], q, a.g.radius_sq, col, 0u);
+                uint16_t* col = reinterpret_cast<uint16_t*>(&S.sl[tid][0]);
+                // hits_d / c: hit counts after the dynamic / static scan; the staged scan reports them clamped at 65 (enough for
+                // everything below: 64 = the cap is reached, 65 = and at least one more)
+                uint32_t hits_d, c;
+                if (!UNSTAGED) {
+                    const uint32_t col_s = (uint32_t)__cvta_generic_to_shared(col), wp_max = col_s + (uint32_t)(YASPH_MAXN + 1) * NB_ROW_BYTES;
+                    // dynamic candidates, ascending slot == ascending sorted index (neighborhood_search.rs:353-366)
+                    hits_d = (list_scan_candidates(cdyn_s, S.crun[0][lc], S.ncand[0][lc], q, a.g.radius_sq, col_s, wp_max) - col_s) / NB_ROW_BYTES;
+                    const uint32_t cd0 = min(hits_d, (uint32_t)YASPH_MAXN);
+                    // static candidates (neighborhood_search.rs:367-381)
+                    c = (list_scan_candidates(cstat_s, S.crun[1][lc], S.ncand[1][lc], q, a.g.radius_sq, col_s + cd0 * NB_ROW_BYTES, wp_max) - col_s) / NB_ROW_BYTES;
+                } else {
+                    hits_d = list_scan_candidates_global<false>(a.pos, &tr, S.crun[0][lc], S.ncand[0][lc], q, a.g.radius_sq, col, 0u);
+                    c = list_scan_candidates_global<true>(a.bpos, &tr, S.crun[1][lc], S.ncand[1][lc], q, a.g.radius_sq, col, min(hits_d, (uint32_t)YASPH_MAXN));
+                }
                 const uint32_t cd = min(hits_d, (uint32_t)YASPH_MAXN);
-                // static candidates (neighborhood_search.rs:367-381)
-                const uint32_t c = !UNSTAGED ? list_scan_candidates(cstat_s, S.crun[1][lc], S.ncand[1][lc], q, a.g.radius_sq, col, cd)
-                                             : list_scan_candidates_global<true>(a.bpos, &tr, S.crun[1][lc], S.ncand[1][lc], q, a.g.radius_sq, col, cd);
                 const uint32_t ct = min(c, (uint32_t)YASPH_MAXN);
                 // the reference's bookkeeping: "too many neighbors" when the 64th entry is written (:360,375); a static hit
                 // with all 64 slots taken by dynamic neighbours indexes neighbor_set[64] and panics (:373) -- dropped here
@@ -805,17 +831,21 @@ __global__ void __launch_bounds__(NB_THREADS) k_build_lists(ListArgs a) {
                 }
                 const uint32_t nkd = (cd + 3u) >> 2, nks = (ct - cd + 3u) >> 2;
                 const unsigned long long own = h.own_lo + tl;
+                const uint32_t* colw = &S.sl[tid][0];
                 for (uint32_t kb = 0; kb < nkd; ++kb) {  // dynamic words, padded with the own slot
-                    unsigned long long w = 0ull;
-#pragma unroll
-                    for (uint32_t e = 0; e < 4; ++e) w |= (kb * 4 + e < cd ? (unsigned long long)col[(kb * 4 + e) * NB_THREADS] : own) << (16 * e);
+                    unsigned long long w = (unsigned long long)colw[2 * kb] | ((unsigned long long)colw[2 * kb + 1] << 32);
+                    const uint32_t valid = cd - kb * 4u;  // >= 1
+                    if (valid < 4u) {
+                        const unsigned long long keep = (1ull << (16u * valid)) - 1ull;
+                        w = (w & keep) | ((own * 0x0001000100010001ull) & ~keep);
+                    }
                     a.lists[list_word_index(h.pstart, h.pcount, kb, tl)] = w;
                 }
                 for (uint32_t kb = 0; kb < nks; ++kb) {  // static words
                     unsigned long long w = 0ull;
 #pragma unroll
                     for (uint32_t e = 0; e < 4; ++e)
-                        if (cd + kb * 4 + e < ct) w |= (unsigned long long)col[(cd + kb * 4 + e) * NB_THREADS] << (16 * e);
+                        if (cd + kb * 4 + e < ct) w |= (unsigned long long)col[cd + kb * 4 + e] << (16 * e);
                     a.lists[list_word_index(h.pstart, h.pcount, nkd + kb, tl)] = w;
                 }
                 a.counts[i] = cd | (ct << 8);
