@@ -362,7 +362,9 @@ def pass_groups(solver, pt, B, K, it_rho, it_div, w_rho, w_div):
     fused = 1.0 - w_div  # fraction of steps whose iteration-0 pass A ran inside the density / alpha sweep
     return {
         "viscosity": (pt["viscosity"], B["viscosity"]),
-        "density_solve": (pt["density_solve"], B["density_iter"] * it_rho),
+        # one GPU: the solve's last Jacobi B also advects and generates the sort keys (OpJacobiBAdvect) -- no separate pass then, its
+        # bytes (24: position + predicted velocity in, position out) are credited to the group that spends the time
+        "density_solve": (pt["density_solve"], B["density_iter"] * it_rho + (B["advect_keygen"] if pt["advect_keygen"] < 1.0 else 0.0)),
         "density_warm": (pt["density_warm"], B["density_warm"] * w_rho),
         "divergence_solve": (pt["divergence_solve"], B["divergence_iter"] * it_div - fused * (20 + L)),
         "divergence_warm": (pt["divergence_warm"], B["divergence_warm"] * w_div),
@@ -375,7 +377,7 @@ def pass_groups(solver, pt, B, K, it_rho, it_div, w_rho, w_div):
 
 PASS_KERNELS = {  # the kernel(s) behind each sweep group, as ncu names them
     "viscosity": ["k_sweep<OpViscosity>"],
-    "density_solve": ["k_sweep<OpJacobiA<0>>", "k_sweep<OpJacobiB<0, 0>>"],
+    "density_solve": ["k_sweep<OpJacobiA<0>>", "k_sweep<OpJacobiB<0, 0>>", "k_sweep<OpJacobiBAdvect>"],
     "divergence_solve": ["k_sweep<OpJacobiB<1, 0>>"],
     "density_alpha": ["k_sweep<OpDensityAlphaDiv>"],
     "lists": ["k_build_lists"],

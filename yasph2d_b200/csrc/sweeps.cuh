@@ -143,8 +143,9 @@ struct SweepLayout {
         return STAGE_HDR + (size_t)cap_dyn * (sizeof(float2) + P0 + P1) + (Op::USES_STATIC ? (size_t)cap_stat * sizeof(float2) : 0) +
                (size_t)cap_pc * (4 + O0 + O1) + (size_t)nk_stage * cap_pc * 8;
     }
+    static constexpr size_t TAIL = Op::WARP_TAIL ? sizeof(RadixHistSmem) : 0;  // behind the stages: the radix digit histograms of a pass that also generates sort keys
     __host__ __device__ static size_t total_bytes(uint32_t cap_dyn, uint32_t cap_stat, uint32_t cap_pc, uint32_t nk_stage, uint32_t nstages) {
-        return HEAD + RUNS + nstages * stage_bytes(cap_dyn, cap_stat, cap_pc, nk_stage);
+        return HEAD + RUNS + nstages * stage_bytes(cap_dyn, cap_stat, cap_pc, nk_stage) + TAIL;
     }
 };
 template <class Op>
@@ -394,6 +395,9 @@ __global__ void __launch_bounds__(SW_THREADS, YASPH_SWEEP_MIN_CTAS) k_sweep(Swee
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    RadixHistSmem* const hist = Op::WARP_TAIL ? reinterpret_cast<RadixHistSmem*>(stage0 + NS * sbytes) : nullptr;
+    if (Op::WARP_TAIL)
+        for (uint32_t q = threadIdx.x; q < RS_PASSES * RS_BINS; q += SW_THREADS) (&hist->h[0][0])[q] = 0u;
     pdl_enter();  // the barriers above are set up while the previous kernel of the stream drains
     if (op.skip(c.ctl)) return;
 #ifdef YASPH_SWEEP_TIMING
@@ -519,6 +523,7 @@ __global__ void __launch_bounds__(SW_THREADS, YASPH_SWEEP_MIN_CTAS) k_sweep(Swee
             if (nk_st != 0xFFFFFFFFu) {
                 for (uint32_t j = (cw + SW_CONSUMER_WARPS - chunk_base % SW_CONSUMER_WARPS) % SW_CONSUMER_WARPS; j < nchunks; j += SW_CONSUMER_WARPS) {
                     const uint32_t wo = j * 32u + lane;  // particle of the tile (a per-tile order by list length was measured to change nothing)
+                    uint32_t tail_key = 0u;  // Op::WARP_TAIL: what the particle hands to the warp-collective step behind the block below
                     if (wo < h.pcount) {
                         const uint32_t tl = wo;
                         const uint32_t i = h.pstart + tl;
@@ -567,11 +572,17 @@ __global__ void __launch_bounds__(SW_THREADS, YASPH_SWEEP_MIN_CTAS) k_sweep(Swee
                                 }
                             }
                         }
-                        double r = op.finish(c, acc, i, pi, s0, s1, active, w0, w1);
+                        double r;
+                        if constexpr (Op::WARP_TAIL)
+                            r = op.finish_tail(c, acc, i, pi, s0, s1, active, w0, w1, tail_key);
+                        else
+                            r = op.finish(c, acc, i, pi, s0, s1, active, w0, w1);
                         if (Op::REDUCE != REDUCE_NONE && c.ghost != nullptr && c.ghost[i]) r = 0.0;
                         if (Op::REDUCE == REDUCE_SUM) racc += r;
                         if (Op::REDUCE == REDUCE_MAX) racc = fmax(racc, r);
                     }
+                    if constexpr (Op::WARP_TAIL)
+                        if (op.tail_on()) radix_hist_add(*hist, tail_key, wo < h.pcount);  // all 32 lanes: the sort's digit histograms
                 }
             }
             chunk_base += nchunks;
@@ -598,6 +609,8 @@ __global__ void __launch_bounds__(SW_THREADS, YASPH_SWEEP_MIN_CTAS) k_sweep(Swee
     // producers have seen the queue empty before their CTA counts itself done)
     // (a reducing sweep does this with the ticket of its reduction below: one atomic round trip less at the end of the launch)
     __syncthreads();
+    if constexpr (Op::WARP_TAIL)
+        if (op.tail_on()) radix_hist_flush(*hist, op.tail_scratch());
     if (Op::REDUCE == REDUCE_NONE && threadIdx.x == 0) {
         __threadfence();
         if (atomicAdd(&c.ctl->cta_done, 1u) == gridDim.x - 1) {
@@ -675,6 +688,7 @@ struct OpDensityAlpha {
     typedef NoPay O0;
     typedef NoPay O1;
     static constexpr int NOWN = 0;
+    static constexpr bool WARP_TAIL = false;
     __device__ __forceinline__ const O0* own0() const { return nullptr; }
     __device__ __forceinline__ const O1* own1() const { return nullptr; }
     struct Acc {
@@ -756,6 +770,7 @@ struct OpViscosity {
     typedef NoPay O0;
     typedef NoPay O1;
     static constexpr int NOWN = 0;
+    static constexpr bool WARP_TAIL = false;
     __device__ __forceinline__ const O0* own0() const { return nullptr; }
     __device__ __forceinline__ const O1* own1() const { return nullptr; }
     typedef float2 Acc;
@@ -838,6 +853,7 @@ struct OpJacobiA {
     typedef float O0;  // rho_i
     typedef float O1;  // alpha_i
     static constexpr int NOWN = 2;
+    static constexpr bool WARP_TAIL = false;
     __device__ __forceinline__ const O0* own0() const { return dens; }
     __device__ __forceinline__ const O1* own1() const { return alpha; }
     typedef float Acc;
@@ -912,6 +928,7 @@ struct OpDensityAlphaDiv {
     typedef NoPay O0;
     typedef NoPay O1;
     static constexpr int NOWN = 0;
+    static constexpr bool WARP_TAIL = false;
     __device__ __forceinline__ const O0* own0() const { return nullptr; }
     __device__ __forceinline__ const O1* own1() const { return nullptr; }
     struct Acc {
@@ -979,6 +996,7 @@ struct OpJacobiB {
     typedef float2 O0;  // v*_i
     typedef float O1;   // accumulated warm-start value of i
     static constexpr int NOWN = 2;
+    static constexpr bool WARP_TAIL = false;
     __device__ __forceinline__ const O0* own0() const { return vstar; }
     __device__ __forceinline__ const O1* own1() const { return warm; }
     typedef float2 Acc;
@@ -1023,6 +1041,39 @@ struct OpJacobiB {
     __device__ __forceinline__ void finalize(const SweepCommon&, double) const {}
 };
 
+// Jacobi B of the density solver that, when it is the solve's LAST correction (decided on the device by pass A of the same iteration),
+// also advects the particles (dfsph.rs:502-509) and generates the keys and digit histograms of the re-sort that follows
+// (neighborhood_search.rs:111-114): the advected position goes to a second array (neighbours of other tiles still read the old one), key
+// and index to the sort's input.  Saves k_advect_keygen's pass over the particles; single GPU only (no slab classification here).
+struct OpJacobiBAdvect : OpJacobiB<0, false> {
+    static constexpr bool WARP_TAIL = true;
+    float2* pos_out;
+    uint32_t* keys;
+    uint32_t* idx;
+    uint32_t* sort_scratch;
+    GridParams grid;
+    uint32_t last;  // set by prepare(): this launch is the solve's last B
+    __device__ __forceinline__ void prepare(const SweepCommon& c) {
+        OpJacobiB<0, false>::prepare(c);
+        last = c.ctl->stop_iter[0] == iter_index + 1u ? 1u : 0u;
+    }
+    __device__ __forceinline__ bool tail_on() const { return last != 0u; }
+    __device__ __forceinline__ uint32_t* tail_scratch() const { return sort_scratch; }
+    __device__ __forceinline__ double finish_tail(const SweepCommon& c, Acc& a, uint32_t i, float2 pi, P0 ki, P1, bool, O0 v, O1 warm_i, uint32_t& key) const {
+        const float2 vn = sub_scalar(v, inv_dt * a * c.mass);  // dfsph.rs:159
+        vstar[i] = vn;
+        warm[i] = (iter_index == 0 ? 0.0f : warm_i) + ki;
+        if (last) {
+            const float2 p = pi + vn * dt;  // dfsph.rs:505
+            pos_out[i] = p;
+            key = position_to_cidx(grid, p);
+            keys[i] = key;
+            idx[i] = i;
+        }
+        return 0.0;
+    }
+};
+
 // ---------------------------------------------------------------------------------------------------------------------
 // WCSPH accelerations
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1037,6 +1088,7 @@ struct OpWcsphAccel {
     typedef NoPay O0;
     typedef NoPay O1;
     static constexpr int NOWN = 0;
+    static constexpr bool WARP_TAIL = false;
     __device__ __forceinline__ const O0* own0() const { return nullptr; }
     __device__ __forceinline__ const O1* own1() const { return nullptr; }
     typedef float2 Acc;

@@ -49,6 +49,7 @@ struct yasph_ctx {
     KernelConsts kc;
     TimeParams tp;
     // particle state (ping-pong pairs are swapped by the gather)
+    float2* pos_adv = nullptr;  // advected positions written by the density solver's last Jacobi B (OpJacobiBAdvect); swapped with pos afterwards
     float2 *pos = nullptr, *pos_alt = nullptr, *vel = nullptr, *vel_alt = nullptr, *vstar = nullptr, *vstar_alt = nullptr, *accel = nullptr;
     float *dens = nullptr, *alpha = nullptr, *kappa = nullptr, *stiff = nullptr, *err_buf = nullptr, *f_alt0 = nullptr, *f_alt1 = nullptr;
     uint32_t *keys[2] = {nullptr, nullptr}, *idx[2] = {nullptr, nullptr};
@@ -157,6 +158,8 @@ struct yasph_ctx {
     bool have_particles = false, lists_valid = false, dfsph_ready = false;
     uint32_t dfsph_n = 0;  // length of the DFSPH solver arrays (alpha / kappa / stiffness) as of their last resize (dfsph.rs:419-423)
     int list_margin_pct = 12;
+    bool fuse_advect = true;         // YASPH_DEBUG_NO_FUSED_ADVECT=1: the separate k_advect_keygen pass (A/B timing)
+    bool advect_fused_now = false;   // the running density solve advects in its last Jacobi B
     bool scan_status_clean = false;  // scan_status is all zero (k_scan_fused cleans up after itself)
     bool pdl = true;  // programmatic dependent launch of the step's kernel chain (YASPH_DEBUG_NO_PDL=1 turns it off for A/B timing)
     bool spec_advect = false, spec_advect_done = false;  // advect + sort enqueued ahead of the density solver's read-back (dfsph_step)
@@ -423,7 +426,7 @@ static size_t worst_smem_bytes(uint32_t cap_dyn, uint32_t cap_stat, uint32_t cap
 }
 
 static void free_all(yasph_ctx* c) {
-    void* ptrs[] = {c->pos, c->pos_alt, c->vel, c->vel_alt, c->vstar, c->vstar_alt, c->accel, c->dens, c->alpha, c->kappa, c->stiff, c->err_buf,
+    void* ptrs[] = {c->pos_adv, c->pos, c->pos_alt, c->vel, c->vel_alt, c->vstar, c->vstar_alt, c->accel, c->dens, c->alpha, c->kappa, c->stiff, c->err_buf,
                     c->f_alt0, c->f_alt1, c->keys[0], c->keys[1], c->idx[0], c->idx[1], c->cell_key, c->cell_start, c->tile_key, c->tile_pstart,
                     c->tile_cstart, c->bpos, c->bpos_alt, c->scell_key, c->scell_start, c->stile_key, c->stile_cstart, c->tile_runs, c->cslot_d,
                     c->cslot_s, c->lists, c->counts, c->tile_nk, c->apron_idx,
@@ -513,6 +516,7 @@ extern "C" int32_t yasph_create(const yasph_config* cfg, yasph_ctx** out) {
     CUC(cudaEventCreateWithFlags(&c->ev_tables, cudaEventDisableTiming));
     if (const char* e = getenv("YASPH_DEBUG_LIST_MARGIN_PCT")) c->list_margin_pct = atoi(e);
     if (const char* e = getenv("YASPH_DEBUG_NO_PDL")) c->pdl = atoi(e) == 0;
+    if (const char* e = getenv("YASPH_DEBUG_NO_FUSED_ADVECT")) c->fuse_advect = atoi(e) == 0;
 
     c->cap_n = cfg->max_particles;
     c->cap_m = cfg->max_boundary;
@@ -547,6 +551,7 @@ extern "C" int32_t yasph_create(const yasph_config* cfg, yasph_ctx** out) {
     const size_t N = c->cap_n, M = c->cap_m, NM = N > M ? N : M;
     CUC(dmalloc(&c->pos, N));
     CUC(dmalloc(&c->pos_alt, N));
+    CUC(dmalloc(&c->pos_adv, N));
     CUC(dmalloc(&c->vel, N));
     CUC(dmalloc(&c->vel_alt, N));
     CUC(dmalloc(&c->vstar, N));
@@ -612,6 +617,7 @@ extern "C" int32_t yasph_create(const yasph_config* cfg, yasph_ctx** out) {
     CUC((prepare_sweep<OpJacobiA<0>>(c)));
     CUC((prepare_sweep<OpJacobiA<1>>(c)));
     CUC((prepare_sweep<OpJacobiB<0, false>>(c)));
+    CUC((prepare_sweep<OpJacobiBAdvect>(c)));
     CUC((prepare_sweep<OpJacobiB<0, true>>(c)));
     CUC((prepare_sweep<OpJacobiB<1, false>>(c)));
     CUC((prepare_sweep<OpJacobiB<1, true>>(c)));
@@ -1996,7 +2002,12 @@ static int32_t jacobi_solve(yasph_ctx* c, bool first_a_done = false) {
     const uint32_t spec = c->cfg.speculative_iterations;
     uint32_t chunk = prev_iters < 1u ? 1u : std::min(prev_iters, std::max(spec, 8u));
     const int solve_pass = SOLVER == 0 ? YASPH_PASS_DENSITY_SOLVE : YASPH_PASS_DIVERGENCE_SOLVE;
+    bool radix_ready = false;  // fused advect: the sort's scratch is prepared for the B launches of the coming chunk
     while (true) {
+        if (SOLVER == 0 && c->advect_fused_now && !radix_ready) {
+            TRY(radix_prepare(c, c->n));
+            radix_ready = true;
+        }
         pass_begin(c, solve_pass);
         for (uint32_t q = 0; q < chunk; ++q, ++it) {
             if (!(first_a_done && it == 0)) {
@@ -2036,13 +2047,29 @@ static int32_t jacobi_solve(yasph_ctx* c, bool first_a_done = false) {
             }
             c->slab.valid[SF_VSTAR] = slab_out_valid(c, {SF_KFAC}, {SF_VSTAR});
             c->slab.valid[warm_field] = it == 0 ? c->slab.valid[SF_KFAC] : slab_own_valid(c, {warm_field, SF_KFAC});
-            OpJacobiB<SOLVER, false> b;
-            b.vstar = c->vstar;
-            b.kfac = c->err_buf;
-            b.warm = warm_arr;
-            b.clamp_min = 0.f;
-            b.iter_index = it;
-            TRY(launch_sweep(c, b));
+            if (SOLVER == 0 && c->advect_fused_now) {
+                OpJacobiBAdvect b;  // the solve's last B also advects and generates the sort keys (sweeps.cuh)
+                b.vstar = c->vstar;
+                b.kfac = c->err_buf;
+                b.warm = warm_arr;
+                b.clamp_min = 0.f;
+                b.iter_index = it;
+                b.pos_out = c->pos_adv;
+                b.keys = c->keys[0];
+                b.idx = c->idx[0];
+                b.sort_scratch = c->radix_scratch;
+                b.grid = c->grid;
+                b.last = 0u;
+                TRY(launch_sweep(c, b));
+            } else {
+                OpJacobiB<SOLVER, false> b;
+                b.vstar = c->vstar;
+                b.kfac = c->err_buf;
+                b.warm = warm_arr;
+                b.clamp_min = 0.f;
+                b.iter_index = it;
+                TRY(launch_sweep(c, b));
+            }
         }
         pass_end(c);  // the pass times are device time of the launches; the read-back below is host latency
         // v* becomes the velocity (dfsph.rs:524) unless the loop goes on: worth a download when this chunk reaches the previous
@@ -2057,7 +2084,14 @@ static int32_t jacobi_solve(yasph_ctx* c, bool first_a_done = false) {
         if (SOLVER == 0 && c->spec_advect && it >= prev_iters) {
             CU(cudaEventRecord(c->ev_tables, c->stream));
             CU(cudaStreamWaitEvent(c->ctl_stream, c->ev_tables, 0));
-            TRY(enqueue_advect_sort(c, true));
+            if (c->advect_fused_now) {  // keys and histograms come out of the last B: only the sort is left to enqueue
+                pass_begin(c, YASPH_PASS_SORT);
+                TRY(radix_sort(c, c->n));
+                pass_end(c);
+                radix_ready = false;  // a sort that turns out to be premature leaves the scratch dirty
+            } else {
+                TRY(enqueue_advect_sort(c, true));
+            }
             spec_now = true;
             c->spec_advect = false;  // once per solve
         }
@@ -2135,11 +2169,18 @@ static int32_t dfsph_step(yasph_ctx* c) {
     c->slab.valid[SF_VSTAR] = slab_own_valid(c, {SF_VEL, SF_ACCEL});  // the ghosts predict with their own (recomputed) accelerations
     c->spec_advect = !c->slab.active;  // one GPU (also under yasph_step_host: no download is in flight before the positions are final)
     c->spec_advect_done = false;
+    // one GPU, every tile staged: the solve's last Jacobi B advects and generates the sort keys itself (OpJacobiBAdvect)
+    c->advect_fused_now = c->fuse_advect && !c->slab.active && !c->unstaged_tiles && c->num_tiles != 0;
     TRY(jacobi_solve<0>(c));  // dfsph.rs:496
     c->spec_advect = false;
     // advect (dfsph.rs:502-509) fused with the key generation of the re-sort (dfsph.rs:512) -- unless it already ran ahead of the read-back
     const bool sorted_ready = c->spec_advect_done;
-    if (!sorted_ready) TRY(enqueue_advect_sort(c, false));
+    if (c->advect_fused_now) {
+        std::swap(c->pos, c->pos_adv);  // the advected positions (the old ones are not needed any more)
+        c->advect_fused_now = false;
+    } else if (!sorted_ready) {
+        TRY(enqueue_advect_sort(c, false));
+    }
     c->slab.valid[SF_POS] = slab_own_valid(c, {SF_POS, SF_VSTAR});
     {
         // the reference also permutes the old velocities, which are discarded at the final swap (quirk Q7): skipped.
