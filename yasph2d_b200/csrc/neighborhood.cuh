@@ -95,7 +95,6 @@ __global__ void __launch_bounds__(KG_THREADS)
             key = position_to_cidx(g, pos[i]);
             if (i < classify_end) key = slab_classify(sp, i, key);
             keys[i] = key;
-            idx[i] = i;
         }
         radix_hist_add(sh, key, i < n);
     }
@@ -119,7 +118,6 @@ __global__ void __launch_bounds__(KG_THREADS)
             pos[i] = p;
             key = slab_classify(sp, i, position_to_cidx(g, p));
             keys[i] = key;
-            idx[i] = i;
         }
         radix_hist_add(sh, key, i < n);
     }
@@ -143,7 +141,6 @@ __global__ void __launch_bounds__(KG_THREADS)
             pos[i] = p;
             key = slab_classify(sp, i, position_to_cidx(g, p));
             keys[i] = key;
-            idx[i] = i;
         }
         radix_hist_add(sh, key, i < n);
     }

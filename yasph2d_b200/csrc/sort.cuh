@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(RS_THREADS, 2)
         const uint32_t i = base + r * 32 + lane;
         const bool valid = i < n;
         key[r] = valid ? keys_in[i] : 0xFFFFFFFFu;
-        val[r] = valid ? vals_in[i] : 0u;
+        val[r] = valid ? (vals_in != nullptr ? vals_in[i] : i) : 0u;  // vals_in == null: the identity (the first pass of a sort)
     }
     __syncthreads();
     RT_MARK(0)  // ticket + load

@@ -1068,7 +1068,6 @@ struct OpJacobiBAdvect : OpJacobiB<0, false> {
             pos_out[i] = p;
             key = position_to_cidx(grid, p);
             keys[i] = key;
-            idx[i] = i;
         }
         return 0.0;
     }

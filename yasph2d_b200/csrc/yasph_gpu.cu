@@ -750,8 +750,9 @@ static int32_t radix_sort_with(yasph_ctx* c, uint32_t n) {
     const uint32_t ntiles = (n + RS_THREADS * ITEMS - 1) / (RS_THREADS * ITEMS);
     int src = 0;
     for (int pass = 0; pass < RS_PASSES; ++pass) {
-        launch_chain(c, k_radix_pass<ITEMS>, ntiles, RS_THREADS, sizeof(RadixPassSmem<ITEMS>), c->stream, c->keys[src], c->idx[src], c->keys[src ^ 1], c->idx[src ^ 1], n,
-                     pass, c->radix_scratch, ntiles);
+        // the first pass reads no index array: the key-generating kernels do not write one, index i belongs to key i
+        launch_chain(c, k_radix_pass<ITEMS>, ntiles, RS_THREADS, sizeof(RadixPassSmem<ITEMS>), c->stream, c->keys[src], pass == 0 ? (uint32_t*)nullptr : c->idx[src],
+                     c->keys[src ^ 1], c->idx[src ^ 1], n, pass, c->radix_scratch, ntiles);
         CHECK_LAUNCH();
         src ^= 1;
     }
