@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_select4_fused(Select4In in, ui
     __shared__ uint32_t chunk_s;
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
     const unsigned lt = lanemask_lt();
+    pdl_enter();
     if (threadIdx.x == 0) chunk_s = atomicAdd(reinterpret_cast<unsigned int*>(status), 1u);
     __syncthreads();
     const uint32_t b = chunk_s;
@@ -160,6 +161,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_select4_fused(Select4In in, ui
         totals_out[2] = t.z;
         totals_out[3] = t.w;
     }
+    // clean-up by the chunk that finishes last (as k_scan_fused): status[1 + nchunks] counts the chunks that are done
+    __shared__ bool last_s;
+    __syncthreads();
+    const uint32_t nch = gridDim.x;
+    if (threadIdx.x == 0) last_s = atomicAdd(reinterpret_cast<unsigned int*>(status + 1 + nch), 1u) == nch - 1u;
+    __syncthreads();
+    if (last_s)
+        for (uint32_t q = threadIdx.x; q < nch + 2u; q += SCAN_THREADS) status[q] = 0ull;
 }
 
 // ---- particle records (migrants, ghosts): SoA block of `count` records, 8-byte arrays first ---------------------------
@@ -202,6 +211,7 @@ __global__ void k_unpack_records(RecordArrays arr, uint32_t first, uint32_t coun
 }
 // a migrant that arrived must lie inside the slab (particles move less than a cell per step; a slab is many cells wide)
 __global__ void k_check_arrivals(const uint8_t* __restrict__ pflag, uint32_t first, uint32_t end, Control* ctl) {
+    pdl_enter();
     const uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x;
     if (i < end && pflag[i] != SLAB_STAY) atomicAdd(&ctl->err_slab, 1u);
 }
@@ -420,6 +430,7 @@ struct RecordExchangeArgs {
     uint32_t host_seq;
 };
 __global__ void __launch_bounds__(256) k_records_exchange(RecordExchangeArgs a) {
+    pdl_enter();
     const RecordArrays& arr = a.arr;
     {   // ---- push
         const uint32_t nml = a.dst_l ? min(a.counts4[0], a.cap_halo) : 0u, ngl = a.dst_l ? min(a.counts4[2], a.cap_halo - nml) : 0u;
@@ -515,6 +526,7 @@ struct NoAfter {
 template <class After>
 __global__ void k_allreduce_peer(void* dev_ptr, int is_double_sum, PeerBoxHeader* const* __restrict__ boxes, int rank, int world, unsigned long long seq,
                                  Control* ctl, After after) {
+    pdl_enter();
     const int lane = threadIdx.x;
     const unsigned parity = (unsigned)(seq & 1ull);
     const double mine = is_double_sum ? *reinterpret_cast<const double*>(dev_ptr) : (double)*reinterpret_cast<const float*>(dev_ptr);

@@ -592,6 +592,8 @@ extern "C" int32_t yasph_create(const yasph_config* cfg, yasph_ctx** out) {
     CUC(dmalloc(&c->scan_chunks, (size_t)scan_num_chunks((uint32_t)NM) + 1));
     CUC(dmalloc(&c->scan_total, 1));
     CUC(dmalloc(&c->scan_status, (size_t)scan_num_chunks((uint32_t)NM) + 3));
+    CUC(cudaMemset(c->scan_status, 0, ((size_t)scan_num_chunks((uint32_t)NM) + 3) * sizeof(unsigned long long)));
+    c->scan_status_clean = true;  // and its users leave it zeroed
     CUC(dmalloc(&c->ctl, 1));
     CUC(dmalloc(&c->ctl_snap, 1));
     CUC(cudaMallocHost((void**)&c->h_ctl, sizeof(Control)));
@@ -777,8 +779,8 @@ static int32_t build_cells(yasph_ctx* c, uint32_t n, bool is_static) {
         HeadFlagsIn in{c->keys[0]};
         HeadCompactOut out{c->keys[0], ck, cs, is_static ? c->stile_key : c->tile_key, is_static ? nullptr : c->tile_pstart,
                            is_static ? c->stile_cstart : c->tile_cstart, is_static ? c->cap_m : c->max_tiles};
-        // k_scan_fused leaves its status words zeroed (its last chunk cleans up); other users of the area (slab mode's selections) do not
-        if (c->slab.active || !c->scan_status_clean) CU(cudaMemsetAsync(c->scan_status, 0, ((size_t)nch + 2) * sizeof(unsigned long long), c->stream));
+        // k_scan_fused and k_select4_fused leave the status words zeroed (the chunk that finishes last cleans up)
+        if (!c->scan_status_clean) CU(cudaMemsetAsync(c->scan_status, 0, ((size_t)nch + 2) * sizeof(unsigned long long), c->stream));
         c->scan_status_clean = true;
         launch_chain(c, k_scan_fused<HeadFlagsIn, HeadCompactOut, FinishCells>, nch, SCAN_THREADS, 0, c->stream, in, n, c->scan_status, out, fin);
         CHECK_LAUNCH();
@@ -1173,8 +1175,8 @@ static int32_t allreduce_scalar(yasph_ctx* c, void* dev_ptr, ncclDataType_t type
     if (!c->slab.active || c->slab.world < 2) return YASPH_OK;
     if (c->slab.fabric) return loopback_allreduce(c, dev_ptr, type == ncclDouble && op == ncclSum);
     if (c->slab.peer) {
-        k_allreduce_peer<NoAfter><<<1, 32, 0, c->stream>>>(dev_ptr, type == ncclDouble && op == ncclSum ? 1 : 0, c->slab.d_boxes, c->slab.rank, c->slab.world,
-                                                           ++c->slab.ar_seq, c->ctl, NoAfter());
+        launch_chain(c, k_allreduce_peer<NoAfter>, 1, 32, 0, c->stream, dev_ptr, type == ncclDouble && op == ncclSum ? 1 : 0, c->slab.d_boxes, c->slab.rank, c->slab.world,
+                     ++c->slab.ar_seq, c->ctl, NoAfter());
         CHECK_LAUNCH();
         c->slab.allreduces++;
         return YASPH_OK;
@@ -1225,8 +1227,9 @@ static int32_t slab_exchange_particles(yasph_ctx* c, const GatherPlan& gp, uint3
     if (n_old) {
         const uint32_t nch = scan_num_chunks(n_old);
         const Select4In in{c->keys[0], sl.pflag, a_lo, a_hi, b_lo, b_hi};
-        CU(cudaMemsetAsync(c->scan_status, 0, ((size_t)nch + 1) * sizeof(unsigned long long), c->stream));
-        k_select4_fused<<<nch, SCAN_THREADS, 0, c->stream>>>(in, n_old, c->scan_status, sl.sel[0], sl.sel[1], sl.sel_g[0], sl.sel_g[1], sl.max_halo, c->ctl->slab_sel4);
+        if (!c->scan_status_clean) CU(cudaMemsetAsync(c->scan_status, 0, ((size_t)nch + 2) * sizeof(unsigned long long), c->stream));
+        c->scan_status_clean = true;  // both users of the status words leave them zeroed
+        launch_chain(c, k_select4_fused, nch, SCAN_THREADS, 0, c->stream, in, n_old, c->scan_status, sl.sel[0], sl.sel[1], sl.sel_g[0], sl.sel_g[1], sl.max_halo, c->ctl->slab_sel4);
         CHECK_LAUNCH();
     } else {
         CU(cudaMemsetAsync(c->ctl->slab_sel4, 0, 4 * sizeof(uint32_t), c->stream));
@@ -1255,7 +1258,7 @@ static int32_t slab_exchange_particles(yasph_ctx* c, const GatherPlan& gp, uint3
         xa.seq = seq, xa.ticket = sl.d_ticket, xa.pflag = sl.pflag, xa.dc = dcnt, xa.ctl = c->ctl, xa.g = c->grid;
         xa.col_lo = sl.col_lo, xa.col_hi = sl.col_hi, xa.W = W;
         xa.host_counts = sl.d_pcounts, xa.host_seq = hseq;
-        k_records_exchange<<<64, 256, 0, c->stream>>>(xa);  // grid-stride (the counts are known on the device only); all CTAs resident
+        launch_chain(c, k_records_exchange, 64, 256, 0, c->stream, xa);  // grid-stride (the counts are known on the device only); all CTAs resident
         CHECK_LAUNCH();
     } else {
         // host-mediated transports (NCCL send / recv, loopback): counts first, then the records
@@ -1331,12 +1334,12 @@ static int32_t slab_exchange_particles(yasph_ctx* c, const GatherPlan& gp, uint3
     // (4) sort keys of the arrivals: migrants are classified (they must lie inside the slab: particles move less than a cell per step and
     // a slab is many cells wide); ghosts keep their keys, they lie outside the slab by construction
     if (n_mig_in + n_ghost_in) {
-        k_keygen<<<keygen_grid(n_mig_in + n_ghost_in, c->num_sms), KG_THREADS, 0, c->stream>>>(c->pos, n_old, (uint32_t)n2, c->grid, c->keys[0], c->idx[0], c->radix_scratch, sp,
-                                                                                               n_old + n_mig_in);
+        launch_chain(c, k_keygen, keygen_grid(n_mig_in + n_ghost_in, c->num_sms), KG_THREADS, 0, c->stream, c->pos, n_old, (uint32_t)n2, c->grid, c->keys[0], c->idx[0],
+                     c->radix_scratch, sp, n_old + n_mig_in);
         CHECK_LAUNCH();
     }
     if (n_mig_in) {
-        k_check_arrivals<<<blocks_for(n_mig_in, 256), 256, 0, c->stream>>>(sl.pflag, n_old, n_old + n_mig_in, c->ctl);
+        launch_chain(c, k_check_arrivals, blocks_for(n_mig_in, 256), 256, 0, c->stream, sl.pflag, n_old, n_old + n_mig_in, c->ctl);
         CHECK_LAUNCH();
     }
     sl.mig_out[0] = cnt.out_m[0];
@@ -2031,8 +2034,8 @@ static int32_t jacobi_solve(yasph_ctx* c, bool first_a_done = false) {
                 // global residual: sum over the ranks, then the loop decision every rank takes identically
                 if (c->slab.peer && c->slab.world > 1) {  // residual all-reduce and the loop decision in one launch
                     JacobiDecideAfter<SOLVER> after{sp, it, (float)c->slab.n_global, c->cfg.fluid_density};
-                    k_allreduce_peer<JacobiDecideAfter<SOLVER>><<<1, 32, 0, c->stream>>>(&c->ctl->resid_sum, 1, c->slab.d_boxes, c->slab.rank, c->slab.world,
-                                                                                        ++c->slab.ar_seq, c->ctl, after);
+                    launch_chain(c, k_allreduce_peer<JacobiDecideAfter<SOLVER>>, 1, 32, 0, c->stream, (void*)&c->ctl->resid_sum, 1, c->slab.d_boxes, c->slab.rank, c->slab.world,
+                                 ++c->slab.ar_seq, c->ctl, after);
                     CHECK_LAUNCH();
                     c->slab.allreduces++;
                 } else {
