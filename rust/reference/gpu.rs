@@ -99,6 +99,35 @@ impl GpuSolver {
     }
 }
 
+impl GpuSolver {
+    /// The frame loop's inner part in ONE call (`main.rs:339-360`: `update()` performs simulation steps while
+    /// `simulation_frame_loop()` answers `PerformStepAndCallAgain`): `steps` simulation steps on the device-resident state, no
+    /// particle array crosses PCIe.  `yasph_step_n` starts each step's first pass ahead of the read-back that ends the previous one;
+    /// the reports carry every step's `dt_ns`, from which the caller advances `TimeManager` exactly as `steps` calls of
+    /// `simulation_step` would.  The host `Vec`s are stale afterwards: `download()` refreshes them when the renderer wants a frame.
+    pub fn simulation_steps_resident(&mut self, steps: u32, time_manager: &mut TimeManager) -> Vec<sys::yasph_step_report> {
+        let mut reps = vec![sys::yasph_step_report::default(); steps as usize];
+        check(self.ctx, unsafe { sys::yasph_step_n(self.ctx, steps, reps.as_mut_ptr()) }, "yasph_step_n");
+        if let Some(last) = reps.last() {
+            self.device_step = Duration::from_nanos(last.dt_ns);
+            time_manager.set_simulation_step(self.device_step);
+        }
+        reps
+    }
+
+    /// Device -> host `Vec`s (positions, velocities, densities in the current sorted order).
+    pub fn download(&mut self, fluid_world: &mut FluidParticleWorld) {
+        let parts = &mut fluid_world.particles;
+        check(
+            self.ctx,
+            unsafe {
+                sys::yasph_download_particles(self.ctx, parts.positions.as_mut_ptr() as *mut f32, parts.velocities.as_mut_ptr() as *mut f32, parts.densities.as_mut_ptr())
+            },
+            "yasph_download_particles",
+        );
+    }
+}
+
 impl Solver for GpuSolver {
     fn clear_cached_data(&mut self) {
         // dfsph.rs:406-412 / wscsph.rs:122-124
