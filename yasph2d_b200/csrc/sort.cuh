@@ -32,7 +32,7 @@ constexpr int RS_ITEMS_CHOICES[2] = {RS_ITEMS, RS_ITEMS + 2};  // (+4 spills too
 constexpr int RS_BINS = 256;
 constexpr int RS_PASSES = 4;
 #ifndef YASPH_RS_LOOKBACK
-#define YASPH_RS_LOOKBACK 8
+#define YASPH_RS_LOOKBACK 4  // measured at 2 M keys, all tiles resident at once: 1 / 2 / 3 / 4 / 8 / 16 -> sort 73 / 71 / 66 / 67 / 71 / 77 us
 #endif
 constexpr int RS_LOOKBACK = YASPH_RS_LOOKBACK;  // predecessor tiles inspected per look-back round trip
 constexpr uint32_t RS_FLAG_LOCAL = 1u << 30, RS_FLAG_GLOBAL = 2u << 30, RS_VALUE_MASK = (1u << 30) - 1u;
