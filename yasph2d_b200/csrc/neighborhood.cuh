@@ -294,7 +294,10 @@ __device__ __forceinline__ uint32_t region_cells_in_block(uint32_t b) {
 
 // One warp per tile: look the region cells up in the dynamic and the static grid, order them by Morton key, assign
 // shared-memory slots, merge them into copy runs.
-constexpr int TT_WARPS = 4;
+#ifndef YASPH_TT_WARPS
+#define YASPH_TT_WARPS 4
+#endif
+constexpr int TT_WARPS = YASPH_TT_WARPS;
 struct TTScratch {
     uint32_t cnt[2][REGION_CELLS];   // [dynamic | static][region cell, row-major]
     uint32_t gs[2][REGION_CELLS];    // first global index

@@ -7,7 +7,10 @@
 namespace yasph {
 
 constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_ITEMS = 16;
+#ifndef YASPH_SCAN_ITEMS
+#define YASPH_SCAN_ITEMS 16
+#endif
+constexpr int SCAN_ITEMS = YASPH_SCAN_ITEMS;
 constexpr int SCAN_CHUNK = SCAN_THREADS * SCAN_ITEMS;  // 4096
 constexpr int SCAN_WARPS = SCAN_THREADS / 32;
 

@@ -1472,7 +1472,7 @@ static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp
     if (n) {
         TileTableArgs ta{c->tile_key, c->tile_pstart, c->tile_cstart, c->cell_key, c->cell_start, c->stile_key, c->stile_cstart,
                          c->scell_key, c->scell_start, c->tile_runs, c->cslot_d, c->cslot_s};
-        launch_chain(c, k_tile_tables, c->num_sms * 16, TT_WARPS * 32, 0, c->stream, ta, c->ctl);
+        launch_chain(c, k_tile_tables, c->num_sms * (64 / TT_WARPS), TT_WARPS * 32, 0, c->stream, ta, c->ctl);
         CHECK_LAUNCH();
     }
     c->slab.halo_lists_valid = false;  // per-pass halo lists of the new structure are built when a pass needs an exchange (ensure_halo_lists)
