@@ -634,8 +634,8 @@ def main():
             steps_done[0] += 1
             if world == 1:
                 return ctx.step_host(pos[: n_cur[0]], vel[: n_cur[0]], den[: n_cur[0]], input_unchanged=unchanged[0])
-            moved[0] += n_cur[0] * 16
-            rep, n_out = ctx.step_host_slab(pos, vel, den, n_cur[0])
+            moved[0] += 0 if unchanged[0] else n_cur[0] * 16
+            rep, n_out = ctx.step_host_slab(pos, vel, den, n_cur[0], input_unchanged=unchanged[0])
             n_cur[0] = n_out
             moved[1] += n_out * 20
             return rep
@@ -650,13 +650,11 @@ def main():
             timeline = {k: round(float(np.mean([t[k] for t in tl])), 1) for k in tl[0]}
         # the same call for a host that only READS the particle arrays between steps (the reference's application, main.rs:242-258):
         # yasph_step_host_ex(YASPH_HOST_INPUT_UNCHANGED) skips the upload; reported beside the headline, never instead of it
-        no_upload = None
-        if world == 1:
-            unchanged[0] = True
-            ums, _, _ = timed(host_step, args.steps, args.warmup)
-            unchanged[0] = False
-            no_upload = {"value": n_total * args.steps / (ums * 1e-3), "ms_per_step": ums / args.steps, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(n_total * 20),
-                         "api": "yasph_step_host_ex(YASPH_HOST_INPUT_UNCHANGED)"}
+        unchanged[0] = True
+        ums, _, _ = timed(host_step, args.steps, args.warmup)
+        unchanged[0] = False
+        no_upload = {"value": n_total * args.steps / (ums * 1e-3), "ms_per_step": ums / args.steps, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(n_total * 20),
+                     "api": "yasph_step_host%s_ex(YASPH_HOST_INPUT_UNCHANGED)" % ("" if world == 1 else "_slab")}
         e2e = {"value": n_total * args.steps / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(n_total * 16), "d2h_bytes_per_step": int(n_total * 20),
                "ms_per_step": ems / args.steps, "device_timeline_us": timeline, "input_unchanged": no_upload, "host_affinity": numa_note,
                "api": "yasph_step_host%s (upload pos+vel, simulation_step, download pos+vel+densities; bytes summed over ranks)" % ("" if world == 1 else "_slab")}

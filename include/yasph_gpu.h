@@ -269,6 +269,10 @@ int32_t yasph_cell_column(const yasph_config* cfg, float x, uint32_t* column);
  * particles after migration out (*n_out <= capacity). */
 int32_t yasph_step_host_slab(yasph_ctx* ctx, float* pos_xy, float* vel_xy, float* densities, uint32_t n_in, uint32_t capacity,
                              uint32_t* n_out, yasph_step_report* report);
+/* The same with options (YASPH_HOST_INPUT_UNCHANGED as for yasph_step_host_ex: the arrays still hold what the previous call on this
+ * context handed back, so nothing is uploaded -- the arrays are outputs only). */
+int32_t yasph_step_host_slab_ex(yasph_ctx* ctx, float* pos_xy, float* vel_xy, float* densities, uint32_t n_in, uint32_t capacity,
+                                uint32_t options, uint32_t* n_out, yasph_step_report* report);
 
 /* ---- measurement ----------------------------------------------------------------------------------------------- */
 #define YASPH_NUM_PASSES 17

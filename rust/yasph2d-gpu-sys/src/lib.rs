@@ -140,6 +140,7 @@ extern "C" {
     // trait Solver (solver/mod.rs:12-18)
     pub fn yasph_clear_cached(ctx: *mut yasph_ctx) -> i32;
     pub fn yasph_step(ctx: *mut yasph_ctx, report: *mut yasph_step_report) -> i32;
+    pub fn yasph_step_host_slab_ex(ctx: *mut yasph_ctx, pos: *mut f32, vel: *mut f32, dens: *mut f32, n_in: u32, capacity: u32, options: u32, n_out: *mut u32, report: *mut yasph_step_report) -> i32;
     pub fn yasph_step_n(ctx: *mut yasph_ctx, steps: u32, reports: *mut yasph_step_report) -> i32;
     pub fn yasph_step_host(ctx: *mut yasph_ctx, pos: *mut f32, vel: *mut f32, dens: *mut f32, n: u32, report: *mut yasph_step_report) -> i32;
     // TimeManager mirror (timemanager.rs:131-138, 252-279)

@@ -89,6 +89,56 @@ def test_slab_frames_equal_single_steps(solver):
             assert np.array_equal(merged_a[s][k], merged_b[s][k]), (s, k)
 
 
+def test_step_host_slab_input_unchanged_equals_uploading():
+    """yasph_step_host_slab_ex(YASPH_HOST_INPUT_UNCHANGED): a host that has not written to the arrays since the previous call skips the
+    upload; arrays and reports equal those of the uploading call step by step (two slabs, loopback; migration included)."""
+    import threading
+
+    from slab_common import base_config
+
+    pos, vel, boundary = scene_arrays("dam")
+    steps, world = 80, 2
+    out = {}
+
+    def run(unchanged):
+        fabric = slab.LoopbackFabric(world)
+        cfg = base_config(2 * len(pos), len(boundary))
+        res, errors = [None] * world, []
+
+        def worker(rank):
+            try:
+                ctx, _, _ = slab.make_slab_context(cfg, rank, world, fabric, pos, vel, boundary)
+                p0, v0, _ = ctx.download_particles()
+                cap = len(pos)
+                hp, hv, hd = np.zeros((cap, 2), np.float32), np.zeros((cap, 2), np.float32), np.zeros(cap, np.float32)
+                n = len(p0)
+                hp[:n], hv[:n] = p0, v0
+                reps = []
+                for s in range(steps):
+                    rep, n = ctx.step_host_slab(hp, hv, hd, n, input_unchanged=unchanged and s > 0)
+                    reps.append((rep.dt_ns, rep.iters_density, rep.iters_divergence, n))
+                res[rank] = (reps, hp[:n].copy(), hv[:n].copy(), hd[:n].copy(), ctx.info().as_dict())
+                ctx.close()
+            except Exception as e:  # noqa: BLE001
+                errors.append((rank, repr(e)))
+
+        ts = [threading.Thread(target=worker, args=(r,), daemon=True) for r in range(world)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join(timeout=120)
+        assert not any(t.is_alive() for t in ts) and not errors, errors
+        fabric.close()
+        return res
+
+    a, b = run(False), run(True)
+    for ra, rb in zip(a, b):
+        assert ra[0] == rb[0]
+        for x, z in zip(ra[1:4], rb[1:4]):
+            assert np.array_equal(x, z)
+    assert sum(r[4]["migrated_in"] for r in a) >= 0 and any(r[0][-1][3] != r[0][0][3] for r in a), "a particle should have migrated"
+
+
 def test_slabs_of_many_sort_tiles_match_single_context():
     """A tank twin of 160 x 192 particles in two slabs of ~15 000 particles: the re-sort of a slab runs over several radix tiles
     (6144 pairs each), and migrants + ghosts appended between key generation and the sort push the count across a tile boundary for

@@ -34,7 +34,7 @@ EXPORTED_SYMBOLS = [
     "yasph_solver_state_get", "yasph_solver_state_set", "yasph_upload_field",
     "yasph_launch_count", "yasph_stream", "yasph_scene_fluid_rect", "yasph_scene_boundary_line", "yasph_scene_boundary_thick_line",
     "yasph_duration_from_secs_f32", "yasph_duration_as_secs_f32",
-    "yasph_comm_unique_id", "yasph_comm_init", "yasph_slab_set", "yasph_slab_get", "yasph_cell_column", "yasph_step_host_slab",
+    "yasph_comm_unique_id", "yasph_comm_init", "yasph_slab_set", "yasph_slab_get", "yasph_cell_column", "yasph_step_host_slab", "yasph_step_host_slab_ex",
     "yasph_loopback_create", "yasph_loopback_destroy", "yasph_comm_init_loopback",
 ]
 
@@ -161,6 +161,7 @@ def lib():
     sig("yasph_loopback_destroy", C.c_int32, vp)
     sig("yasph_comm_init_loopback", C.c_int32, vp, vp, C.c_int32)
     sig("yasph_step_host_slab", C.c_int32, vp, f32p, f32p, f32p, C.c_uint32, C.c_uint32, u32p, rp)
+    sig("yasph_step_host_slab_ex", C.c_int32, vp, f32p, f32p, f32p, C.c_uint32, C.c_uint32, C.c_uint32, u32p, rp)
     _lib = L
     return L
 

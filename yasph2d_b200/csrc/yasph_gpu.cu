@@ -2733,12 +2733,22 @@ extern "C" int32_t yasph_cell_column(const yasph_config* cfg, float x, uint32_t*
 
 extern "C" int32_t yasph_step_host_slab(yasph_ctx* c, float* pos_xy, float* vel_xy, float* densities, uint32_t n_in, uint32_t capacity, uint32_t* n_out,
                                         yasph_step_report* report) {
+    return yasph_step_host_slab_ex(c, pos_xy, vel_xy, densities, n_in, capacity, 0u, n_out, report);
+}
+extern "C" int32_t yasph_step_host_slab_ex(yasph_ctx* c, float* pos_xy, float* vel_xy, float* densities, uint32_t n_in, uint32_t capacity, uint32_t options,
+                                           uint32_t* n_out, yasph_step_report* report) {
     if (!c || !pos_xy || !vel_xy || !n_out) return YASPH_ERR_INVALID_ARGUMENT;
     if (!c->slab.active) return fail(c, YASPH_ERR_STATE, "yasph_step_host_slab: yasph_slab_set has not been called");
     if (n_in > c->cap_n || n_in > capacity) return fail(c, YASPH_ERR_CAPACITY, "yasph_step_host_slab: n_in=%u out of range", n_in);
     CU(cudaSetDevice(c->device));
     auto& sl = c->slab;
-    if (c->have_particles && c->lists_valid && n_in == sl.n_own) {
+    if (options & YASPH_HOST_INPUT_UNCHANGED) {
+        // the caller has not written to the arrays since the previous call handed them back: the device still holds this rank's
+        // particles (between its ghosts, in the sorted order) -- nothing to upload, the arrays are outputs only
+        if (!c->have_particles || !c->lists_valid || n_in != sl.n_own)
+            return fail(c, YASPH_ERR_STATE, "yasph_step_host_slab_ex: YASPH_HOST_INPUT_UNCHANGED, but the device holds %u owned particles and the call passes %u",
+                        c->have_particles ? sl.n_own : 0u, n_in);
+    } else if (c->have_particles && c->lists_valid && n_in == sl.n_own) {
         // the arrays are the owned particles in the order of the last download: put them back between the ghosts
         TRY(ensure_own_index(c));
         if (n_in) {

@@ -115,11 +115,13 @@ class SlabContext(GpuContext):
         self._ck(capi.lib().yasph_slab_get(self.h, C.byref(out)))
         return out
 
-    def step_host_slab(self, pos, vel, dens, n_in):
-        """pos/vel/dens: host arrays with spare capacity; returns (report, n_out)."""
+    def step_host_slab(self, pos, vel, dens, n_in, input_unchanged=False):
+        """pos/vel/dens: host arrays with spare capacity; returns (report, n_out).  input_unchanged: the arrays still hold what the
+        previous call handed back (the upload is skipped)."""
         rep = capi.StepReport()
         n_out = C.c_uint32(0)
-        self._ck(capi.lib().yasph_step_host_slab(self.h, _f32p(pos), _f32p(vel), _f32p(dens), int(n_in), len(pos), C.byref(n_out), C.byref(rep)))
+        self._ck(capi.lib().yasph_step_host_slab_ex(self.h, _f32p(pos), _f32p(vel), _f32p(dens), int(n_in), len(pos),
+                                                    capi.HOST_INPUT_UNCHANGED if input_unchanged else 0, C.byref(n_out), C.byref(rep)))
         return rep, n_out.value
 
     def local_field(self, field, dtype, width=1):
