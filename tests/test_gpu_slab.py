@@ -91,8 +91,11 @@ def test_slab_frames_equal_single_steps(solver):
 
 def test_step_host_slab_input_unchanged_equals_uploading():
     """yasph_step_host_slab_ex(YASPH_HOST_INPUT_UNCHANGED): a host that has not written to the arrays since the previous call skips the
-    upload; arrays and reports equal those of the uploading call step by step (two slabs, loopback; migration included)."""
+    upload; arrays and reports equal those of the uploading call step by step (two slabs, loopback; migration included).  The second
+    run also uses pinned arrays with room for max_particles: positions and densities then leave on the copy stream in mid-step."""
     import threading
+
+    import torch
 
     from slab_common import base_config
 
@@ -100,7 +103,7 @@ def test_step_host_slab_input_unchanged_equals_uploading():
     steps, world = 80, 2
     out = {}
 
-    def run(unchanged):
+    def run(unchanged, pinned=False):
         fabric = slab.LoopbackFabric(world)
         cfg = base_config(2 * len(pos), len(boundary))
         res, errors = [None] * world, []
@@ -109,8 +112,13 @@ def test_step_host_slab_input_unchanged_equals_uploading():
             try:
                 ctx, _, _ = slab.make_slab_context(cfg, rank, world, fabric, pos, vel, boundary)
                 p0, v0, _ = ctx.download_particles()
-                cap = len(pos)
-                hp, hv, hd = np.zeros((cap, 2), np.float32), np.zeros((cap, 2), np.float32), np.zeros(cap, np.float32)
+                cap = int(cfg.max_particles) if pinned else len(pos)
+                if pinned:
+                    keep = [torch.zeros((cap, 2), dtype=torch.float32, pin_memory=True), torch.zeros((cap, 2), dtype=torch.float32, pin_memory=True),
+                            torch.zeros((cap,), dtype=torch.float32, pin_memory=True)]
+                    hp, hv, hd = (t.numpy() for t in keep)
+                else:
+                    hp, hv, hd = np.zeros((cap, 2), np.float32), np.zeros((cap, 2), np.float32), np.zeros(cap, np.float32)
                 n = len(p0)
                 hp[:n], hv[:n] = p0, v0
                 reps = []
@@ -131,11 +139,11 @@ def test_step_host_slab_input_unchanged_equals_uploading():
         fabric.close()
         return res
 
-    a, b = run(False), run(True)
-    for ra, rb in zip(a, b):
-        assert ra[0] == rb[0]
-        for x, z in zip(ra[1:4], rb[1:4]):
-            assert np.array_equal(x, z)
+    a, b, p = run(False), run(True), run(True, pinned=True)
+    for ra, rb, rp in zip(a, b, p):
+        assert ra[0] == rb[0] == rp[0]
+        for x, z, q in zip(ra[1:4], rb[1:4], rp[1:4]):
+            assert np.array_equal(x, z) and np.array_equal(x, q)
     assert sum(r[4]["migrated_in"] for r in a) >= 0 and any(r[0][-1][3] != r[0][0][3] for r in a), "a particle should have migrated"
 
 

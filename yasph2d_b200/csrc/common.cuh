@@ -265,7 +265,7 @@ struct Control {
     // tile queue of the persistent sweeps (sweeps.cuh): tiles handed out beyond the first one per CTA, CTAs that have finished
     unsigned int tile_next, cta_done;
     // slab mode (multi-GPU): counts of the ordered selections of a neighbourhood update
-    unsigned long long slab_migrants;    // low word: migrants to the left rank, high word: to the right rank
+    unsigned long long slab_migrants;    // owned particles counted by a mid-step selection (yasph_step_host_slab: checked with the step's last control block)
     unsigned long long slab_ghost_send;  // own particles in the first / last owned column (sent as ghosts)
     unsigned long long slab_send;        // per-pass halo send lists (left | right), in sorted order
     unsigned long long slab_ghost;       // ghosts from the left | right rank, in sorted order

@@ -142,6 +142,7 @@ struct yasph_ctx {
         uint32_t n_own = 0, n_ghost[2] = {0, 0}, n_send[2] = {0, 0};
         uint32_t mig_out[2] = {0, 0}, mig_in = 0;
         bool own_idx_valid = false;
+        bool own_count_unchecked = false;  // own_idx was built in mid-step without reading its count back (checked with the step's last control block)
         uint64_t halo_exchanges = 0, allreduces = 0;
         // peer-memory transport (slab.cuh): the own mailbox, the peers' mailboxes as mapped into this process, sequence numbers
         bool peer = false, peer_tried = false;
@@ -1384,6 +1385,21 @@ static int32_t submit_downloads(yasph_ctx* c) {
     }
     return YASPH_OK;
 }
+static int32_t ensure_own_index(yasph_ctx* c, bool no_wait);
+// Slab mode: the caller gets the OWNED particles only -- they are compacted through `scratch` first (the order of the last download).
+template <typename T>
+static int32_t early_download_owned(yasph_ctx* c, float** host_dst, const T* dev, T* scratch, int which) {
+    if (!*host_dst) return YASPH_OK;
+    auto& sl = c->slab;
+    if (!sl.active) return early_download(c, host_dst, dev, (size_t)c->n * sizeof(T), which);
+    if (sl.n_ghost[0] + sl.n_ghost[1] == 0) return early_download(c, host_dst, dev, (size_t)sl.n_own * sizeof(T), which);
+    TRY(ensure_own_index(c, true));
+    if (sl.n_own) {
+        k_own_compact<T><<<blocks_for(sl.n_own, 256), 256, 0, c->stream>>>(dev, sl.own_idx, sl.n_own, scratch);
+        CHECK_LAUNCH();
+    }
+    return early_download(c, host_dst, scratch, (size_t)sl.n_own * sizeof(T), which);
+}
 static int32_t early_velocities(yasph_ctx* c, const float2* final_vel) {
     if (!c->early_vel_out) return YASPH_OK;
     if (c->cfg.flags & YASPH_FLAG_PROFILE_PASSES) CU(cudaEventRecord(c->ev_host[4], c->stream));
@@ -1518,6 +1534,8 @@ static int32_t neighborhood_update(yasph_ctx* c, bool keys_ready, GatherPlan& gp
         if (g0 != sl.n_ghost[0] || g1 != sl.n_ghost[1])
             return fail(c, YASPH_ERR_STATE, "rank %d: %u | %u ghosts in the sorted structure, %u | %u were exchanged", sl.rank, g0, g1, sl.n_ghost[0], sl.n_ghost[1]);
         sl.n_own = n - g0 - g1;
+        // yasph_step_host_slab: the sorted positions are final -- the owned ones leave on the copy stream while the step goes on
+        if (positions_final) TRY(early_download_owned(c, &c->early_pos_out, c->pos, c->pos_alt, 0));
     }
     c->num_tiles = n ? c->h_ctl->num_tiles : 0u;
     // Staging capacities of the tile kernels: the largest tile, unless that exceeds the configured limits or the shared memory of
@@ -1621,11 +1639,19 @@ static int32_t reset_particle_set(yasph_ctx* c, uint32_t n) {
 }
 
 // slab mode: sorted positions of the owned particles (built on demand, valid until the next neighbourhood update)
-static int32_t ensure_own_index(yasph_ctx* c) {
+// no_wait: in mid-step (yasph_step_host_slab hands results over while the step still computes) the count is not read back here;
+// it travels with the step's last control block and is checked there
+static int32_t ensure_own_index(yasph_ctx* c, bool no_wait) {
     auto& sl = c->slab;
     if (!sl.active || sl.own_idx_valid) return YASPH_OK;
     if (!sl.own_idx) CU(dmalloc(&sl.own_idx, (size_t)c->cap_n));
-    TRY(select_pair(c, OwnSelIn{sl.pflag}, c->n, sl.own_idx, sl.own_idx, nullptr, c->cap_n, &c->ctl->slab_own));
+    // (the deferred count has its own word of the control block: slab_own is borrowed by the halo lists in mid-step)
+    TRY(select_pair(c, OwnSelIn{sl.pflag}, c->n, sl.own_idx, sl.own_idx, nullptr, c->cap_n, no_wait ? &c->ctl->slab_migrants : &c->ctl->slab_own));
+    if (no_wait) {
+        sl.own_idx_valid = true;
+        sl.own_count_unchecked = true;
+        return YASPH_OK;
+    }
     unsigned long long cnt = 0;
     CU(cudaMemcpyAsync(&cnt, &c->ctl->slab_own, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -1642,7 +1668,7 @@ static int32_t download_array(yasph_ctx* c, const T* src, T* scratch, void* host
         if (n) CU(cudaMemcpyAsync(host_out, src, n * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
         return YASPH_OK;
     }
-    TRY(ensure_own_index(c));
+    TRY(ensure_own_index(c, false));
     const uint32_t n = c->slab.n_own;
     if (!n) return YASPH_OK;
     k_own_compact<T><<<blocks_for(n, 256), 256, 0, c->stream>>>(src, c->slab.own_idx, n, scratch);
@@ -2227,7 +2253,7 @@ static int32_t dfsph_step(yasph_ctx* c) {
         TRY(launch_sweep(c, da));
     }
     pass_end(c);
-    TRY(early_download(c, &c->early_dens_out, c->dens, (size_t)c->n * sizeof(float), 1));  // densities are final (dfsph.rs:516)
+    TRY(early_download_owned(c, &c->early_dens_out, c->dens, c->f_alt0, 1));  // densities are final (dfsph.rs:516)
     c->slab.valid[SF_DENS] = c->slab.valid[SF_ALPHA] = slab_out_valid(c, {SF_POS}, {});
     TRY(jacobi_solve<1>(c, fuse_div_a0));  // dfsph.rs:521
     std::swap(c->vel, c->vstar);    // dfsph.rs:524
@@ -2275,7 +2301,7 @@ static int32_t wcsph_step(yasph_ctx* c) {
     pass_begin(c, YASPH_PASS_DENSITY_ALPHA);
     TRY((launch_density<1, true>(c)));  // Poly6, wscsph.rs:154; + Tait pressure per particle (wscsph.rs:91-92)
     pass_end(c);
-    TRY(early_download(c, &c->early_dens_out, c->dens, (size_t)n * sizeof(float), 1));  // densities are final (wscsph.rs:154)
+    TRY(early_download_owned(c, &c->early_dens_out, c->dens, c->f_alt0, 1));  // densities are final (wscsph.rs:154)
     c->slab.valid[SF_DENS] = c->slab.valid[SF_VSTAR] = slab_out_valid(c, {SF_POS}, {});  // (rho, p) lives in the v* buffer
     TRY(slab_refresh(c, SF_VSTAR, c->vstar));  // (rho, p) and v of the ghosts, if stale in the first ghost column
     TRY(slab_refresh(c, SF_VEL, c->vel));
@@ -2750,7 +2776,7 @@ extern "C" int32_t yasph_step_host_slab_ex(yasph_ctx* c, float* pos_xy, float* v
                         c->have_particles ? sl.n_own : 0u, n_in);
     } else if (c->have_particles && c->lists_valid && n_in == sl.n_own) {
         // the arrays are the owned particles in the order of the last download: put them back between the ghosts
-        TRY(ensure_own_index(c));
+        TRY(ensure_own_index(c, false));
         if (n_in) {
             CU(cudaMemcpyAsync(c->pos_alt, pos_xy, (size_t)n_in * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
             CU(cudaMemcpyAsync(c->vel_alt, vel_xy, (size_t)n_in * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
@@ -2767,23 +2793,40 @@ extern "C" int32_t yasph_step_host_slab_ex(yasph_ctx* c, float* pos_xy, float* v
             CU(cudaMemcpyAsync(c->vel, vel_xy, (size_t)n_in * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
         }
     }
+    // Pinned host arrays with room for every particle this rank can own take the positions and densities as soon as they are final,
+    // on the copy stream, while the step goes on (as yasph_step_host does); the velocities and everything else follow at the end.
+    const bool roomy = capacity >= c->cap_n;
+    c->early_pos_out = roomy && is_pinned_host(pos_xy) ? pos_xy : nullptr;
+    c->early_dens_out = roomy && densities && is_pinned_host(densities) ? densities : nullptr;
+    sl.own_count_unchecked = false;
     // every rank steps, also one that currently owns no particle (the collectives are matched)
-    if (c->cfg.solver == YASPH_SOLVER_WCSPH)
-        TRY(wcsph_step(c));
-    else
-        TRY(dfsph_step(c));
-    TRY(read_control(c));
+    int32_t rc = c->cfg.solver == YASPH_SOLVER_WCSPH ? wcsph_step(c) : dfsph_step(c);
+    if (rc == YASPH_OK) rc = submit_downloads(c);
+    if (rc == YASPH_OK) rc = read_control(c);
+    const bool late_pos = c->early_pos_out != nullptr || !(roomy && is_pinned_host(pos_xy));
+    const bool late_dens = densities && (c->early_dens_out != nullptr || !(roomy && is_pinned_host(densities)));
+    c->early_pos_out = c->early_dens_out = nullptr;
+    if (rc != YASPH_OK) {
+        c->pending[0].host = c->pending[1].host = nullptr;
+        cudaStreamSynchronize(c->stream);
+        cudaStreamSynchronize(c->copy_stream);  // nothing of this call stays in flight towards the caller's arrays
+        return rc;
+    }
     pass_resolve(c);
-    TRY(check_capacity_flags(c));
+    rc = check_capacity_flags(c);
+    if (rc == YASPH_OK && sl.own_count_unchecked && (uint32_t)(c->h_ctl->slab_migrants & 0xFFFFFFFFull) != sl.n_own)
+        rc = fail(c, YASPH_ERR_STATE, "rank %d: %llu owned particles flagged, %u expected", sl.rank, c->h_ctl->slab_migrants & 0xFFFFFFFFull, sl.n_own);
+    sl.own_count_unchecked = false;
     fill_report(c, report);
-    if (c->h_ctl->nonfinite) return fail(c, YASPH_ERR_NONFINITE, "non-finite Jacobi residual (solver mask %u)", c->h_ctl->nonfinite);
+    if (rc == YASPH_OK && c->h_ctl->nonfinite) rc = fail(c, YASPH_ERR_NONFINITE, "non-finite Jacobi residual (solver mask %u)", c->h_ctl->nonfinite);
     *n_out = sl.n_own;
-    if (sl.n_own > capacity) return fail(c, YASPH_ERR_CAPACITY, "yasph_step_host_slab: %u owned particles after the step > capacity %u", sl.n_own, capacity);
-    TRY(download_array(c, c->pos, c->pos_alt, pos_xy));
-    TRY(download_array(c, c->vel, c->vel_alt, vel_xy));
-    if (densities) TRY(download_array(c, c->dens, c->f_alt0, densities));
-    CU(cudaStreamSynchronize(c->stream));
-    return YASPH_OK;
+    if (rc == YASPH_OK && sl.n_own > capacity) rc = fail(c, YASPH_ERR_CAPACITY, "yasph_step_host_slab: %u owned particles after the step > capacity %u", sl.n_own, capacity);
+    if (rc == YASPH_OK) rc = download_array(c, c->vel, c->vel_alt, vel_xy);
+    if (rc == YASPH_OK && late_pos) rc = download_array(c, c->pos, c->pos_alt, pos_xy);
+    if (rc == YASPH_OK && late_dens) rc = download_array(c, c->dens, c->f_alt0, densities);
+    cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->copy_stream);
+    return rc;
 }
 
 #include "scene.inl"
